@@ -1,0 +1,237 @@
+"""ctypes bindings for the test-only checkers.  TEST INFRASTRUCTURE ONLY.
+
+`Oracle("port")` wraps oracle/liboracle.so (hrm_oracle.c, the plain-C restatement) and
+`Oracle("ref")` wraps oracle/_ref/libhrm_ref.so (the reference's own sources compiled from
+/root/reference by oracle/Makefile).  Both expose the same Python methods so that tests can
+run one against the other.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs may import this module; the product (hashreadmapper_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libhrm_ref.so")
+REFERENCE_ROOT = "/root/reference"
+
+
+def build(want_ref=True):
+    """Compile the checkers (building the checker is not using it)."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    if want_ref and os.path.isdir(REFERENCE_ROOT):
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+class Alignment(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "sw_score", "sw_score_next_best", "ref_begin", "ref_end", "query_begin", "query_end",
+        "ref_end_next_best", "mismatches", "flag", "cigar_len")]
+
+    def astuple(self):
+        return tuple(getattr(self, n) for n, _ in self._fields_[:9])
+
+
+class MappedRead(C.Structure):
+    _fields_ = [("orientation", C.c_int32), ("hammingDistance", C.c_int32), ("shift", C.c_int32),
+                ("chromosomeId", C.c_int32), ("position", C.c_int64)]
+
+
+MAPPED_DTYPE = np.dtype([("orientation", "<i4"), ("hammingDistance", "<i4"), ("shift", "<i4"),
+                         ("chromosomeId", "<i4"), ("position", "<i8")])
+ALIGN_DTYPE = np.dtype([(n, "<i4") for n, _ in Alignment._fields_])
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Oracle:
+    def __init__(self, kind="port"):
+        self.kind = kind
+        if kind == "port":
+            if not os.path.exists(PORT_SO):
+                build(want_ref=False)
+            self.lib = C.CDLL(PORT_SO)
+            self.pfx = "orc_"
+        elif kind == "ref":
+            if not os.path.exists(REF_SO):
+                raise FileNotFoundError(REF_SO + " (run `make -C oracle ref` where /root/reference exists)")
+            self.lib = C.CDLL(REF_SO)
+            self.pfx = "ref_"
+        else:
+            raise ValueError(kind)
+        f = self._f
+        f("murmur64").restype = C.c_uint64
+        f("murmur64").argtypes = [C.c_uint64]
+        f("edit_distance_nw").restype = C.c_int
+        f("edit_distance_nw").argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        f("tables_query").restype = C.c_int64
+        if kind == "port":
+            f("tables_build").restype = C.c_void_p
+            f("filter_by_frequency").restype = C.c_int64
+            f("mapq").restype = C.c_uint32
+        else:
+            f("tables_build").restype = C.c_void_p
+            f("num_threads").restype = C.c_int
+
+    def _f(self, name):
+        return getattr(self.lib, self.pfx + name)
+
+    # ---- P1 ----
+    def convert_ascii(self, seq: bytes, mode: int) -> bytes:
+        if self.kind != "port":
+            raise NotImplementedError
+        out = C.create_string_buffer(len(seq))
+        self.lib.orc_convert_ascii(out, seq, C.c_int64(len(seq)), mode)
+        return out.raw
+
+    def encode_2bit(self, seq: bytes) -> np.ndarray:
+        n = (len(seq) + 15) // 16
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self._f("encode_2bit")(_p(out, C.c_uint32), seq, len(seq))
+        return out[:n]
+
+    def decode_2bit(self, enc: np.ndarray, length: int) -> bytes:
+        out = C.create_string_buffer(max(length, 1))
+        enc = np.ascontiguousarray(enc, dtype=np.uint32)
+        self._f("decode_2bit")(out, _p(enc, C.c_uint32), length)
+        return out.raw[:length]
+
+    def revcomp_2bit(self, enc: np.ndarray, length: int) -> np.ndarray:
+        enc = np.ascontiguousarray(enc, dtype=np.uint32)
+        out = np.zeros_like(enc)
+        self._f("revcomp_2bit")(_p(out, C.c_uint32), _p(enc, C.c_uint32), length)
+        return out
+
+    def revcomp_ascii(self, seq: bytes) -> bytes:
+        out = C.create_string_buffer(max(len(seq), 1))
+        self._f("revcomp_ascii")(out, seq, len(seq))
+        return out.raw[:len(seq)]
+
+    # ---- H1/H2 ----
+    def murmur64(self, x: int) -> int:
+        return self._f("murmur64")(C.c_uint64(x & 0xFFFFFFFFFFFFFFFF))
+
+    def canonical_kmers(self, enc: np.ndarray, length: int, k: int) -> np.ndarray:
+        enc = np.ascontiguousarray(enc, dtype=np.uint32)
+        out = np.zeros(max(length - k + 1, 1), dtype=np.uint64)
+        n = self._f("canonical_kmers")(_p(enc, C.c_uint32), length, k, _p(out, C.c_uint64))
+        return out[:n]
+
+    def minhash_batch(self, enc: np.ndarray, lens: np.ndarray, k: int, H: int):
+        """enc: [n, pitch_words] u32, lens: [n] i32 -> (sigs [n,H] u64, valid [n,H] u8)"""
+        enc = np.ascontiguousarray(enc, dtype=np.uint32)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        n = lens.shape[0]
+        pitch = enc.shape[1] if enc.ndim == 2 else 0
+        sigs = np.zeros((n, H), dtype=np.uint64)
+        valid = np.zeros((n, H), dtype=np.uint8)
+        if n:
+            self._f("minhash_batch")(_p(enc, C.c_uint32), C.c_int64(pitch), _p(lens, C.c_int32), n, k, H,
+                                     _p(sigs, C.c_uint64), _p(valid, C.c_uint8))
+        return sigs, valid
+
+    # ---- H3 ----
+    def tables_build(self, sigs, valid, ids=None, max_results_per_map=65535, loadfactor=0.8, stable=1):
+        sigs = np.ascontiguousarray(sigs, dtype=np.uint64)
+        valid = np.ascontiguousarray(valid, dtype=np.uint8)
+        n, H = sigs.shape
+        idp = None
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.uint32)
+            idp = _p(ids, C.c_uint32)
+        if self.kind == "port":
+            h = self.lib.orc_tables_build(_p(sigs, C.c_uint64), _p(valid, C.c_uint8), idp, C.c_int64(n), H,
+                                          max_results_per_map)
+        else:
+            h = self.lib.ref_tables_build(_p(sigs, C.c_uint64), _p(valid, C.c_uint8), idp, C.c_int64(n), H,
+                                          max_results_per_map, C.c_float(loadfactor), stable)
+        return C.c_void_p(h), H
+
+    def tables_free(self, handle):
+        self._f("tables_free")(handle[0])
+
+    def tables_query(self, handle, qsigs, qvalid):
+        """-> (num_per_seq [nq] i32, offsets [nq+1] i64, values [total] u32)"""
+        h, H = handle
+        qsigs = np.ascontiguousarray(qsigs, dtype=np.uint64)
+        qvalid = np.ascontiguousarray(qvalid, dtype=np.uint8)
+        nq = qsigs.shape[0]
+        num = np.zeros(nq, dtype=np.int32)
+        off = np.zeros(nq + 1, dtype=np.int64)
+        total = self._f("tables_query")(h, _p(qsigs, C.c_uint64), _p(qvalid, C.c_uint8), C.c_int64(nq),
+                                        _p(num, C.c_int32), _p(off, C.c_int64), None)
+        vals = np.zeros(max(total, 1), dtype=np.uint32)
+        self._f("tables_query")(h, _p(qsigs, C.c_uint64), _p(qvalid, C.c_uint8), C.c_int64(nq),
+                                _p(num, C.c_int32), _p(off, C.c_int64), _p(vals, C.c_uint32))
+        return num, off, vals[:total]
+
+    # ---- C1 (port only; the reference implementation is CUDA-only) ----
+    def filter_by_frequency(self, values, offsets, min_hits):
+        values = np.ascontiguousarray(values, dtype=np.uint32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        nseg = offsets.shape[0] - 1
+        outv = np.zeros(max(values.shape[0], 1), dtype=np.uint32)
+        outo = np.zeros(nseg + 1, dtype=np.int64)
+        total = self.lib.orc_filter_by_frequency(_p(values, C.c_uint32), _p(offsets, C.c_int64), C.c_int64(nseg),
+                                                 min_hits, _p(outv, C.c_uint32), _p(outo, C.c_int64))
+        return outv[:total], outo
+
+    # ---- S2 / S3 ----
+    def window_location(self, secB, secE, pos, w, ext):
+        l, r, ln, sp = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._f("window_location")(secB, secE, pos, w, ext, C.byref(l), C.byref(r), C.byref(ln), C.byref(sp))
+        return l.value, r.value, ln.value, sp.value
+
+    def shd(self, anchor2bit, La, cand2bit, Lc, rate=0.05):
+        a = np.ascontiguousarray(anchor2bit, dtype=np.uint32)
+        c = np.ascontiguousarray(cand2bit, dtype=np.uint32)
+        s, sc, o = C.c_int(), C.c_int(), C.c_int()
+        self._f("shd")(_p(a, C.c_uint32), La, _p(c, C.c_uint32), Lc, C.c_float(rate), C.byref(s), C.byref(sc),
+                       C.byref(o))
+        return s.value, sc.value, o.value
+
+    # ---- whole seeding pass, reference direction (port only) ----
+    def map_pass_refdir(self, genome: bytes, chrom_off, reads: np.ndarray, read_len, k=16, w=128, H=16,
+                        min_hits=4, max_results_per_map=65535, rate=0.05, batchsize=2048):
+        chrom_off = np.ascontiguousarray(chrom_off, dtype=np.int64)
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        read_len = np.ascontiguousarray(read_len, dtype=np.int32)
+        n = read_len.shape[0]
+        out = np.zeros(n, dtype=MAPPED_DTYPE)
+        stats = np.zeros(4, dtype=np.int64)
+        self.lib.orc_map_pass_refdir(genome, _p(chrom_off, C.c_int64), chrom_off.shape[0] - 1,
+                                     _p(reads, C.c_char), reads.shape[1], _p(read_len, C.c_int32), C.c_int64(n),
+                                     k, w, H, min_hits, max_results_per_map, C.c_float(rate), batchsize,
+                                     out.ctypes.data_as(C.c_void_p), _p(stats, C.c_int64))
+        return out, stats
+
+    # ---- V2 / V3 ----
+    def ssw_align(self, query: bytes, ref: bytes, mask_len: int):
+        al = Alignment()
+        cig = C.create_string_buffer(4096)
+        self._f("ssw_align")(query, len(query), ref, len(ref), mask_len, C.byref(al), cig, 4096)
+        return al.astuple(), cig.value.decode()
+
+    def edit_distance_nw(self, q: bytes, t: bytes) -> int:
+        return self._f("edit_distance_nw")(q, len(q), t, len(t))
+
+    def verify_inputs(self, read: bytes, orientation: int, chrom: bytes, pos: int, w: int, conv: int):
+        rl = len(read)
+        q = C.create_string_buffer(rl + 1)
+        qrc = C.create_string_buffer(rl + 1)
+        ref = C.create_string_buffer(w + 1)
+        wl = C.c_int()
+        self.lib.orc_verify_inputs(read, rl, orientation, chrom, C.c_int64(len(chrom)), C.c_int64(pos), w, conv,
+                                   q, qrc, ref, C.byref(wl))
+        return q.raw[:rl], qrc.raw[:rl], ref.raw[:wl.value]
+
+    def mapq(self, s1, s2):
+        return self.lib.orc_mapq(s1, s2)

@@ -1,0 +1,262 @@
+// ref_shim.cpp -- thin extern "C" wrapper around the REFERENCE'S OWN code, compiled from the
+// sources where they lie under /root/reference (never copied into this repo).
+//
+// TEST INFRASTRUCTURE ONLY.  Output goes to oracle/_ref/libhrm_ref.so (git-ignored).  It is
+// used (a) to pin oracle/hrm_oracle.c, (b) to generate tests/golden/*, and (c) as the
+// "reference" CPU baseline of bench.py.  Nothing in the product links it.
+//
+// Everything here is glue: argument marshalling and the loops that the reference keeps in
+// its driver (src/gpu/main_gpu.cu) -- the arithmetic is the reference's.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <memory>
+#include <algorithm>
+#include <numeric>
+#include <omp.h>
+
+#include <config.hpp>
+#include <sequencehelpers.hpp>
+#include <helpers/hashers.cuh>
+#include <cpuhashtable.hpp>
+#include <groupbykey.hpp>
+#include <ssw_cpp.h>
+#include <edlib.h>
+#include <cigar.hpp>
+
+using care::CpuReadOnlyMultiValueHashTable;
+using care::GroupByKeyCpu;
+
+extern "C" {
+
+// ---- P1 -------------------------------------------------------------------------------
+void ref_encode_2bit(uint32_t* out, const char* seq, int len)
+{
+    SequenceHelpers::encodeSequence2Bit(out, seq, len);
+}
+void ref_decode_2bit(char* out, const uint32_t* enc, int len)
+{
+    SequenceHelpers::decode2BitSequence(out, enc, len);
+}
+void ref_revcomp_2bit(uint32_t* out, const uint32_t* in, int len)
+{
+    SequenceHelpers::reverseComplementSequence2Bit(out, in, len);
+}
+void ref_revcomp_ascii(char* out, const char* in, int len)
+{
+    std::string s = SequenceHelpers::reverseComplementSequenceDecoded(in, len);
+    std::memcpy(out, s.data(), (size_t)len);
+}
+
+// ---- H1/H2: host twin of minhashSignatures3264Kernel (gpusequencehasher.cuh:116-169) ----
+uint64_t ref_murmur64(uint64_t x) { return hashers::MurmurHash<std::uint64_t>::hash(x); }
+
+int ref_canonical_kmers(const uint32_t* enc, int len, int k, uint64_t* out)
+{
+    int n = 0;
+    SequenceHelpers::forEachEncodedCanonicalKmerFromEncodedSequence(
+        enc, len, k, [&](std::uint64_t kmer, int /*pos*/) { out[n++] = kmer; });
+    return n;
+}
+
+void ref_minhash(const uint32_t* enc, int len, int k, int H, uint64_t* sig, uint8_t* valid)
+{
+    constexpr int maximum_kmer_length = max_k<std::uint64_t>::value;
+    const std::uint64_t kmer_mask = std::numeric_limits<std::uint64_t>::max() >> ((maximum_kmer_length - k) * 2);
+    for (int j = 0; j < H; j++) {
+        const int hashFuncId = j;
+        if (len >= k) {
+            std::uint64_t minHashValue = std::numeric_limits<std::uint64_t>::max();
+            SequenceHelpers::forEachEncodedCanonicalKmerFromEncodedSequence(
+                enc, len, k, [&](std::uint64_t kmer, int /*pos*/) {
+                    using hasher = hashers::MurmurHash<std::uint64_t>;
+                    const auto hashvalue = hasher::hash(kmer + hashFuncId);
+                    minHashValue = std::min(minHashValue, hashvalue);
+                });
+            sig[j] = minHashValue & kmer_mask;
+            valid[j] = 1;
+        } else {
+            sig[j] = std::numeric_limits<std::uint64_t>::max();
+            valid[j] = 0;
+        }
+    }
+}
+
+void ref_minhash_batch(const uint32_t* enc, int64_t pitch_words, const int32_t* lens, int n, int k,
+                       int H, uint64_t* sigs, uint8_t* valid)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < n; i++)
+        ref_minhash(enc + (int64_t)i * pitch_words, lens[i], k, H, sigs + (int64_t)i * H,
+                    valid + (int64_t)i * H);
+}
+
+// ---- H3 / H3q: the reference's CPU tables (cpuhashtable.hpp:465-679, groupbykey.hpp:49-229),
+// driven as FakeGpuMinhasher does (fakegpuminhasher.cuh:268-293, 360-376, 394-442, 692-720) ----
+struct RefTables {
+    using Table = CpuReadOnlyMultiValueHashTable<kmer_type, read_number>;
+    int H;
+    int maxResultsPerMap;
+    std::vector<std::unique_ptr<Table>> t;
+};
+
+void* ref_tables_build(const uint64_t* sigs, const uint8_t* valid, const uint32_t* ids, int64_t n,
+                       int H, int max_results_per_map, float loadfactor, int stable)
+{
+    auto* T = new RefTables;
+    T->H = H;
+    T->maxResultsPerMap = max_results_per_map;
+    for (int j = 0; j < H; j++) {
+        auto tab = std::make_unique<RefTables::Table>((std::uint64_t)n, loadfactor);
+        std::vector<kmer_type> keys;
+        std::vector<read_number> vals;
+        keys.reserve(n);
+        vals.reserve(n);
+        for (int64_t i = 0; i < n; i++) {
+            if (!valid[i * H + j]) continue;
+            keys.push_back(sigs[i * H + j]);
+            vals.push_back(ids ? ids[i] : (read_number)i);
+        }
+        if (!keys.empty()) tab->insert(keys.data(), vals.data(), (int)keys.size());
+        auto groupByKey = [&](auto& k_, auto& v_, auto& countsPrefixSum) {
+            // stable == 0: exactly the call FakeGpuMinhasher::compact makes on its CPU path
+            //   (fakegpuminhasher.cuh:405-421: valuesOfSameKeyMustBeSorted = false).
+            // stable == 1: the stable branch (groupbykey.hpp:113-119); values of a key ascend in
+            //   insertion order, which is also what the default GPU group-by (radix sort + iota
+            //   values, groupbykey.hpp:347-358) yields.
+            GroupByKeyCpu<kmer_type, read_number, read_number> op(false, max_results_per_map, 1);
+            if (stable) {
+                op.valuesOfSameKeyMustBeSorted = true;
+                op.executeWithIotaValues(k_, v_, countsPrefixSum);
+            } else {
+                op.execute(k_, v_, countsPrefixSum);
+            }
+        };
+        tab->finalize(groupByKey, nullptr);
+        T->t.push_back(std::move(tab));
+    }
+    return T;
+}
+
+void ref_tables_free(void* p) { delete (RefTables*)p; }
+
+int64_t ref_tables_query(void* p, const uint64_t* qsigs, const uint8_t* qvalid, int64_t nq,
+                         int32_t* num_per_seq, int64_t* offsets, uint32_t* values)
+{
+    auto* T = (RefTables*)p;
+    const int H = T->H;
+    // pass 1: counts (determineNumValues)
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < nq; i++) {
+        int numValues = 0;
+        for (int map = 0; map < H; ++map) {
+            if (!qvalid[i * H + map]) continue;
+            auto qr = T->t[map]->query(qsigs[i * H + map]);
+            if (qr.numValues <= T->maxResultsPerMap) numValues += qr.numValues;
+        }
+        num_per_seq[i] = numValues;
+    }
+    int64_t total = 0;
+    for (int64_t i = 0; i < nq; i++) {
+        offsets[i] = total;
+        total += num_per_seq[i];
+    }
+    offsets[nq] = total;
+    if (values) {
+        // pass 2: copy ranges in map order (retrieveValues)
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int64_t i = 0; i < nq; i++) {
+            int64_t w = offsets[i];
+            for (int map = 0; map < H; ++map) {
+                if (!qvalid[i * H + map]) continue;
+                auto qr = T->t[map]->query(qsigs[i * H + map]);
+                if (qr.numValues <= T->maxResultsPerMap && qr.numValues > 0) {
+                    std::copy(qr.valuesBegin, qr.valuesBegin + qr.numValues, values + w);
+                    w += qr.numValues;
+                }
+            }
+        }
+    }
+    return total;
+}
+
+// ---- V2: the reference's SSW (src/ssw.c, src/ssw_cpp.cpp) ----
+struct ref_alignment {
+    int32_t sw_score, sw_score_next_best, ref_begin, ref_end, query_begin, query_end,
+        ref_end_next_best, mismatches, flag, cigar_len;
+};
+
+void ref_ssw_align(const char* query, int qlen, const char* ref, int rlen, int maskLen,
+                   ref_alignment* al, char* cigar, int cigar_cap)
+{
+    static thread_local StripedSmithWaterman::Aligner aligner;
+    StripedSmithWaterman::Filter filter;
+    StripedSmithWaterman::Alignment a;
+    std::string q(query, (size_t)qlen); // Align() uses strlen(query)
+    std::string r(ref, (size_t)rlen);
+    const uint16_t flag = aligner.Align(q.c_str(), r.c_str(), rlen, filter, &a, maskLen);
+    al->sw_score = a.sw_score;
+    al->sw_score_next_best = a.sw_score_next_best;
+    al->ref_begin = a.ref_begin;
+    al->ref_end = a.ref_end;
+    al->query_begin = a.query_begin;
+    al->query_end = a.query_end;
+    al->ref_end_next_best = a.ref_end_next_best;
+    al->mismatches = a.mismatches;
+    al->flag = flag;
+    al->cigar_len = (int)a.cigar_string.size();
+    if (cigar_cap > 0) {
+        const size_t n = std::min((size_t)cigar_cap - 1, a.cigar_string.size());
+        std::memcpy(cigar, a.cigar_string.data(), n);
+        cigar[n] = 0;
+    }
+}
+
+// batch form used by the CPU baseline: 2 alignments per read, OpenMP over reads
+void ref_ssw_align_batch(const char* queries, int q_pitch, const int32_t* qlens, const char* refs,
+                         int r_pitch, const int32_t* rlens, const int32_t* maskLens, int64_t n,
+                         ref_alignment* out, char* cigars, int cigar_pitch)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; i++)
+        ref_ssw_align(queries + i * q_pitch, qlens[i], refs + i * r_pitch, rlens[i], maskLens[i],
+                      out + i, cigars + i * cigar_pitch, cigar_pitch);
+}
+
+// ---- V3: edlib as called by the reference (mappinghandler.cu:968-987) ----
+int ref_edit_distance_nw(const char* q, int qlen, const char* t, int tlen)
+{
+    EdlibAlignResult result = edlibAlign(q, qlen, t, tlen, edlibDefaultAlignConfig());
+    int d = result.status == EDLIB_STATUS_OK ? result.editDistance : -1;
+    edlibFreeAlignResult(result);
+    return d;
+}
+
+void ref_edit_distance_nw_batch(const char* queries, int q_pitch, const int32_t* qlens,
+                                const char* refs, int r_pitch, const int32_t* rlens, int64_t n,
+                                int32_t* out)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; i++)
+        out[i] = ref_edit_distance_nw(queries + i * q_pitch, qlens[i], refs + i * r_pitch, rlens[i]);
+}
+
+// ---- cigar parser (src/cigar.cpp) : returns number of entries, ops as chars ----
+int ref_cigar_parse(const char* s, char* ops, int32_t* lens, int cap)
+{
+    Cigar c{std::string(s)};
+    int n = 0;
+    for (const auto& e : c.getEntries()) {
+        if (n < cap) {
+            ops[n] = Cigar::opToChar(e.first);
+            lens[n] = e.second;
+        }
+        n++;
+    }
+    return n;
+}
+
+int ref_num_threads() { return omp_get_max_threads(); }
+
+} // extern "C"
