@@ -1,0 +1,847 @@
+// k3_table.cu -- K3: GPU-resident multi-value open-addressing hash tables (one per hash function).
+// ref: GpuMinhasher include/gpu/gpuminhasher.cuh:20-110; the results reproduced are those of the
+//      default CPU backend FakeGpuMinhasher include/gpu/fakegpuminhasher.cuh:199-442,568-728 with
+//      CpuReadOnlyMultiValueHashTable include/cpuhashtable.hpp:465-679 finalised by GroupByKey
+//      include/groupbykey.hpp:97-228 / 312-530.  Design precedent for a device table: warpcore
+//      (include/gpu/gpuhashtable.cuh:303-1111) -- not used as an oracle.
+//
+// Layout in HBM (DESIGN.md "K3"): table j = power-of-two array of 32-byte buckets, each bucket two
+// 16-byte slots {u64 key, u32 value offset, u32 count}; values of all tables in one u32 array.
+// A bucket is exactly one DRAM sector, so a lookup that ends in its home bucket moves one sector.
+// Build (one-off): stable radix sort of (key, id) pairs per table (CUB, build path only), run
+// detection, truncation to the first min(maxResultsPerMap, 65535) ids, CAS insertion of the distinct
+// keys.  Probe (hot path): two-lane cooperative groups, double hashing over buckets, query keys
+// staged into shared memory with TMA (cp.async.bulk + mbarrier), results staged in shared memory
+// and written coalesced.
+#include "k3_table.cuh"
+#include "core_minhash.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <string.h>
+
+namespace hrm {
+
+// ------------------------------------------------------------------------------------------
+// build kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t invalid_key(int k) { return k < 32 ? (1ULL << (2 * k)) : ~0ULL; }
+
+// sigs[n][H] -> per-table staging (key, id); invalid signatures get a key that sorts last
+__global__ void __launch_bounds__(256) stage_pairs_kernel(const uint64_t* __restrict__ sigs,
+                                                          const uint8_t* __restrict__ valid, int64_t n, int H,
+                                                          int Hsig, int first_func, int k, const uint32_t* __restrict__ ids,
+                                                          uint32_t first_id, int64_t at,
+                                                          uint64_t* const* __restrict__ stage_keys,
+                                                          uint32_t* const* __restrict__ stage_vals)
+{
+    // thread per (table, sequence), sequence fastest => coalesced staging writes
+    const int64_t total = n * H;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int j = (int)(t / n);
+        const int64_t i = t - (int64_t)j * n;
+        uint64_t key = sigs[i * Hsig + j];
+        const bool ok = valid ? valid[i * Hsig + j] != 0 : key != ~0ULL;
+        if (!ok) key = invalid_key(k);
+        stage_keys[first_func + j][at + i] = key;
+        stage_vals[first_func + j][at + i] = ids ? ids[i] : first_id + (uint32_t)i;
+    }
+}
+
+// flags[i] = 1 where a new valid key run starts; counts valid pairs
+__global__ void __launch_bounds__(256) mark_heads_kernel(const uint64_t* __restrict__ keys, int64_t n, uint64_t inv,
+                                                         int32_t* __restrict__ flags,
+                                                         unsigned long long* __restrict__ valid_count)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long local = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t key = keys[i];
+        const bool v = key != inv && key != SLOT_EMPTY;
+        flags[i] = (v && (i == 0 || keys[i - 1] != key)) ? 1 : 0;
+        local += v ? 1 : 0;
+    }
+    // warp aggregate then one atomic per warp
+    for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(valid_count, local);
+}
+
+// head_pos[u] = index of the first pair of distinct key u
+__global__ void __launch_bounds__(256) head_positions_kernel(const int32_t* __restrict__ flags,
+                                                             const int32_t* __restrict__ excl, int64_t n,
+                                                             int32_t* __restrict__ head_pos)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (flags[i]) head_pos[excl[i]] = (int32_t)i;
+}
+
+__device__ __forceinline__ void bucket_hash(uint64_t key, uint32_t mask, uint32_t& b, uint32_t& step)
+{
+    const uint64_t h = murmur64(key + 0x5ad0dedULL);
+    b = (uint32_t)h & mask;
+    step = (uint32_t)(h >> 32) | 1u; // odd => visits every bucket of a power-of-two table
+}
+
+// one thread per distinct key: claim a slot with CAS, then publish (offset, count)
+__global__ void __launch_bounds__(256) insert_keys_kernel(const uint64_t* __restrict__ keys,
+                                                          const int32_t* __restrict__ head_pos, int64_t nkeys,
+                                                          int64_t nvalid, uint32_t value_base, uint32_t upper,
+                                                          Slot* __restrict__ slots, uint32_t mask,
+                                                          unsigned long long* __restrict__ errors)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < nkeys; u += stride) {
+        const int64_t pos = head_pos[u];
+        const int64_t end = u + 1 < nkeys ? (int64_t)head_pos[u + 1] : nvalid;
+        const uint64_t key = keys[pos];
+        int64_t cnt = end - pos;
+        if (cnt > upper) cnt = upper; // ref: groupbykey.hpp:177-191 keeps the FIRST `upper` values
+        uint32_t b, step;
+        bucket_hash(key, mask, b, step);
+        bool done = false;
+        for (uint64_t probe = 0; probe <= (uint64_t)mask && !done; probe++) {
+            for (int sub = 0; sub < 2 && !done; sub++) {
+                Slot* s = slots + ((size_t)b * 2 + sub);
+                const unsigned long long prev =
+                    atomicCAS(reinterpret_cast<unsigned long long*>(&s->key), (unsigned long long)SLOT_EMPTY,
+                              (unsigned long long)key);
+                if (prev == SLOT_EMPTY) {
+                    s->off = value_base + (uint32_t)pos;
+                    s->cnt = (uint32_t)cnt;
+                    done = true;
+                }
+            }
+            b = (b + step) & mask;
+        }
+        if (!done) atomicAdd(errors, 1ULL);
+    }
+}
+
+__global__ void fill_u64_kernel(uint64_t* p, int64_t n, uint64_t v)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// probe kernel (hot path)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+
+constexpr int PROBE_THREADS = 256;
+constexpr int PROBE_LOOKUPS = 1024; // lookups (query x table) per tile
+
+// One lookup by a two-lane cooperative group (lane parity selects the slot of the bucket).
+// Returns (off, cnt) in both lanes; touches += slots examined.
+__device__ __forceinline__ uint2 probe_pair(const TableRef& T, uint64_t key, int sub, unsigned pairmask,
+                                            uint32_t max_results, uint32_t& touches)
+{
+    uint2 res = make_uint2(0u, 0u);
+    if (key == SLOT_EMPTY) return res; // invalid signature (len < k)
+    uint32_t b, step;
+    bucket_hash(key, T.bucket_mask, b, step);
+    const uint4* slots = reinterpret_cast<const uint4*>(T.slots);
+    for (uint32_t probe = 0; probe <= T.bucket_mask; probe++) {
+        const uint4 s = __ldg(slots + ((size_t)b * 2 + sub));
+        const uint64_t skey = ((uint64_t)s.y << 32) | s.x;
+        const bool hit = skey == key;
+        const bool empty = skey == SLOT_EMPTY;
+        uint32_t off = hit ? s.z : 0u, cnt = hit ? s.w : 0u;
+        off |= __shfl_xor_sync(pairmask, off, 1);
+        cnt |= __shfl_xor_sync(pairmask, cnt, 1);
+        const int flags = (hit ? 1 : 0) | (empty ? 2 : 0);
+        const int both = flags | __shfl_xor_sync(pairmask, flags, 1);
+        touches += 1;
+        if (both & 1) {
+            if (cnt <= max_results) res = make_uint2(off, cnt); // ref: fakegpuminhasher.cuh:280-285
+            break;
+        }
+        if (both & 2) break; // a free slot in the bucket ends the probe sequence: key absent
+        b = (b + step) & T.bucket_mask;
+    }
+    return res;
+}
+
+__global__ void __launch_bounds__(PROBE_THREADS) probe_count_kernel(const uint64_t* __restrict__ sigs, int n, int H,
+                                                                    int TQ, TablesParam tabs, uint32_t max_results,
+                                                                    uint2* __restrict__ ranges,
+                                                                    int32_t* __restrict__ num_per_seq,
+                                                                    unsigned long long* __restrict__ touches_out,
+                                                                    int sigs_aligned)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* sbuf = reinterpret_cast<uint64_t*>(smem_raw);                       // [2][PROBE_LOOKUPS]
+    uint2* rbuf = reinterpret_cast<uint2*>(sbuf + 2 * PROBE_LOOKUPS);             // [PROBE_LOOKUPS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + PROBE_LOOKUPS);           // [2]
+
+    const int tid = threadIdx.x;
+    const int numTiles = (n + TQ - 1) / TQ;
+    const int tileElems = TQ * H;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto tile_elems = [&](int tile) {
+        const int q0 = tile * TQ;
+        const int nq = (n - q0) < TQ ? (n - q0) : TQ;
+        return nq * H;
+    };
+    auto tma_ok = [&](int tile) {
+        return sigs_aligned && ((tile_elems(tile) * 8) % 16 == 0) && ((((size_t)tile * tileElems) * 8) % 16 == 0);
+    };
+    auto issue = [&](int tile, int st) {
+        const uint32_t bytes = (uint32_t)tile_elems(tile) * 8u;
+        mbar_expect_tx(&bars[st], bytes);
+        tma_load_1d(sbuf + (size_t)st * PROBE_LOOKUPS, sigs + (size_t)tile * tileElems, bytes, &bars[st]);
+    };
+
+    uint32_t phase[2] = {0u, 0u};
+    uint32_t touches = 0;
+    const int sub = tid & 1;
+    const int group = tid >> 1;
+    const unsigned pairmask = 3u << ((tid & 31) & ~1);
+
+    int tile = blockIdx.x;
+    int it = 0;
+    if (tid == 0 && tile < numTiles && tma_ok(tile)) issue(tile, 0);
+    for (; tile < numTiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < numTiles && tma_ok(next)) issue(next, st ^ 1);
+        const int elems = tile_elems(tile);
+        uint64_t* keys = sbuf + (size_t)st * PROBE_LOOKUPS;
+        if (tma_ok(tile)) {
+            mbar_wait(&bars[st], phase[st]);
+            phase[st] ^= 1u;
+        } else {
+            for (int e = tid; e < elems; e += PROBE_THREADS) keys[e] = sigs[(size_t)tile * tileElems + e];
+            __syncthreads();
+        }
+        // lookups: element e = local query * H + table
+        for (int e = group; e < elems; e += PROBE_THREADS / 2) {
+            const int t = e % H;
+            const uint2 r = probe_pair(tabs.t[t], keys[e], sub, pairmask, max_results, touches);
+            if (sub == 0) rbuf[e] = r;
+        }
+        __syncthreads();
+        // coalesced write-out of ranges + per-query totals
+        uint2* gout = ranges + (size_t)tile * tileElems;
+        for (int e = tid; e < elems; e += PROBE_THREADS) gout[e] = rbuf[e];
+        const int q0 = tile * TQ;
+        for (int q = tid; q * H < elems; q += PROBE_THREADS) {
+            int sum = 0;
+            for (int t = 0; t < H; t++) sum += (int)rbuf[q * H + t].y;
+            num_per_seq[q0 + q] = sum;
+        }
+        __syncthreads(); // rbuf and sbuf[st] are free again
+    }
+    // slot touches: every bucket visit examines both slots
+    touches = sub == 0 ? touches * 2 : 0;
+    for (int d = 16; d > 0; d >>= 1) touches += __shfl_xor_sync(0xffffffffu, touches, d);
+    if ((tid & 31) == 0 && touches && touches_out) atomicAdd(touches_out, (unsigned long long)touches);
+}
+
+// values of query q: buckets of tables 0..H-1 concatenated at d_values[offsets[q] ...]; one warp per query
+__global__ void __launch_bounds__(256) retrieve_kernel(const uint2* __restrict__ ranges, int n, int H,
+                                                       const uint32_t* __restrict__ table_values,
+                                                       const int32_t* __restrict__ offsets,
+                                                       uint32_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = warp0; q < n; q += nwarps) {
+        int64_t w = offsets[q];
+        for (int t0 = 0; t0 < H; t0 += 32) {
+            const int t = t0 + lane;
+            const uint2 r = t < H ? ranges[q * H + t] : make_uint2(0u, 0u);
+            // exclusive prefix of counts over the lanes
+            int incl = (int)r.y;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int excl = incl - (int)r.y;
+            if (total <= 64) { // common case: each lane copies its own short bucket
+                for (uint32_t v = 0; v < r.y; v++) out[w + excl + v] = table_values[r.x + v];
+            } else { // long buckets: the whole warp copies bucket after bucket
+                for (int tt = 0; tt < 32; tt++) {
+                    const uint32_t off = __shfl_sync(0xffffffffu, r.x, tt);
+                    const uint32_t cnt = __shfl_sync(0xffffffffu, r.y, tt);
+                    const int ex = __shfl_sync(0xffffffffu, excl, tt);
+                    for (uint32_t v = lane; v < cnt; v += 32) out[w + ex + v] = table_values[off + v];
+                }
+            }
+            w += total;
+        }
+    }
+}
+
+static unsigned capped_grid(int64_t items, int block, int waves)
+{
+    int64_t g = HRM_SDIV(items, (int64_t)block);
+    const int64_t cap = (int64_t)num_sms() * waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+hrm_status minhasher_count_sigs(hrm_minhasher* mh, QueryHandle* qh, const uint64_t* d_sigs, int n,
+                                int32_t* d_num_per_seq, cudaStream_t s)
+{
+    const int H = mh->H;
+    HRM_TRY(qh->ranges.reserve(sizeof(uint2) * (size_t)n * H));
+    const int TQ = PROBE_LOOKUPS / H > 0 ? PROBE_LOOKUPS / H : 1;
+    const int numTiles = (n + TQ - 1) / TQ;
+    const size_t smem = sizeof(uint64_t) * 2 * PROBE_LOOKUPS + sizeof(uint2) * PROBE_LOOKUPS + 2 * sizeof(uint64_t);
+    int grid = numTiles;
+    const int cap = num_sms() * 8; // 8 resident CTAs of 256 threads per SM
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    const int aligned = (reinterpret_cast<uintptr_t>(d_sigs) & 15) == 0 ? 1 : 0;
+    HRM_LAUNCH(probe_count_kernel, grid, PROBE_THREADS, smem, s, d_sigs, n, H, TQ, mh->param,
+               (uint32_t)mh->max_results, qh->ranges.as<uint2>(), d_num_per_seq, mh->d_touches, aligned);
+    qh->stage = 1;
+    qh->n = n;
+    return HRM_OK;
+}
+
+hrm_status minhasher_retrieve(hrm_minhasher* mh, QueryHandle* qh, int n, uint32_t* d_values,
+                              const int32_t* d_offsets, cudaStream_t s)
+{
+    if (n == 0) return HRM_OK;
+    HRM_LAUNCH(retrieve_kernel, capped_grid((int64_t)n * 32, 256, 16), 256, 0, s, qh->ranges.as<uint2>(), n, mh->H,
+               mh->values, d_offsets, d_values);
+    return HRM_OK;
+}
+
+QueryHandle* minhasher_handle(hrm_minhasher* mh, int id)
+{
+    std::lock_guard<std::mutex> lk(mh->mtx);
+    if (id < 0 || id >= (int)mh->handles.size() || !mh->handles[id]) return nullptr;
+    return mh->handles[id].get();
+}
+
+static void free_staging(hrm_minhasher* mh)
+{
+    for (auto p : mh->stage_keys)
+        if (p) cudaFree(p);
+    for (auto p : mh->stage_vals)
+        if (p) cudaFree(p);
+    mh->stage_keys.clear();
+    mh->stage_vals.clear();
+}
+
+} // namespace hrm
+
+using namespace hrm;
+
+extern "C" hrm_status hrm_minhasher_create(hrm_minhasher** out, int64_t max_sequences, int max_results_per_map, int k,
+                                           float load_factor)
+{
+    HRM_REQUIRE(out != nullptr, "out");
+    *out = nullptr;
+    HRM_TRY(ensure_device());
+    HRM_REQUIRE(k >= 1 && k <= 32, "1 <= k <= 32");
+    HRM_REQUIRE(max_sequences >= 0 && max_sequences < (1LL << 32), "max_sequences must fit read_number (u32)");
+    HRM_REQUIRE(max_results_per_map >= 0, "max_results_per_map");
+    HRM_REQUIRE(load_factor > 0.f && load_factor <= 1.f, "0 < load_factor <= 1");
+    auto* mh = new hrm_minhasher;
+    mh->k = k;
+    mh->max_results = max_results_per_map;
+    mh->load = load_factor;
+    mh->max_sequences = max_sequences;
+    cudaGetDevice(&mh->device);
+    memset(&mh->param, 0, sizeof mh->param);
+    if (cudaMalloc(&mh->d_touches, sizeof(unsigned long long)) != cudaSuccess) {
+        set_error("cudaMalloc failed");
+        delete mh;
+        return HRM_ERR_NOMEM;
+    }
+    cudaMemset(mh->d_touches, 0, sizeof(unsigned long long));
+    *out = mh;
+    return HRM_OK;
+}
+
+extern "C" void hrm_minhasher_destroy(hrm_minhasher* mh)
+{
+    if (!mh) return;
+    free_staging(mh);
+    if (mh->values) cudaFree(mh->values);
+    for (auto p : mh->slots)
+        if (p) cudaFree(p);
+    if (mh->d_touches) cudaFree(mh->d_touches);
+    delete mh;
+}
+
+extern "C" int hrm_minhasher_add_tables(hrm_minhasher* mh, int n, const int32_t* h_hash_function_ids, hrm_stream)
+{
+    if (!mh || n < 0 || mh->compacted) return 0;
+    int added = 0;
+    for (int t = 0; t < n; t++) {
+        if (mh->H >= MAX_TABLES) break;
+        if (h_hash_function_ids && h_hash_function_ids[t] != mh->H) break; // ids must be 0,1,2,...
+        uint64_t* kp = nullptr;
+        uint32_t* vp = nullptr;
+        const size_t cap = (size_t)(mh->max_sequences > 0 ? mh->max_sequences : 1);
+        if (cudaMalloc(&kp, sizeof(uint64_t) * cap) != cudaSuccess) {
+            cudaGetLastError();
+            break; // ref: fewer tables than requested signals memory shortage
+        }
+        if (cudaMalloc(&vp, sizeof(uint32_t) * cap) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(kp);
+            break;
+        }
+        mh->stage_keys.push_back(kp);
+        mh->stage_vals.push_back(vp);
+        mh->table_count.push_back(0);
+        mh->H++;
+        added++;
+    }
+    return added;
+}
+
+static hrm_status stage_signatures(hrm_minhasher* mh, const uint64_t* d_sigs, const uint8_t* d_valid, int64_t n, int Hsig,
+                                   int first_func, int num_funcs, const uint32_t* d_ids, uint32_t first_id,
+                                   cudaStream_t s)
+{
+    // device copies of the staging pointer tables
+    Scratch kp, vp;
+    HRM_TRY(kp.alloc(sizeof(uint64_t*) * MAX_TABLES, s));
+    HRM_TRY(vp.alloc(sizeof(uint32_t*) * MAX_TABLES, s));
+    HRM_CUDA(cudaMemcpyAsync(kp.p, mh->stage_keys.data(), sizeof(uint64_t*) * mh->H, cudaMemcpyHostToDevice, s));
+    HRM_CUDA(cudaMemcpyAsync(vp.p, mh->stage_vals.data(), sizeof(uint32_t*) * mh->H, cudaMemcpyHostToDevice, s));
+    HRM_LAUNCH(stage_pairs_kernel, capped_grid(n * num_funcs, 256, 16), 256, 0, s, d_sigs, d_valid, n, num_funcs, Hsig,
+               first_func, mh->k, d_ids, first_id, mh->table_count[first_func], kp.as<uint64_t*>(), vp.as<uint32_t*>());
+    // the pointer tables are pageable host memory: make sure the copies are done before returning
+    HRM_CUDA(cudaStreamSynchronize(s));
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_minhasher_insert(hrm_minhasher* mh, const uint32_t* d_seq2bit, int64_t pitch_words,
+                                           const int32_t* d_lengths, int64_t n, const uint32_t* d_ids, uint32_t first_id,
+                                           int first_hash_func, int num_hash_funcs, hrm_stream stream)
+{
+    HRM_REQUIRE(mh != nullptr, "minhasher");
+    if (mh->compacted) {
+        set_error("insert after compact");
+        return HRM_ERR_STATE;
+    }
+    HRM_REQUIRE(first_hash_func >= 0 && num_hash_funcs >= 1 && first_hash_func + num_hash_funcs <= mh->H,
+                "hash function range");
+    for (int j = first_hash_func; j < first_hash_func + num_hash_funcs; j++)
+        HRM_REQUIRE(mh->table_count[j] == mh->table_count[first_hash_func], "tables of one insert call must be equally filled");
+    HRM_REQUIRE(n >= 0 && mh->table_count[first_hash_func] + n <= mh->max_sequences, "more sequences than max_sequences");
+    if (n == 0) return HRM_OK;
+    cudaStream_t s = as_stream(stream);
+    // hash with functions 0..first+num-1 and keep the requested columns (ids are 0..H-1)
+    const int Hsig = first_hash_func + num_hash_funcs;
+    Scratch sigs, valid;
+    HRM_TRY(sigs.alloc(sizeof(uint64_t) * (size_t)n * Hsig, s));
+    HRM_TRY(valid.alloc((size_t)n * Hsig, s));
+    HRM_TRY(minhash_rows(d_seq2bit, pitch_words, d_lengths, n, mh->k, Hsig, sigs.as<uint64_t>(), valid.as<uint8_t>(), s));
+    // stage columns [first, first+num): pass a pointer offset by first_hash_func columns
+    HRM_TRY(stage_signatures(mh, sigs.as<uint64_t>() + first_hash_func, valid.as<uint8_t>() + first_hash_func, n, Hsig,
+                             first_hash_func, num_hash_funcs, d_ids, first_id, s));
+    for (int j = first_hash_func; j < first_hash_func + num_hash_funcs; j++) mh->table_count[j] += n;
+    mh->inserted = mh->table_count[0];
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_minhasher_insert_signatures(hrm_minhasher* mh, const uint64_t* d_sigs, const uint8_t* d_valid,
+                                                      int64_t n, const uint32_t* d_ids, uint32_t first_id,
+                                                      hrm_stream stream)
+{
+    HRM_REQUIRE(mh != nullptr, "minhasher");
+    if (mh->compacted) {
+        set_error("insert after compact");
+        return HRM_ERR_STATE;
+    }
+    HRM_REQUIRE(mh->H > 0, "no tables");
+    for (int j = 0; j < mh->H; j++)
+        HRM_REQUIRE(mh->table_count[j] == mh->table_count[0], "tables must be equally filled");
+    HRM_REQUIRE(n >= 0 && mh->table_count[0] + n <= mh->max_sequences, "more sequences than max_sequences");
+    if (n == 0) return HRM_OK;
+    HRM_TRY(stage_signatures(mh, d_sigs, d_valid, n, mh->H, 0, mh->H, d_ids, first_id, as_stream(stream)));
+    for (int j = 0; j < mh->H; j++) mh->table_count[j] += n;
+    mh->inserted = mh->table_count[0];
+    return HRM_OK;
+}
+
+extern "C" int hrm_minhasher_check_insertion_errors(hrm_minhasher*, int, int, hrm_stream) { return 0; }
+
+extern "C" hrm_status hrm_minhasher_compact(hrm_minhasher* mh, hrm_stream stream)
+{
+    HRM_REQUIRE(mh != nullptr, "minhasher");
+    if (mh->compacted) return HRM_OK;
+    cudaStream_t s = as_stream(stream);
+    const int H = mh->H;
+    for (int j = 0; j < H; j++)
+        HRM_REQUIRE(mh->table_count[j] == mh->table_count[0], "compact: tables are not equally filled");
+    const int64_t n = H > 0 ? mh->table_count[0] : 0;
+    mh->inserted = n;
+    HRM_REQUIRE((int64_t)H * n < (1LL << 32), "value offsets must fit 32 bits");
+    mh->slots.assign(H, nullptr);
+    mh->nbuckets.assign(H, 0);
+    mh->nkeys.assign(H, 0);
+    mh->values_count = (int64_t)H * n;
+    HRM_CUDA(cudaMalloc(&mh->values, sizeof(uint32_t) * (size_t)(mh->values_count > 0 ? mh->values_count : 1)));
+    const uint16_t bs = (uint16_t)mh->max_results; // ref: BucketSize(maxValuesPerKey) groupbykey.hpp:178
+    const uint32_t upper = bs < 65535 ? bs : 65535;
+    const int end_bit = mh->k < 32 ? 2 * mh->k + 1 : 64;
+    const uint64_t inv = mh->k < 32 ? (1ULL << (2 * mh->k)) : ~0ULL;
+
+    Scratch keys_sorted, flags, excl, head_pos, cub_tmp, counters;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    HRM_TRY(keys_sorted.alloc(sizeof(uint64_t) * nn, s));
+    HRM_TRY(flags.alloc(sizeof(int32_t) * nn, s));
+    HRM_TRY(excl.alloc(sizeof(int32_t) * (nn + 1), s));
+    HRM_TRY(head_pos.alloc(sizeof(int32_t) * (nn + 1), s));
+    HRM_TRY(counters.alloc(sizeof(unsigned long long) * 4, s));
+    size_t tmp_bytes = 0;
+    if (n > 0) {
+        HRM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                                 (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, end_bit, s));
+        HRM_TRY(cub_tmp.alloc(tmp_bytes, s));
+    }
+    for (int j = 0; j < H; j++) {
+        int64_t nkeys = 0, nvalid = 0;
+        uint32_t* vals_out = mh->values + (size_t)j * n;
+        if (n > 0) {
+            HRM_REQUIRE(n < (1LL << 31), "at most 2^31-1 sequences per table");
+            HRM_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, mh->stage_keys[j], keys_sorted.as<uint64_t>(),
+                                                     mh->stage_vals[j], vals_out, (int)n, 0, end_bit, s));
+            g_launches.fetch_add(1);
+            HRM_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(unsigned long long) * 4, s));
+            HRM_LAUNCH(mark_heads_kernel, capped_grid(n, 256, 16), 256, 0, s, keys_sorted.as<uint64_t>(), n, inv,
+                       flags.as<int32_t>(), counters.as<unsigned long long>());
+            HRM_TRY(exclusive_scan_i32(flags.as<int32_t>(), excl.as<int32_t>(), n,
+                                       reinterpret_cast<int64_t*>(counters.as<unsigned long long>() + 1), s));
+            HRM_LAUNCH(head_positions_kernel, capped_grid(n, 256, 16), 256, 0, s, flags.as<int32_t>(), excl.as<int32_t>(),
+                       n, head_pos.as<int32_t>());
+            unsigned long long h_cnt[2];
+            HRM_CUDA(cudaMemcpyAsync(h_cnt, counters.p, sizeof h_cnt, cudaMemcpyDeviceToHost, s));
+            HRM_CUDA(cudaStreamSynchronize(s));
+            nvalid = (int64_t)h_cnt[0];
+            nkeys = (int64_t)h_cnt[1];
+        }
+        // power-of-two bucket count with nkeys / (2 * nbuckets) <= load factor
+        int64_t want = (int64_t)((double)nkeys / (double)mh->load / 2.0) + 1;
+        int64_t nb = 1;
+        while (nb < want) nb <<= 1;
+        HRM_REQUIRE(nb <= (1LL << 31), "table too large");
+        Slot* sl = nullptr;
+        HRM_CUDA(cudaMalloc(&sl, sizeof(Slot) * (size_t)nb * 2));
+        mh->slots[j] = sl;
+        mh->nbuckets[j] = nb;
+        mh->nkeys[j] = nkeys;
+        // empty pattern: every 64-bit word = ~0 (key == SLOT_EMPTY; payload irrelevant)
+        HRM_CUDA(cudaMemsetAsync(sl, 0xFF, sizeof(Slot) * (size_t)nb * 2, s));
+        if (nkeys > 0) {
+            HRM_LAUNCH(insert_keys_kernel, capped_grid(nkeys, 256, 16), 256, 0, s, keys_sorted.as<uint64_t>(),
+                       head_pos.as<int32_t>(), nkeys, nvalid, (uint32_t)((size_t)j * n), upper, sl, (uint32_t)(nb - 1),
+                       counters.as<unsigned long long>() + 2);
+        }
+        mh->param.t[j].slots = sl;
+        mh->param.t[j].bucket_mask = (uint32_t)(nb - 1);
+        // staging of this table is no longer needed
+        cudaFree(mh->stage_keys[j]);
+        cudaFree(mh->stage_vals[j]);
+        mh->stage_keys[j] = nullptr;
+        mh->stage_vals[j] = nullptr;
+    }
+    unsigned long long h_err = 0;
+    HRM_CUDA(cudaMemcpyAsync(&h_err, counters.as<unsigned long long>() + 2, sizeof h_err, cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    if (n > 0 && h_err != 0) {
+        set_error("hash table insertion failed for %llu keys", h_err);
+        return HRM_ERR_CUDA;
+    }
+    mh->compacted = true;
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_minhasher_finish(hrm_minhasher* mh, hrm_stream)
+{
+    HRM_REQUIRE(mh != nullptr, "minhasher");
+    free_staging(mh);
+    mh->finished = true;
+    return HRM_OK;
+}
+
+extern "C" int hrm_minhasher_handle_create(hrm_minhasher* mh)
+{
+    if (!mh) return HRM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(mh->mtx);
+    mh->handles.emplace_back(new QueryHandle);
+    mh->handles.back()->in_use = true;
+    return (int)mh->handles.size() - 1;
+}
+
+extern "C" hrm_status hrm_minhasher_handle_destroy(hrm_minhasher* mh, int handle)
+{
+    HRM_REQUIRE(mh != nullptr, "minhasher");
+    std::lock_guard<std::mutex> lk(mh->mtx);
+    HRM_REQUIRE(handle >= 0 && handle < (int)mh->handles.size() && mh->handles[handle], "handle");
+    mh->handles[handle].reset(); // ref: destroyHandle nulls the slot (fakegpuminhasher.cuh:181-190)
+    return HRM_OK;
+}
+
+static hrm_status finish_count(hrm_minhasher* mh, QueryHandle* qh, int n, const int32_t* d_num_per_seq, int64_t* h_total,
+                               cudaStream_t s)
+{
+    // total = sum of counts (one scan over a scratch copy; the reference reduces on the host)
+    Scratch tmp;
+    HRM_TRY(tmp.alloc(sizeof(int32_t) * ((size_t)n + 1) + sizeof(int64_t), s));
+    HRM_TRY(qh->misc.reserve(sizeof(int64_t)));
+    HRM_TRY(exclusive_scan_i32(d_num_per_seq, tmp.as<int32_t>(), n, qh->misc.as<int64_t>(), s));
+    int64_t total = 0;
+    HRM_CUDA(cudaMemcpyAsync(&total, qh->misc.p, sizeof total, cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s)); // ref: fakegpuminhasher.cuh:260 synchronises as well
+    if (total > 0x7fffffffLL) {
+        set_error("total number of values %lld exceeds int (ref: main_gpu.cu:87)", (long long)total);
+        return HRM_ERR_OVERFLOW;
+    }
+    if (h_total) *h_total = total;
+    (void)mh;
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_minhasher_count_signatures(hrm_minhasher* mh, int handle, const uint64_t* d_sigs,
+                                                     const uint8_t* /*d_valid: invalid <=> sig == ~0*/, int n,
+                                                     int32_t* d_num_per_seq, int64_t* h_total, hrm_stream stream)
+{
+    HRM_REQUIRE(mh != nullptr, "minhasher");
+    if (!mh->compacted) {
+        set_error("query before compact");
+        return HRM_ERR_STATE;
+    }
+    QueryHandle* qh = minhasher_handle(mh, handle);
+    HRM_REQUIRE(qh != nullptr, "handle");
+    HRM_REQUIRE(n >= 0, "n");
+    if (n == 0) { // ref: returns immediately (fakegpuminhasher.cuh:216)
+        if (h_total) *h_total = 0;
+        qh->stage = 1;
+        qh->n = 0;
+        return HRM_OK;
+    }
+    cudaStream_t s = as_stream(stream);
+    HRM_TRY(minhasher_count_sigs(mh, qh, d_sigs, n, d_num_per_seq, s));
+    return finish_count(mh, qh, n, d_num_per_seq, h_total, s);
+}
+
+extern "C" hrm_status hrm_minhasher_count(hrm_minhasher* mh, int handle, const uint32_t* d_seq2bit, int64_t pitch_words,
+                                          const int32_t* d_lengths, int n, int32_t* d_num_per_seq, int64_t* h_total,
+                                          hrm_stream stream)
+{
+    HRM_REQUIRE(mh != nullptr, "minhasher");
+    if (!mh->compacted) {
+        set_error("query before compact");
+        return HRM_ERR_STATE;
+    }
+    QueryHandle* qh = minhasher_handle(mh, handle);
+    HRM_REQUIRE(qh != nullptr, "handle");
+    HRM_REQUIRE(n >= 0, "n");
+    if (n == 0) {
+        if (h_total) *h_total = 0;
+        qh->stage = 1;
+        qh->n = 0;
+        return HRM_OK;
+    }
+    cudaStream_t s = as_stream(stream);
+    HRM_TRY(qh->sigs.reserve(sizeof(uint64_t) * (size_t)n * mh->H));
+    HRM_TRY(minhash_rows(d_seq2bit, pitch_words, d_lengths, n, mh->k, mh->H, qh->sigs.as<uint64_t>(), nullptr, s));
+    HRM_TRY(minhasher_count_sigs(mh, qh, qh->sigs.as<uint64_t>(), n, d_num_per_seq, s));
+    return finish_count(mh, qh, n, d_num_per_seq, h_total, s);
+}
+
+extern "C" hrm_status hrm_minhasher_retrieve(hrm_minhasher* mh, int handle, int n, int64_t total, uint32_t* d_values,
+                                             const int32_t* d_num_per_seq, int32_t* d_offsets, hrm_stream stream)
+{
+    HRM_REQUIRE(mh != nullptr, "minhasher");
+    QueryHandle* qh = minhasher_handle(mh, handle);
+    HRM_REQUIRE(qh != nullptr, "handle");
+    if (qh->stage != 1 || qh->n != n) { // ref: assert(previousStage == NumValues) fakegpuminhasher.cuh:328
+        set_error("retrieve must follow count on the same handle with the same n");
+        return HRM_ERR_STATE;
+    }
+    qh->stage = 0;
+    if (n == 0) return HRM_OK;
+    cudaStream_t s = as_stream(stream);
+    if (total == 0) { // ref: fakegpuminhasher.cuh:332-335
+        HRM_CUDA(cudaMemsetAsync(d_offsets, 0, sizeof(int32_t) * ((size_t)n + 1), s));
+        return HRM_OK;
+    }
+    HRM_TRY(exclusive_scan_i32(d_num_per_seq, d_offsets, n, nullptr, s));
+    return minhasher_retrieve(mh, qh, n, d_values, d_offsets, s);
+}
+
+extern "C" hrm_status hrm_minhasher_info(const hrm_minhasher* mh, hrm_minhasher_info_t* out)
+{
+    HRM_REQUIRE(mh != nullptr && out != nullptr, "args");
+    memset(out, 0, sizeof *out);
+    out->k = mh->k;
+    out->num_tables = mh->H;
+    out->max_results_per_map = mh->max_results;
+    out->load_factor = mh->load;
+    out->num_inserted = mh->inserted;
+    out->is_compacted = mh->compacted ? 1 : 0;
+    out->has_gpu_tables = 1;
+    int64_t bytes = 0;
+    if (mh->compacted) {
+        for (int j = 0; j < mh->H; j++) {
+            out->num_keys_total += mh->nkeys[j];
+            bytes += mh->nbuckets[j] * 32;
+        }
+        out->num_values_total = mh->values_count;
+        bytes += mh->values_count * 4;
+    }
+    for (auto p : mh->stage_keys)
+        if (p) bytes += mh->max_sequences * 12;
+    out->device_bytes = bytes;
+    return HRM_OK;
+}
+
+// ---- serialisation (own format; ref: writeToStream/loadFromStream fakegpuminhasher.cuh:498-532) ----
+namespace {
+struct SerHeader {
+    char magic[8]; // "HRMB200\0"
+    int32_t version, k, max_results, H;
+    float load;
+    int32_t pad;
+    int64_t inserted, values_count;
+};
+} // namespace
+
+extern "C" hrm_status hrm_minhasher_serialize(const hrm_minhasher* mh, void* h_buf, int64_t* h_size)
+{
+    HRM_REQUIRE(mh != nullptr && h_size != nullptr, "args");
+    if (!mh->compacted) {
+        set_error("serialize before compact");
+        return HRM_ERR_STATE;
+    }
+    int64_t need = sizeof(SerHeader) + sizeof(int64_t) * 2 * mh->H + mh->values_count * 4;
+    for (int j = 0; j < mh->H; j++) need += mh->nbuckets[j] * 32;
+    if (!h_buf) {
+        *h_size = need;
+        return HRM_OK;
+    }
+    HRM_REQUIRE(*h_size >= need, "buffer too small");
+    char* p = (char*)h_buf;
+    SerHeader hd;
+    memset(&hd, 0, sizeof hd);
+    memcpy(hd.magic, "HRMB200", 8);
+    hd.version = 1;
+    hd.k = mh->k;
+    hd.max_results = mh->max_results;
+    hd.H = mh->H;
+    hd.load = mh->load;
+    hd.inserted = mh->inserted;
+    hd.values_count = mh->values_count;
+    memcpy(p, &hd, sizeof hd);
+    p += sizeof hd;
+    for (int j = 0; j < mh->H; j++) {
+        memcpy(p, &mh->nbuckets[j], 8);
+        p += 8;
+        memcpy(p, &mh->nkeys[j], 8);
+        p += 8;
+    }
+    HRM_CUDA(cudaMemcpy(p, mh->values, (size_t)mh->values_count * 4, cudaMemcpyDeviceToHost));
+    p += mh->values_count * 4;
+    for (int j = 0; j < mh->H; j++) {
+        HRM_CUDA(cudaMemcpy(p, mh->slots[j], (size_t)mh->nbuckets[j] * 32, cudaMemcpyDeviceToHost));
+        p += mh->nbuckets[j] * 32;
+    }
+    *h_size = need;
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_minhasher_deserialize(hrm_minhasher** out, const void* h_buf, int64_t size)
+{
+    HRM_REQUIRE(out != nullptr && h_buf != nullptr, "args");
+    *out = nullptr;
+    HRM_REQUIRE(size >= (int64_t)sizeof(SerHeader), "truncated");
+    const char* p = (const char*)h_buf;
+    SerHeader hd;
+    memcpy(&hd, p, sizeof hd);
+    p += sizeof hd;
+    HRM_REQUIRE(memcmp(hd.magic, "HRMB200", 8) == 0 && hd.version == 1, "bad magic/version");
+    HRM_REQUIRE(hd.H >= 0 && hd.H <= MAX_TABLES, "bad table count");
+    hrm_minhasher* mh = nullptr;
+    HRM_TRY(hrm_minhasher_create(&mh, hd.inserted, hd.max_results, hd.k, hd.load));
+    mh->H = hd.H;
+    mh->inserted = hd.inserted;
+    mh->values_count = hd.values_count;
+    mh->slots.assign(hd.H, nullptr);
+    mh->nbuckets.assign(hd.H, 0);
+    mh->nkeys.assign(hd.H, 0);
+    int64_t need = sizeof(SerHeader) + 16LL * hd.H + hd.values_count * 4;
+    for (int j = 0; j < hd.H; j++) {
+        memcpy(&mh->nbuckets[j], p, 8);
+        p += 8;
+        memcpy(&mh->nkeys[j], p, 8);
+        p += 8;
+        need += mh->nbuckets[j] * 32;
+    }
+    if (size < need) {
+        hrm_minhasher_destroy(mh);
+        set_error("truncated minhasher image");
+        return HRM_ERR_INVALID;
+    }
+    cudaError_t e = cudaMalloc(&mh->values, (size_t)(hd.values_count > 0 ? hd.values_count : 1) * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(mh->values, p, (size_t)hd.values_count * 4, cudaMemcpyHostToDevice);
+    p += hd.values_count * 4;
+    for (int j = 0; j < hd.H && e == cudaSuccess; j++) {
+        Slot* sl = nullptr;
+        e = cudaMalloc(&sl, (size_t)mh->nbuckets[j] * 32);
+        if (e != cudaSuccess) break;
+        mh->slots[j] = sl;
+        e = cudaMemcpy(sl, p, (size_t)mh->nbuckets[j] * 32, cudaMemcpyHostToDevice);
+        p += mh->nbuckets[j] * 32;
+        mh->param.t[j].slots = sl;
+        mh->param.t[j].bucket_mask = (uint32_t)(mh->nbuckets[j] - 1);
+    }
+    if (e != cudaSuccess) {
+        set_error("deserialize: %s", cudaGetErrorString(e));
+        hrm_minhasher_destroy(mh);
+        return HRM_ERR_CUDA;
+    }
+    mh->compacted = true;
+    mh->finished = true;
+    *out = mh;
+    return HRM_OK;
+}

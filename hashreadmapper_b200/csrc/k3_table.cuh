@@ -1,0 +1,80 @@
+// k3_table.cuh -- internal interface of the minhasher object (K3).
+#pragma once
+#include "runtime.cuh"
+#include <vector>
+#include <memory>
+#include <mutex>
+
+namespace hrm {
+
+// 16-byte slot; two slots form one 32-byte bucket (= one DRAM sector)
+struct alignas(16) Slot {
+    uint64_t key;
+    uint32_t off;   // index into the minhasher's value array
+    uint32_t cnt;   // bucket size after truncation
+};
+static_assert(sizeof(Slot) == 16, "slot must be 16 bytes (SURVEY 8d: 16 B per probe)");
+
+constexpr uint64_t SLOT_EMPTY = ~0ULL;   // ref: emptySlot cpuhashtable.hpp:277-278
+constexpr int MAX_TABLES = 64;           // ref: assert(numTables <= 64) fakegpuminhasher.cuh:541
+
+struct TableRef {
+    const Slot* slots;
+    uint32_t bucket_mask; // nbuckets - 1 (power of two)
+    uint32_t pad;
+};
+struct TablesParam {
+    TableRef t[MAX_TABLES];
+};
+
+struct QueryHandle {
+    GrowBuf sigs;    // [n][H] u64 (when hashing inside count)
+    GrowBuf ranges;  // [n][H] uint2 (off, cnt)
+    GrowBuf misc;    // totals
+    int stage = 0;   // 0 none, 1 counted
+    int n = 0;
+    bool in_use = false;
+};
+
+} // namespace hrm
+
+struct hrm_minhasher {
+    int k = 16;
+    int max_results = 65535;
+    float load = 0.8f;
+    int64_t max_sequences = 0;
+    int H = 0;
+    int64_t inserted = 0;
+    bool compacted = false;
+    bool finished = false;
+    int device = 0;
+    // build staging, one pair of device arrays per table
+    std::vector<uint64_t*> stage_keys;
+    std::vector<uint32_t*> stage_vals;
+    std::vector<int64_t> table_count; // sequences staged per table
+    // compacted form
+    uint32_t* values = nullptr;      // H * inserted entries; table j at [j*inserted, ...)
+    int64_t values_count = 0;
+    std::vector<hrm::Slot*> slots;   // per table
+    std::vector<int64_t> nbuckets;
+    std::vector<int64_t> nkeys;
+    hrm::TablesParam param;
+    // handles
+    std::mutex mtx;
+    std::vector<std::unique_ptr<hrm::QueryHandle>> handles;
+    // counters of the last count call (slot touches), device side
+    unsigned long long* d_touches = nullptr;
+};
+
+namespace hrm {
+// device-side pieces used by the fused mapper
+hrm_status minhasher_count_sigs(hrm_minhasher* mh, QueryHandle* qh, const uint64_t* d_sigs, int n,
+                                int32_t* d_num_per_seq, cudaStream_t s);
+hrm_status minhasher_retrieve(hrm_minhasher* mh, QueryHandle* qh, int n, uint32_t* d_values,
+                              const int32_t* d_offsets, cudaStream_t s);
+QueryHandle* minhasher_handle(hrm_minhasher* mh, int id);
+hrm_status minhash_rows(const uint32_t* d_seq2bit, int64_t pitch_words, const int32_t* d_lengths, int64_t n, int k,
+                        int H, uint64_t* d_sigs, uint8_t* d_valid, cudaStream_t s);
+hrm_status minhash_windows(const uint32_t* d_chrom2bit, int64_t chrom_len, int k, int w, int H, int64_t first_window,
+                           int64_t n_windows, uint64_t* d_sigs, uint8_t* d_valid, cudaStream_t s);
+} // namespace hrm

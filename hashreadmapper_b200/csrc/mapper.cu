@@ -1,0 +1,382 @@
+// mapper.cu -- the fused read-mapping path in the north_star direction: a 3N index over the
+// reference windows lives in HBM and batches of reads probe it.
+// ref: performMappingGpu src/gpu/main_gpu.cu:859-1160 (driver), WindowBatchProcessor::operator()
+//      :471-854 (per 2048-window batch: H2D ASCII, encode, minhash, CPU table query, H2D ids, filter,
+//      gather reads, H2D genome slice, extended windows, HiLo, SHD, D2H, host arg-min; >= 6 stream
+//      syncs per batch), Mappinghandler::go src/gpu/mappinghandler.cu:67 (verification on the host).
+// Candidate (read, window) pairs are symmetric in the direction of the index, so
+// indexing windows and probing with reads yields the same pairs as long as no bucket exceeds
+// min(maxResultsPerMap, 65535) entries (then the truncation applies to windows instead of reads --
+// DESIGN.md "bucket caps").  One pass = one (read conversion, genome conversion) pair = exactly the
+// reference pipeline on pre-converted input; passes are merged per read by smaller Hamming distance,
+// earlier pass first.  One stream sync per pass (to size the candidate buffer), none per window.
+#include "pipeline.cuh"
+#include "k3_table.cuh"
+#include "mapper.hpp"
+#include <string.h>
+
+namespace hrm {
+
+__global__ void __launch_bounds__(256) merge_pass_kernel(hrm_mapped_read* __restrict__ best,
+                                                         const hrm_mapped_read* __restrict__ cur, int64_t n, int first)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const hrm_mapped_read c = cur[i];
+        if (first) {
+            best[i] = c;
+            continue;
+        }
+        const hrm_mapped_read b = best[i];
+        if (c.orientation != HRM_ORIENT_NONE &&
+            (b.orientation == HRM_ORIENT_NONE || c.hamming_distance < b.hamming_distance))
+            best[i] = c;
+    }
+}
+
+__global__ void __launch_bounds__(256) count_mapped_kernel(const hrm_mapped_read* __restrict__ m, int64_t n,
+                                                           unsigned long long* __restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long local = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        local += m[i].orientation != HRM_ORIENT_NONE ? 1 : 0;
+    for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+__global__ void max_len_kernel(const int32_t* __restrict__ len, int64_t n, int* __restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int local = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) local = max(local, len[i]);
+    local = __reduce_max_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, local);
+}
+
+static unsigned mgrid(int64_t items)
+{
+    int64_t g = HRM_SDIV(items, (int64_t)256);
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+} // namespace hrm
+
+using namespace hrm;
+
+extern "C" void hrm_mapper_default_config(hrm_mapper_config* cfg)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->k = 16;                      // ref: options.hpp kmerlength
+    cfg->window_size = 128;           // ref: options.hpp windowSize
+    cfg->num_tables = 16;             // ref: options.hpp hashmaps
+    cfg->min_table_hits = 4;          // ref: options.hpp minTableHits
+    cfg->max_results_per_map = 65535; // ref: options.hpp maxResultsPerMap
+    cfg->load_factor = 0.8f;          // ref: options.hpp hashtableLoadfactor
+    cfg->max_hamming_percent = 0.05f; // ref: options.hpp maxHammingPercent
+    cfg->mapper_type = HRM_MAPPER_SW;
+    cfg->num_passes = 1;
+    cfg->read_conversion[0] = HRM_CONV_NONE;
+    cfg->genome_conversion[0] = HRM_CONV_NONE;
+    cfg->verify_conversion[0] = HRM_CONV_CT; // ref: stage V always converts C->T (mappinghandler.cu:456-473)
+}
+
+extern "C" hrm_status hrm_mapper_create(hrm_mapper** out, const hrm_mapper_config* cfg)
+{
+    HRM_REQUIRE(out != nullptr && cfg != nullptr, "args");
+    *out = nullptr;
+    HRM_TRY(ensure_device());
+    HRM_REQUIRE(cfg->k >= 1 && cfg->k <= 32, "1 <= k <= 32 (ref: main_gpu.cu:1305)");
+    HRM_REQUIRE(cfg->num_tables >= 1 && cfg->num_tables <= 48, "1 <= hashmaps <= 48 (ref: main_gpu.cu:1306)");
+    HRM_REQUIRE(cfg->num_tables >= cfg->min_table_hits, "hashmaps >= minTableHits (ref: main_gpu.cu:1309)");
+    HRM_REQUIRE(cfg->window_size >= cfg->k && cfg->window_size <= HRM_SW_MAX_REF, "k <= windowSize <= 512");
+    HRM_REQUIRE(cfg->num_passes >= 1 && cfg->num_passes <= HRM_MAX_PASSES, "1 <= num_passes <= 4");
+    HRM_REQUIRE(cfg->load_factor > 0.f && cfg->load_factor <= 1.f, "load factor");
+    for (int p = 0; p < cfg->num_passes; p++) {
+        HRM_REQUIRE(cfg->read_conversion[p] >= 0 && cfg->read_conversion[p] <= 2, "read_conversion");
+        HRM_REQUIRE(cfg->genome_conversion[p] >= 0 && cfg->genome_conversion[p] <= 2, "genome_conversion");
+        HRM_REQUIRE(cfg->verify_conversion[p] >= 0 && cfg->verify_conversion[p] <= 2, "verify_conversion");
+    }
+    auto* m = new hrm_mapper;
+    m->cfg = *cfg;
+    *out = m;
+    return HRM_OK;
+}
+
+extern "C" void hrm_mapper_destroy(hrm_mapper* m)
+{
+    if (!m) return;
+    for (int c = 0; c < 3; c++) {
+        if (m->index[c]) hrm_minhasher_destroy(m->index[c]);
+        if (m->genome[c]) hrm_genome_destroy(m->genome[c]);
+    }
+    if (m->d_win_prefix) cudaFree(m->d_win_prefix);
+    delete m;
+}
+
+extern "C" hrm_status hrm_mapper_set_genome(hrm_mapper* m, const char* h_ascii, const int64_t* h_chrom_offsets,
+                                            int n_chrom, hrm_stream stream)
+{
+    HRM_REQUIRE(m != nullptr && h_ascii != nullptr && h_chrom_offsets != nullptr && n_chrom >= 1, "args");
+    HRM_REQUIRE(m->genome[0] == nullptr && m->genome[1] == nullptr && m->genome[2] == nullptr, "genome already set");
+    cudaStream_t s = as_stream(stream);
+    const hrm_mapper_config& cfg = m->cfg;
+    m->n_chrom = n_chrom;
+    m->chrom_off.assign(h_chrom_offsets, h_chrom_offsets + n_chrom + 1);
+    m->host_genome.assign(h_ascii + h_chrom_offsets[0], (size_t)(h_chrom_offsets[n_chrom] - h_chrom_offsets[0]));
+    const int64_t stride = cfg.window_size - cfg.k + 1;
+    std::vector<int64_t> prefix(n_chrom + 1, 0);
+    for (int c = 0; c < n_chrom; c++) {
+        const int64_t len = h_chrom_offsets[c + 1] - h_chrom_offsets[c];
+        m->chrom_len.push_back(len);
+        prefix[c + 1] = prefix[c] + (len + stride - 1) / stride;
+    }
+    m->num_windows = prefix[n_chrom];
+    HRM_REQUIRE(m->num_windows < (1LL << 32), "window ids are 32 bit");
+    HRM_CUDA(cudaMalloc(&m->d_win_prefix, sizeof(int64_t) * (size_t)(n_chrom + 1)));
+    HRM_CUDA(cudaMemcpy(m->d_win_prefix, prefix.data(), sizeof(int64_t) * (size_t)(n_chrom + 1), cudaMemcpyHostToDevice));
+
+    for (int p = 0; p < cfg.num_passes; p++) {
+        const int gc = cfg.genome_conversion[p];
+        if (m->genome[gc]) continue;
+        HRM_TRY(hrm_genome_create_from_ascii(&m->genome[gc], h_ascii, h_chrom_offsets, n_chrom, gc, stream));
+        hrm_minhasher* mh = nullptr;
+        HRM_TRY(hrm_minhasher_create(&mh, m->num_windows, cfg.max_results_per_map, cfg.k, cfg.load_factor));
+        m->index[gc] = mh;
+        const int added = hrm_minhasher_add_tables(mh, cfg.num_tables, nullptr, stream);
+        if (added != cfg.num_tables) {
+            set_error("not enough device memory for %d hash tables (got %d)", cfg.num_tables, added);
+            return HRM_ERR_NOMEM; // ref: gpuminhasherconstruction.cu:71
+        }
+        // sketch the windows chromosome by chromosome in bounded chunks and stage them
+        const int64_t CHUNK = 4LL << 20;
+        Scratch sg, vd;
+        const int64_t maxchunk = m->num_windows < CHUNK ? m->num_windows : CHUNK;
+        HRM_TRY(sg.alloc(sizeof(uint64_t) * (size_t)maxchunk * cfg.num_tables, s));
+        HRM_TRY(vd.alloc((size_t)maxchunk * cfg.num_tables, s));
+        for (int c = 0; c < n_chrom; c++) {
+            const int64_t nw = prefix[c + 1] - prefix[c];
+            for (int64_t at = 0; at < nw; at += CHUNK) {
+                const int64_t cnt = (nw - at) < CHUNK ? (nw - at) : CHUNK;
+                HRM_TRY(minhash_windows(m->genome[gc]->chrom_words[c], m->chrom_len[c], cfg.k, cfg.window_size,
+                                        cfg.num_tables, at, cnt, sg.as<uint64_t>(), vd.as<uint8_t>(), s));
+                HRM_TRY(hrm_minhasher_insert_signatures(mh, sg.as<uint64_t>(), vd.as<uint8_t>(), cnt, nullptr,
+                                                        (uint32_t)(prefix[c] + at), stream));
+            }
+        }
+        HRM_TRY(hrm_minhasher_compact(mh, stream));
+        HRM_TRY(hrm_minhasher_finish(mh, stream));
+        m->index_handle[gc] = hrm_minhasher_handle_create(mh);
+    }
+    HRM_CUDA(cudaStreamSynchronize(s));
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_mapper_info(const hrm_mapper* m, hrm_mapper_info_t* out)
+{
+    HRM_REQUIRE(m != nullptr && out != nullptr, "args");
+    memset(out, 0, sizeof *out);
+    out->num_windows = m->num_windows;
+    out->num_passes = m->cfg.num_passes;
+    for (int c = 0; c < 3; c++) {
+        if (m->genome[c]) out->genome_device_bytes += m->genome[c]->device_bytes();
+        if (m->index[c]) {
+            hrm_minhasher_info_t mi;
+            hrm_minhasher_info(m->index[c], &mi);
+            out->index_device_bytes += mi.device_bytes;
+            out->num_keys_total += mi.num_keys_total;
+            for (int j = 0; j < m->index[c]->H; j++) out->table_slots_total += m->index[c]->nbuckets[j] * 2;
+        }
+    }
+    return HRM_OK;
+}
+
+// packs the batch once per distinct read conversion used by the passes
+static hrm_status pack_batch(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch, const int32_t* d_lengths,
+                             int64_t n, hrm_stream stream)
+{
+    const hrm_mapper_config& cfg = m->cfg;
+    m->packed_pitch = ascii_pitch / 16;
+    bool done[3] = {false, false, false};
+    for (int p = 0; p < cfg.num_passes; p++) {
+        const int rc = cfg.read_conversion[p];
+        if (done[rc]) continue;
+        done[rc] = true;
+        HRM_TRY(m->packed[rc].reserve(sizeof(uint32_t) * (size_t)n * m->packed_pitch));
+        HRM_TRY(hrm_encode_2bit(d_reads_ascii, ascii_pitch, d_lengths, n, rc, m->packed[rc].as<uint32_t>(),
+                                m->packed_pitch, stream));
+    }
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch,
+                                    const int32_t* d_lengths, int64_t n, hrm_mapped_read* d_out,
+                                    hrm_batch_stats* h_stats, hrm_stream stream)
+{
+    HRM_REQUIRE(m != nullptr, "mapper");
+    HRM_REQUIRE(m->d_win_prefix != nullptr, "hrm_mapper_set_genome has not been called");
+    HRM_REQUIRE(n >= 0 && n < (1LL << 31) / (m->cfg.num_tables > 0 ? m->cfg.num_tables : 1),
+                "batch too large: n * hashmaps must fit int");
+    HRM_REQUIRE(ascii_pitch > 0 && ascii_pitch % 16 == 0, "ascii_pitch must be a positive multiple of 16");
+    cudaStream_t s = as_stream(stream);
+    const hrm_mapper_config& cfg = m->cfg;
+    const int64_t launches0 = g_launches.load();
+    hrm_batch_stats st;
+    memset(&st, 0, sizeof st);
+    st.num_reads = n;
+    if (n == 0) {
+        if (h_stats) *h_stats = st;
+        return HRM_OK;
+    }
+    const int H = cfg.num_tables;
+    HRM_TRY(pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
+    HRM_TRY(m->sigs.reserve(sizeof(uint64_t) * (size_t)n * H));
+    HRM_TRY(m->num.reserve(sizeof(int32_t) * ((size_t)n + 1)));
+    HRM_TRY(m->off.reserve(sizeof(int32_t) * ((size_t)n + 1)));
+    HRM_TRY(m->newoff.reserve(sizeof(int32_t) * ((size_t)n + 1)));
+    HRM_TRY(m->passres.reserve(sizeof(hrm_mapped_read) * (size_t)n));
+    HRM_TRY(m->misc.reserve(64));
+    int64_t* d_tot = m->misc.as<int64_t>();           // [0] values total, [1] filtered total
+    unsigned long long* d_cnt = m->misc.as<unsigned long long>() + 2;
+    int last_rc = -1;
+    for (int p = 0; p < cfg.num_passes; p++) {
+        const int rc = cfg.read_conversion[p], gc = cfg.genome_conversion[p];
+        hrm_minhasher* mh = m->index[gc];
+        QueryHandle* qh = minhasher_handle(mh, m->index_handle[gc]);
+        HRM_REQUIRE(qh != nullptr, "index handle");
+        const uint32_t* reads = m->packed[rc].as<uint32_t>();
+        // K2 (skipped when the previous pass sketched the same converted reads)
+        if (rc != last_rc)
+            HRM_TRY(minhash_rows(reads, m->packed_pitch, d_lengths, n, cfg.k, H, m->sigs.as<uint64_t>(), nullptr, s));
+        last_rc = rc;
+        // K3b probe -> per-read counts, scan -> offsets + total
+        HRM_TRY(minhasher_count_sigs(mh, qh, m->sigs.as<uint64_t>(), (int)n, m->num.as<int32_t>(), s));
+        HRM_TRY(exclusive_scan_i32(m->num.as<int32_t>(), m->off.as<int32_t>(), n, d_tot, s));
+        int64_t total = 0;
+        HRM_CUDA(cudaMemcpyAsync(&total, d_tot, sizeof total, cudaMemcpyDeviceToHost, s));
+        HRM_CUDA(cudaStreamSynchronize(s)); // the one sync of this pass: sizes the candidate buffers
+        if (total > 0x7fffffffLL) {
+            set_error("candidate values of one batch exceed int: use smaller batches");
+            return HRM_ERR_OVERFLOW;
+        }
+        st.num_probes += n * H;
+        st.num_values += total;
+        hrm_mapped_read* passout = m->passres.as<hrm_mapped_read>();
+        Scratch values, cands;
+        HRM_TRY(values.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
+        HRM_TRY(cands.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
+        if (total > 0) HRM_TRY(minhasher_retrieve(mh, qh, (int)n, values.as<uint32_t>(), m->off.as<int32_t>(), s));
+        qh->stage = 0;
+        // K4 sort + RLE + threshold, then dense candidate lists
+        HRM_TRY(filter_segments(values.as<uint32_t>(), m->off.as<int32_t>(), (int)n, cfg.min_table_hits,
+                                m->num.as<int32_t>(), m->newoff.as<int32_t>(), d_tot + 1, s));
+        HRM_TRY(compact_segments(values.as<uint32_t>(), m->off.as<int32_t>(), m->newoff.as<int32_t>(), (int)n,
+                                 cands.as<uint32_t>(), s));
+        // K5 + per-read arg-min
+        HRM_TRY(best_windows(reads, m->packed_pitch, d_lengths, n, cands.as<uint32_t>(), m->newoff.as<int32_t>(),
+                             m->genome[gc], m->d_win_prefix, cfg.k, cfg.window_size, cfg.max_hamming_percent, p,
+                             passout, s));
+        HRM_LAUNCH(merge_pass_kernel, mgrid(n), 256, 0, s, d_out, passout, n, p == 0 ? 1 : 0);
+        if (h_stats) {
+            int64_t ftotal = 0;
+            HRM_CUDA(cudaMemcpyAsync(&ftotal, d_tot + 1, sizeof ftotal, cudaMemcpyDeviceToHost, s));
+            HRM_CUDA(cudaStreamSynchronize(s));
+            st.num_candidates += ftotal;
+        }
+    }
+    if (h_stats) {
+        HRM_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));
+        HRM_LAUNCH(count_mapped_kernel, mgrid(n), 256, 0, s, d_out, n, d_cnt);
+        unsigned long long mapped = 0;
+        HRM_CUDA(cudaMemcpyAsync(&mapped, d_cnt, sizeof mapped, cudaMemcpyDeviceToHost, s));
+        for (int c = 0; c < 3; c++) {
+            if (!m->index[c]) continue;
+            unsigned long long t = 0;
+            HRM_CUDA(cudaMemcpyAsync(&t, m->index[c]->d_touches, sizeof t, cudaMemcpyDeviceToHost, s));
+            HRM_CUDA(cudaStreamSynchronize(s));
+            st.num_slot_touches += (int64_t)(t - m->touches_seen[c]);
+            m->touches_seen[c] = t;
+        }
+        HRM_CUDA(cudaStreamSynchronize(s));
+        st.num_mapped = (int64_t)mapped;
+        st.num_kernel_launches = g_launches.load() - launches0;
+        *h_stats = st;
+    }
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_verify_batch(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch,
+                                       const int32_t* d_lengths, int64_t n, const hrm_mapped_read* d_mapped,
+                                       hrm_read_record* d_records, char* d_cigars, int64_t cigar_pitch,
+                                       hrm_batch_stats* h_stats, hrm_stream stream)
+{
+    HRM_REQUIRE(m != nullptr, "mapper");
+    HRM_REQUIRE(m->d_win_prefix != nullptr, "hrm_mapper_set_genome has not been called");
+    HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && cigar_pitch > 0, "sizes");
+    cudaStream_t s = as_stream(stream);
+    const int64_t launches0 = g_launches.load();
+    if (n == 0) return HRM_OK;
+    const hrm_mapper_config& cfg = m->cfg;
+    HRM_TRY(pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
+    HRM_TRY(m->misc.reserve(64));
+    int* d_maxlen = m->misc.as<int>() + 8;
+    HRM_CUDA(cudaMemsetAsync(d_maxlen, 0, sizeof(int), s));
+    HRM_LAUNCH(max_len_kernel, mgrid(n), 256, 0, s, d_lengths, n, d_maxlen);
+    int maxlen = 0;
+    HRM_CUDA(cudaMemcpyAsync(&maxlen, d_maxlen, sizeof maxlen, cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    HRM_REQUIRE(maxlen <= HRM_SW_MAX_QUERY, "read longer than HRM_SW_MAX_QUERY");
+    VerifyParams VP;
+    memset(&VP, 0, sizeof VP);
+    VP.num_passes = cfg.num_passes;
+    VP.w = cfg.window_size;
+    VP.mapper_type = cfg.mapper_type;
+    for (int p = 0; p < cfg.num_passes; p++) {
+        VP.pass[p].reads = m->packed[cfg.read_conversion[p]].as<uint32_t>();
+        VP.pass[p].read_pitch = m->packed_pitch;
+        VP.pass[p].G = m->genome[cfg.genome_conversion[p]]->dev();
+        VP.pass[p].verify_conv = cfg.verify_conversion[p];
+    }
+    HRM_TRY(verify_reads(VP, d_lengths, n, maxlen, d_mapped, d_records, d_cigars, cigar_pitch, s));
+    if (h_stats) h_stats->num_kernel_launches += g_launches.load() - launches0;
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_ascii, int64_t ascii_pitch,
+                                           const int32_t* h_lengths, int64_t n, hrm_read_record* h_records,
+                                           char* h_cigars, int64_t cigar_pitch, hrm_batch_stats* h_stats,
+                                           hrm_stream stream)
+{
+    HRM_REQUIRE(m != nullptr && h_reads_ascii != nullptr && h_lengths != nullptr && h_records != nullptr, "args");
+    HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && cigar_pitch > 0, "sizes");
+    cudaStream_t s = as_stream(stream);
+    if (n == 0) {
+        if (h_stats) memset(h_stats, 0, sizeof *h_stats);
+        return HRM_OK;
+    }
+    Scratch d_ascii, d_len, d_mapped, d_rec, d_cig;
+    HRM_TRY(d_ascii.alloc((size_t)(n * ascii_pitch), s));
+    HRM_TRY(d_len.alloc(sizeof(int32_t) * (size_t)n, s));
+    HRM_TRY(d_mapped.alloc(sizeof(hrm_mapped_read) * (size_t)n, s));
+    HRM_TRY(d_rec.alloc(sizeof(hrm_read_record) * (size_t)n, s));
+    HRM_TRY(d_cig.alloc((size_t)(2 * n * cigar_pitch), s));
+    HRM_CUDA(cudaMemcpyAsync(d_ascii.p, h_reads_ascii, (size_t)(n * ascii_pitch), cudaMemcpyHostToDevice, s));
+    HRM_CUDA(cudaMemcpyAsync(d_len.p, h_lengths, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+    hrm_batch_stats st;
+    memset(&st, 0, sizeof st);
+    HRM_TRY(hrm_map_batch(m, d_ascii.as<char>(), ascii_pitch, d_len.as<int32_t>(), n, d_mapped.as<hrm_mapped_read>(),
+                          h_stats ? &st : nullptr, stream));
+    HRM_TRY(hrm_verify_batch(m, d_ascii.as<char>(), ascii_pitch, d_len.as<int32_t>(), n,
+                             d_mapped.as<hrm_mapped_read>(), d_rec.as<hrm_read_record>(), d_cig.as<char>(), cigar_pitch,
+                             h_stats ? &st : nullptr, stream));
+    HRM_CUDA(cudaMemcpyAsync(h_records, d_rec.p, sizeof(hrm_read_record) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (h_cigars)
+        HRM_CUDA(cudaMemcpyAsync(h_cigars, d_cig.p, (size_t)(2 * n * cigar_pitch), cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    if (h_stats) *h_stats = st;
+    return HRM_OK;
+}
+

@@ -1,0 +1,28 @@
+// mapper.hpp -- the mapper object (shared by mapper.cu and sam.cpp).
+#pragma once
+#include "runtime.cuh"
+#include "store.cuh"
+#include <string>
+#include <vector>
+
+struct hrm_minhasher;
+
+struct hrm_mapper {
+    hrm_mapper_config cfg;
+    // one genome + index per distinct genome conversion
+    hrm_genome* genome[3] = {nullptr, nullptr, nullptr};
+    hrm_minhasher* index[3] = {nullptr, nullptr, nullptr};
+    int index_handle[3] = {-1, -1, -1};
+    int64_t* d_win_prefix = nullptr; // n_chrom + 1
+    int64_t num_windows = 0;
+    int n_chrom = 0;
+    std::vector<int64_t> chrom_len;
+    std::string host_genome; // kept for SAM output (RNEXT column prints the window, ref: mappinghandler.cu:257)
+    std::vector<int64_t> chrom_off;
+    // per-batch buffers that only grow
+    hrm::GrowBuf packed[3];  // reads packed per read conversion
+    hrm::GrowBuf sigs, num, off, newoff, passres, misc;
+    int64_t packed_pitch = 0;
+    unsigned long long touches_seen[3] = {0, 0, 0};
+};
+

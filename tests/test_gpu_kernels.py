@@ -1,0 +1,282 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (hashreadmapper_b200.api -> libhrm_b200.so),
+against the oracle (plain-C restatement of the reference, itself pinned against the reference's own
+code in test_oracle_pin.py).  Bit-exact: all integer / byte / index work.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from util import rs, mutate, rows, pack_rows, ssw_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def tt(api, a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def as_u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def as_u64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+# ---- K1 ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("conv", [0, 1, 2])
+def test_k1_encode_rows(cuda, port, conv):
+    rng = random.Random(10 + conv)
+    seqs = [rs(rng, rng.randint(0, 260), "ACGTNacgt") for _ in range(300)] + [b"", b"A", b"C" * 16, b"G" * 17, b"T" * 256]
+    a, lens = rows(seqs, fill=ord("T"))  # padding bytes are garbage on purpose
+    out = as_u32(cuda.encode_2bit(tt(cuda, a), tt(cuda, lens), conv))
+    for i, s in enumerate(seqs):
+        exp = port.encode_2bit(port.convert_ascii(s, conv)) if s else np.zeros(0, np.uint32)
+        assert (out[i, :len(exp)] == exp).all(), (i, s)
+        assert (out[i, len(exp):] == 0).all()
+
+
+def test_k1_encode_contiguous_unaligned(cuda, port):
+    import torch
+    rng = random.Random(3)
+    g = rs(rng, 100003, "ACGTN")
+    buf = torch.from_numpy(np.frombuffer(b"xxxxx" + g, dtype=np.uint8).copy()).cuda()
+    for conv in (0, 1, 2):
+        exp = port.encode_2bit(port.convert_ascii(g, conv))
+        assert (as_u32(cuda.encode_2bit_contiguous(buf[5:], conv)) == exp).all()
+        al = torch.from_numpy(np.frombuffer(g, dtype=np.uint8).copy()).cuda()
+        assert (as_u32(cuda.encode_2bit_contiguous(al, conv)) == exp).all()
+
+
+# ---- K2 ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,H", [(16, 16), (4, 1), (12, 5), (20, 48), (31, 8), (32, 16)])
+def test_k2_minhash_rows(cuda, port, k, H):
+    rng = random.Random(k * 100 + H)
+    seqs = [rs(rng, rng.choice([150, 150, 250, 15, 16, 17, 31, 32, 33, 1, 0, 100]), "ACGT") for _ in range(200)]
+    seqs += [rs(rng, 150, "AGT") for _ in range(50)]
+    enc = pack_rows(port, seqs, 17)
+    lens = np.array([len(s) for s in seqs], np.int32)
+    es, ev = port.minhash_batch(enc, lens, k, H)
+    sigs, valid = cuda.minhash(tt(cuda, enc.view(np.int32)), tt(cuda, lens), k, H)
+    assert (as_u64(sigs) == es).all()
+    assert (valid.cpu().numpy() == ev).all()
+
+
+@pytest.mark.parametrize("k,w", [(16, 128), (12, 64), (24, 256), (32, 128)])
+def test_k2_minhash_windows(cuda, port, k, w):
+    rng = random.Random(k + w)
+    g = rs(rng, 20011, "ACGT")
+    genome = cuda.Genome(g, [0, len(g)])
+    stride = w - k + 1
+    nw = genome.getNumWindowsInChromosome(0, k, w)
+    assert nw == (len(g) + stride - 1) // stride
+    sigs, valid = cuda.minhash_windows(genome.chromosome2BitPtr(0), len(g), k, w, 16, 0, nw)
+    wins = [g[i * stride:i * stride + w] for i in range(nw)]
+    enc = pack_rows(port, wins, (w + 15) // 16)
+    es, ev = port.minhash_batch(enc, np.array([len(x) for x in wins], np.int32), k, 16)
+    assert (as_u64(sigs) == es).all()
+    assert (valid.cpu().numpy() == ev).all()
+    # a sub-range
+    s2, _ = cuda.minhash_windows(genome.chromosome2BitPtr(0), len(g), k, w, 16, 7, 20)
+    assert (as_u64(s2) == es[7:27]).all()
+
+
+# ---- K3 ------------------------------------------------------------------------------------------
+def _query_both(cuda, port, mh, handle, orc_tables, qenc, qlens, k, H):
+    num, total = mh.determineNumValues(handle, tt(cuda, qenc.view(np.int32)), tt(cuda, qlens))
+    vals, offs = mh.retrieveValues(handle, len(qlens), total, num)
+    qs, qv = port.minhash_batch(qenc, qlens, k, H)
+    en, eo, evals = port.tables_query(orc_tables, qs, qv)
+    assert total == len(evals)
+    assert (num.cpu().numpy() == en).all()
+    assert (offs.cpu().numpy().astype(np.int64) == eo).all()
+    assert (as_u32(vals) == evals).all()  # same order: tables 0..H-1, insertion order inside a bucket
+
+
+@pytest.mark.parametrize("cap", [65535, 3])
+def test_k3_minhasher_reference_direction(cuda, port, cap):
+    """reads inserted, windows query -- the reference's direction (gpuminhasherconstruction.cu, main_gpu.cu:534)"""
+    rng = random.Random(77 + cap)
+    k, H, w = 16, 16, 128
+    g = rs(rng, 30000, "AGT")
+    reads = []
+    for _ in range(1500):
+        p = rng.randint(0, len(g) - 150)
+        reads.append(mutate(rng, g[p:p + 150], 0.01, 0)[:150])
+    reads += [b"ACGT", b""] + [reads[0]] * 8  # too-short reads are skipped; duplicates share buckets
+    enc = pack_rows(port, reads, 10)
+    lens = np.array([len(r) for r in reads], np.int32)
+    mh = cuda.Minhasher(len(reads), cap, k, 0.8)
+    assert mh.addHashTables(H, list(range(H))) == H
+    half = len(reads) // 2
+    # two insert batches, the second split over two groups of tables
+    mh.insert(tt(cuda, enc[:half].view(np.int32)), tt(cuda, lens[:half]), None, 0)
+    mh.insert(tt(cuda, enc[half:].view(np.int32)), tt(cuda, lens[half:]), None, half, 0, 8)
+    mh.insert(tt(cuda, enc[half:].view(np.int32)), tt(cuda, lens[half:]), None, half, 8, 8)
+    mh.compact()
+    mh.constructionIsFinished()
+    info = mh.getInfo()
+    assert info.is_compacted == 1 and info.num_inserted == len(reads)
+    rsig, rval = port.minhash_batch(enc, lens, k, H)
+    T = port.tables_build(rsig, rval, None, cap)
+    stride = w - k + 1
+    wins = [g[i * stride:i * stride + w] for i in range((len(g) + stride - 1) // stride)] + [b"ACG", rs(rng, 128)]
+    qenc = pack_rows(port, wins, 8)
+    qlens = np.array([len(x) for x in wins], np.int32)
+    h = mh.makeMinhasherHandle()
+    _query_both(cuda, port, mh, h, T, qenc, qlens, k, H)
+    # stage order is enforced (ref: fakegpuminhasher.cuh:328)
+    import hashreadmapper_b200 as hb
+    with pytest.raises(hb.HrmError):
+        mh.retrieveValues(h, len(qlens), 0, tt(cuda, np.zeros(len(qlens), np.int32)))
+    # serialisation round trip
+    mh2 = cuda.Minhasher.loadFromBytes(mh.writeToBytes())
+    h2 = mh2.makeMinhasherHandle()
+    _query_both(cuda, port, mh2, h2, T, qenc, qlens, k, H)
+    mh.destroyHandle(h)
+    port.tables_free(T)
+
+
+def test_k3_empty_and_all_miss(cuda, port):
+    rng = random.Random(5)
+    k, H = 16, 4
+    reads = [rs(rng, 100) for _ in range(64)]
+    enc = pack_rows(port, reads, 7)
+    lens = np.array([len(r) for r in reads], np.int32)
+    mh = cuda.Minhasher(64, 65535, k, 0.8)
+    assert mh.addHashTables(H) == H
+    mh.insert(tt(cuda, enc.view(np.int32)), tt(cuda, lens))
+    mh.compact()
+    h = mh.makeMinhasherHandle()
+    q = [rs(rng, 100) for _ in range(33)]
+    qenc = pack_rows(port, q, 7)
+    qlens = np.array([len(x) for x in q], np.int32)
+    num, total = mh.determineNumValues(h, tt(cuda, qenc.view(np.int32)), tt(cuda, qlens))
+    assert total == 0 and int(num.sum()) == 0
+    vals, offs = mh.retrieveValues(h, len(q), total, num)
+    assert (offs.cpu().numpy() == 0).all()
+
+
+# ---- K4 ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("min_hits", [4, 1, 2, 16])
+def test_k4_filter_by_frequency(cuda, port, min_hits):
+    rng = np.random.RandomState(min_hits)
+    sizes = list(rng.randint(0, 40, size=500)) + [0, 1, 255, 256, 257, 1000, 5000, 9000, 20000, 0]
+    rng.shuffle(sizes)
+    offs = np.zeros(len(sizes) + 1, np.int64)
+    offs[1:] = np.cumsum(sizes)
+    vals = np.zeros(int(offs[-1]), np.uint32)
+    for i, n in enumerate(sizes):
+        hi = max(2, n // 3 + 1)
+        vals[offs[i]:offs[i + 1]] = rng.randint(0, hi, size=n).astype(np.uint32) * 65537 + (1 << 31) * (i % 2)
+    ev, eo = port.filter_by_frequency(vals, offs, min_hits)
+    dv = tt(cuda, vals.view(np.int32))
+    dnum = tt(cuda, np.array(sizes, np.int32))
+    doff = tt(cuda, offs.astype(np.int32))
+    total = cuda.filter_by_frequency(dv, dnum, doff, min_hits)
+    assert total == len(ev)
+    assert (doff.cpu().numpy().astype(np.int64) == eo).all()
+    assert (dnum.cpu().numpy().astype(np.int64) == np.diff(eo)).all()
+    assert (as_u32(dv)[:total] == ev).all()
+    seg = cuda.segment_ids(doff, total).cpu().numpy()
+    exp_seg = np.repeat(np.arange(len(sizes)), np.diff(eo))
+    assert (seg == exp_seg).all()
+
+
+# ---- S2 / S3 -------------------------------------------------------------------------------------
+def test_s2_extended_windows(cuda, port):
+    rng = random.Random(8)
+    g = rs(rng, 5000, "ACGT")
+    genome = cuda.Genome(g, [0, len(g)])
+    w, k = 128, 16
+    stride = w - k + 1
+    nw = (len(g) + stride - 1) // stride
+    pos = np.array([i * stride for i in range(nw)] * 3, np.int32)
+    rl = np.array([rng.choice([150, 100, 250, 36]) for _ in pos], np.int32)
+    pw = (w + 250 + 15) // 16
+    out, left, right, ln = genome.extendedWindows(0, w, tt(cuda, pos), tt(cuda, rl), pw)
+    out = as_u32(out)
+    for i in range(len(pos)):
+        M = 250
+        secB = max(0, 0 - M // 2)
+        secE = min(len(g), int(pos.max()) + w + M // 2)
+        l, r, length, sp = port.window_location(secB, secE, int(pos[i]), w, int(rl[i]) // 2)
+        assert (int(left[i]), int(right[i]), int(ln[i])) == (l, r, length)
+        exp = port.encode_2bit(g[secB + sp:secB + sp + length])
+        assert (out[i, :len(exp)] == exp).all()
+        assert (out[i, len(exp):] == 0).all()
+
+
+def test_s3_shifted_hamming(cuda, port):
+    rng = random.Random(9)
+    anchors, cands = [], []
+    for it in range(1500):
+        Lc = rng.choice([150, 150, 250, 100, 36, 33, 32, 31])
+        La = Lc + rng.randint(-2, 160)
+        La = max(La, 1)
+        A = rs(rng, La, "AGT" if it % 2 else "ACGT")
+        if it % 3 and La >= Lc:
+            st = rng.randint(0, La - Lc)
+            c = bytearray(A[st:st + Lc])
+            for _ in range(rng.randint(0, 12)):
+                c[rng.randrange(Lc)] = rng.choice(b"ACGT")
+            c = bytes(c)
+            if it % 6 == 1:
+                c = port.revcomp_ascii(c)
+        else:
+            c = rs(rng, Lc)
+        anchors.append(A)
+        cands.append(c)
+    for rate in (0.05, 0.1):
+        ea = pack_rows(port, anchors, 26)
+        ec = pack_rows(port, cands, 16)
+        la = np.array([len(x) for x in anchors], np.int32)
+        lc = np.array([len(x) for x in cands], np.int32)
+        sh, sc, ori = cuda.shifted_hamming(tt(cuda, ea.view(np.int32)), tt(cuda, la), tt(cuda, ec.view(np.int32)),
+                                           tt(cuda, lc), rate)
+        sh, sc, ori = sh.cpu().numpy(), sc.cpu().numpy(), ori.cpu().numpy()
+        nacc = 0
+        for i in range(len(anchors)):
+            exp = port.shd(ea[i], int(la[i]), ec[i], int(lc[i]), rate)
+            assert int(ori[i]) == exp[2], (i, exp)
+            if exp[2] != 3:  # shift/score of rejected candidates are unspecified
+                nacc += 1
+                assert (int(sh[i]), int(sc[i])) == exp[:2], (i, exp)
+            elif lc[i] > la[i]:
+                assert (int(sh[i]), int(sc[i])) == exp[:2]
+        assert nacc > 300
+
+
+# ---- V2 / V3 -------------------------------------------------------------------------------------
+def test_v2_sw_align(cuda, port):
+    cases = ssw_cases(21, 3000)
+    qa, ql = rows([c[0] for c in cases], 272)
+    ra, rl = rows([c[1] for c in cases], 272)
+    ml = np.array([c[2] for c in cases], np.int32)
+    al, cigs = cuda.sw_align(tt(cuda, qa), tt(cuda, ql), tt(cuda, ra), tt(cuda, rl), tt(cuda, ml), cigar_pitch=512)
+    bad = 0
+    for i, (q, r, m) in enumerate(cases):
+        exp, ecig = port.ssw_align(q, r, m)
+        got = tuple(int(al[n][i]) for n in al.dtype.names[:9])
+        if got != exp or cigs[i] != ecig:
+            bad += 1
+            if bad < 5:
+                print("MISMATCH", i, exp, ecig, got, cigs[i])
+    assert bad == 0
+
+
+def test_v3_edit_distance(cuda, port):
+    rng = random.Random(4)
+    qs, ts = [], []
+    for it in range(1500):
+        q = rs(rng, rng.randint(1, 300), "AGTN")
+        t = mutate(rng, q, 0.05, 0.05) if it % 2 else rs(rng, rng.randint(1, 200), "AGT")
+        qs.append(q)
+        ts.append(t or b"G")
+    qa, ql = rows(qs, 304)
+    ta, tl = rows(ts, 400)
+    d = cuda.edit_distance(tt(cuda, qa), tt(cuda, ql), tt(cuda, ta), tt(cuda, tl)).cpu().numpy()
+    for i in range(len(qs)):
+        assert int(d[i]) == port.edit_distance_nw(qs[i], ts[i]), i

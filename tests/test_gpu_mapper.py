@@ -1,0 +1,163 @@
+"""GPU parity of the fused path (hrm_map_batch / hrm_verify_batch / hrm_mapper_map_reads) against the
+oracle's restatement of the REFERENCE'S pipeline in the reference's own direction (tables over reads,
+windows streamed in batches of 2048): identical MappedRead per read, identical raw SSW fields and
+CIGARs, identical edit distances -- on pre-converted input per pass, plus size-independent
+properties at larger sizes.
+"""
+import numpy as np
+import pytest
+
+from hashreadmapper_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_pass(port, genome, off, reads, lens, rconv, gconv, **kw):
+    g = port.convert_ascii(genome, gconv)
+    r = np.frombuffer(port.convert_ascii(reads.tobytes(), rconv), dtype=np.uint8).reshape(reads.shape)
+    return port.map_pass_refdir(g, off, r, lens, **kw)
+
+
+def merge(passes):
+    best = passes[0].copy()
+    which = np.where(best["orientation"] != 3, 0, -1).astype(np.int32)
+    for p, cur in enumerate(passes[1:], start=1):
+        better = (cur["orientation"] != 3) & ((best["orientation"] == 3) | (cur["hammingDistance"] < best["hammingDistance"]))
+        best[better] = cur[better]
+        which[better] = p
+    return best, which
+
+
+def check_mapped(got, exp, which):
+    m = exp["orientation"] != 3
+    assert (got["orientation"] == exp["orientation"]).all()
+    for a, b in (("hamming_distance", "hammingDistance"), ("shift", "shift"), ("chromosome_id", "chromosomeId"),
+                 ("position", "position")):
+        assert (got[a][m] == exp[b][m]).all(), a
+    assert (got["pass"] == which).all()
+
+
+@pytest.mark.parametrize("conf", ["single_none", "single_ct", "directional", "nondirectional"])
+def test_map_and_verify_small(cuda, port, conf):
+    import torch
+    genome, off = synth.make_genome([60000, 25013], seed=11)
+    nondir = conf == "nondirectional"
+    reads, lens, truth = synth.make_reads(genome, off, 3000, 150, error_rate=0.02 if conf != "single_none" else 0.0,
+                                          nondirectional=nondir, seed=12)
+    if conf == "single_none":  # plain 4-letter mapping of unconverted reads (the reference as shipped)
+        reads, lens, truth = synth.make_reads(genome, off, 3000, 150, error_rate=0.01, conversion_rate=0.0, seed=12)
+    # a few junk / short reads
+    reads[5, :150] = np.frombuffer(b"ACGT" * 37 + b"AC", dtype=np.uint8)
+    lens[7] = 12
+    lens[9] = 40
+    cfg = {"single_none": cuda.default_config(), "single_ct": cuda.default_config(),
+           "directional": cuda.directional_config(), "nondirectional": cuda.nondirectional_config()}[conf]
+    if conf == "single_ct":
+        cfg.read_conversion[0] = cfg.genome_conversion[0] = cfg.verify_conversion[0] = 1
+    mp = cuda.Mapper(cfg)
+    mp.setGenome(genome, off, ["chrA", "chrB"])
+    info = mp.info()
+    assert info.num_windows == sum((int(l) + 112) // 113 for l in np.diff(off))
+    # oracle, pass by pass
+    passes = []
+    for p in range(cfg.num_passes):
+        res, stats = oracle_pass(port, genome, off, reads, lens, cfg.read_conversion[p], cfg.genome_conversion[p])
+        passes.append(res)
+    exp, which = merge(passes)
+    assert (exp["orientation"] != 3).sum() > 1500
+    d_reads = torch.from_numpy(reads).cuda()
+    d_lens = torch.from_numpy(lens).cuda()
+    out, st = mp.mapBatch(d_reads, d_lens)
+    import hashreadmapper_b200 as hb
+    got = out.cpu().numpy().view(hb.MAPPED_DTYPE).reshape(-1)
+    check_mapped(got, exp, which)
+    assert st.num_mapped == (exp["orientation"] != 3).sum()
+    assert st.num_kernel_launches > 0 and st.num_probes == len(lens) * 16 * cfg.num_passes
+    # verification records through the host-buffer entry point
+    rec, cig, st2 = mp.mapReads(reads, lens, cigar_pitch=96)
+    check_mapped(rec["mapped"], exp, which)
+    nchk = 0
+    for i in range(len(lens)):
+        if exp["orientation"][i] == 3:
+            assert (rec["alignments"][i]["sw_score"] == 0).all()
+            continue
+        p = which[i]
+        gconv, rconv, vconv = cfg.genome_conversion[p], cfg.read_conversion[p], cfg.verify_conversion[p]
+        c = int(exp["chromosomeId"][i])
+        chrom = port.convert_ascii(genome[off[c]:off[c + 1]], gconv)
+        rd = port.convert_ascii(reads[i, :lens[i]].tobytes(), rconv)
+        q, qrc, ref = port.verify_inputs(rd, int(exp["orientation"][i]), chrom, int(exp["position"][i]), 128, vconv)
+        ml = max(15, int(lens[i]) // 2)
+        assert rec["window_length"][i] == len(ref) and rec["mask_len"][i] == ml
+        for a, qq in enumerate((q, qrc)):
+            ea, ecig = port.ssw_align(qq, ref, ml)
+            ga = tuple(int(rec["alignments"][i][a][n]) for n in hb.ALIGN_DTYPE.names[:9])
+            gc = bytes(cig[2 * i + a, :rec["alignments"][i][a]["cigar_len"]]).decode()
+            assert ga == ea and gc == ecig, (i, a, ea, ecig, ga, gc)
+        nchk += 1
+    assert nchk > 1500
+    sam = mp.samFormat(rec, cig, reads, lens)
+    assert sam.startswith(b"@HD\tVN:1.4\n@SQ\tSN:0\tLN:")
+    assert sam.count(b"\n") == 1 + len(lens) + 1 + len(lens)
+
+
+def test_edlib_mode(cuda, port):
+    genome, off = synth.make_genome([40000], seed=3)
+    reads, lens, _ = synth.make_reads(genome, off, 800, 150, error_rate=0.01, seed=4)
+    cfg = cuda.directional_config(mapper_type=1)
+    mp = cuda.Mapper(cfg)
+    mp.setGenome(genome, off)
+    rec, cig, st = mp.mapReads(reads, lens)
+    n = 0
+    for i in range(len(lens)):
+        m = rec["mapped"][i]
+        if m["orientation"] == 3:
+            continue
+        p = int(m["pass"])
+        chrom = port.convert_ascii(genome, cfg.genome_conversion[p])
+        rd = port.convert_ascii(reads[i, :lens[i]].tobytes(), cfg.read_conversion[p])
+        q, qrc, ref = port.verify_inputs(rd, int(m["orientation"]), chrom, int(m["position"]), 128,
+                                         cfg.verify_conversion[p])
+        assert int(rec["edit_distance"][i][0]) == port.edit_distance_nw(q, ref)
+        assert int(rec["edit_distance"][i][1]) == port.edit_distance_nw(qrc, ref)
+        n += 1
+    assert n > 500
+
+
+def test_properties_at_scale(cuda, port):
+    """size-independent properties on a larger instance: truth recovery, idempotence, batch independence"""
+    import torch
+    import hashreadmapper_b200 as hb
+    genome, off = synth.make_genome([3_000_000, 1_500_000], seed=21)
+    reads, lens, truth = synth.make_reads(genome, off, 200_000, 150, error_rate=0.01, seed=22)
+    mp = cuda.Mapper(cuda.directional_config())
+    mp.setGenome(genome, off)
+    d_reads = torch.from_numpy(reads).cuda()
+    d_lens = torch.from_numpy(lens).cuda()
+    out, st = mp.mapBatch(d_reads, d_lens)
+    a = out.cpu().numpy().view(hb.MAPPED_DTYPE).reshape(-1).copy()
+    mapped = a["orientation"] != 3
+    assert mapped.mean() > 0.9
+    # mapped reads land on their true locus: window start + shift == true start (substitution-only reads)
+    ok = mapped & (a["chromosome_id"] == truth["chrom"]) & (a["position"] + a["shift"] == truth["pos"])
+    assert ok.sum() / mapped.sum() > 0.99
+    # + strand reads come from the C->T index in forward orientation, - strand reads from the G->A index as RC
+    assert ((a["pass"][ok] == 0) == truth["strand"][ok]).all()
+    assert ((a["orientation"][ok] == 1) == truth["strand"][ok]).all()
+    # idempotence and independence of the batch composition
+    out2, _ = mp.mapBatch(d_reads, d_lens)
+    assert (out2.cpu().numpy() == out.cpu().numpy()).all()
+    half = len(lens) // 2
+    o1, _ = mp.mapBatch(d_reads[:half].contiguous(), d_lens[:half].contiguous())
+    o2, _ = mp.mapBatch(d_reads[half:].contiguous(), d_lens[half:].contiguous())
+    cat = np.concatenate([o1.cpu().numpy(), o2.cpu().numpy()])
+    assert (cat == out.cpu().numpy()).all()
+    # a sample against the oracle's reference-direction pipeline restricted to that sample
+    idx = np.arange(0, len(lens), 400)
+    passes = []
+    for p in range(2):
+        g = port.convert_ascii(genome, 1 + p)
+        r = np.frombuffer(port.convert_ascii(reads[idx].tobytes(), 1), dtype=np.uint8).reshape(len(idx), -1)
+        passes.append(port.map_pass_refdir(g, off, r, lens[idx])[0])
+    exp, which = merge(passes)
+    check_mapped(a[idx], exp, which)

@@ -1,0 +1,204 @@
+"""CPU tests of everything that does not need a GPU: the product's per-item arithmetic compiled for
+the host (tests/host_harness, test-only), the C-ABI library's exports, the sharding logic over gloo.
+"""
+import ctypes as C
+import os
+import random
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from util import rs, mutate, ssw_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HH_SRC = os.path.join(ROOT, "tests", "host_harness", "harness.cpp")
+HH_SO = os.path.join(ROOT, "tests", "host_harness", "libhh.so")
+u32p = C.POINTER(C.c_uint32)
+
+
+@pytest.fixture(scope="module")
+def hh():
+    newest = max(os.path.getmtime(os.path.join(ROOT, "hashreadmapper_b200", "csrc", f))
+                 for f in os.listdir(os.path.join(ROOT, "hashreadmapper_b200", "csrc")) if f.startswith(("core_", "hrm_common")))
+    if not os.path.exists(HH_SO) or os.path.getmtime(HH_SO) < max(newest, os.path.getmtime(HH_SRC)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-x", "c++", HH_SRC, "-o", HH_SO])
+    return C.CDLL(HH_SO)
+
+
+def test_core_pack(hh, port):
+    rng = random.Random(3)
+    for it in range(600):
+        L = rng.randint(1, 200)
+        s = rs(rng, L, "ACGTNacgt")
+        for conv in (0, 1, 2):
+            exp = port.encode_2bit(port.convert_ascii(s, conv))
+            for al in (0, 1):
+                out = np.zeros((L + 15) // 16, np.uint32)
+                hh.hh_encode_2bit(s + b"\0" * 32, L, conv, out.ctypes.data_as(u32p), al)
+                assert (out == exp).all()
+
+
+def test_core_minhash(hh, port):
+    rng = random.Random(4)
+    for it in range(150):
+        G = rs(rng, rng.randint(40, 600))
+        enc = port.encode_2bit(G)
+        start = rng.randint(0, len(G) - 1)
+        L = rng.randint(1, len(G) - start)
+        k = rng.choice([4, 11, 16, 21, 31, 32])
+        H = rng.choice([1, 16, 48])
+        es, ev = port.minhash_batch(port.encode_2bit(G[start:start + L])[None, :], np.array([L]), k, H)
+        sig = np.zeros(H, np.uint64)
+        val = np.zeros(H, np.uint8)
+        hh.hh_minhash(enc.ctypes.data_as(u32p), C.c_int64(len(enc)), C.c_int64(start), L, k, H,
+                      sig.ctypes.data_as(C.POINTER(C.c_uint64)), val.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert (sig == es[0]).all() and (val == ev[0]).all()
+
+
+def test_core_shd_and_window(hh, port):
+    rng = random.Random(5)
+    nacc = 0
+    for it in range(1200):
+        Lc = rng.randint(20, 300)
+        La = max(Lc + rng.randint(-2, 160), 1)
+        G = rs(rng, La + rng.randint(0, 40), "AGT" if it % 2 else "ACGT")
+        base = rng.randint(0, len(G) - La)
+        A = G[base:base + La]
+        if it % 3 and La >= Lc:
+            st = rng.randint(0, La - Lc)
+            c = bytearray(A[st:st + Lc])
+            for _ in range(rng.randint(0, 10)):
+                c[rng.randrange(Lc)] = rng.choice(b"ACGT")
+            c = bytes(c)
+            if it % 6 == 1:
+                c = port.revcomp_ascii(c)
+        else:
+            c = rs(rng, Lc)
+        rate = rng.choice([0.05, 0.03, 0.1, 0.5])
+        exp = port.shd(port.encode_2bit(A), La, port.encode_2bit(c), Lc, rate)
+        eg, ec = port.encode_2bit(G), port.encode_2bit(c)
+        s, sc, o = C.c_int(), C.c_int(), C.c_int()
+        hh.hh_shd(eg.ctypes.data_as(u32p), C.c_int64(len(eg)), C.c_int64(base), La, ec.ctypes.data_as(u32p),
+                  C.c_int64(len(ec)), Lc, C.c_float(rate), C.byref(s), C.byref(sc), C.byref(o))
+        if exp[2] == 3:
+            assert o.value == 3
+        else:
+            nacc += 1
+            assert (s.value, sc.value, o.value) == exp
+    assert nacc > 400
+    # the chromosome-end formulation equals the reference's per-batch section formulation
+    for it in range(5000):
+        n = rng.randint(300, 3000)
+        p = rng.randint(0, n - 1)
+        w = rng.choice([64, 128, 256])
+        e = rng.randint(0, 130)
+        M = 2 * e + rng.choice([0, 1, 2, 10])
+        for plast in (p, p + rng.randint(0, 5) * (w - 15)):
+            secB = max(0, p - rng.randint(0, 3) * (w - 15) - M // 2)
+            secE = min(n, plast + w + M // 2)
+            l, r, ln, sp = port.window_location(secB, secE, p, w, e)
+            a, b, c = C.c_int(), C.c_int(), C.c_int()
+            hh.hh_window_location(C.c_int64(n), C.c_int64(p), w, e, C.byref(a), C.byref(b), C.byref(c))
+            assert (a.value, b.value, c.value) == (l, r, ln)
+
+
+def test_core_sw_and_myers(hh, port):
+    from oracle.pyoracle import Alignment
+    for q, r, ml in ssw_cases(31, 1500):
+        al = Alignment()
+        cig = C.create_string_buffer(4096)
+        hh.hh_sw_align(q, len(q), r, len(r), ml, C.byref(al), cig, 4096)
+        assert (al.astuple(), cig.value.decode()) == port.ssw_align(q, r, ml)
+    rng = random.Random(6)
+    for it in range(800):
+        q = rs(rng, rng.randint(1, 300), "AGTN")
+        t = (mutate(rng, q, 0.05, 0.05) if it % 2 else rs(rng, rng.randint(1, 200), "AGT")) or b"G"
+        assert hh.hh_myers(q, len(q), t, len(t)) == port.edit_distance_nw(q, t)
+
+
+def test_cabi_exports_every_declared_symbol():
+    """the library loads without a GPU and exports exactly what include/hrm_b200.h declares"""
+    import hashreadmapper_b200 as hb
+    lib = hb.load()
+    hdr = open(os.path.join(ROOT, "include", "hrm_b200.h")).read()
+    declared = set(re.findall(r"\b(hrm_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"hrm_stream", "hrm_status"}
+    assert len(declared) >= 50
+    for name in sorted(declared):
+        assert hasattr(lib, name), "library does not export " + name
+        assert name in hb.SIGNATURES, "python binding lacks " + name
+    assert lib.hrm_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    import hashreadmapper_b200 as hb
+    lib = hb.load()
+    assert lib.hrm_device_count() == 0
+    h = C.c_void_p()
+    st = lib.hrm_minhasher_create(C.byref(h), 10, 65535, 16, C.c_float(0.8))
+    assert st == hb._lib.HRM_ERR_CUDA and b"no CPU fallback" in lib.hrm_last_error()
+    st = lib.hrm_encode_2bit(None, 16, None, 1, 0, None, 1, None)
+    assert st == hb._lib.HRM_ERR_CUDA
+    import hashreadmapper_b200.api as api
+    with pytest.raises(hb.HrmError):
+        api.Mapper()
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "hashreadmapper_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                for pat in ("oracle/", "oracle.", "liboracle", "pyoracle", "hrm_oracle", "libhrm_ref", "orc_",
+                            "ref_shim", "import oracle", "from oracle"):
+                    assert pat not in txt, (f, "uses the checker: " + pat)
+
+
+WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from hashreadmapper_b200 import parallel, MAPPED_DTYPE
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+n = 1001
+lo, hi = parallel.shard_range(n, dist.get_rank(), 2)
+rec = np.zeros(hi - lo, dtype=MAPPED_DTYPE)
+rec["position"] = np.arange(lo, hi)
+rec["orientation"] = 1 + (np.arange(lo, hi) % 3)
+full = parallel.gather_records(rec, n)
+mx = parallel.max_over_ranks(float(dist.get_rank() + 1))
+sm = parallel.sum_over_ranks(float(hi - lo))
+if dist.get_rank() == 0:
+    assert (full["position"] == np.arange(n)).all() and (full["orientation"] == 1 + np.arange(n) % 3).all()
+    assert mx == 2.0 and sm == n
+    print("OK")
+else:
+    assert full is None
+dist.destroy_process_group()
+"""
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    from hashreadmapper_b200 import parallel
+    for n in (0, 1, 7, 1001):
+        for w in (1, 2, 3, 8):
+            parts = [parallel.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in parts) - min(h - l for l, h in parts) <= 1
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE) for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e.decode()
+    assert b"OK" in outs[0][0]

@@ -1,0 +1,167 @@
+"""CPU tests: the oracle (oracle/hrm_oracle.c) against (a) the golden fixture generated from the
+reference's own code, (b) the known answers of SURVEY.md Appendix C, and (c) -- where
+oracle/_ref/libhrm_ref.so exists -- the reference's own code on fresh random inputs.
+"""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from util import rs, mutate, ssw_cases
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.json")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(GOLD) as f:
+        return json.load(f)
+
+
+def test_known_answers(port):
+    s = b"ACGTACGTTTGACCAGTAGGCATTACGGATCAGGCATCAGGACTTTACG"
+    e = port.encode_2bit(s)
+    sig, val = port.minhash_batch(e[None, :], np.array([len(s)]), 16, 4)
+    assert sig[0].tolist() == [3092148114, 1517188485, 663417955, 2793855263]
+    assert port.decode_2bit(e, len(s)) == s
+    al, cig = port.ssw_align(b"CTGAGCCGGTAAATC", b"CAGCCTTTCTGACCCGGAAATCAAAATAGGCACAACAAA", 15)
+    assert al == (21, 8, 8, 21, 0, 14, 4, 2, 0) and cig == "4=1X4=1I5="
+    assert port.edit_distance_nw(b"ACTTTGTTTGATTAG", b"ATTTTGTTGATTTAG") == 3
+    assert port.convert_ascii(b"ACGTNCcG", 1) == b"ATGTNTcG"
+    assert port.convert_ascii(b"ACGTNGgG", 2) == b"ACATNAgA"
+
+
+def test_golden_encode_minhash(port, gold):
+    for g in gold["encode"]:
+        s = g["seq"].encode()
+        e = port.encode_2bit(s)
+        assert e.tolist() == g["words"]
+        assert port.revcomp_2bit(e, len(s)).tolist() == g["rc_words"]
+        assert port.revcomp_ascii(s).hex() == g["rc_ascii"]
+    for g in gold["minhash"]:
+        s = g["seq"].encode()
+        sig, val = port.minhash_batch(port.encode_2bit(s)[None, :], np.array([len(s)]), g["k"], 16)
+        assert sig[0].tolist() == g["sig"] and val[0].tolist() == g["valid"]
+    for x, h in gold["murmur64"]:
+        assert port.murmur64(x) == h
+
+
+def test_golden_tables(port, gold):
+    t = gold["tables"]
+    sig = np.random.RandomState(t["sig_seed"]).randint(0, 60, size=(t["n"], t["H"])).astype(np.uint64)
+    val = (np.random.RandomState(t["valid_seed"]).rand(t["n"], t["H"]) > 0.05).astype(np.uint8)
+    q = np.random.RandomState(t["query_seed"]).randint(0, 70, size=(50, t["H"])).astype(np.uint64)
+    qv = np.ones((50, t["H"]), np.uint8)
+    qv[::7] = 0
+    for cap, res in t["results"].items():
+        T = port.tables_build(sig, val, None, int(cap))
+        num, off, vals = port.tables_query(T, q, qv)
+        assert num.tolist() == res["num"] and vals.tolist() == res["values"]
+        port.tables_free(T)
+
+
+def test_golden_window_shd(port, gold):
+    for args, res in gold["window_location"]:
+        assert list(port.window_location(*args)) == res
+    for g in gold["shd"]:
+        A, c = g["anchor"].encode(), g["cand"].encode()
+        got = port.shd(port.encode_2bit(A), len(A), port.encode_2bit(c), len(c), g["rate"])
+        assert list(got) == g["result"]
+
+
+def test_golden_ssw_edit(port, gold):
+    assert len(gold["ssw"]) > 300
+    for g in gold["ssw"]:
+        al, cig = port.ssw_align(g["q"].encode(), g["r"].encode(), g["mask"])
+        assert list(al) == g["al"] and cig == g["cigar"], g
+    for a, b, d in gold["edit"]:
+        assert port.edit_distance_nw(a.encode(), b.encode()) == d
+
+
+def test_filter_semantics(port):
+    """C1 has no CPU twin in the reference; its stated semantics (cuda_unique_by_count.cuh:79-172)"""
+    vals = np.array([5, 1, 5, 5, 9, 1, 5, 7, 7, 7, 7, 3], np.uint32)
+    off = np.array([0, 7, 7, 12], np.int64)
+    v, o = port.filter_by_frequency(vals, off, 4)
+    assert v.tolist() == [5, 7] and o.tolist() == [0, 1, 1, 2]
+    v, o = port.filter_by_frequency(vals, off, 1)
+    assert v.tolist() == [1, 5, 9, 3, 7] and o.tolist() == [0, 3, 3, 5]
+    v, o = port.filter_by_frequency(vals, off, 2)
+    assert v.tolist() == [1, 5, 7]
+
+
+# ---- against the reference's own code on fresh inputs (only where it was built) -------------------
+def test_ref_encode_kmers_minhash(port, ref):
+    rng = random.Random(1)
+    for it in range(150):
+        L = rng.randint(1, 300)
+        s = rs(rng, L, "ACGTN" if it % 5 == 0 else "ACGT")
+        a, b = port.encode_2bit(s), ref.encode_2bit(s)
+        assert (a == b).all()
+        assert (port.revcomp_2bit(a, L) == ref.revcomp_2bit(a, L)).all()
+        assert port.revcomp_ascii(s) == ref.revcomp_ascii(s)
+        for k in (4, 16, 21, 32):
+            if L >= k:
+                assert (port.canonical_kmers(a, L, k) == ref.canonical_kmers(a, L, k)).all()
+            sa, va = port.minhash_batch(a[None, :], np.array([L]), k, 16)
+            sb, vb = ref.minhash_batch(a[None, :], np.array([L]), k, 16)
+            assert (sa == sb).all() and (va == vb).all()
+
+
+def test_ref_tables(port, ref):
+    rng = random.Random(2)
+    for it in range(12):
+        n = rng.randint(1, 2000)
+        H = rng.choice([1, 4, 16])
+        sig = np.random.RandomState(it).randint(0, rng.choice([5, 50, 5000]), size=(n, H)).astype(np.uint64)
+        val = (np.random.RandomState(it + 99).rand(n, H) > 0.05).astype(np.uint8)
+        cap = rng.choice([65535, 3, 10])
+        hp, hr = port.tables_build(sig, val, None, cap), ref.tables_build(sig, val, None, cap)
+        q = np.random.RandomState(it + 5).randint(0, 60, size=(100, H)).astype(np.uint64)
+        qv = np.ones((100, H), np.uint8)
+        qv[::7] = 0
+        for x, y in zip(port.tables_query(hp, q, qv), ref.tables_query(hr, q, qv)):
+            assert (x == y).all()
+        port.tables_free(hp)
+        ref.tables_free(hr)
+
+
+def test_ref_shd_window(port, ref):
+    rng = random.Random(3)
+    for it in range(600):
+        Lc = rng.randint(20, 260)
+        La = max(Lc + rng.randint(-3, 140), 1)
+        A = rs(rng, La, "AGT" if it % 2 else "ACGT")
+        if it % 3 and La >= Lc:
+            st = rng.randint(0, La - Lc)
+            c = bytearray(A[st:st + Lc])
+            for _ in range(rng.randint(0, 12)):
+                c[rng.randrange(Lc)] = rng.choice(b"ACGT")
+            c = bytes(c)
+            if it % 6 == 1:
+                c = port.revcomp_ascii(c)
+        else:
+            c = rs(rng, Lc)
+        rate = rng.choice([0.05, 0.5, 0.03])
+        ea, ec = port.encode_2bit(A), port.encode_2bit(c)
+        assert port.shd(ea, La, ec, Lc, rate) == ref.shd(ea, La, ec, Lc, rate)
+    for it in range(3000):
+        args = (rng.randint(0, 500), rng.randint(500, 2000), rng.randint(500, 1900), rng.choice([64, 128, 256]),
+                rng.randint(0, 130))
+        assert port.window_location(*args) == ref.window_location(*args)
+
+
+def test_ref_ssw_edit(port, ref):
+    bad = 0
+    for q, r, ml in ssw_cases(99, 2500):
+        a, b = port.ssw_align(q, r, ml), ref.ssw_align(q, r, ml)
+        if a != b and b[0][0] != 0:
+            bad += 1
+    assert bad == 0
+    rng = random.Random(5)
+    for it in range(500):
+        q = rs(rng, rng.randint(1, 200), "AGT")
+        t = (mutate(rng, q, 0.05, 0.05) if it % 2 else rs(rng, rng.randint(1, 200), "AGT")) or b"G"
+        assert port.edit_distance_nw(q, t) == ref.edit_distance_nw(q, t)
