@@ -260,3 +260,186 @@ int ref_cigar_parse(const char* s, char* ops, int32_t* lens, int cap)
 int ref_num_threads() { return omp_get_max_threads(); }
 
 } // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Whole CPU path, reference direction, assembled from the reference's own functions with the
+// reference's own parallelisation (OpenMP over sequences / a parallel loop over reads).  This is
+// the CPU baseline that bench.py times.  Glue only: the loops mirror
+// gpuminhasherconstruction.cu:168-214 (build), main_gpu.cu:471-854 (window batches) and
+// mappinghandler.cu:397-595 (verification).  The frequency filter has no CPU implementation in the
+// reference (CUDA only, cuda_unique_by_count.cuh); it is restated with std::sort.
+// ---------------------------------------------------------------------------------------------
+extern "C" void ref_window_location(int, int, int, int, int, int*, int*, int*, int*);
+extern "C" void ref_shd(const uint32_t*, int, const uint32_t*, int, float, int*, int*, int*);
+
+struct ref_mapped_read {
+    int32_t orientation, hammingDistance, shift, chromosomeId;
+    int64_t position;
+};
+
+#include <chrono>
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" {
+
+// times[0] = read side (encode + minhash + table build), times[1] = window streaming (encode,
+// minhash, query, filter), times[2] = extended windows + SHD + arg-min, times[3] = verification.
+// conv_* are applied up front on the ASCII (the reference sees pre-converted input).
+// mapper_type 0: 2 x SSW per mapped read, 1: 2 x edlib.  sw_out may be NULL.
+void ref_cpu_pipeline(const char* genome, const int64_t* chrom_off, int nchrom, const char* reads, int read_pitch,
+                      const int32_t* read_len, int64_t n_reads, int k, int w, int H, int min_hits,
+                      int max_results_per_map, float rate, int batchsize, int mapper_type,
+                      ref_mapped_read* out, ref_alignment* sw_out, int32_t* ed_out, double* times)
+{
+    double t0 = now_s();
+    int maxReadLen = 0;
+    for (int64_t r = 0; r < n_reads; r++) maxReadLen = std::max(maxReadLen, (int)read_len[r]);
+    const int rpw = SequenceHelpers::getEncodedNumInts2Bit(std::max(maxReadLen, 1));
+    std::vector<unsigned int> renc((size_t)std::max<int64_t>(n_reads, 1) * rpw, 0u);
+    std::vector<uint64_t> rs((size_t)std::max<int64_t>(n_reads, 1) * H);
+    std::vector<uint8_t> rv((size_t)std::max<int64_t>(n_reads, 1) * H);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t r = 0; r < n_reads; r++) {
+        SequenceHelpers::encodeSequence2Bit(renc.data() + r * rpw, reads + r * (int64_t)read_pitch, read_len[r]);
+        ref_minhash(renc.data() + r * rpw, read_len[r], k, H, rs.data() + r * H, rv.data() + r * H);
+        out[r].orientation = 3;
+        out[r].hammingDistance = 0;
+        out[r].shift = 0;
+        out[r].chromosomeId = 0;
+        out[r].position = 0;
+    }
+    void* T = ref_tables_build(rs.data(), rv.data(), nullptr, n_reads, H, max_results_per_map, 0.8f, 0);
+    times[0] = now_s() - t0;
+    times[1] = times[2] = times[3] = 0;
+
+    const int stride = w - k + 1;
+    const int wpw = SequenceHelpers::getEncodedNumInts2Bit(w);
+    const int xpw = SequenceHelpers::getEncodedNumInts2Bit(w + maxReadLen) + 1;
+    for (int c = 0; c < nchrom; c++) {
+        const char* chr = genome + chrom_off[c];
+        const int64_t clen = chrom_off[c + 1] - chrom_off[c];
+        const int64_t nwin = (clen + stride - 1) / stride;
+        for (int64_t b0 = 0; b0 < nwin; b0 += batchsize) {
+            double t1 = now_s();
+            const int64_t b1 = std::min<int64_t>(b0 + batchsize, nwin);
+            const int nb = (int)(b1 - b0);
+            int64_t secB = b0 * stride - maxReadLen / 2, secE = (b1 - 1) * stride + w + maxReadLen / 2;
+            secB = std::max<int64_t>(secB, 0);
+            secE = std::min<int64_t>(secE, clen);
+            std::vector<unsigned int> wenc((size_t)nb * wpw, 0u);
+            std::vector<int32_t> wlen(nb);
+            std::vector<uint64_t> ws((size_t)nb * H);
+            std::vector<uint8_t> wv((size_t)nb * H);
+#pragma omp parallel for schedule(dynamic, 16)
+            for (int i = 0; i < nb; i++) {
+                const int64_t p = (b0 + i) * stride;
+                wlen[i] = (int)(p + w <= clen ? w : clen - p);
+                SequenceHelpers::encodeSequence2Bit(wenc.data() + (size_t)i * wpw, chr + p, wlen[i]);
+                ref_minhash(wenc.data() + (size_t)i * wpw, wlen[i], k, H, ws.data() + (size_t)i * H, wv.data() + (size_t)i * H);
+            }
+            std::vector<int32_t> num(nb);
+            std::vector<int64_t> off(nb + 1);
+            int64_t total = ref_tables_query(T, ws.data(), wv.data(), nb, num.data(), off.data(), nullptr);
+            std::vector<uint32_t> vals((size_t)std::max<int64_t>(total, 1));
+            if (total > 0) ref_tables_query(T, ws.data(), wv.data(), nb, num.data(), off.data(), vals.data());
+            // frequency filter per window
+            std::vector<int64_t> foff(nb + 1, 0);
+            std::vector<uint32_t> flt((size_t)std::max<int64_t>(total, 1));
+            std::vector<int32_t> fcnt(nb, 0);
+#pragma omp parallel for schedule(dynamic, 16)
+            for (int i = 0; i < nb; i++) {
+                uint32_t* b = vals.data() + off[i];
+                uint32_t* e = vals.data() + off[i + 1];
+                std::sort(b, e);
+                int kept = 0;
+                for (uint32_t* p = b; p < e;) {
+                    uint32_t* q = p;
+                    while (q < e && *q == *p) ++q;
+                    if (q - p >= min_hits || min_hits <= 1) b[kept++] = *p;
+                    p = q;
+                }
+                fcnt[i] = kept;
+            }
+            for (int i = 0; i < nb; i++) foff[i + 1] = foff[i] + fcnt[i];
+            for (int i = 0; i < nb; i++) std::copy(vals.data() + off[i], vals.data() + off[i] + fcnt[i], flt.data() + foff[i]);
+            const int64_t ncand = foff[nb];
+            times[1] += now_s() - t1;
+            t1 = now_s();
+            std::vector<int> c_shift(std::max<int64_t>(ncand, 1)), c_score(std::max<int64_t>(ncand, 1)),
+                c_ori(std::max<int64_t>(ncand, 1)), c_left(std::max<int64_t>(ncand, 1)), c_win(std::max<int64_t>(ncand, 1));
+            for (int i = 0; i < nb; i++)
+                for (int64_t e = foff[i]; e < foff[i + 1]; e++) c_win[e] = i;
+#pragma omp parallel for schedule(dynamic, 64)
+            for (int64_t e = 0; e < ncand; e++) {
+                const uint32_t rid = flt[e];
+                const int64_t p = (b0 + c_win[e]) * stride;
+                int left, right, len, sp;
+                ref_window_location((int)secB, (int)secE, (int)p, w, read_len[rid] / 2, &left, &right, &len, &sp);
+                std::vector<unsigned int> x(xpw, 0u);
+                SequenceHelpers::encodeSequence2Bit(x.data(), chr + secB + sp, len);
+                ref_shd(x.data(), len, renc.data() + (size_t)rid * rpw, read_len[rid], rate, &c_shift[e], &c_score[e], &c_ori[e]);
+                c_left[e] = left;
+            }
+            for (int64_t e = 0; e < ncand; e++) { // ref: main_gpu.cu:777-821, serial, window order
+                if (c_ori[e] == 3) continue;
+                ref_mapped_read& br = out[flt[e]];
+                if (br.orientation == 3 || br.hammingDistance > c_score[e]) {
+                    br.orientation = c_ori[e];
+                    br.hammingDistance = c_score[e];
+                    br.shift = c_shift[e] - c_left[e];
+                    br.chromosomeId = c;
+                    br.position = (b0 + c_win[e]) * stride;
+                }
+            }
+            times[2] += now_s() - t1;
+        }
+    }
+    ref_tables_free(T);
+
+    // verification (mappinghandler.cu:397-595): 3N(read'), 3N(RC(read')) vs 3N(window), C->T
+    double t2 = now_s();
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t r = 0; r < n_reads; r++) {
+        if (sw_out) {
+            std::memset(&sw_out[2 * r], 0, 2 * sizeof(ref_alignment));
+        }
+        if (ed_out) ed_out[2 * r] = ed_out[2 * r + 1] = -1;
+        if (out[r].orientation == 3) continue;
+        const int L = read_len[r];
+        std::vector<unsigned int> enc(renc.begin() + r * rpw, renc.begin() + (r + 1) * rpw);
+        if (out[r].orientation == 2) SequenceHelpers::reverseComplementSequenceInplace2Bit(enc.data(), L);
+        std::string rd = SequenceHelpers::get2BitString(enc.data(), L);
+        std::string rc = SequenceHelpers::reverseComplementSequenceDecoded(rd.data(), L);
+        const char* chr = genome + chrom_off[out[r].chromosomeId];
+        const int64_t clen = chrom_off[out[r].chromosomeId + 1] - chrom_off[out[r].chromosomeId];
+        const int64_t wl = out[r].position + w < clen ? w : clen - out[r].position;
+        std::string win(chr + out[r].position, (size_t)wl);
+        for (auto* s : {&rd, &rc, &win})
+            for (auto& ch : *s)
+                if (ch == 'C') ch = 'T';
+        const int maskLen = std::max(15, L / 2);
+        char cig[8];
+        ref_alignment a0, a1;
+        if (mapper_type == 0) {
+            ref_ssw_align(rd.data(), L, win.data(), (int)wl, maskLen, &a0, cig, 0);
+            ref_ssw_align(rc.data(), L, win.data(), (int)wl, maskLen, &a1, cig, 0);
+            if (sw_out) {
+                sw_out[2 * r] = a0;
+                sw_out[2 * r + 1] = a1;
+            }
+        } else {
+            const int d0 = ref_edit_distance_nw(rd.data(), L, win.data(), (int)wl);
+            const int d1 = ref_edit_distance_nw(rc.data(), L, win.data(), (int)wl);
+            if (ed_out) {
+                ed_out[2 * r] = d0;
+                ed_out[2 * r + 1] = d1;
+            }
+        }
+    }
+    times[3] = now_s() - t2;
+}
+
+} // extern "C"

@@ -64,7 +64,8 @@ def test_map_and_verify_small(cuda, port, conf):
         res, stats = oracle_pass(port, genome, off, reads, lens, cfg.read_conversion[p], cfg.genome_conversion[p])
         passes.append(res)
     exp, which = merge(passes)
-    assert (exp["orientation"] != 3).sum() > 1500
+    nmapped_exp = int((exp["orientation"] != 3).sum())
+    assert nmapped_exp > (1200 if conf == "single_ct" else 2400)  # one strand only maps on the C->T index alone
     d_reads = torch.from_numpy(reads).cuda()
     d_lens = torch.from_numpy(lens).cuda()
     out, st = mp.mapBatch(d_reads, d_lens)
@@ -92,10 +93,11 @@ def test_map_and_verify_small(cuda, port, conf):
         for a, qq in enumerate((q, qrc)):
             ea, ecig = port.ssw_align(qq, ref, ml)
             ga = tuple(int(rec["alignments"][i][a][n]) for n in hb.ALIGN_DTYPE.names[:9])
-            gc = bytes(cig[2 * i + a, :rec["alignments"][i][a]["cigar_len"]]).decode()
-            assert ga == ea and gc == ecig, (i, a, ea, ecig, ga, gc)
+            clen = int(rec["alignments"][i][a]["cigar_len"])
+            gc = bytes(cig[2 * i + a, :min(clen, cig.shape[1])]).decode()  # long cigars are cut at cigar_pitch
+            assert ga == ea and clen == len(ecig) and gc == ecig[:cig.shape[1]], (i, a, ea, ecig, ga, gc)
         nchk += 1
-    assert nchk > 1500
+    assert nchk == nmapped_exp
     sam = mp.samFormat(rec, cig, reads, lens)
     assert sam.startswith(b"@HD\tVN:1.4\n@SQ\tSN:0\tLN:")
     assert sam.count(b"\n") == 1 + len(lens) + 1 + len(lens)
