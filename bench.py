@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- reads mapped / second of the hashreadmapper hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): 1 M synthetic 150 bp directional bisulfite reads (1 % substitution
+errors) against a 46 Mbp chr21-size synthetic reference, k=16, 16 hash tables, w=128, minTableHits=4,
+maxHammingPercent=0.05, SW verification with CIGAR.  A step = one pass of the whole hot path
+(K1 pack, K2 minhash, K3 probe, K4 collect, K5 SHD best window, K7 SW+CIGAR) over one 1 M-read batch
+per GPU, both 3N indexes (C->T and G->A) resident in HBM.  N > 1: weak scaling, every rank maps its
+own 1 M-read shard against its replica of the index; no data-path collective.
+
+One JSON line on stdout (rank 0).  `value` = reads/s with the reads already in HBM; `e2e` = the same
+through hrm_mapper_map_reads with pinned HOST buffers (H2D reads, D2H records + CIGARs inside the
+timed region); `roofline` = the hash-probe kernel against the measured HBM peak; `cpu_baseline` /
+`--impl reference` = the reference's own CPU functions (oracle/_ref, built from /root/reference)
+timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_, W_, H_, T_ = 16, 128, 16, 4
+READ_LEN = 150
+ERR = 0.01
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+
+    Q = ("uuid,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.uuid = uuid
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8 or (self.uuid and self.uuid not in f[0]):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # under load = samples in the upper half of what was seen
+        srt = sorted(sm)
+        return {"sm_mhz": float(np.median(srt[len(srt) // 2:])), "sm_max_mhz": float(max(mx)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def workload(args, rank):
+    from hashreadmapper_b200 import synth
+    genome, off = synth.make_genome([args.genome_bp], seed=20240601)
+    reads, lens, truth = synth.make_reads(genome, off, args.reads, READ_LEN, error_rate=ERR, seed=20240602 + rank)
+    return genome, off, reads, lens, truth
+
+
+def reference_step(ref, port, genome_ct, genome_ga, off, reads, lens):
+    """one step of the reference arm: the reference's CPU functions on a read sample, both 3N passes"""
+    from oracle.pyoracle import ref_cpu_pipeline
+    tot = np.zeros(4)
+    mapped = np.zeros(len(lens), dtype=bool)
+    for g in (genome_ct, genome_ga):
+        out, _, _, times = ref_cpu_pipeline(ref, g, off, reads, lens, k=K_, w=W_, H=H_, min_hits=T_,
+                                            want_alignments=False)
+        tot += times
+        mapped |= out["orientation"] != 3
+    return tot, int(mapped.sum())
+
+
+def run_reference(args, rank, world):
+    """--impl reference: rank 0 alone times the reference's CPU implementation of the path"""
+    if rank != 0:
+        return
+    from oracle.pyoracle import Oracle, have_ref
+    from hashreadmapper_b200 import synth
+    cfg = {"workload": "1M x 150bp directional BS reads vs 46 Mbp synthetic reference (BASELINE configs[1])",
+           "reads_per_gpu": args.reads, "genome_bp": args.genome_bp, "k": K_, "hashmaps": H_, "window": W_,
+           "min_table_hits": T_, "passes": "C->T index + G->A index", "verification": "SW+CIGAR"}
+    if not have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhrm_ref.so was not built "
+                          "(needs /root/reference at build time)"}))
+        return
+    ref, port = Oracle("ref"), Oracle("port")
+    genome, off = synth.make_genome([args.genome_bp], seed=20240601)
+    S = min(args.cpu_sample, args.reads)
+    reads, lens, _ = synth.make_reads(genome, off, S, READ_LEN, error_rate=ERR, seed=20240602)
+    reads_ct = np.frombuffer(port.convert_ascii(reads.tobytes(), 1), dtype=np.uint8).reshape(reads.shape)
+    g_ct, g_ga = port.convert_ascii(genome, 1), port.convert_ascii(genome, 2)
+    cores = ref.lib.ref_num_threads()
+    for _ in range(args.warmup):
+        reference_step(ref, port, g_ct, g_ga, off, reads_ct[:max(S // 10, 1000)], lens[:max(S // 10, 1000)])
+    t0 = time.perf_counter()
+    acc = np.zeros(4)
+    for _ in range(args.steps):
+        t, nm = reference_step(ref, port, g_ct, g_ga, off, reads_ct, lens)
+        acc += t
+    wall = time.perf_counter() - t0
+    ms = wall / args.steps * 1e3
+    per = acc / args.steps
+    # fixed part: streaming + sketching all windows (times[1]); the rest scales with the number of reads
+    scale = args.reads / S
+    full_s = per[1] + scale * (per[0] + per[2] + per[3])
+    value = args.reads / full_s
+    line = {"metric": "reads mapped/sec", "value": value, "unit": "reads/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer", "data": "synthetic",
+            "config": dict(cfg, reference_sample_reads=S),
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "reference",
+                             "sample": ("%d of %d reads per step against the full reference; window streaming (%.2f s) "
+                                        "counted once, per-read stages (%.2f s) scaled x%.1f to the full workload; "
+                                        "measured on the sample alone: %.0f reads/s"
+                                        % (S, args.reads, per[1], per[0] + per[2] + per[3], scale, S / (ms / 1e3))),
+                             "stage_seconds_per_step": {"reads_build": per[0], "windows_query_filter": per[1],
+                                                        "shd": per[2], "verify_ssw": per[3]}},
+            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
+    ap.add_argument("--genome-bp", type=int, default=46_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=50_000, help="reads in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU path"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import hashreadmapper_b200 as hb
+    import hashreadmapper_b200.api as api
+    from hashreadmapper_b200 import parallel
+
+    genome, off, reads, lens, truth = workload(args, rank)
+    n = len(lens)
+    cfg = api.directional_config()
+    mp = api.Mapper(cfg)
+    t0 = time.perf_counter()
+    mp.setGenome(genome, off, ["chrS"])
+    torch.cuda.synchronize()
+    index_s = time.perf_counter() - t0
+    info = mp.info()
+
+    d_reads = torch.from_numpy(reads).cuda()
+    d_lens = torch.from_numpy(lens).cuda()
+    CIG = 64
+
+    def step():
+        mapped, _ = mp.mapBatch(d_reads, d_lens, want_stats=False)
+        rec, cig, _ = mp.verifyBatch(d_reads, d_lens, mapped, cigar_pitch=CIG)
+        return mapped, rec, cig
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # one accounted step (untimed) for the roofline bookkeeping
+    torch.cuda.synchronize()
+    _, st = mp.mapBatch(d_reads, d_lens, want_stats=True)
+    launches_map = st.num_kernel_launches
+    mapped, _ = mp.mapBatch(d_reads, d_lens, want_stats=False)
+    from hashreadmapper_b200 import _lib as L
+    import ctypes as C
+    st2 = L.BatchStats()
+    rec = torch.empty((n, C.sizeof(L.ReadRecord) // 4), dtype=torch.int32, device=d_reads.device)
+    cigs = torch.empty((2 * n, CIG), dtype=torch.uint8, device=d_reads.device)
+    L.check(mp.lib.hrm_verify_batch(mp.h, C.c_void_p(d_reads.data_ptr()), reads.shape[1], C.c_void_p(d_lens.data_ptr()),
+                                    n, C.c_void_p(mapped.data_ptr()), C.c_void_p(rec.data_ptr()),
+                                    C.c_void_p(cigs.data_ptr()), CIG, C.byref(st2),
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    launches_step = int(launches_map - 1 + st2.num_kernel_launches)  # minus the stats-only counting kernel
+    del rec, cigs
+
+    # ---- timed region: device-resident reads ---------------------------------------------------------
+    uuid = ""
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        pass
+    sampler = ClockSampler(uuid)
+    mp.setProfiling(True)
+    mp.stageTimes()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    stages = mp.stageTimes()
+    mp.setProfiling(False)
+    total_ms = parallel.max_over_ranks(dev_ms)
+    ms_per_step = total_ms / args.steps
+    value = world * n * args.steps / (total_ms / 1e3)
+
+    # ---- end to end: pinned host buffers through hrm_mapper_map_reads --------------------------------
+    h_reads = torch.from_numpy(reads).pin_memory()
+    h_lens = torch.from_numpy(lens).pin_memory()
+    h_rec = torch.empty((n * hb.RECORD_DTYPE.itemsize,), dtype=torch.uint8).pin_memory()
+    h_cig = torch.empty((2 * n, CIG), dtype=torch.uint8).pin_memory()
+    rec_np = h_rec.numpy().view(hb.RECORD_DTYPE)
+    for _ in range(2):
+        mp.mapReads(h_reads.numpy(), h_lens.numpy(), CIG, rec_np, h_cig.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mp.mapReads(h_reads.numpy(), h_lens.numpy(), CIG, rec_np, h_cig.numpy())
+    torch.cuda.synchronize()
+    e2e_s = parallel.max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = world * n * args.steps / e2e_s
+    n_mapped = int((rec_np["mapped"]["orientation"] != 3).sum())
+    ok = (rec_np["mapped"]["orientation"] != 3) & (rec_np["mapped"]["position"] + rec_np["mapped"]["shift"] == truth["pos"])
+    h2d = n * reads.shape[1] + n * 4
+    d2h = n * hb.RECORD_DTYPE.itemsize + 2 * n * CIG
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the hash-probe kernel (K3b) -----------------------------------------------------
+    peak, peak_src = peaks()
+    probe_ms, probe_spans = stages["probe"]
+    probe_launch_ms = probe_ms / max(probe_spans, 1)
+    launches_per_step_probe = probe_spans / args.steps
+    P = st.num_slot_touches / cfg.num_passes          # slots examined per probe launch
+    Q = n
+    alg_bytes = 16.0 * P + (8.0 * H_ + 4.0) * Q       # 16 B per slot touch + signatures in + count out
+    achieved = alg_bytes / (probe_launch_ms / 1e3) / 1e9 if probe_launch_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "probe_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    stage_ms = {k: v[0] / args.steps for k, v in stages.items()}
+    stage_sum = sum(stage_ms.values())
+    roofline = {"kernel": "hrm::probe_count_kernel (K3b hash probe)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": probe_launch_ms,
+                "launches_per_step": launches_per_step_probe,
+                "slot_touches_per_launch": P, "lookups_per_launch": Q * H_,
+                "share_of_step": probe_ms / args.steps / ms_per_step if ms_per_step > 0 else None,
+                "note": "algorithmic bytes = 16 B x slots examined + (8H+4) B x reads (SURVEY 8d); two 16-B slots "
+                        "share one 32-B DRAM sector"}
+
+    line = {"metric": "reads mapped/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/u64 integer", "data": "synthetic",
+            "config": {"workload": "1M x 150bp directional BS reads vs 46 Mbp synthetic reference (BASELINE configs[1])",
+                       "reads_per_gpu": n, "genome_bp": args.genome_bp, "k": K_, "hashmaps": H_, "window": W_,
+                       "min_table_hits": T_, "passes": "C->T index + G->A index", "verification": "SW+CIGAR",
+                       "parallelism": "reads sharded x%d, index replicated" % world,
+                       "l2": "inputs larger than L2 (reads %.0f MB + index %.0f MB per GPU)"
+                             % (reads.nbytes / 1e6, info.index_device_bytes / 1e6),
+                       "index_build_s": index_s, "windows": int(info.num_windows),
+                       "index_device_bytes": int(info.index_device_bytes), "table_slots": int(info.table_slots_total),
+                       "table_keys": int(info.num_keys_total)},
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "hrm_mapper_map_reads (pinned host buffers)"},
+            "gpu_launches": int(launches_step * args.steps),
+            "roofline": roofline,
+            "stages_ms_per_step": stage_ms, "stages_unaccounted_ms": ms_per_step - stage_sum,
+            "mapped_fraction": n_mapped / n, "mapped_at_true_locus_fraction": float(ok.sum()) / max(n_mapped, 1),
+            "candidates_per_read": st.num_candidates / n, "values_per_read": st.num_values / n,
+            "clocks": clocks}
+
+    # ---- CPU baseline: the reference's own functions on this box's host cores (rank 0, N = 1) -------
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle.pyoracle import Oracle, have_ref
+            port = Oracle("port")
+            S = min(args.cpu_sample, n)
+            r_ct = np.frombuffer(port.convert_ascii(reads[:S].tobytes(), 1), dtype=np.uint8).reshape(S, -1)
+            g_ct, g_ga = port.convert_ascii(genome, 1), port.convert_ascii(genome, 2)
+            if have_ref():
+                ref = Oracle("ref")
+                t0 = time.perf_counter()
+                per, nm = reference_step(ref, port, g_ct, g_ga, off, r_ct, lens[:S])
+                wall = time.perf_counter() - t0
+                scale = n / S
+                full_s = per[1] + scale * (per[0] + per[2] + per[3])
+                line["cpu_baseline"] = {
+                    "value": n / full_s, "unit": "reads/s", "cores": int(ref.lib.ref_num_threads()), "kind": "reference",
+                    "sample": ("%d of %d reads against the full reference, both 3N passes, %.1f s wall; window "
+                               "streaming (%.2f s) counted once, per-read stages (%.2f s) scaled x%.1f; measured on the "
+                               "sample alone: %.0f reads/s" % (S, n, wall, per[1], per[0] + per[2] + per[3], scale,
+                                                               S / wall)),
+                    "stage_seconds": {"reads_build": per[0], "windows_query_filter": per[1], "shd": per[2],
+                                      "verify_ssw": per[3]}}
+            else:
+                S2 = min(S, 5000)
+                t0 = time.perf_counter()
+                for g in (g_ct, g_ga):
+                    port.map_pass_refdir(g, off, r_ct[:S2], lens[:S2])
+                wall = time.perf_counter() - t0
+                line["cpu_baseline"] = {"value": S2 / wall, "unit": "reads/s", "cores": 1, "kind": "port",
+                                        "sample": "%d reads, seeding+SHD only (scalar oracle port, no SSW)" % S2}
+        except Exception as e:  # the baseline must never break the measurement
+            line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference",
+                                    "sample": "failed: %r" % (e,)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -137,6 +137,8 @@ SIGNATURES = {
     "hrm_map_batch": (I32, [P, P, I64, P, I64, P, C.POINTER(BatchStats), VP]),
     "hrm_verify_batch": (I32, [P, P, I64, P, I64, P, P, P, I64, C.POINTER(BatchStats), VP]),
     "hrm_mapper_map_reads": (I32, [P, P, I64, P, I64, P, P, I64, C.POINTER(BatchStats), VP]),
+    "hrm_mapper_set_profiling": (I32, [P, C.c_int]),
+    "hrm_mapper_stage_times": (I32, [P, C.POINTER(C.c_float), C.POINTER(I32)]),
     "hrm_sam_format": (I32, [P, P, P, I64, P, I64, P, I64, U32, P, C.c_int, P, I64, C.POINTER(I64)]),
 }
 

@@ -404,6 +404,18 @@ class Mapper:
         check(self.lib.hrm_mapper_info(self.h, C.byref(info)))
         return info
 
+    STAGES = ["pack", "minhash", "probe", "scan", "retrieve", "filter", "shd", "merge", "verify"]
+
+    def setProfiling(self, enable=True):
+        check(self.lib.hrm_mapper_set_profiling(self.h, int(enable)))
+
+    def stageTimes(self):
+        """-> {stage: (ms summed since the last call, number of spans)}"""
+        ms = (C.c_float * len(self.STAGES))()
+        sp = (C.c_int32 * len(self.STAGES))()
+        check(self.lib.hrm_mapper_stage_times(self.h, ms, sp))
+        return {n: (float(ms[i]), int(sp[i])) for i, n in enumerate(self.STAGES)}
+
     def mapBatch(self, reads_ascii: torch.Tensor, lengths: torch.Tensor, want_stats=True):
         """device-resident reads -> device tensor of hrm_mapped_read (as [n, 8] int32) + stats"""
         n, pitch = reads_ascii.shape

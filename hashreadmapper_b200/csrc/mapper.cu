@@ -232,7 +232,10 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
         return HRM_OK;
     }
     const int H = cfg.num_tables;
+    StageTimer& T = m->timer;
+    T.begin(HRM_STAGE_PACK, s);
     HRM_TRY(pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
+    T.end(s);
     HRM_TRY(m->sigs.reserve(sizeof(uint64_t) * (size_t)n * H));
     HRM_TRY(m->num.reserve(sizeof(int32_t) * ((size_t)n + 1)));
     HRM_TRY(m->off.reserve(sizeof(int32_t) * ((size_t)n + 1)));
@@ -249,14 +252,21 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
         HRM_REQUIRE(qh != nullptr, "index handle");
         const uint32_t* reads = m->packed[rc].as<uint32_t>();
         // K2 (skipped when the previous pass sketched the same converted reads)
-        if (rc != last_rc)
+        if (rc != last_rc) {
+            T.begin(HRM_STAGE_MINHASH, s);
             HRM_TRY(minhash_rows(reads, m->packed_pitch, d_lengths, n, cfg.k, H, m->sigs.as<uint64_t>(), nullptr, s));
+            T.end(s);
+        }
         last_rc = rc;
         // K3b probe -> per-read counts, scan -> offsets + total
+        T.begin(HRM_STAGE_PROBE, s);
         HRM_TRY(minhasher_count_sigs(mh, qh, m->sigs.as<uint64_t>(), (int)n, m->num.as<int32_t>(), s));
+        T.end(s);
+        T.begin(HRM_STAGE_SCAN, s);
         HRM_TRY(exclusive_scan_i32(m->num.as<int32_t>(), m->off.as<int32_t>(), n, d_tot, s));
         int64_t total = 0;
         HRM_CUDA(cudaMemcpyAsync(&total, d_tot, sizeof total, cudaMemcpyDeviceToHost, s));
+        T.end(s);
         HRM_CUDA(cudaStreamSynchronize(s)); // the one sync of this pass: sizes the candidate buffers
         if (total > 0x7fffffffLL) {
             set_error("candidate values of one batch exceed int: use smaller batches");
@@ -268,18 +278,26 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
         Scratch values, cands;
         HRM_TRY(values.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
         HRM_TRY(cands.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
+        T.begin(HRM_STAGE_RETRIEVE, s);
         if (total > 0) HRM_TRY(minhasher_retrieve(mh, qh, (int)n, values.as<uint32_t>(), m->off.as<int32_t>(), s));
+        T.end(s);
         qh->stage = 0;
+        T.begin(HRM_STAGE_FILTER, s);
         // K4 sort + RLE + threshold, then dense candidate lists
         HRM_TRY(filter_segments(values.as<uint32_t>(), m->off.as<int32_t>(), (int)n, cfg.min_table_hits,
                                 m->num.as<int32_t>(), m->newoff.as<int32_t>(), d_tot + 1, s));
         HRM_TRY(compact_segments(values.as<uint32_t>(), m->off.as<int32_t>(), m->newoff.as<int32_t>(), (int)n,
                                  cands.as<uint32_t>(), s));
+        T.end(s);
         // K5 + per-read arg-min
+        T.begin(HRM_STAGE_SHD, s);
         HRM_TRY(best_windows(reads, m->packed_pitch, d_lengths, n, cands.as<uint32_t>(), m->newoff.as<int32_t>(),
                              m->genome[gc], m->d_win_prefix, cfg.k, cfg.window_size, cfg.max_hamming_percent, p,
                              passout, s));
+        T.end(s);
+        T.begin(HRM_STAGE_MERGE, s);
         HRM_LAUNCH(merge_pass_kernel, mgrid(n), 256, 0, s, d_out, passout, n, p == 0 ? 1 : 0);
+        T.end(s);
         if (h_stats) {
             int64_t ftotal = 0;
             HRM_CUDA(cudaMemcpyAsync(&ftotal, d_tot + 1, sizeof ftotal, cudaMemcpyDeviceToHost, s));
@@ -320,6 +338,7 @@ extern "C" hrm_status hrm_verify_batch(hrm_mapper* m, const char* d_reads_ascii,
     const int64_t launches0 = g_launches.load();
     if (n == 0) return HRM_OK;
     const hrm_mapper_config& cfg = m->cfg;
+    m->timer.begin(HRM_STAGE_VERIFY, s);
     HRM_TRY(pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
     HRM_TRY(m->misc.reserve(64));
     int* d_maxlen = m->misc.as<int>() + 8;
@@ -341,6 +360,7 @@ extern "C" hrm_status hrm_verify_batch(hrm_mapper* m, const char* d_reads_ascii,
         VP.pass[p].verify_conv = cfg.verify_conversion[p];
     }
     HRM_TRY(verify_reads(VP, d_lengths, n, maxlen, d_mapped, d_records, d_cigars, cigar_pitch, s));
+    m->timer.end(s);
     if (h_stats) h_stats->num_kernel_launches += g_launches.load() - launches0;
     return HRM_OK;
 }
@@ -380,3 +400,32 @@ extern "C" hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_as
     return HRM_OK;
 }
 
+
+extern "C" hrm_status hrm_mapper_set_profiling(hrm_mapper* m, int enable)
+{
+    HRM_REQUIRE(m != nullptr, "mapper");
+    m->timer.enabled = enable != 0;
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_mapper_stage_times(hrm_mapper* m, float* h_ms, int32_t* h_spans)
+{
+    HRM_REQUIRE(m != nullptr && h_ms != nullptr, "args");
+    for (int i = 0; i < HRM_NUM_STAGES; i++) {
+        h_ms[i] = 0.f;
+        if (h_spans) h_spans[i] = 0;
+    }
+    for (auto& sp : m->timer.spans) {
+        HRM_CUDA(cudaEventSynchronize(sp.b));
+        float ms = 0.f;
+        HRM_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        if (sp.stage >= 0 && sp.stage < HRM_NUM_STAGES) {
+            h_ms[sp.stage] += ms;
+            if (h_spans) h_spans[sp.stage]++;
+        }
+        m->timer.pool.push_back(sp.a);
+        m->timer.pool.push_back(sp.b);
+    }
+    m->timer.spans.clear();
+    return HRM_OK;
+}

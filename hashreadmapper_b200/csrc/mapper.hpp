@@ -1,4 +1,4 @@
-// mapper.hpp -- the mapper object (shared by mapper.cu and sam.cpp).
+// mapper.hpp -- the mapper object (shared by mapper.cu and sam.cu).
 #pragma once
 #include "runtime.cuh"
 #include "store.cuh"
@@ -6,6 +6,50 @@
 #include <vector>
 
 struct hrm_minhasher;
+
+namespace hrm {
+// CUDA-event spans around the stages of the fused path (enabled by hrm_mapper_set_profiling)
+struct StageTimer {
+    bool enabled = false;
+    struct Span {
+        int stage;
+        cudaEvent_t a, b;
+    };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get()
+    {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(int stage, cudaStream_t s)
+    {
+        if (!enabled) return;
+        Span sp{stage, get(), get()};
+        cudaEventRecord(sp.a, s);
+        spans.push_back(sp);
+    }
+    void end(cudaStream_t s)
+    {
+        if (!enabled || spans.empty()) return;
+        cudaEventRecord(spans.back().b, s);
+    }
+    ~StageTimer()
+    {
+        for (auto& sp : spans) {
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+} // namespace hrm
 
 struct hrm_mapper {
     hrm_mapper_config cfg;
@@ -24,5 +68,5 @@ struct hrm_mapper {
     hrm::GrowBuf sigs, num, off, newoff, passres, misc;
     int64_t packed_pitch = 0;
     unsigned long long touches_seen[3] = {0, 0, 0};
+    hrm::StageTimer timer;
 };
-

@@ -433,6 +433,25 @@ hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_ascii, int64_
                                 char* h_cigars, int64_t cigar_pitch, hrm_batch_stats* h_stats,
                                 hrm_stream stream);
 
+/* Per-stage device timing of the fused path (replaces the reference's nvtx ranges + CpuTimer lines,
+ * ref: include/helpers/nvtx_markers.cuh:15-58, main_gpu.cu:484-775, include/helpers/timers.cuh).
+ * When enabled, CUDA events are recorded around every stage on the caller's stream (no extra
+ * synchronisation); hrm_mapper_stage_times sums them per stage since the last call (it waits for
+ * the recorded events) and resets the accumulation. */
+#define HRM_STAGE_PACK 0      /* K1 */
+#define HRM_STAGE_MINHASH 1   /* K2 */
+#define HRM_STAGE_PROBE 2     /* K3b: the probe kernel alone */
+#define HRM_STAGE_SCAN 3      /* offsets + the pass' one host sync */
+#define HRM_STAGE_RETRIEVE 4  /* K3b: value gather */
+#define HRM_STAGE_FILTER 5    /* K4 */
+#define HRM_STAGE_SHD 6       /* K5 + per-read arg-min */
+#define HRM_STAGE_MERGE 7
+#define HRM_STAGE_VERIFY 8    /* K6/K7 */
+#define HRM_NUM_STAGES 9
+hrm_status hrm_mapper_set_profiling(hrm_mapper* m, int enable);
+hrm_status hrm_mapper_stage_times(hrm_mapper* m, float* h_ms /* [HRM_NUM_STAGES] */,
+                                  int32_t* h_spans /* [HRM_NUM_STAGES], may be NULL */);
+
 /* ref: Mappinghandler::printtoSAM src/gpu/mappinghandler.cu:196-293 (SW mode).  Host-side text
  * formatting of n records into h_out (capacity cap); *h_written = bytes needed.  `with_header`
  * emits the @HD/@SQ/@PG/@CO block.  first_read_id = id of record 0.  h_chrom_names: n_chrom

@@ -235,3 +235,25 @@ class Oracle:
 
     def mapq(self, s1, s2):
         return self.lib.orc_mapq(s1, s2)
+
+
+def ref_cpu_pipeline(ref: "Oracle", genome: bytes, chrom_off, reads: np.ndarray, read_len, k=16, w=128, H=16,
+                     min_hits=4, max_results_per_map=65535, rate=0.05, batchsize=2048, mapper_type=0,
+                     want_alignments=True):
+    """The reference's CPU path assembled from its own functions (oracle/ref_shim.cpp: ref_cpu_pipeline).
+    -> (mapped MAPPED_DTYPE [n], alignments ALIGN_DTYPE [n,2] or None, edit [n,2], times[4])"""
+    assert ref.kind == "ref"
+    chrom_off = np.ascontiguousarray(chrom_off, dtype=np.int64)
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    read_len = np.ascontiguousarray(read_len, dtype=np.int32)
+    n = read_len.shape[0]
+    out = np.zeros(n, dtype=MAPPED_DTYPE)
+    sw = np.zeros((n, 2), dtype=ALIGN_DTYPE) if want_alignments else None
+    ed = np.zeros((n, 2), dtype=np.int32)
+    times = np.zeros(4, dtype=np.float64)
+    ref.lib.ref_cpu_pipeline(genome, _p(chrom_off, C.c_int64), chrom_off.shape[0] - 1, _p(reads, C.c_char),
+                             reads.shape[1], _p(read_len, C.c_int32), C.c_int64(n), k, w, H, min_hits,
+                             max_results_per_map, C.c_float(rate), batchsize, mapper_type,
+                             out.ctypes.data_as(C.c_void_p), sw.ctypes.data_as(C.c_void_p) if sw is not None else None,
+                             ed.ctypes.data_as(C.c_void_p), _p(times, C.c_double))
+    return out, sw, ed, times

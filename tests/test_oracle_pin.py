@@ -165,3 +165,29 @@ def test_ref_ssw_edit(port, ref):
         q = rs(rng, rng.randint(1, 200), "AGT")
         t = (mutate(rng, q, 0.05, 0.05) if it % 2 else rs(rng, rng.randint(1, 200), "AGT")) or b"G"
         assert port.edit_distance_nw(q, t) == ref.edit_distance_nw(q, t)
+
+
+def test_ref_whole_pipeline(port, ref):
+    """the oracle's pipeline restatement == the reference's own functions driven in the reference's order"""
+    from hashreadmapper_b200 import synth
+    from oracle.pyoracle import ref_cpu_pipeline
+    genome, off = synth.make_genome([50000, 20011], seed=5)
+    reads, lens, _ = synth.make_reads(genome, off, 1500, 150, error_rate=0.02, seed=6)
+    lens[3] = 10
+    for conv_g in (1, 2):
+        g = port.convert_ascii(genome, conv_g)
+        exp, stats = port.map_pass_refdir(g, off, reads, lens)
+        got, sw, ed, times = ref_cpu_pipeline(ref, g, off, reads, lens)
+        m = exp["orientation"] != 3
+        assert m.sum() > 500
+        assert (got["orientation"] == exp["orientation"]).all()
+        for f in ("hammingDistance", "shift", "chromosomeId", "position"):
+            assert (got[f][m] == exp[f][m]).all(), f
+        # verification inputs + SSW through the oracle == the reference's
+        for i in np.nonzero(m)[0][:200]:
+            chrom = g[off[exp["chromosomeId"][i]]:off[exp["chromosomeId"][i] + 1]]
+            q, qrc, r = port.verify_inputs(reads[i, :lens[i]].tobytes(), int(exp["orientation"][i]), chrom,
+                                           int(exp["position"][i]), 128, 1)
+            for a, qq in enumerate((q, qrc)):
+                ea, _ = port.ssw_align(qq, r, max(15, int(lens[i]) // 2))
+                assert ea == tuple(int(sw[i][a][n]) for n in sw.dtype.names[:9])
