@@ -287,6 +287,9 @@ struct SwScratch {
     int maxops;
 };
 
+HRM_HD void sw_finish(const int8_t* q, int qlen, const int8_t* r, const SwScratch& S, SwAlignment* al, char* cigar,
+                      int cigar_cap);
+
 // Whole Align().  q/r: translated codes.  cigar: cap bytes (no NUL needed).
 HRM_HD void sw_align(const int8_t* q, int qlen, const int8_t* r, int rlen, int maskLen, const SwScratch& S,
                      SwAlignment* al, char* cigar, int cigar_cap)
@@ -314,11 +317,20 @@ HRM_HD void sw_align(const int8_t* q, int qlen, const int8_t* r, int rlen, int m
     // reverse pass: read[read_end1 .. 0] against ref[ref_end1 .. 0]
     const SwEnds br = sw_pass(r, 1, ref_end1 + 1, q, read_end1, -1, read_end1 + 1, word ? 8 : 16,
                               word ? score1 : (score1 & 255), maskLen, S.H, S.E, S.maxColumn);
-    const int ref_begin1 = br.ref;
-    const int read_begin1 = read_end1 - br.read;
-    int flag = score1 > br.score ? 2 : 0;
-    al->ref_begin = ref_begin1;
-    al->query_begin = read_begin1;
+    al->ref_begin = br.ref;
+    al->query_begin = read_end1 - br.read;
+    al->flag = score1 > br.score ? 2 : 0;
+    sw_finish(q, qlen, r, S, al, cigar, cigar_cap);
+}
+
+// Second half of Align(): banded trace back + ConvertAlignment + CalculateNumberMismatch, given the
+// ends/begins found by the two passes (al->sw_score, ref_begin/end, query_begin/end, flag 0|2).
+HRM_HD void sw_finish(const int8_t* q, int qlen, const int8_t* r, const SwScratch& S, SwAlignment* al, char* cigar,
+                      int cigar_cap)
+{
+    const int score1 = al->sw_score, ref_end1 = al->ref_end, read_end1 = al->query_end;
+    const int ref_begin1 = al->ref_begin, read_begin1 = al->query_begin;
+    int flag = al->flag;
     const int refLen = ref_end1 - ref_begin1 + 1;
     const int readLen = read_end1 - read_begin1 + 1;
     int nops = 0;

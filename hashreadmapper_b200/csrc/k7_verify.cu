@@ -1,61 +1,309 @@
-// k7_verify.cu -- K6/K7: verification of mapped reads on the device.
+// k7_verify.cu -- K6/K7: verification of mapped reads on the device (integer-ALU bound).
 // ref: Mappinghandler::CSSW src/gpu/mappinghandler.cu:383-600 (serial per-read prep on one host
 //      thread, then 2 x Aligner::Align per read on a host ThreadPool), edlibAligner :841-1010,
-//      StripedSmithWaterman::Aligner::Align src/ssw_cpp.cpp:361-400, ssw_align src/ssw.c:818-922,
-//      edlibAlign src/edlib.cpp:1474-1476.
-// Round-1 mapping: one thread per alignment running the scalar restatement of core_sw.cuh with its
-// DP rows in a per-thread scratch slice (L1/L2 resident); inputs are built on the fly from the packed
-// read and the packed genome (no ASCII materialisation, no host prep loop).  DESIGN.md lists the
-// warp-wavefront version as the next optimisation of this kernel.
+//      StripedSmithWaterman::Aligner::Align src/ssw_cpp.cpp:361-400, ssw_align src/ssw.c:818-922
+//      (sw_sse2_byte :197-386, sw_sse2_word :412-588, banded_sw :590-774), edlibAlign src/edlib.cpp:1474.
+//
+// Two kernels per batch of alignments:
+//  A. sw_passes_kernel -- one WARP per alignment.  The forward and the reverse DP pass run as an
+//     anti-diagonal wavefront: lane l owns R consecutive read rows (H, E in registers), processes
+//     reference column t-l at step t and hands the bottom H/F of its strip plus the running column
+//     maximum (with its first row) to lane l+1 by warp shuffle.  Lane 31 sees every finished column:
+//     it tracks score / first end column / smallest end row exactly like the striped SSE2 kernels and
+//     stores the per-column maxima (with the byte-mode and the word-mode pad rows) in shared memory
+//     for the second-best scan.  Inputs are built on the fly from the packed read and the packed
+//     genome (stage-V 3N conversion applied on the codes): no ASCII, no host prep loop.
+//  B. sw_finish_kernel -- one THREAD per alignment: the reference's banded trace back restated
+//     literally (core_sw.cuh: sw_banded) on the small begin..end rectangle, then the =/X/I/D/S CIGAR.
+// Work per alignment: ~(L+pad) x w cell updates forward, <= that backward, band x L for the trace.
 #include "pipeline.cuh"
 #include "core_sw.cuh"
 
 namespace hrm {
 
-struct SwPool {
+__host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// sources of (query codes, ref codes, maskLen)
+// ------------------------------------------------------------------------------------------------
+struct AsciiSrc { // function-level API: ASCII rows
+    const char* queries;
+    int64_t qpitch;
+    const int32_t* qlen;
+    const char* refs;
+    int64_t rpitch;
+    const int32_t* rlen;
+    const int32_t* mask_len;
+    int maxQ, maxR;
+    static constexpr int SKIP_FLAG = 1; // sizes outside the limits: reported like a failed trace back
+    // returns false when the item must be skipped
+    __device__ __forceinline__ bool load(int64_t e, int8_t* sq, int8_t* sr, int tid, int nthr, int& ql, int& rl,
+                                         int& ml) const
+    {
+        ql = qlen[e];
+        rl = rlen[e];
+        ml = mask_len[e];
+        if (ql < 0 || ql > maxQ || rl < 0 || rl > maxR) return false;
+        for (int i = tid; i < ql; i += nthr) sq[i] = sw_translate((unsigned char)queries[e * qpitch + i]);
+        for (int i = tid; i < rl; i += nthr) sr[i] = sw_translate((unsigned char)refs[e * rpitch + i]);
+        return true;
+    }
+};
+
+__device__ __forceinline__ int conv_code(int c, int conv)
+{
+    if (conv == HRM_CONV_CT && c == 1) return 3;
+    if (conv == HRM_CONV_GA && c == 2) return 0;
+    return c;
+}
+
+struct PackedSrc { // fused path: item t = 2 * read + a
+    VerifyParams VP;
+    const int32_t* read_len;
+    const hrm_mapped_read* mapped;
+    int maxQ, maxR;
+    static constexpr int SKIP_FLAG = 0; // unmapped read: zero-initialised alignments (ref: mappinghandler.cu:548)
+    __device__ __forceinline__ bool load(int64_t t, int8_t* sq, int8_t* sr, int tid, int nthr, int& ql, int& rl,
+                                         int& ml) const
+    {
+        const int64_t rd = t >> 1;
+        const int a = (int)(t & 1);
+        const hrm_mapped_read m = mapped[rd];
+        const int L = read_len[rd];
+        ql = L;
+        rl = 0;
+        ml = L / 2 < 15 ? 15 : L / 2; // ref: mappinghandler.cu:453-454
+        if (m.orientation == HRM_ORIENT_NONE || m.pass < 0 || m.pass >= VP.num_passes || L <= 0 || L > maxQ)
+            return false;
+        const VerifyPass& P = VP.pass[m.pass];
+        const uint32_t* rw = P.reads + rd * P.read_pitch;
+        const int64_t clen = P.G.chrom_len[m.chromosome_id];
+        const uint32_t* cw = P.G.chrom_words[m.chromosome_id];
+        int wl = (int)((m.position + VP.w < clen) ? VP.w : clen - m.position); // ref: mappinghandler.cu:434-440
+        if (wl > maxR) wl = maxR;
+        rl = wl;
+        // readsequence = RC(read) when SHD chose RC (:420-423); alignment 1 uses RC(readsequence) (:461-465)
+        const bool rc = (m.orientation == HRM_ORIENT_REVCOMP) != (a == 1);
+        for (int j = tid; j < L; j += nthr) {
+            const int c = rc ? 3 - (int)get_nuc(rw, L - 1 - j) : (int)get_nuc(rw, j);
+            sq[j] = (int8_t)conv_code(c, P.verify_conv);
+        }
+        for (int j = tid; j < wl; j += nthr) sr[j] = (int8_t)conv_code((int)get_nuc(cw, m.position + j), P.verify_conv);
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernel A: wavefront passes
+// ------------------------------------------------------------------------------------------------
+struct WfOut {
+    int maxv, end_col, end_row;
+};
+
+// rows [lane*R, lane*R+R) of the (padded) read; columns col0, col0+cstep, ... (ncols of them)
+template <int R>
+__device__ __forceinline__ WfOut wf_pass(const int8_t* sq, int qoff, int qdir, int nreal, int padB, int padW,
+                                         const int8_t* sr, int col0, int cstep, int ncols, int terminate,
+                                         int init_end_col, int16_t* cmB, int16_t* cmW, int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    int Hp[R], E[R], qc[R];
+    const int row0 = lane * R;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int row = row0 + r;
+        Hp[r] = 0;
+        E[r] = 0;
+        qc[r] = row < nreal ? (int)sq[qoff + qdir * row] : -1; // pad rows score 0 (ref: qP_byte ssw.c:177)
+    }
+    int outH = 0, outF = 0;
+    unsigned outKB = 0, outKW = 0; // (column max << 16) | (0xFFFF - first row attaining it)
+    int prevRecvH = 0;
+    int runmax = 0, end_col = init_end_col, end_row = 0, done = 0;
+    const int nsteps = ncols + 31;
+    for (int t = 0; t < nsteps; ++t) {
+        int recvH = __shfl_up_sync(FULL, outH, 1);
+        int recvF = __shfl_up_sync(FULL, outF, 1);
+        unsigned recvKB = __shfl_up_sync(FULL, outKB, 1);
+        unsigned recvKW = __shfl_up_sync(FULL, outKW, 1);
+        if (lane == 0) {
+            recvH = 0;
+            recvF = 0;
+            recvKB = 0;
+            recvKW = 0;
+        }
+        const int crel = t - lane;
+        if (crel >= 0 && crel < ncols) {
+            const int col = col0 + cstep * crel;
+            const int rc = sr[col];
+            int diag = crel == 0 ? 0 : prevRecvH;
+            prevRecvH = recvH;
+            int F = recvF;
+            unsigned kB = recvKB, kW = recvKW;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int row = row0 + r;
+                const int hprev = Hp[r];
+                const int s = qc[r] < 0 ? 0 : ((rc == qc[r] && rc < 4) ? 2 : -2);
+                int h = max(max(diag + s, 0), max(E[r], F));
+                diag = hprev;
+                Hp[r] = h;
+                const unsigned key = ((unsigned)h << 16) | (unsigned)(0xFFFF - row);
+                if (row < padB) kB = max(kB, key);
+                if (row < padW) kW = max(kW, key);
+                const int ho = max(h - HRM_SW_GAPO, 0);
+                E[r] = max(E[r] - HRM_SW_GAPE, ho);
+                F = max(F - HRM_SW_GAPE, ho);
+            }
+            outH = Hp[R - 1];
+            outF = F;
+            outKB = kB;
+            outKW = kW;
+            if (lane == 31) {
+                cmB[col] = (int16_t)(kB >> 16);
+                cmW[col] = (int16_t)(kW >> 16);
+                if (!done) {
+                    const int cm = (int)(kB >> 16);
+                    if (cm > runmax) { // ref: ssw.c:321-335 strict increase; :343-351 smallest row
+                        runmax = cm;
+                        end_col = col;
+                        end_row = 0xFFFF - (int)(kB & 0xFFFFu);
+                    }
+                    if (cm == terminate) done = 1; // ref: ssw.c:339
+                }
+            }
+        }
+        if (terminate >= 0 && __shfl_sync(FULL, done, 31)) break;
+    }
+    WfOut o;
+    o.maxv = __shfl_sync(FULL, runmax, 31);
+    o.end_col = __shfl_sync(FULL, end_col, 31);
+    o.end_row = __shfl_sync(FULL, end_row, 31);
+    return o;
+}
+
+__device__ __forceinline__ void zero_alignment(hrm_alignment& o)
+{
+    o.sw_score = o.sw_score_next_best = o.ref_begin = o.ref_end = o.query_begin = o.query_end = 0;
+    o.ref_end_next_best = o.mismatches = o.flag = o.cigar_len = 0;
+}
+
+// best column maximum over [lo, hi) of cm[]: (value, first column) ; warp-wide
+__device__ __forceinline__ unsigned scan_cols(const int16_t* cm, int lo, int hi, int lane)
+{
+    unsigned best = 0;
+    for (int c = lo + lane; c < hi; c += 32) {
+        const unsigned key = ((unsigned)(uint16_t)cm[c] << 16) | (unsigned)(0xFFFF - c);
+        best = key > best ? key : best;
+    }
+    return best;
+}
+
+template <int R, class Src>
+__global__ void __launch_bounds__(256) sw_passes_kernel(Src src, int64_t n, int QP, int RP,
+                                                        hrm_alignment* __restrict__ out, int64_t out_stride_items,
+                                                        int64_t out_offset_items)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t per_warp = (size_t)QP + RP + 4 * (size_t)RP;
+    int8_t* sq = (int8_t*)(smem + per_warp * wid);
+    int8_t* sr = sq + QP;
+    int16_t* cmB = (int16_t*)(sr + RP);
+    int16_t* cmW = cmB + RP;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = warp0; e < n; e += nwarps) {
+        int ql, rl, ml;
+        __syncwarp();
+        const bool ok = src.load(e, sq, sr, lane, 32, ql, rl, ml);
+        __syncwarp();
+        hrm_alignment o;
+        zero_alignment(o);
+        if (ok && ql > 0) {
+            const int padB = (int)align_up(ql, 16), padW = (int)align_up(ql, 8);
+            WfOut f = wf_pass<R>(sq, 0, 1, ql, padB, padW, sr, 0, 1, rl, -1, -1, cmB, cmW, lane);
+            __syncwarp();
+            const int score1 = f.maxv, ref_end1 = f.end_col, read_end1 = f.end_row < ql - 1 ? f.end_row : ql - 1;
+            const bool word = score1 + 2 >= 255; // ref: ssw.c:329 byte overflow -> word pass (:846-849)
+            o.sw_score = score1;
+            o.ref_end = ref_end1;
+            o.query_end = read_end1;
+            // second best (ref: ssw.c:368-381 byte, :570-583 word)
+            int score2 = 0, ref2 = 0;
+            if (score1 > 0 || word) {
+                const int16_t* cm = word ? cmW : cmB;
+                const int e1 = (ref_end1 - ml) > 0 ? (ref_end1 - ml) : 0;
+                int e2 = (ref_end1 + ml) > rl ? rl : (ref_end1 + ml);
+                unsigned k1 = scan_cols(cm, 0, e1, lane);
+                unsigned k2 = scan_cols(cm, e2 + (word ? 0 : 1), rl, lane);
+                k1 = __reduce_max_sync(0xffffffffu, k1);
+                k2 = __reduce_max_sync(0xffffffffu, k2);
+                // the reference scans the left range first and replaces only on strictly greater
+                const unsigned v1 = k1 >> 16, v2 = k2 >> 16;
+                if (v1 > 0) {
+                    score2 = (int)v1;
+                    ref2 = 0xFFFF - (int)(k1 & 0xFFFFu);
+                }
+                if (v2 > (unsigned)score2) {
+                    score2 = (int)v2;
+                    ref2 = 0xFFFF - (int)(k2 & 0xFFFFu);
+                }
+            }
+            o.sw_score_next_best = ml >= 15 ? score2 : 0;
+            o.ref_end_next_best = ml >= 15 ? ref2 : -1;
+            if (score1 == 0 || ref_end1 < 0) { // undefined in the reference (ssw.c:220): deterministic convention
+                o.ref_begin = -1;
+                o.query_begin = -1;
+            } else {
+                __syncwarp();
+                const int nr = read_end1 + 1;
+                const int pad = (int)align_up(nr, word ? 8 : 16);
+                WfOut b = wf_pass<R>(sq, read_end1, -1, nr, pad, pad, sr, ref_end1, -1, ref_end1 + 1, score1,
+                                     word ? 0 : -1, cmB, cmW, lane);
+                const int brow = b.end_row < nr - 1 ? b.end_row : nr - 1;
+                o.ref_begin = b.end_col;
+                o.query_begin = read_end1 - brow;
+                o.flag = score1 > b.maxv ? 2 : 0; // ref: ssw.c:890-893
+            }
+        }
+        if (!ok) o.flag = Src::SKIP_FLAG;
+        if (lane == 0) out[out_offset_items + e * out_stride_items] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel B: banded trace back + CIGAR, one thread per alignment
+// ------------------------------------------------------------------------------------------------
+struct TracePool {
     unsigned char* base;
-    int64_t per_thread;  // bytes per thread slice
-    int maxQ, maxR, maxLen, maxops;
+    int64_t per_thread;
+    int maxLen, maxops;
     int64_t dir_cap;
 };
 
-__host__ __device__ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
-
-static SwPool sw_pool_layout(int maxQ, int maxR)
+static TracePool trace_pool_layout(int maxQ, int maxR)
 {
-    SwPool P;
+    TracePool P;
     P.base = nullptr;
-    P.maxQ = maxQ;
-    P.maxR = maxR;
     P.maxLen = maxQ > maxR ? maxQ : maxR;
     P.maxops = 2 * P.maxLen + 8;
     P.dir_cap = (int64_t)(2 * P.maxLen + 1) * maxQ;
     int64_t b = 0;
-    b += align_up(maxQ + 16, 16);                                  // q codes
-    b += align_up(maxR + 16, 16);                                  // r codes
-    b += align_up((int64_t)sizeof(int16_t) * (maxQ + 32), 16) * 2; // H, E
-    b += align_up((int64_t)sizeof(int16_t) * (maxR + 16), 16);     // maxColumn
-    b += align_up((int64_t)sizeof(int32_t) * (2 * P.maxLen + 32), 16) * 3; // hb eb hc
-    b += align_up(P.dir_cap + 16, 16);                             // dir
-    b += align_up(P.maxops, 16);                                   // ops
-    b += align_up((int64_t)sizeof(int32_t) * P.maxops, 16);        // lens
+    b += align_up((int64_t)sizeof(int32_t) * (2 * P.maxLen + 32), 16) * 3;
+    b += align_up(P.dir_cap + 16, 16);
+    b += align_up(P.maxops, 16);
+    b += align_up((int64_t)sizeof(int32_t) * P.maxops, 16);
     P.per_thread = b;
     return P;
 }
 
-__device__ __forceinline__ void sw_pool_carve(const SwPool& P, int64_t slot, int8_t*& q, int8_t*& r, SwScratch& S)
+__device__ __forceinline__ void trace_pool_carve(const TracePool& P, int64_t slot, SwScratch& S)
 {
     unsigned char* p = P.base + slot * P.per_thread;
-    q = (int8_t*)p;
-    p += align_up(P.maxQ + 16, 16);
-    r = (int8_t*)p;
-    p += align_up(P.maxR + 16, 16);
-    S.H = (int16_t*)p;
-    p += align_up((int64_t)sizeof(int16_t) * (P.maxQ + 32), 16);
-    S.E = (int16_t*)p;
-    p += align_up((int64_t)sizeof(int16_t) * (P.maxQ + 32), 16);
-    S.maxColumn = (int16_t*)p;
-    p += align_up((int64_t)sizeof(int16_t) * (P.maxR + 16), 16);
+    S.H = nullptr;
+    S.E = nullptr;
+    S.maxColumn = nullptr;
     S.hb = (int32_t*)p;
     p += align_up((int64_t)sizeof(int32_t) * (2 * P.maxLen + 32), 16);
     S.eb = (int32_t*)p;
@@ -71,49 +319,47 @@ __device__ __forceinline__ void sw_pool_carve(const SwPool& P, int64_t slot, int
     S.maxops = P.maxops;
 }
 
-// ---- function-level API: ASCII rows ------------------------------------------------------------
-__global__ void __launch_bounds__(128) sw_rows_kernel(const char* __restrict__ queries, int64_t qpitch,
-                                                      const int32_t* __restrict__ qlen,
-                                                      const char* __restrict__ refs, int64_t rpitch,
-                                                      const int32_t* __restrict__ rlen,
-                                                      const int32_t* __restrict__ mask_len, int64_t n, SwPool P,
-                                                      hrm_alignment* __restrict__ out, char* __restrict__ cigars,
-                                                      int64_t cigar_pitch)
+template <class Src>
+__global__ void __launch_bounds__(128) sw_finish_kernel(Src src, int64_t n, int slice_bytes, int QP, TracePool P,
+                                                        hrm_alignment* __restrict__ out, int64_t out_stride_items,
+                                                        int64_t out_offset_items, char* __restrict__ cigars,
+                                                        int64_t cigar_pitch)
 {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int8_t* q = (int8_t*)(smem + (size_t)slice_bytes * threadIdx.x);
+    int8_t* r = q + QP;
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nslots = (int64_t)gridDim.x * blockDim.x;
-    int8_t *q, *r;
     SwScratch S;
-    sw_pool_carve(P, slot, q, r, S);
+    trace_pool_carve(P, slot, S);
     for (int64_t e = slot; e < n; e += nslots) {
-        const int ql = qlen[e], rl = rlen[e];
-        SwAlignment al;
+        hrm_alignment* po = out + out_offset_items + e * out_stride_items;
+        hrm_alignment o = *po;
         char* cig = cigars + e * cigar_pitch;
-        if (ql < 0 || ql > P.maxQ || rl < 0 || rl > P.maxR) {
-            al.sw_score = al.sw_score_next_best = al.ref_begin = al.ref_end = al.query_begin = al.query_end = 0;
-            al.ref_end_next_best = al.mismatches = al.cigar_len = 0;
-            al.flag = 1;
-        } else {
-            for (int i = 0; i < ql; i++) q[i] = sw_translate((unsigned char)queries[e * qpitch + i]);
-            for (int i = 0; i < rl; i++) r[i] = sw_translate((unsigned char)refs[e * rpitch + i]);
-            sw_align(q, ql, r, rl, mask_len[e], S, &al, cig, (int)cigar_pitch);
+        int ql, rl, ml;
+        if (o.flag != 1 && o.sw_score > 0 && o.ref_begin >= 0 && src.load(e, q, r, 0, 1, ql, rl, ml)) {
+            SwAlignment al;
+            al.sw_score = o.sw_score;
+            al.sw_score_next_best = o.sw_score_next_best;
+            al.ref_begin = o.ref_begin;
+            al.ref_end = o.ref_end;
+            al.query_begin = o.query_begin;
+            al.query_end = o.query_end;
+            al.ref_end_next_best = o.ref_end_next_best;
+            al.mismatches = 0;
+            al.flag = o.flag;
+            al.cigar_len = 0;
+            sw_finish(q, ql, r, S, &al, cig, (int)cigar_pitch);
+            o.mismatches = al.mismatches;
+            o.flag = al.flag;
+            o.cigar_len = al.cigar_len;
+            *po = o;
         }
-        hrm_alignment o;
-        o.sw_score = al.sw_score;
-        o.sw_score_next_best = al.sw_score_next_best;
-        o.ref_begin = al.ref_begin;
-        o.ref_end = al.ref_end;
-        o.query_begin = al.query_begin;
-        o.query_end = al.query_end;
-        o.ref_end_next_best = al.ref_end_next_best;
-        o.mismatches = al.mismatches;
-        o.flag = al.flag;
-        o.cigar_len = al.cigar_len;
-        out[e] = o;
-        if (al.cigar_len < cigar_pitch) cig[al.cigar_len] = 0;
+        if (o.cigar_len < cigar_pitch) cig[o.cigar_len] = 0;
     }
 }
 
+// ---- edit distance (function-level API and edlib mode) ------------------------------------------
 __global__ void __launch_bounds__(128) edit_rows_kernel(const char* __restrict__ queries, int64_t qpitch,
                                                         const int32_t* __restrict__ qlen,
                                                         const char* __restrict__ targets, int64_t tpitch,
@@ -130,99 +376,120 @@ __global__ void __launch_bounds__(128) edit_rows_kernel(const char* __restrict__
     }
 }
 
-// ---- fused verification: thread t = 2*read + a (a = 0: 3N(read'), a = 1: 3N(RC(read'))) -----------
-__device__ __forceinline__ int conv_code(int c, int conv)
+__global__ void __launch_bounds__(128) edit_packed_kernel(PackedSrc src, int64_t n, int slice_bytes, int QP,
+                                                          hrm_read_record* __restrict__ records)
 {
-    if (conv == HRM_CONV_CT && c == 1) return 3;
-    if (conv == HRM_CONV_GA && c == 2) return 0;
-    return c;
-}
-
-__global__ void __launch_bounds__(128) verify_kernel(VerifyParams VP, const int32_t* __restrict__ read_len, int64_t n,
-                                                     const hrm_mapped_read* __restrict__ mapped, SwPool P,
-                                                     hrm_read_record* __restrict__ records, char* __restrict__ cigars,
-                                                     int64_t cigar_pitch)
-{
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nslots = (int64_t)gridDim.x * blockDim.x;
-    int8_t *q, *r;
-    SwScratch S;
-    sw_pool_carve(P, slot, q, r, S);
-    for (int64_t t = slot; t < 2 * n; t += nslots) {
-        const int64_t rd = t >> 1;
-        const int a = (int)(t & 1);
-        const hrm_mapped_read m = mapped[rd];
-        hrm_read_record* rec = records + rd;
-        char* cig = cigars + t * cigar_pitch;
-        const int L = read_len[rd];
-        SwAlignment al;
-        al.sw_score = al.sw_score_next_best = al.ref_begin = al.ref_end = al.query_begin = al.query_end = 0;
-        al.ref_end_next_best = al.mismatches = al.flag = al.cigar_len = 0;
-        int ed = -1, wl = 0;
-        int maskLen = L / 2; // ref: mappinghandler.cu:453-454
-        maskLen = maskLen < 15 ? 15 : maskLen;
-        const bool ok = m.orientation != HRM_ORIENT_NONE && m.pass >= 0 && m.pass < VP.num_passes && L > 0 &&
-                        L <= P.maxQ;
-        if (ok) {
-            const VerifyPass& VPp = VP.pass[m.pass];
-            const uint32_t* rw = VPp.reads + rd * VPp.read_pitch;
-            const int64_t clen = VPp.G.chrom_len[m.chromosome_id];
-            const uint32_t* cw = VPp.G.chrom_words[m.chromosome_id];
-            // ref: mappinghandler.cu:434-440 window length (strict <)
-            wl = (int)((m.position + VP.w < clen) ? VP.w : clen - m.position);
-            if (wl > P.maxR) wl = P.maxR;
-            // readsequence = RC(read) if the SHD orientation was RC (:420-423); alignment 1 uses RC(readsequence)
-            const bool rc = (m.orientation == HRM_ORIENT_REVCOMP) != (a == 1);
-            for (int j = 0; j < L; j++) {
-                const int c = rc ? 3 - (int)get_nuc(rw, L - 1 - j) : (int)get_nuc(rw, j);
-                q[j] = (int8_t)conv_code(c, VPp.verify_conv);
-            }
-            for (int j = 0; j < wl; j++) r[j] = (int8_t)conv_code((int)get_nuc(cw, m.position + j), VPp.verify_conv);
-            if (VP.mapper_type == HRM_MAPPER_SW) {
-                sw_align(q, L, r, wl, maskLen, S, &al, cig, (int)cigar_pitch);
-            } else {
-                // edlib mode: global edit distance on the same strings (bytes "ACGT"[code])
-                unsigned char* qa = (unsigned char*)S.dir;
-                unsigned char* ta = qa + P.maxQ + 16;
-                for (int j = 0; j < L; j++) qa[j] = (unsigned char)("ACGT"[q[j] & 3]);
-                for (int j = 0; j < wl; j++) ta[j] = (unsigned char)("ACGT"[r[j] & 3]);
-                ed = myers_nw(qa, L, ta, wl);
-            }
+    extern __shared__ __align__(16) unsigned char smem[];
+    int8_t* q = (int8_t*)(smem + (size_t)slice_bytes * threadIdx.x);
+    int8_t* r = q + QP;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * n; t += stride) {
+        int ql, rl, ml, d = -1;
+        if (src.load(t, q, r, 0, 1, ql, rl, ml) && ql <= 64 * HRM_MYERS_MAX_BLOCKS) {
+            for (int j = 0; j < ql; j++) q[j] = (int8_t)("ACGT"[q[j] & 3]);
+            for (int j = 0; j < rl; j++) r[j] = (int8_t)("ACGT"[r[j] & 3]);
+            d = myers_nw((const unsigned char*)q, ql, (const unsigned char*)r, rl);
         }
-        if (al.cigar_len < cigar_pitch) cig[al.cigar_len] = 0;
-        hrm_alignment o;
-        o.sw_score = al.sw_score;
-        o.sw_score_next_best = al.sw_score_next_best;
-        o.ref_begin = al.ref_begin;
-        o.ref_end = al.ref_end;
-        o.query_begin = al.query_begin;
-        o.query_end = al.query_end;
-        o.ref_end_next_best = al.ref_end_next_best;
-        o.mismatches = al.mismatches;
-        o.flag = al.flag;
-        o.cigar_len = al.cigar_len;
-        rec->alignments[a] = o;
-        rec->edit_distance[a] = ed;
-        if (a == 0) {
-            rec->mapped = m;
-            rec->window_length = wl;
-            rec->mask_len = maskLen;
-        }
+        records[t >> 1].edit_distance[t & 1] = d;
     }
 }
 
-static hrm_status sw_pool_make(SwPool& P, int64_t n_items, Scratch& mem, int& blocks, cudaStream_t s)
+// record header: mapped read, window length, mask length (+ zeroed alignments / distances)
+__global__ void __launch_bounds__(256) record_header_kernel(VerifyParams VP, const int32_t* __restrict__ read_len,
+                                                            const hrm_mapped_read* __restrict__ mapped, int64_t n,
+                                                            hrm_read_record* __restrict__ records)
 {
-    // concurrency bounded by a scratch budget (B200: plenty of HBM, keep it modest anyway)
-    const int64_t budget = 6LL << 30;
-    int64_t slots = (int64_t)num_sms() * 128 * 2;
-    if (slots > n_items) slots = n_items;
-    if (slots * P.per_thread > budget) slots = budget / P.per_thread;
-    if (slots < 128) slots = 128;
-    blocks = (int)HRM_SDIV(slots, (int64_t)128);
-    slots = (int64_t)blocks * 128;
-    HRM_TRY(mem.alloc((size_t)(slots * P.per_thread), s));
-    P.base = mem.as<unsigned char>();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const hrm_mapped_read m = mapped[i];
+        const int L = read_len[i];
+        hrm_read_record rec;
+        rec.mapped = m;
+        zero_alignment(rec.alignments[0]);
+        zero_alignment(rec.alignments[1]);
+        rec.edit_distance[0] = rec.edit_distance[1] = -1;
+        int wl = 0;
+        if (m.orientation != HRM_ORIENT_NONE && m.pass >= 0 && m.pass < VP.num_passes) {
+            const int64_t clen = VP.pass[m.pass].G.chrom_len[m.chromosome_id];
+            wl = (int)((m.position + VP.w < clen) ? VP.w : clen - m.position);
+        }
+        rec.window_length = wl;
+        rec.mask_len = L / 2 < 15 ? 15 : L / 2;
+        records[i] = rec;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <class Src>
+static hrm_status run_sw(const Src& src, int64_t n, int maxQ, int maxR, hrm_alignment* d_out, int64_t out_stride,
+                         int64_t out_offset, char* d_cigars, int64_t cigar_pitch, cudaStream_t s)
+{
+    if (n == 0) return HRM_OK;
+    const int QP = (int)align_up(maxQ > 16 ? maxQ : 16, 16), RP = (int)align_up(maxR > 16 ? maxR : 16, 16);
+    // kernel A
+    {
+        const size_t smemA = ((size_t)QP + RP + 4 * (size_t)RP) * 8;
+        int64_t blocks = HRM_SDIV(n, (int64_t)8);
+        const int64_t cap = (int64_t)num_sms() * 8;
+        if (blocks > cap) blocks = cap;
+        const int rows = (int)align_up(maxQ, 16);
+#define HRM_LAUNCH_A(RR)                                                                                        \
+    do {                                                                                                        \
+        auto kern = sw_passes_kernel<RR, Src>;                                                                  \
+        if (smemA > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA); \
+        HRM_LAUNCH(kern, (unsigned)blocks, 256, smemA, s, src, n, QP, RP, d_out, out_stride, out_offset);       \
+    } while (0)
+        if (rows <= 128) HRM_LAUNCH_A(4);
+        else if (rows <= 160) HRM_LAUNCH_A(5);
+        else if (rows <= 256) HRM_LAUNCH_A(8);
+        else if (rows <= 512) HRM_LAUNCH_A(16);
+        else {
+            set_error("query longer than 512 bases");
+            return HRM_ERR_INVALID;
+        }
+#undef HRM_LAUNCH_A
+    }
+    // kernel B
+    {
+        TracePool P = trace_pool_layout(maxQ > 16 ? maxQ : 16, maxR > 16 ? maxR : 16);
+        int slice = (int)align_up(QP + RP, 4) + 4; // odd number of words: conflict-free private slices
+        if (((slice / 4) & 1) == 0) slice += 4;
+        int threads = 128;
+        while ((size_t)slice * threads > 200 * 1024 && threads > 32) threads >>= 1;
+        const size_t smemB = (size_t)slice * threads;
+        const int64_t budget = 6LL << 30;
+        int64_t slots = (int64_t)num_sms() * threads * 4;
+        if (slots > n) slots = n;
+        if (slots * P.per_thread > budget) slots = budget / P.per_thread;
+        if (slots < threads) slots = threads;
+        const int blocks = (int)HRM_SDIV(slots, (int64_t)threads);
+        slots = (int64_t)blocks * threads;
+        Scratch mem;
+        HRM_TRY(mem.alloc((size_t)(slots * P.per_thread), s));
+        P.base = mem.as<unsigned char>();
+        auto kern = sw_finish_kernel<Src>;
+        if (smemB > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
+        HRM_LAUNCH(kern, blocks, threads, smemB, s, src, n, slice, QP, P, d_out, out_stride, out_offset, d_cigars,
+                   cigar_pitch);
+    }
+    return HRM_OK;
+}
+
+__global__ void __launch_bounds__(256) scatter_alignments_kernel(const hrm_alignment* __restrict__ al,
+                                                                 hrm_read_record* __restrict__ records, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * n; t += stride)
+        records[t >> 1].alignments[t & 1] = al[t];
+}
+
+hrm_status scatter_alignments(const hrm_alignment* al, hrm_read_record* records, int64_t n, cudaStream_t s)
+{
+    int64_t blocks = HRM_SDIV(2 * n, (int64_t)256);
+    if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+    HRM_LAUNCH(scatter_alignments_kernel, (unsigned)blocks, 256, 0, s, al, records, n);
     return HRM_OK;
 }
 
@@ -231,11 +498,32 @@ hrm_status verify_reads(const VerifyParams& VP, const int32_t* d_read_len, int64
                         cudaStream_t s)
 {
     if (n == 0) return HRM_OK;
-    SwPool P = sw_pool_layout(max_read_len > 16 ? max_read_len : 16, VP.w);
-    Scratch mem;
-    int blocks = 1;
-    HRM_TRY(sw_pool_make(P, 2 * n, mem, blocks, s));
-    HRM_LAUNCH(verify_kernel, blocks, 128, 0, s, VP, d_read_len, n, d_mapped, P, d_records, d_cigars, cigar_pitch);
+    int64_t hb = HRM_SDIV(n, (int64_t)256);
+    if (hb > (int64_t)num_sms() * 16) hb = (int64_t)num_sms() * 16;
+    HRM_LAUNCH(record_header_kernel, (unsigned)hb, 256, 0, s, VP, d_read_len, d_mapped, n, d_records);
+    PackedSrc src;
+    src.VP = VP;
+    src.read_len = d_read_len;
+    src.mapped = d_mapped;
+    src.maxQ = max_read_len > 16 ? max_read_len : 16;
+    src.maxR = VP.w;
+    if (VP.mapper_type == HRM_MAPPER_SW) {
+        // run the two alignments of every read as consecutive items into a dense temporary, then scatter
+        Scratch tmp;
+        HRM_TRY(tmp.alloc(sizeof(hrm_alignment) * (size_t)(2 * n), s));
+        HRM_TRY(run_sw(src, 2 * n, src.maxQ, src.maxR, tmp.as<hrm_alignment>(), 1, 0, d_cigars, cigar_pitch, s));
+        HRM_TRY(scatter_alignments(tmp.as<hrm_alignment>(), d_records, n, s));
+    } else {
+        const int QP = (int)align_up(src.maxQ, 16), RP = (int)align_up(src.maxR > 16 ? src.maxR : 16, 16);
+        int slice = (int)align_up(QP + RP, 4) + 4;
+        if (((slice / 4) & 1) == 0) slice += 4;
+        const size_t smem = (size_t)slice * 128;
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(edit_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int64_t blocks = HRM_SDIV(2 * n, (int64_t)128);
+        if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
+        HRM_LAUNCH(edit_packed_kernel, (unsigned)blocks, 128, smem, s, src, n, slice, QP, d_records);
+    }
     return HRM_OK;
 }
 
@@ -250,18 +538,18 @@ extern "C" hrm_status hrm_sw_align(const char* d_queries, int64_t query_pitch, c
 {
     HRM_TRY(ensure_device());
     HRM_REQUIRE(n >= 0 && query_pitch > 0 && ref_pitch > 0 && cigar_pitch > 0, "sizes");
-    HRM_REQUIRE(query_pitch <= HRM_SW_MAX_QUERY + 16 && ref_pitch <= HRM_SW_MAX_REF + 16,
-                "pitch exceeds HRM_SW_MAX_QUERY / HRM_SW_MAX_REF");
     if (n == 0) return HRM_OK;
-    cudaStream_t s = as_stream(stream);
-    SwPool P = sw_pool_layout((int)(query_pitch < HRM_SW_MAX_QUERY ? query_pitch : HRM_SW_MAX_QUERY),
-                              (int)(ref_pitch < HRM_SW_MAX_REF ? ref_pitch : HRM_SW_MAX_REF));
-    Scratch mem;
-    int blocks = 1;
-    HRM_TRY(sw_pool_make(P, n, mem, blocks, s));
-    HRM_LAUNCH(sw_rows_kernel, blocks, 128, 0, s, d_queries, query_pitch, d_query_len, d_refs, ref_pitch, d_ref_len,
-               d_mask_len, n, P, d_out, d_cigars, cigar_pitch);
-    return HRM_OK;
+    AsciiSrc src;
+    src.queries = d_queries;
+    src.qpitch = query_pitch;
+    src.qlen = d_query_len;
+    src.refs = d_refs;
+    src.rpitch = ref_pitch;
+    src.rlen = d_ref_len;
+    src.mask_len = d_mask_len;
+    src.maxQ = (int)(query_pitch < HRM_SW_MAX_QUERY ? query_pitch : HRM_SW_MAX_QUERY);
+    src.maxR = (int)(ref_pitch < HRM_SW_MAX_REF ? ref_pitch : HRM_SW_MAX_REF);
+    return run_sw(src, n, src.maxQ, src.maxR, d_out, 1, 0, d_cigars, cigar_pitch, as_stream(stream));
 }
 
 extern "C" hrm_status hrm_edit_distance(const char* d_queries, int64_t query_pitch, const int32_t* d_query_len,

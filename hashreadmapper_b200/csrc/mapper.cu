@@ -232,6 +232,12 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
         return HRM_OK;
     }
     const int H = cfg.num_tables;
+    if (h_stats) // slot-touch counters are reported per call
+        for (int c = 0; c < 3; c++)
+            if (m->index[c]) {
+                HRM_CUDA(cudaMemsetAsync(m->index[c]->d_touches, 0, sizeof(unsigned long long), s));
+                m->touches_seen[c] = 0;
+            }
     StageTimer& T = m->timer;
     T.begin(HRM_STAGE_PACK, s);
     HRM_TRY(pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
