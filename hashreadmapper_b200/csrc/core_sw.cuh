@@ -138,6 +138,9 @@ HRM_HD int sw_dir_code(uint8_t cell, int state)
     return (cell & 16) ? 5 : 4;
 }
 
+HRM_HD int sw_traceback(const uint8_t* dir, int width_d, int band_width, int refLen, int readLen, char* ops,
+                        int32_t* lens, int maxops);
+
 // banded_sw.  ref/read point at the sub-sequences.  hb/eb/hc: 2*len+16 ints each where
 // len = max(refLen, readLen); dir: dir_cap bytes.  ops/lens: cigar out (op chars M/I/D), capacity
 // maxops.  Returns number of ops, -1 if the trace back fails (reference: flag 1), -2 if scratch
@@ -146,7 +149,7 @@ HRM_HD int sw_banded(const int8_t* ref, const int8_t* read, int refLen, int read
                      int band_width, int32_t* h_b, int32_t* e_b, int32_t* h_c, uint8_t* dir, int64_t dir_cap,
                      char* ops, int32_t* lens, int maxops)
 {
-    int i, j, e, f, temp1, temp2, l, max = 0;
+    int i, j, f, temp1, temp2, max = 0;
     const int len = refLen > readLen ? refLen : readLen;
     int width, width_d;
     do {
@@ -199,11 +202,18 @@ HRM_HD int sw_banded(const int8_t* ref, const int8_t* read, int refLen, int read
         band_width *= 2;
     } while (max < score && band_width <= len);
     band_width /= 2;
+    return sw_traceback(dir, width_d, band_width, refLen, readLen, ops, lens, maxops);
+}
 
-    i = readLen - 1;
-    j = refLen - 1;
-    e = 0;
-    l = 0;
+// trace back through the direction bytes of the last band iteration (ref: ssw.c:675-764).
+// Returns the number of cigar ops (op chars M/I/D, in alignment order) or -1 on failure.
+HRM_HD int sw_traceback(const uint8_t* dir, int width_d, int band_width, int refLen, int readLen, char* ops,
+                        int32_t* lens, int maxops)
+{
+    int i = readLen - 1;
+    int j = refLen - 1;
+    int e = 0;
+    int l = 0;
     char op = 'M', prev_op = 'M';
     int state = 2;
     while (i >= 0 && j > 0) {
@@ -289,6 +299,8 @@ struct SwScratch {
 
 HRM_HD void sw_finish(const int8_t* q, int qlen, const int8_t* r, const SwScratch& S, SwAlignment* al, char* cigar,
                       int cigar_cap);
+HRM_HD void sw_emit_cigar(const int8_t* q, int qlen, const int8_t* r, SwAlignment* al, const char* ops,
+                          const int32_t* lens, int nops, char* cigar, int cigar_cap);
 
 // Whole Align().  q/r: translated codes.  cigar: cap bytes (no NUL needed).
 HRM_HD void sw_align(const int8_t* q, int qlen, const int8_t* r, int rlen, int maskLen, const SwScratch& S,
@@ -347,7 +359,14 @@ HRM_HD void sw_finish(const int8_t* q, int qlen, const int8_t* r, const SwScratc
         }
     }
     al->flag = flag;
-    // ConvertAlignment + CalculateNumberMismatch
+    sw_emit_cigar(q, qlen, r, al, S.ops, S.lens, nops, cigar, cigar_cap);
+}
+
+// ConvertAlignment + CalculateNumberMismatch (ref: ssw_cpp.cpp:54-90, :126-210): S / = / X / I / D string
+HRM_HD void sw_emit_cigar(const int8_t* q, int qlen, const int8_t* r, SwAlignment* al, const char* ops,
+                          const int32_t* lens, int nops, char* cigar, int cigar_cap)
+{
+    const int read_end1 = al->query_end, ref_begin1 = al->ref_begin, read_begin1 = al->query_begin;
     int pos = 0, mism = 0;
     if (read_begin1 > 0) pos = sw_append(cigar, pos, cigar_cap, read_begin1, 'S');
     const int8_t* rp = r + ref_begin1;
@@ -355,8 +374,8 @@ HRM_HD void sw_finish(const int8_t* q, int qlen, const int8_t* r, const SwScratc
     bool in_M = false, in_X = false;
     int length_M = 0, length_X = 0;
     for (int c = 0; c < nops; c++) {
-        const char op = S.ops[c];
-        const int length = S.lens[c];
+        const char op = ops[c];
+        const int length = lens[c];
         if (op == 'M') {
             for (int t = 0; t < length; t++) {
                 if (*rp != *qp) {

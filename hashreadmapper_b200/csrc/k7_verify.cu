@@ -273,89 +273,182 @@ __global__ void __launch_bounds__(256) sw_passes_kernel(Src src, int64_t n, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel B: banded trace back + CIGAR, one thread per alignment
+// kernel B: banded trace back + CIGAR, one WARP per alignment
 // ------------------------------------------------------------------------------------------------
+// The reference's banded_sw (ssw.c:590-774) walks the band cell by cell.  Its F recurrence
+//   f(j) = max(h_c(j-1) - gapO, f(j-1) - gapE),  df(j) = (h_c(j-1) - gapO > f(j-1) - gapE) ? 5 : 4
+// does not change -- value and direction code alike -- when h_c(j-1) = max(H'(j-1), max(f(j-1),0)) is
+// replaced by H'(j-1) = max(E+, diagonal): where f dominates, opening from it (f - gapO) loses to
+// extending it (f - gapE).  With g(j) = f(j) + j the recurrence becomes a prefix maximum of
+// a(j) = H'(j-1) - gapO + j, so the lanes of a warp evaluate up to 32 band cells of a row at once and
+// combine them with a shuffle scan; E and the diagonal come from the previous row kept in shared
+// memory with the reference's own band-relative indexing (including its band-edge zeroing).
 struct TracePool {
-    unsigned char* base;
-    int64_t per_thread;
-    int maxLen, maxops;
-    int64_t dir_cap;
+    unsigned char* base; // global: direction bytes, one slice per resident warp
+    int64_t per_warp;
+    int wmax;            // ints per h_b / e_b / h_c array
+    int maxops;
 };
 
-static TracePool trace_pool_layout(int maxQ, int maxR)
+__device__ __forceinline__ int warp_banded(const int8_t* ref, const int8_t* read, int refLen, int readLen, int score,
+                                           int32_t* hb, int32_t* eb, int32_t* hc, uint8_t* dir, int64_t dir_cap,
+                                           int lane, int& out_band, int& out_width_d)
 {
-    TracePool P;
-    P.base = nullptr;
-    P.maxLen = maxQ > maxR ? maxQ : maxR;
-    P.maxops = 2 * P.maxLen + 8;
-    P.dir_cap = (int64_t)(2 * P.maxLen + 1) * maxQ;
-    int64_t b = 0;
-    b += align_up((int64_t)sizeof(int32_t) * (2 * P.maxLen + 32), 16) * 3;
-    b += align_up(P.dir_cap + 16, 16);
-    b += align_up(P.maxops, 16);
-    b += align_up((int64_t)sizeof(int32_t) * P.maxops, 16);
-    P.per_thread = b;
-    return P;
-}
-
-__device__ __forceinline__ void trace_pool_carve(const TracePool& P, int64_t slot, SwScratch& S)
-{
-    unsigned char* p = P.base + slot * P.per_thread;
-    S.H = nullptr;
-    S.E = nullptr;
-    S.maxColumn = nullptr;
-    S.hb = (int32_t*)p;
-    p += align_up((int64_t)sizeof(int32_t) * (2 * P.maxLen + 32), 16);
-    S.eb = (int32_t*)p;
-    p += align_up((int64_t)sizeof(int32_t) * (2 * P.maxLen + 32), 16);
-    S.hc = (int32_t*)p;
-    p += align_up((int64_t)sizeof(int32_t) * (2 * P.maxLen + 32), 16);
-    S.dir = (uint8_t*)p;
-    S.dir_cap = P.dir_cap;
-    p += align_up(P.dir_cap + 16, 16);
-    S.ops = (char*)p;
-    p += align_up(P.maxops, 16);
-    S.lens = (int32_t*)p;
-    S.maxops = P.maxops;
+    const unsigned FULL = 0xffffffffu;
+    const int NEG = -(1 << 28);
+    int band = refLen - readLen;
+    band = (band < 0 ? -band : band) + 1;
+    const int len = refLen > readLen ? refLen : readLen;
+    int maxv = 0, width = 0, width_d = 0;
+    do {
+        width = band * 2 + 3;
+        width_d = band * 2 + 1;
+        if ((int64_t)width_d * readLen > dir_cap) return -2;
+        for (int j = lane; j < width + 8; j += 32) {
+            hb[j] = 0;
+            eb[j] = 0;
+            hc[j] = 0;
+        }
+        __syncwarp();
+        int lmax = 0;
+        for (int i = 0; i < readLen; i++) {
+            const int beg = (i - band) > 0 ? (i - band) : 0;
+            const int end = (i + band) < (refLen - 1) ? (i + band) : (refLen - 1);
+            const int edge = end + 1 < width - 1 ? end + 1 : width - 1;
+            if (lane == 0) { // ref: ssw.c:635
+                hb[0] = 0;
+                eb[0] = 0;
+                hb[edge] = 0;
+                eb[edge] = 0;
+                hc[0] = 0;
+            }
+            __syncwarp();
+            const int xi = beg; // max(i - band, 0)
+            const int xp = (i - 1 - band) > 0 ? (i - 1 - band) : 0;
+            uint8_t* line = dir + (int64_t)width_d * i;
+            const int ri = read[i];
+            int carry_g = beg - 1; // g(beg-1) = f_init + beg - 1 with f_init = 0
+            int carry_H = 0;       // h_c[0]
+            const int ncell = end - beg + 1;
+            for (int c0 = 0; c0 < ncell; c0 += 32) {
+                const int j = beg + c0 + lane;
+                const bool act = j <= end;
+                const int u = j - xi + 1;
+                int e = 0, de = 2, e1 = 0, diagv = 0, Hq = 0;
+                if (act) {
+                    const int ue = j - xp + 1, ud = j - xp;
+                    const int t1 = i == 0 ? -HRM_SW_GAPO : hb[ue] - HRM_SW_GAPO;
+                    const int t2 = i == 0 ? -HRM_SW_GAPE : eb[ue] - HRM_SW_GAPE;
+                    e = t1 > t2 ? t1 : t2;
+                    de = t1 > t2 ? 3 : 2;
+                    e1 = e > 0 ? e : 0;
+                    diagv = hb[ud] + sw_score(ref[j], ri);
+                    Hq = e1 > diagv ? e1 : diagv;
+                }
+                int Hleft = __shfl_up_sync(FULL, Hq, 1);
+                if (lane == 0) Hleft = carry_H;
+                const int a = act ? Hleft - HRM_SW_GAPO + j : NEG;
+                int incl = a;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl = incl > o ? incl : o;
+                }
+                int prevIncl = __shfl_up_sync(FULL, incl, 1);
+                if (lane == 0) prevIncl = NEG;
+                const int gprev = carry_g > prevIncl ? carry_g : prevIncl;
+                const int g = carry_g > incl ? carry_g : incl;
+                const int f = g - j;
+                const int df = a > gprev ? 5 : 4;
+                const int f1 = f > 0 ? f : 0;
+                const int temp1 = e1 > f1 ? e1 : f1;
+                const int h = temp1 > diagv ? temp1 : diagv;
+                const int dh = temp1 <= diagv ? 1 : (e1 > f1 ? de : df);
+                __syncwarp(); // every lane has read the previous row before anyone overwrites e_b
+                if (act) {
+                    eb[u] = e;
+                    hc[u] = h;
+                    line[j - xi] = (uint8_t)(0x80 | dh | (de == 3 ? 8 : 0) | (df == 5 ? 16 : 0));
+                    lmax = h > lmax ? h : lmax;
+                }
+                const int last = (ncell - 1 - c0) < 31 ? (ncell - 1 - c0) : 31;
+                carry_g = __shfl_sync(FULL, g, last);
+                carry_H = __shfl_sync(FULL, Hq, last);
+                __syncwarp();
+            }
+            for (int x = ncell + lane; x < width_d; x += 32) line[x] = 0; // cells outside the band: not written
+            const int ulast = end - xi + 1;
+            for (int j = 1 + lane; j <= ulast; j += 32) hb[j] = hc[j]; // ref: ssw.c:669
+            __syncwarp();
+        }
+        lmax = __reduce_max_sync(FULL, lmax);
+        maxv = lmax > maxv ? lmax : maxv;
+        band *= 2;
+    } while (maxv < score && band <= len);
+    band /= 2;
+    out_band = band;
+    out_width_d = width_d;
+    return 0;
 }
 
 template <class Src>
-__global__ void __launch_bounds__(128) sw_finish_kernel(Src src, int64_t n, int slice_bytes, int QP, TracePool P,
-                                                        hrm_alignment* __restrict__ out, int64_t out_stride_items,
-                                                        int64_t out_offset_items, char* __restrict__ cigars,
+__global__ void __launch_bounds__(256) sw_finish_kernel(Src src, int64_t n, int QP, int RP, TracePool P,
+                                                        hrm_alignment* __restrict__ out, char* __restrict__ cigars,
                                                         int64_t cigar_pitch)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    int8_t* q = (int8_t*)(smem + (size_t)slice_bytes * threadIdx.x);
-    int8_t* r = q + QP;
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nslots = (int64_t)gridDim.x * blockDim.x;
-    SwScratch S;
-    trace_pool_carve(P, slot, S);
-    for (int64_t e = slot; e < n; e += nslots) {
-        hrm_alignment* po = out + out_offset_items + e * out_stride_items;
-        hrm_alignment o = *po;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t per_warp = (size_t)QP + RP + 3 * sizeof(int32_t) * (size_t)P.wmax +
+                            align_up(P.maxops, 16) + sizeof(int32_t) * (size_t)P.maxops;
+    unsigned char* base = smem + align_up((int64_t)per_warp, 16) * wid;
+    int8_t* sq = (int8_t*)base;
+    int8_t* sr = sq + QP;
+    int32_t* hb = (int32_t*)(sr + RP);
+    int32_t* eb = hb + P.wmax;
+    int32_t* hc = eb + P.wmax;
+    char* ops = (char*)(hc + P.wmax);
+    int32_t* lens = (int32_t*)(ops + align_up(P.maxops, 16));
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    uint8_t* dir = P.base + warp0 * P.per_warp;
+    for (int64_t e = warp0; e < n; e += nwarps) {
+        hrm_alignment o = out[e];
         char* cig = cigars + e * cigar_pitch;
         int ql, rl, ml;
-        if (o.flag != 1 && o.sw_score > 0 && o.ref_begin >= 0 && src.load(e, q, r, 0, 1, ql, rl, ml)) {
-            SwAlignment al;
-            al.sw_score = o.sw_score;
-            al.sw_score_next_best = o.sw_score_next_best;
-            al.ref_begin = o.ref_begin;
-            al.ref_end = o.ref_end;
-            al.query_begin = o.query_begin;
-            al.query_end = o.query_end;
-            al.ref_end_next_best = o.ref_end_next_best;
-            al.mismatches = 0;
-            al.flag = o.flag;
-            al.cigar_len = 0;
-            sw_finish(q, ql, r, S, &al, cig, (int)cigar_pitch);
-            o.mismatches = al.mismatches;
-            o.flag = al.flag;
-            o.cigar_len = al.cigar_len;
-            *po = o;
+        __syncwarp();
+        if (o.flag != 1 && o.sw_score > 0 && o.ref_begin >= 0 && src.load(e, sq, sr, lane, 32, ql, rl, ml)) {
+            __syncwarp();
+            const int refLen = o.ref_end - o.ref_begin + 1, readLen = o.query_end - o.query_begin + 1;
+            int band = 0, width_d = 0, nops = 0, flag = o.flag;
+            const int rc = warp_banded(sr + o.ref_begin, sq + o.query_begin, refLen, readLen, o.sw_score, hb, eb, hc, dir,
+                                       P.per_warp, lane, band, width_d);
+            __syncwarp();
+            if (lane == 0) {
+                SwAlignment al;
+                al.sw_score = o.sw_score;
+                al.sw_score_next_best = o.sw_score_next_best;
+                al.ref_begin = o.ref_begin;
+                al.ref_end = o.ref_end;
+                al.query_begin = o.query_begin;
+                al.query_end = o.query_end;
+                al.ref_end_next_best = o.ref_end_next_best;
+                al.mismatches = 0;
+                al.cigar_len = 0;
+                if (rc == 0) nops = sw_traceback(dir, width_d, band, refLen, readLen, ops, lens, P.maxops);
+                else nops = -1;
+                if (nops < 0) { // ref: banded_sw failed -> flag 1, empty path (ssw.c:910)
+                    flag = 1;
+                    nops = 0;
+                }
+                al.flag = flag;
+                sw_emit_cigar(sq, ql, sr, &al, ops, lens, nops, cig, (int)cigar_pitch);
+                o.mismatches = al.mismatches;
+                o.flag = al.flag;
+                o.cigar_len = al.cigar_len;
+                out[e] = o;
+            }
         }
-        if (o.cigar_len < cigar_pitch) cig[o.cigar_len] = 0;
+        if (lane == 0 && o.cigar_len < cigar_pitch) cig[o.cigar_len] = 0;
     }
 }
 
@@ -453,26 +546,25 @@ static hrm_status run_sw(const Src& src, int64_t n, int maxQ, int maxR, hrm_alig
     }
     // kernel B
     {
-        TracePool P = trace_pool_layout(maxQ > 16 ? maxQ : 16, maxR > 16 ? maxR : 16);
-        int slice = (int)align_up(QP + RP, 4) + 4; // odd number of words: conflict-free private slices
-        if (((slice / 4) & 1) == 0) slice += 4;
-        int threads = 128;
-        while ((size_t)slice * threads > 200 * 1024 && threads > 32) threads >>= 1;
-        const size_t smemB = (size_t)slice * threads;
-        const int64_t budget = 6LL << 30;
-        int64_t slots = (int64_t)num_sms() * threads * 4;
-        if (slots > n) slots = n;
-        if (slots * P.per_thread > budget) slots = budget / P.per_thread;
-        if (slots < threads) slots = threads;
-        const int blocks = (int)HRM_SDIV(slots, (int64_t)threads);
-        slots = (int64_t)blocks * threads;
+        const int maxLen = (maxQ > maxR ? maxQ : maxR) > 16 ? (maxQ > maxR ? maxQ : maxR) : 16;
+        TracePool P;
+        P.wmax = (int)align_up(2 * maxLen + 3 + 8 + 1, 4);
+        P.maxops = 2 * maxLen + 8;
+        P.per_warp = align_up((int64_t)(2 * maxLen + 1) * (maxQ > 16 ? maxQ : 16) + 16, 256);
+        const size_t per_warp = (size_t)align_up((int64_t)((size_t)QP + RP + 3 * sizeof(int32_t) * (size_t)P.wmax +
+                                                        align_up(P.maxops, 16) + sizeof(int32_t) * (size_t)P.maxops), 16);
+        int warps = 8;
+        while (per_warp * warps > 200 * 1024 && warps > 1) warps >>= 1;
+        const size_t smemB = per_warp * warps;
+        int64_t blocks = HRM_SDIV(n, (int64_t)warps);
+        const int64_t cap = (int64_t)num_sms() * 8;
+        if (blocks > cap) blocks = cap;
         Scratch mem;
-        HRM_TRY(mem.alloc((size_t)(slots * P.per_thread), s));
+        HRM_TRY(mem.alloc((size_t)(blocks * warps * P.per_warp), s));
         P.base = mem.as<unsigned char>();
         auto kern = sw_finish_kernel<Src>;
         if (smemB > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
-        HRM_LAUNCH(kern, blocks, threads, smemB, s, src, n, slice, QP, P, d_out, out_stride, out_offset, d_cigars,
-                   cigar_pitch);
+        HRM_LAUNCH(kern, (unsigned)blocks, warps * 32, smemB, s, src, n, QP, RP, P, d_out, d_cigars, cigar_pitch);
     }
     return HRM_OK;
 }
