@@ -145,60 +145,72 @@ HRM_HD int sw_traceback(const uint8_t* dir, int width_d, int band_width, int ref
 // len = max(refLen, readLen); dir: dir_cap bytes.  ops/lens: cigar out (op chars M/I/D), capacity
 // maxops.  Returns number of ops, -1 if the trace back fails (reference: flag 1), -2 if scratch
 // is too small (caller sizes it so that this cannot happen).
+// one band iteration of banded_sw (ref: ssw.c:614-670): fills dir (width_d * readLen direction bytes) and
+// returns the maximum H seen.  hb/eb/hc need width + 8 = 2*band_width + 11 ints.
+HRM_HD int sw_banded_once(const int8_t* ref, const int8_t* read, int refLen, int readLen, int band_width,
+                          int32_t* h_b, int32_t* e_b, int32_t* h_c, uint8_t* dir)
+{
+    int i, j, f, temp1, temp2, max = 0;
+    const int width = band_width * 2 + 3;
+    const int width_d = band_width * 2 + 1;
+    for (int64_t t = 0; t < (int64_t)width_d * readLen; t++) dir[t] = 0;
+    for (j = 0; j < width + 8; j++) {
+        h_b[j] = 0;
+        e_b[j] = 0;
+        h_c[j] = 0;
+    }
+    for (i = 0; i < readLen; i++) {
+        int beg = 0, end = refLen - 1, u = 0, edge;
+        j = i - band_width;
+        beg = beg > j ? beg : j;
+        j = i + band_width;
+        end = end < j ? end : j;
+        edge = end + 1 < width - 1 ? end + 1 : width - 1;
+        f = h_b[0] = e_b[0] = h_b[edge] = e_b[edge] = h_c[0] = 0;
+        uint8_t* line = dir + (int64_t)width_d * i;
+        const int xi = (i - band_width) > 0 ? (i - band_width) : 0;
+        const int xp = (i - 1 - band_width) > 0 ? (i - 1 - band_width) : 0;
+        for (j = beg; j <= end; j++) {
+            u = j - xi + 1;
+            const int ue = j - xp + 1;     // (i-1, j)
+            const int ub = j - 1 - xi + 1; // (i, j-1)
+            const int ud = j - 1 - xp + 1; // (i-1, j-1)
+            temp1 = i == 0 ? -HRM_SW_GAPO : h_b[ue] - HRM_SW_GAPO;
+            temp2 = i == 0 ? -HRM_SW_GAPE : e_b[ue] - HRM_SW_GAPE;
+            e_b[u] = temp1 > temp2 ? temp1 : temp2;
+            const int de = temp1 > temp2 ? 3 : 2;
+            temp1 = h_c[ub] - HRM_SW_GAPO;
+            temp2 = f - HRM_SW_GAPE;
+            f = temp1 > temp2 ? temp1 : temp2;
+            const int df = temp1 > temp2 ? 5 : 4;
+            const int e1 = e_b[u] > 0 ? e_b[u] : 0;
+            const int f1 = f > 0 ? f : 0;
+            temp1 = e1 > f1 ? e1 : f1;
+            temp2 = h_b[ud] + sw_score(ref[j], read[i]);
+            h_c[u] = temp1 > temp2 ? temp1 : temp2;
+            if (h_c[u] > max) max = h_c[u];
+            int dh;
+            if (temp1 <= temp2) dh = 1;
+            else dh = e1 > f1 ? de : df;
+            line[j - xi] = (uint8_t)(0x80 | dh | (de == 3 ? 8 : 0) | (df == 5 ? 16 : 0));
+        }
+        for (j = 1; j <= u; j++) h_b[j] = h_c[j];
+    }
+    return max;
+}
+
 HRM_HD int sw_banded(const int8_t* ref, const int8_t* read, int refLen, int readLen, int score,
                      int band_width, int32_t* h_b, int32_t* e_b, int32_t* h_c, uint8_t* dir, int64_t dir_cap,
                      char* ops, int32_t* lens, int maxops)
 {
-    int i, j, f, temp1, temp2, max = 0;
+    int max = 0;
     const int len = refLen > readLen ? refLen : readLen;
-    int width, width_d;
+    int width_d;
     do {
-        width = band_width * 2 + 3;
         width_d = band_width * 2 + 1;
         if ((int64_t)width_d * readLen > dir_cap) return -2;
-        for (int64_t t = 0; t < (int64_t)width_d * readLen; t++) dir[t] = 0;
-        for (j = 0; j < width + 8; j++) {
-            h_b[j] = 0;
-            e_b[j] = 0;
-            h_c[j] = 0;
-        }
-        for (i = 0; i < readLen; i++) {
-            int beg = 0, end = refLen - 1, u = 0, edge;
-            j = i - band_width;
-            beg = beg > j ? beg : j;
-            j = i + band_width;
-            end = end < j ? end : j;
-            edge = end + 1 < width - 1 ? end + 1 : width - 1;
-            f = h_b[0] = e_b[0] = h_b[edge] = e_b[edge] = h_c[0] = 0;
-            uint8_t* line = dir + (int64_t)width_d * i;
-            const int xi = (i - band_width) > 0 ? (i - band_width) : 0;
-            const int xp = (i - 1 - band_width) > 0 ? (i - 1 - band_width) : 0;
-            for (j = beg; j <= end; j++) {
-                u = j - xi + 1;
-                const int ue = j - xp + 1;     // (i-1, j)
-                const int ub = j - 1 - xi + 1; // (i, j-1)
-                const int ud = j - 1 - xp + 1; // (i-1, j-1)
-                temp1 = i == 0 ? -HRM_SW_GAPO : h_b[ue] - HRM_SW_GAPO;
-                temp2 = i == 0 ? -HRM_SW_GAPE : e_b[ue] - HRM_SW_GAPE;
-                e_b[u] = temp1 > temp2 ? temp1 : temp2;
-                const int de = temp1 > temp2 ? 3 : 2;
-                temp1 = h_c[ub] - HRM_SW_GAPO;
-                temp2 = f - HRM_SW_GAPE;
-                f = temp1 > temp2 ? temp1 : temp2;
-                const int df = temp1 > temp2 ? 5 : 4;
-                const int e1 = e_b[u] > 0 ? e_b[u] : 0;
-                const int f1 = f > 0 ? f : 0;
-                temp1 = e1 > f1 ? e1 : f1;
-                temp2 = h_b[ud] + sw_score(ref[j], read[i]);
-                h_c[u] = temp1 > temp2 ? temp1 : temp2;
-                if (h_c[u] > max) max = h_c[u];
-                int dh;
-                if (temp1 <= temp2) dh = 1;
-                else dh = e1 > f1 ? de : df;
-                line[j - xi] = (uint8_t)(0x80 | dh | (de == 3 ? 8 : 0) | (df == 5 ? 16 : 0));
-            }
-            for (j = 1; j <= u; j++) h_b[j] = h_c[j];
-        }
+        const int m = sw_banded_once(ref, read, refLen, readLen, band_width, h_b, e_b, h_c, dir);
+        if (m > max) max = m; // ref: `max` persists across band doublings (ssw.c:600)
         band_width *= 2;
     } while (max < score && band_width <= len);
     band_width /= 2;

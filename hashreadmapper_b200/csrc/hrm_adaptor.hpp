@@ -1,0 +1,148 @@
+// hrm_adaptor.hpp -- the reference-side binding: a C++ class that derives from the reference's abstract
+// care::gpu::GpuMinhasher (include/gpu/gpuminhasher.cuh:20-110) and forwards every virtual to the C ABI
+// of libhrm_b200.so.  Drop this header next to the reference's sources, compile it with the reference
+// (nvcc, -I<reference>/include, rmm on the include path as in the reference's Makefile:23-31), link
+// -lhrm_b200, and construct B200Minhasher where constructGpuMinhasherFromGpuReadStorage
+// (src/gpu/gpuminhasherconstruction.cu:256-330) constructs FakeGpuMinhasher / SingleGpuMinhasher.
+// Nothing else of the reference changes: WindowBatchProcessor (src/gpu/main_gpu.cu:431-856) holds the
+// minhasher through `const GpuMinhasher*` and keeps calling determineNumValues / retrieveValues.
+//
+// Error behaviour mirrors CUDACHECK (include/gpu/cudaerrorcheck.cuh:42-58): a non-zero hrm_status is
+// re-thrown as std::runtime_error carrying hrm_last_error().
+//
+// tests/test_host_logic.py::test_adaptor_compiles_against_reference compiles this header against the
+// reference's own headers when /root/reference is present.
+#pragma once
+#include <gpu/gpuminhasher.cuh>   // the reference's interface
+
+#include <fstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "hrm_b200.h"
+
+namespace hrm_b200 {
+
+inline void hrm_check(hrm_status st)
+{
+    if (st != HRM_OK) throw std::runtime_error(std::string("libhrm_b200: ") + hrm_last_error());
+}
+
+class B200Minhasher : public care::gpu::GpuMinhasher {
+public:
+    // ref: FakeGpuMinhasher(int maxNumKeys, int maxValuesPerKey, int k, float loadfactor)
+    //      include/gpu/fakegpuminhasher.cuh:150-153
+    B200Minhasher(int maxNumKeys, int maxValuesPerKey, int k, float loadfactor)
+    {
+        hrm_check(hrm_minhasher_create(&mh_, maxNumKeys, maxValuesPerKey, k, loadfactor));
+    }
+    ~B200Minhasher() override { hrm_minhasher_destroy(mh_); }
+    B200Minhasher(const B200Minhasher&) = delete;
+    B200Minhasher& operator=(const B200Minhasher&) = delete;
+
+    care::MinhasherHandle makeMinhasherHandle() const override
+    {
+        const int id = hrm_minhasher_handle_create(mh_);
+        if (id < 0) hrm_check(id);
+        return constructHandle(id);
+    }
+    void destroyHandle(care::MinhasherHandle& handle) const override
+    {
+        hrm_check(hrm_minhasher_handle_destroy(mh_, handle.getId()));
+        handle = constructHandle(std::numeric_limits<int>::max());
+    }
+
+    void setHostMemoryLimitForConstruction(std::size_t) override {}   // tables live on the device
+    void setDeviceMemoryLimitsForConstruction(const std::vector<std::size_t>&) override {}
+    void setThreadPool(care::ThreadPool*) override {}                // no host threads needed
+    int addHashTables(int numAdditionalTables, const int* hashFunctionIds, cudaStream_t stream) override
+    {
+        return hrm_minhasher_add_tables(mh_, numAdditionalTables, hashFunctionIds, stream);
+    }
+    void compact(cudaStream_t stream) override { hrm_check(hrm_minhasher_compact(mh_, stream)); }
+    void constructionIsFinished(cudaStream_t stream) override { hrm_check(hrm_minhasher_finish(mh_, stream)); }
+
+    void insert(const unsigned int* d_sequenceData2Bit, int numSequences, const int* d_sequenceLengths,
+                std::size_t encodedSequencePitchInInts, const read_number* d_readIds, const read_number* /*h_readIds*/,
+                int firstHashfunction, int numHashfunctions, const int* /*h_hashFunctionNumbers*/, cudaStream_t stream,
+                rmm::mr::device_memory_resource* /*mr*/) override
+    {
+        hrm_check(hrm_minhasher_insert(mh_, d_sequenceData2Bit, (int64_t)encodedSequencePitchInInts, d_sequenceLengths,
+                                       numSequences, d_readIds, 0u, firstHashfunction, numHashfunctions, stream));
+    }
+    int checkInsertionErrors(int firstHashfunction, int numHashfunctions, cudaStream_t stream) override
+    {
+        return hrm_minhasher_check_insertion_errors(mh_, firstHashfunction, numHashfunctions, stream);
+    }
+
+    void determineNumValues(care::MinhasherHandle& queryHandle, const unsigned int* d_sequenceData2Bit,
+                            std::size_t encodedSequencePitchInInts, const int* d_sequenceLengths, int numSequences,
+                            int* d_numValuesPerSequence, int& totalNumValues, cudaStream_t stream,
+                            rmm::mr::device_memory_resource* /*mr*/) const override
+    {
+        int64_t total = 0;
+        hrm_check(hrm_minhasher_count(mh_, queryHandle.getId(), d_sequenceData2Bit, (int64_t)encodedSequencePitchInInts,
+                                      d_sequenceLengths, numSequences, d_numValuesPerSequence, &total, stream));
+        totalNumValues = (int)total;
+    }
+    void retrieveValues(care::MinhasherHandle& queryHandle, int numSequences, int totalNumValues, read_number* d_values,
+                        const int* d_numValuesPerSequence, int* d_offsets, cudaStream_t stream,
+                        rmm::mr::device_memory_resource* /*mr*/) const override
+    {
+        hrm_check(hrm_minhasher_retrieve(mh_, queryHandle.getId(), numSequences, totalNumValues, d_values,
+                                         d_numValuesPerSequence, d_offsets, stream));
+    }
+
+    ::MemoryUsage getMemoryInfo() const noexcept override
+    {
+        ::MemoryUsage mu{};
+        hrm_minhasher_info_t info;
+        if (hrm_minhasher_info(mh_, &info) == HRM_OK) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            mu.device[dev] = (std::size_t)info.device_bytes;
+        }
+        return mu;
+    }
+    ::MemoryUsage getMemoryInfo(const care::MinhasherHandle&) const noexcept override { return ::MemoryUsage{}; }
+    int getNumResultsPerMapThreshold() const noexcept override { return info().max_results_per_map; }
+    int getNumberOfMaps() const noexcept override { return info().num_tables; }
+    int getKmerSize() const noexcept override { return info().k; }
+    bool hasGpuTables() const noexcept override { return true; }
+
+    void writeToStream(std::ostream& os) const override
+    {
+        int64_t size = 0;
+        hrm_check(hrm_minhasher_serialize(mh_, nullptr, &size));
+        std::vector<char> buf((std::size_t)size);
+        hrm_check(hrm_minhasher_serialize(mh_, buf.data(), &size));
+        os.write(reinterpret_cast<const char*>(&size), sizeof size);
+        os.write(buf.data(), size);
+    }
+    int loadFromStream(std::ifstream& is, int /*numMapsUpperLimit*/) override
+    {
+        int64_t size = 0;
+        is.read(reinterpret_cast<char*>(&size), sizeof size);
+        std::vector<char> buf((std::size_t)size);
+        is.read(buf.data(), size);
+        hrm_minhasher* fresh = nullptr;
+        hrm_check(hrm_minhasher_deserialize(&fresh, buf.data(), size));
+        hrm_minhasher_destroy(mh_);
+        mh_ = fresh;
+        return info().num_tables;
+    }
+    bool canWriteToStream() const noexcept override { return true; }
+    bool canLoadFromStream() const noexcept override { return true; }
+
+private:
+    hrm_minhasher_info_t info() const noexcept
+    {
+        hrm_minhasher_info_t i{};
+        hrm_minhasher_info(mh_, &i);
+        return i;
+    }
+    hrm_minhasher* mh_ = nullptr;
+};
+
+} // namespace hrm_b200

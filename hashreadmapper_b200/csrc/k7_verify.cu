@@ -391,10 +391,83 @@ __device__ __forceinline__ int warp_banded(const int8_t* ref, const int8_t* read
     return 0;
 }
 
+// ---- B1: narrow bands (|refLen - readLen| + 1 <= BW): one THREAD per alignment, everything on chip -------
+// True alignments of substitution-only reads need band 1 and a single band iteration; their whole banded DP
+// is 3 cells per row.  State: h_b/e_b/h_c in local arrays, direction bytes + codes in a private shared-memory
+// slice.  Anything that needs a wider band, band doubling or a long op list goes to the warp kernel (B2).
+constexpr int SMALL_BW = 1;
+constexpr int SMALL_MAXOPS = 40;
+
 template <class Src>
-__global__ void __launch_bounds__(256) sw_finish_kernel(Src src, int64_t n, int QP, int RP, TracePool P,
-                                                        hrm_alignment* __restrict__ out, char* __restrict__ cigars,
-                                                        int64_t cigar_pitch)
+__global__ void __launch_bounds__(128) sw_finish_small_kernel(Src src, int64_t n, int slice_bytes, int QP, int RP,
+                                                              hrm_alignment* __restrict__ out,
+                                                              char* __restrict__ cigars, int64_t cigar_pitch,
+                                                              int32_t* __restrict__ worklist,
+                                                              int32_t* __restrict__ work_count)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    int8_t* q = (int8_t*)(smem + (size_t)slice_bytes * threadIdx.x);
+    int8_t* r = q + QP;
+    uint8_t* dir = (uint8_t*)(r + RP);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        hrm_alignment o = out[e];
+        char* cig = cigars + e * cigar_pitch;
+        if (o.flag == 1 || o.sw_score <= 0 || o.ref_begin < 0) {
+            if (o.cigar_len < cigar_pitch) cig[o.cigar_len] = 0;
+            continue;
+        }
+        const int refLen = o.ref_end - o.ref_begin + 1, readLen = o.query_end - o.query_begin + 1;
+        int band = refLen - readLen;
+        band = (band < 0 ? -band : band) + 1;
+        bool defer = band > SMALL_BW;
+        int ql = 0, rl = 0, ml = 0;
+        if (!defer) defer = !src.load(e, q, r, 0, 1, ql, rl, ml);
+        if (!defer) {
+            int32_t hb[2 * SMALL_BW + 3 + 8], eb[2 * SMALL_BW + 3 + 8], hc[2 * SMALL_BW + 3 + 8];
+            const int mx = sw_banded_once(r + o.ref_begin, q + o.query_begin, refLen, readLen, band, hb, eb, hc, dir);
+            const int len = refLen > readLen ? refLen : readLen;
+            if (mx < o.sw_score && band * 2 <= len) defer = true; // the reference would double the band
+            if (!defer) {
+                char ops[SMALL_MAXOPS];
+                int32_t lens[SMALL_MAXOPS];
+                int nops = sw_traceback(dir, 2 * band + 1, band, refLen, readLen, ops, lens, SMALL_MAXOPS);
+                if (nops >= SMALL_MAXOPS) defer = true; // may have been truncated: let B2 redo it
+                if (!defer) {
+                    SwAlignment al;
+                    al.sw_score = o.sw_score;
+                    al.sw_score_next_best = o.sw_score_next_best;
+                    al.ref_begin = o.ref_begin;
+                    al.ref_end = o.ref_end;
+                    al.query_begin = o.query_begin;
+                    al.query_end = o.query_end;
+                    al.ref_end_next_best = o.ref_end_next_best;
+                    al.mismatches = 0;
+                    al.cigar_len = 0;
+                    al.flag = o.flag;
+                    if (nops < 0) {
+                        al.flag = 1;
+                        nops = 0;
+                    }
+                    sw_emit_cigar(q, ql, r, &al, ops, lens, nops, cig, (int)cigar_pitch);
+                    o.mismatches = al.mismatches;
+                    o.flag = al.flag;
+                    o.cigar_len = al.cigar_len;
+                    out[e] = o;
+                    if (o.cigar_len < cigar_pitch) cig[o.cigar_len] = 0;
+                }
+            }
+        }
+        if (defer) worklist[atomicAdd(work_count, 1)] = (int32_t)e;
+    }
+}
+
+// ---- B2: everything else, one WARP per alignment (work list written by B1) ---------------------------
+template <class Src>
+__global__ void __launch_bounds__(256) sw_finish_kernel(Src src, const int32_t* __restrict__ worklist,
+                                                        const int32_t* __restrict__ work_count, int QP, int RP,
+                                                        TracePool P, hrm_alignment* __restrict__ out,
+                                                        char* __restrict__ cigars, int64_t cigar_pitch)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -411,7 +484,9 @@ __global__ void __launch_bounds__(256) sw_finish_kernel(Src src, int64_t n, int 
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     uint8_t* dir = P.base + warp0 * P.per_warp;
-    for (int64_t e = warp0; e < n; e += nwarps) {
+    const int64_t nwork = *work_count;
+    for (int64_t wi = warp0; wi < nwork; wi += nwarps) {
+        const int64_t e = worklist[wi];
         hrm_alignment o = out[e];
         char* cig = cigars + e * cigar_pitch;
         int ql, rl, ml;
@@ -544,8 +619,29 @@ static hrm_status run_sw(const Src& src, int64_t n, int maxQ, int maxR, hrm_alig
         }
 #undef HRM_LAUNCH_A
     }
-    // kernel B
+    // kernel B1 (thread per alignment, narrow band) + B2 (warp per alignment, the rest)
     {
+        HRM_REQUIRE(n < (1LL << 31), "too many alignments in one call");
+        Scratch wl;
+        HRM_TRY(wl.alloc(sizeof(int32_t) * ((size_t)n + 1), s));
+        int32_t* work_count = wl.as<int32_t>();
+        int32_t* worklist = wl.as<int32_t>() + 1;
+        HRM_CUDA(cudaMemsetAsync(work_count, 0, sizeof(int32_t), s));
+        {
+            const int maxQq = maxQ > 16 ? maxQ : 16;
+            int slice = (int)align_up(QP + RP + (2 * SMALL_BW + 1) * maxQq, 4) + 4; // odd number of words
+            if (((slice / 4) & 1) == 0) slice += 4;
+            int threads = 128;
+            while ((size_t)slice * threads > 100 * 1024 && threads > 32) threads >>= 1;
+            const size_t smemS = (size_t)slice * threads;
+            int64_t blocks = HRM_SDIV(n, (int64_t)threads);
+            const int64_t cap = (int64_t)num_sms() * 8;
+            if (blocks > cap) blocks = cap;
+            auto kern = sw_finish_small_kernel<Src>;
+            if (smemS > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
+            HRM_LAUNCH(kern, (unsigned)blocks, threads, smemS, s, src, n, slice, QP, RP, d_out, d_cigars, cigar_pitch,
+                       worklist, work_count);
+        }
         const int maxLen = (maxQ > maxR ? maxQ : maxR) > 16 ? (maxQ > maxR ? maxQ : maxR) : 16;
         TracePool P;
         P.wmax = (int)align_up(2 * maxLen + 3 + 8 + 1, 4);
@@ -556,15 +652,19 @@ static hrm_status run_sw(const Src& src, int64_t n, int maxQ, int maxR, hrm_alig
         int warps = 8;
         while (per_warp * warps > 200 * 1024 && warps > 1) warps >>= 1;
         const size_t smemB = per_warp * warps;
+        int resident = (int)((220 * 1024) / (smemB + 1024));
+        if (resident < 1) resident = 1;
+        if (resident > 8) resident = 8;
         int64_t blocks = HRM_SDIV(n, (int64_t)warps);
-        const int64_t cap = (int64_t)num_sms() * 8;
+        const int64_t cap = (int64_t)num_sms() * resident; // one wave of resident CTAs, each loops over the list
         if (blocks > cap) blocks = cap;
         Scratch mem;
         HRM_TRY(mem.alloc((size_t)(blocks * warps * P.per_warp), s));
         P.base = mem.as<unsigned char>();
         auto kern = sw_finish_kernel<Src>;
         if (smemB > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
-        HRM_LAUNCH(kern, (unsigned)blocks, warps * 32, smemB, s, src, n, QP, RP, P, d_out, d_cigars, cigar_pitch);
+        HRM_LAUNCH(kern, (unsigned)blocks, warps * 32, smemB, s, src, worklist, work_count, QP, RP, P, d_out, d_cigars,
+                   cigar_pitch);
     }
     return HRM_OK;
 }

@@ -202,3 +202,20 @@ def test_sharding_world_size_2_gloo(tmp_path):
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e.decode()
     assert b"OK" in outs[0][0]
+
+
+def test_adaptor_compiles_against_reference(tmp_path):
+    """drop-in proof: B200Minhasher derives from the reference's abstract care::gpu::GpuMinhasher and is
+    instantiable (every pure virtual overridden) -- compiled against the reference's own headers"""
+    R = "/root/reference"
+    if not os.path.isdir(R):
+        pytest.skip("needs /root/reference (build container only)")
+    src = tmp_path / "adapt.cu"
+    src.write_text('#include "hrm_adaptor.hpp"\n'
+                   'care::gpu::GpuMinhasher* make(){ return new hrm_b200::B200Minhasher(1000, 65535, 16, 0.8f); }\n')
+    cmd = ["nvcc", "-std=c++17", "-x", "cu", "-w", "--expt-extended-lambda", "--expt-relaxed-constexpr",
+           "-gencode", "arch=compute_100a,code=sm_100a", "-I" + R + "/dependencies/rmm/include",
+           "-I" + R + "/dependencies/spdlog/include", "-I" + R + "/include", "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "hashreadmapper_b200", "csrc"), "-c", str(src), "-o", str(tmp_path / "adapt.o")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
