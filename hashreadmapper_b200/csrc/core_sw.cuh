@@ -138,22 +138,36 @@ HRM_HD int sw_dir_code(uint8_t cell, int state)
     return (cell & 16) ? 5 : 4;
 }
 
-HRM_HD int sw_traceback(const uint8_t* dir, int width_d, int band_width, int refLen, int readLen, char* ops,
-                        int32_t* lens, int maxops);
 
 // banded_sw.  ref/read point at the sub-sequences.  hb/eb/hc: 2*len+16 ints each where
 // len = max(refLen, readLen); dir: dir_cap bytes.  ops/lens: cigar out (op chars M/I/D), capacity
 // maxops.  Returns number of ops, -1 if the trace back fails (reference: flag 1), -2 if scratch
 // is too small (caller sizes it so that this cannot happen).
-// one band iteration of banded_sw (ref: ssw.c:614-670): fills dir (width_d * readLen direction bytes) and
-// returns the maximum H seen.  hb/eb/hc need width + 8 = 2*band_width + 11 ints.
+// direction-byte storage: row-major cells (row = read position, x = band-relative column)
+struct DirLinear { // private contiguous slice
+    uint8_t* p;
+    HRM_HD uint8_t& at(int64_t idx) const { return p[idx]; }
+};
+struct DirInterleaved { // 32 lanes of a warp interleaved byte-wise: lanes in lock step coalesce
+    uint8_t* p;
+    int lane;
+    HRM_HD uint8_t& at(int64_t idx) const { return p[idx * 32 + lane]; }
+};
+
+template <class DirT>
+HRM_HD int sw_traceback(DirT dir, int row_stride, int width_d, int band_width, int refLen, int readLen, char* ops,
+                        int32_t* lens, int maxops);
+
+// one band iteration of banded_sw (ref: ssw.c:614-670): fills the direction bytes (row i at
+// row_stride * i, width_d = 2*band_width+1 cells per row, cells outside the band zero = "not written")
+// and returns the maximum H seen.  hb/eb/hc need width + 8 = 2*band_width + 11 ints.
+template <class DirT>
 HRM_HD int sw_banded_once(const int8_t* ref, const int8_t* read, int refLen, int readLen, int band_width,
-                          int32_t* h_b, int32_t* e_b, int32_t* h_c, uint8_t* dir)
+                          int32_t* h_b, int32_t* e_b, int32_t* h_c, DirT dir, int row_stride)
 {
     int i, j, f, temp1, temp2, max = 0;
     const int width = band_width * 2 + 3;
     const int width_d = band_width * 2 + 1;
-    for (int64_t t = 0; t < (int64_t)width_d * readLen; t++) dir[t] = 0;
     for (j = 0; j < width + 8; j++) {
         h_b[j] = 0;
         e_b[j] = 0;
@@ -167,7 +181,7 @@ HRM_HD int sw_banded_once(const int8_t* ref, const int8_t* read, int refLen, int
         end = end < j ? end : j;
         edge = end + 1 < width - 1 ? end + 1 : width - 1;
         f = h_b[0] = e_b[0] = h_b[edge] = e_b[edge] = h_c[0] = 0;
-        uint8_t* line = dir + (int64_t)width_d * i;
+        const int64_t line = (int64_t)row_stride * i;
         const int xi = (i - band_width) > 0 ? (i - band_width) : 0;
         const int xp = (i - 1 - band_width) > 0 ? (i - 1 - band_width) : 0;
         for (j = beg; j <= end; j++) {
@@ -192,8 +206,9 @@ HRM_HD int sw_banded_once(const int8_t* ref, const int8_t* read, int refLen, int
             int dh;
             if (temp1 <= temp2) dh = 1;
             else dh = e1 > f1 ? de : df;
-            line[j - xi] = (uint8_t)(0x80 | dh | (de == 3 ? 8 : 0) | (df == 5 ? 16 : 0));
+            dir.at(line + (j - xi)) = (uint8_t)(0x80 | dh | (de == 3 ? 8 : 0) | (df == 5 ? 16 : 0));
         }
+        for (j = (end - xi + 1) > 0 ? (end - xi + 1) : 0; j < width_d; j++) dir.at(line + j) = 0; // not written
         for (j = 1; j <= u; j++) h_b[j] = h_c[j];
     }
     return max;
@@ -209,17 +224,18 @@ HRM_HD int sw_banded(const int8_t* ref, const int8_t* read, int refLen, int read
     do {
         width_d = band_width * 2 + 1;
         if ((int64_t)width_d * readLen > dir_cap) return -2;
-        const int m = sw_banded_once(ref, read, refLen, readLen, band_width, h_b, e_b, h_c, dir);
+        const int m = sw_banded_once(ref, read, refLen, readLen, band_width, h_b, e_b, h_c, DirLinear{dir}, width_d);
         if (m > max) max = m; // ref: `max` persists across band doublings (ssw.c:600)
         band_width *= 2;
     } while (max < score && band_width <= len);
     band_width /= 2;
-    return sw_traceback(dir, width_d, band_width, refLen, readLen, ops, lens, maxops);
+    return sw_traceback(DirLinear{dir}, width_d, width_d, band_width, refLen, readLen, ops, lens, maxops);
 }
 
 // trace back through the direction bytes of the last band iteration (ref: ssw.c:675-764).
 // Returns the number of cigar ops (op chars M/I/D, in alignment order) or -1 on failure.
-HRM_HD int sw_traceback(const uint8_t* dir, int width_d, int band_width, int refLen, int readLen, char* ops,
+template <class DirT>
+HRM_HD int sw_traceback(DirT dir, int row_stride, int width_d, int band_width, int refLen, int readLen, char* ops,
                         int32_t* lens, int maxops)
 {
     int i = readLen - 1;
@@ -232,7 +248,7 @@ HRM_HD int sw_traceback(const uint8_t* dir, int width_d, int band_width, int ref
         const int xi = (i - band_width) > 0 ? (i - band_width) : 0;
         const int x = j - xi;
         int code = 0;
-        if (x >= 0 && x < width_d) code = sw_dir_code(dir[(int64_t)width_d * i + x], state);
+        if (x >= 0 && x < width_d) code = sw_dir_code(dir.at((int64_t)row_stride * i + x), state);
         switch (code) {
         case 1: --i; --j; state = 2; op = 'M'; break;
         case 2: --i; state = 0; op = 'I'; break;

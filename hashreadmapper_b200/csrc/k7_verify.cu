@@ -391,26 +391,36 @@ __device__ __forceinline__ int warp_banded(const int8_t* ref, const int8_t* read
     return 0;
 }
 
-// ---- B1: narrow bands (|refLen - readLen| + 1 <= BW): one THREAD per alignment, everything on chip -------
-// True alignments of substitution-only reads need band 1 and a single band iteration; their whole banded DP
-// is 3 cells per row.  State: h_b/e_b/h_c in local arrays, direction bytes + codes in a private shared-memory
-// slice.  Anything that needs a wider band, band doubling or a long op list goes to the warp kernel (B2).
-constexpr int SMALL_BW = 1;
-constexpr int SMALL_MAXOPS = 40;
-
-template <class Src>
-__global__ void __launch_bounds__(128) sw_finish_small_kernel(Src src, int64_t n, int slice_bytes, int QP, int RP,
-                                                              hrm_alignment* __restrict__ out,
-                                                              char* __restrict__ cigars, int64_t cigar_pitch,
-                                                              int32_t* __restrict__ worklist,
-                                                              int32_t* __restrict__ work_count)
+// ---- B1 / B2: one THREAD per alignment -------------------------------------------------------------
+// The literal banded DP (core_sw.cuh: sw_banded_once) is most instruction-efficient with one alignment per
+// thread; what limits it is where its state lives.  B1 (BWMAX = 1): true alignments of substitution-only
+// reads need band 1 and one band iteration -- h_b/e_b/h_c in local arrays, direction bytes and codes in a
+// private shared-memory slice.  B2 (BWMAX = 16): the gapped "other strand" alignments -- same code, direction
+// bytes in a global scratch interleaved across the 32 lanes of the warp (lanes in lock step coalesce).
+// Anything that needs a wider band or a longer op list than the kernel holds is appended to the next work
+// list; the last stage (B3) is the warp-per-alignment kernel, which has no limits.
+template <class Src, int BWMAX, int MAXOPS, bool FROM_LIST, bool SMEM_DIR>
+__global__ void __launch_bounds__(128) sw_finish_thread_kernel(Src src, int64_t n, const int32_t* __restrict__ in_list,
+                                                               const int32_t* __restrict__ in_count,
+                                                               int slice_bytes, int QP, int RP, int dir_rows,
+                                                               uint8_t* __restrict__ dir_pool,
+                                                               hrm_alignment* __restrict__ out,
+                                                               char* __restrict__ cigars, int64_t cigar_pitch,
+                                                               int32_t* __restrict__ worklist,
+                                                               int32_t* __restrict__ work_count)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     int8_t* q = (int8_t*)(smem + (size_t)slice_bytes * threadIdx.x);
     int8_t* r = q + QP;
-    uint8_t* dir = (uint8_t*)(r + RP);
+    constexpr int WD = 2 * BWMAX + 1;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const int64_t total = FROM_LIST ? (int64_t)*in_count : n;
+    // direction bytes: shared slice (linear) or global, interleaved over the lanes of the warp
+    DirLinear dlin{(uint8_t*)(r + RP)};
+    DirInterleaved dint{dir_pool + (gtid >> 5) * ((int64_t)WD * dir_rows * 32), (int)(threadIdx.x & 31)};
+    for (int64_t it = gtid; it < total; it += stride) {
+        const int64_t e = FROM_LIST ? (int64_t)in_list[it] : it;
         hrm_alignment o = out[e];
         char* cig = cigars + e * cigar_pitch;
         if (o.flag == 1 || o.sw_score <= 0 || o.ref_begin < 0) {
@@ -418,21 +428,37 @@ __global__ void __launch_bounds__(128) sw_finish_small_kernel(Src src, int64_t n
             continue;
         }
         const int refLen = o.ref_end - o.ref_begin + 1, readLen = o.query_end - o.query_begin + 1;
+        const int len = refLen > readLen ? refLen : readLen;
         int band = refLen - readLen;
         band = (band < 0 ? -band : band) + 1;
-        bool defer = band > SMALL_BW;
+        bool defer = band > BWMAX || readLen > dir_rows;
         int ql = 0, rl = 0, ml = 0;
         if (!defer) defer = !src.load(e, q, r, 0, 1, ql, rl, ml);
         if (!defer) {
-            int32_t hb[2 * SMALL_BW + 3 + 8], eb[2 * SMALL_BW + 3 + 8], hc[2 * SMALL_BW + 3 + 8];
-            const int mx = sw_banded_once(r + o.ref_begin, q + o.query_begin, refLen, readLen, band, hb, eb, hc, dir);
-            const int len = refLen > readLen ? refLen : readLen;
-            if (mx < o.sw_score && band * 2 <= len) defer = true; // the reference would double the band
+            int32_t hb[2 * BWMAX + 3 + 8], eb[2 * BWMAX + 3 + 8], hc[2 * BWMAX + 3 + 8];
+            int mx = 0;
+            while (true) { // ref: do { ... band_width *= 2; } while (max < score && band_width <= len)
+                int m;
+                if (SMEM_DIR) m = sw_banded_once(r + o.ref_begin, q + o.query_begin, refLen, readLen, band, hb, eb, hc, dlin, WD);
+                else m = sw_banded_once(r + o.ref_begin, q + o.query_begin, refLen, readLen, band, hb, eb, hc, dint, WD);
+                mx = m > mx ? m : mx;
+                if (mx < o.sw_score && band * 2 <= len) {
+                    band *= 2;
+                    if (band > BWMAX) {
+                        defer = true;
+                        break;
+                    }
+                    continue;
+                }
+                break;
+            }
             if (!defer) {
-                char ops[SMALL_MAXOPS];
-                int32_t lens[SMALL_MAXOPS];
-                int nops = sw_traceback(dir, 2 * band + 1, band, refLen, readLen, ops, lens, SMALL_MAXOPS);
-                if (nops >= SMALL_MAXOPS) defer = true; // may have been truncated: let B2 redo it
+                char ops[MAXOPS];
+                int32_t lens[MAXOPS];
+                int nops;
+                if (SMEM_DIR) nops = sw_traceback(dlin, WD, 2 * band + 1, band, refLen, readLen, ops, lens, MAXOPS);
+                else nops = sw_traceback(dint, WD, 2 * band + 1, band, refLen, readLen, ops, lens, MAXOPS);
+                if (nops >= MAXOPS) defer = true; // may have been truncated: let the next stage redo it
                 if (!defer) {
                     SwAlignment al;
                     al.sw_score = o.sw_score;
@@ -462,7 +488,7 @@ __global__ void __launch_bounds__(128) sw_finish_small_kernel(Src src, int64_t n
     }
 }
 
-// ---- B2: everything else, one WARP per alignment (work list written by B1) ---------------------------
+// ---- B3: everything else, one WARP per alignment (work list written by B2) ---------------------------
 template <class Src>
 __global__ void __launch_bounds__(256) sw_finish_kernel(Src src, const int32_t* __restrict__ worklist,
                                                         const int32_t* __restrict__ work_count, int QP, int RP,
@@ -509,7 +535,7 @@ __global__ void __launch_bounds__(256) sw_finish_kernel(Src src, const int32_t* 
                 al.ref_end_next_best = o.ref_end_next_best;
                 al.mismatches = 0;
                 al.cigar_len = 0;
-                if (rc == 0) nops = sw_traceback(dir, width_d, band, refLen, readLen, ops, lens, P.maxops);
+                if (rc == 0) nops = sw_traceback(DirLinear{dir}, width_d, width_d, band, refLen, readLen, ops, lens, P.maxops);
                 else nops = -1;
                 if (nops < 0) { // ref: banded_sw failed -> flag 1, empty path (ssw.c:910)
                     flag = 1;
@@ -619,29 +645,38 @@ static hrm_status run_sw(const Src& src, int64_t n, int maxQ, int maxR, hrm_alig
         }
 #undef HRM_LAUNCH_A
     }
-    // kernel B1 (thread per alignment, narrow band) + B2 (warp per alignment, the rest)
+    // kernel B1 (thread/alignment, band 1, on chip) -> B3 (warp/alignment, everything else)
     {
         HRM_REQUIRE(n < (1LL << 31), "too many alignments in one call");
         Scratch wl;
-        HRM_TRY(wl.alloc(sizeof(int32_t) * ((size_t)n + 1), s));
-        int32_t* work_count = wl.as<int32_t>();
-        int32_t* worklist = wl.as<int32_t>() + 1;
-        HRM_CUDA(cudaMemsetAsync(work_count, 0, sizeof(int32_t), s));
+        HRM_TRY(wl.alloc(sizeof(int32_t) * (2 * (size_t)n + 8), s));
+        int32_t* count1 = wl.as<int32_t>();
+        int32_t* count2 = wl.as<int32_t>() + 1;
+        int32_t* list1 = wl.as<int32_t>() + 4;
+        int32_t* list2 = list1 + n;
+        HRM_CUDA(cudaMemsetAsync(count1, 0, 2 * sizeof(int32_t), s));
+        const int maxQq = maxQ > 16 ? maxQ : 16;
         {
-            const int maxQq = maxQ > 16 ? maxQ : 16;
-            int slice = (int)align_up(QP + RP + (2 * SMALL_BW + 1) * maxQq, 4) + 4; // odd number of words
+            int slice = (int)align_up(QP + RP + 3 * maxQq, 4) + 4; // odd number of words
             if (((slice / 4) & 1) == 0) slice += 4;
-            int threads = 128;
-            while ((size_t)slice * threads > 100 * 1024 && threads > 32) threads >>= 1;
+            const int threads = 128;
             const size_t smemS = (size_t)slice * threads;
             int64_t blocks = HRM_SDIV(n, (int64_t)threads);
             const int64_t cap = (int64_t)num_sms() * 8;
             if (blocks > cap) blocks = cap;
-            auto kern = sw_finish_small_kernel<Src>;
+            auto kern = sw_finish_thread_kernel<Src, 1, 40, false, true>;
             if (smemS > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
-            HRM_LAUNCH(kern, (unsigned)blocks, threads, smemS, s, src, n, slice, QP, RP, d_out, d_cigars, cigar_pitch,
-                       worklist, work_count);
+            HRM_LAUNCH(kern, (unsigned)blocks, threads, smemS, s, src, n, (const int32_t*)nullptr,
+                       (const int32_t*)nullptr, slice, QP, RP, maxQq, (uint8_t*)nullptr, d_out, d_cigars, cigar_pitch,
+                       list1, count1);
         }
+        // (a thread-per-alignment stage for bands <= 16 with its state in local memory was measured slower than the
+        //  warp kernel on the gapped "other strand" alignments -- divergent band iterations; instantiate
+        //  sw_finish_thread_kernel<Src, 16, 128, true, false> between B1 and B3 to try it again)
+        (void)list2;
+        (void)count2;
+        int32_t* worklist = list1;
+        int32_t* work_count = count1;
         const int maxLen = (maxQ > maxR ? maxQ : maxR) > 16 ? (maxQ > maxR ? maxQ : maxR) : 16;
         TracePool P;
         P.wmax = (int)align_up(2 * maxLen + 3 + 8 + 1, 4);
