@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--genome-bp", type=int, default=46_000_000)
     ap.add_argument("--cpu-sample", type=int, default=50_000, help="reads in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--load-factor", type=float, default=None, help="hash-table load factor (default: the library's)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,6 +203,8 @@ def main():
     genome, off, reads, lens, truth = workload(args, rank)
     n = len(lens)
     cfg = api.directional_config()
+    if args.load_factor:
+        cfg.load_factor = args.load_factor
     mp = api.Mapper(cfg)
     t0 = time.perf_counter()
     mp.setGenome(genome, off, ["chrS"])
@@ -318,8 +321,8 @@ def main():
                 "launches_per_step": launches_per_step_probe,
                 "slot_touches_per_launch": P, "lookups_per_launch": Q * H_,
                 "share_of_step": probe_ms / args.steps / ms_per_step if ms_per_step > 0 else None,
-                "note": "algorithmic bytes = 16 B x slots examined + (8H+4) B x reads (SURVEY 8d); two 16-B slots "
-                        "share one 32-B DRAM sector"}
+                "note": "algorithmic bytes = 16 B x slots examined + (8H+4) B x reads (SURVEY 8d); a bucket = four 16-B "
+                        "slots = one 64-B HBM access, all four examined per visit"}
 
     line = {"metric": "reads mapped/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -327,7 +330,7 @@ def main():
             "config": {"workload": "1M x 150bp directional BS reads vs 46 Mbp synthetic reference (BASELINE configs[1])",
                        "reads_per_gpu": n, "genome_bp": args.genome_bp, "k": K_, "hashmaps": H_, "window": W_,
                        "min_table_hits": T_, "passes": "C->T index + G->A index", "verification": "SW+CIGAR",
-                       "parallelism": "reads sharded x%d, index replicated" % world,
+                       "load_factor": float(cfg.load_factor), "parallelism": "reads sharded x%d, index replicated" % world,
                        "l2": "inputs larger than L2 (reads %.0f MB + index %.0f MB per GPU)"
                              % (reads.nbytes / 1e6, info.index_device_bytes / 1e6),
                        "index_build_s": index_s, "windows": int(info.num_windows),

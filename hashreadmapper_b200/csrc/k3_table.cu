@@ -5,14 +5,14 @@
 //      include/groupbykey.hpp:97-228 / 312-530.  Design precedent for a device table: warpcore
 //      (include/gpu/gpuhashtable.cuh:303-1111) -- not used as an oracle.
 //
-// Layout in HBM (DESIGN.md "K3"): table j = power-of-two array of 32-byte buckets, each bucket two
-// 16-byte slots {u64 key, u32 value offset, u32 count}; values of all tables in one u32 array.
-// A bucket is exactly one DRAM sector, so a lookup that ends in its home bucket moves one sector.
+// Layout in HBM (DESIGN.md "K3"): table j = array of 64-byte buckets, each bucket four 16-byte slots
+// {u64 key, u32 value offset, u32 count}; values of all tables in one u32 array.  A bucket is exactly
+// one HBM access (64 B), so a lookup that ends in its home bucket moves one DRAM atom and uses all of it.
 // Build (one-off): stable radix sort of (key, id) pairs per table (CUB, build path only), run
 // detection, truncation to the first min(maxResultsPerMap, 65535) ids, CAS insertion of the distinct
-// keys.  Probe (hot path): two-lane cooperative groups, double hashing over buckets, query keys
-// staged into shared memory with TMA (cp.async.bulk + mbarrier), results staged in shared memory
-// and written coalesced.
+// keys.  Probe (hot path): one thread per (query, table) lookup reads the whole bucket with two 256-bit
+// loads (LDG.E.256), linear probing over buckets; query keys staged into shared memory with TMA
+// (cp.async.bulk + mbarrier, double buffered); ranges written coalesced, per-query totals by warp shuffle.
 #include "k3_table.cuh"
 #include "core_minhash.cuh"
 #include <cub/device/device_radix_sort.cuh>
@@ -75,18 +75,20 @@ __global__ void __launch_bounds__(256) head_positions_kernel(const int32_t* __re
         if (flags[i]) head_pos[excl[i]] = (int32_t)i;
 }
 
-__device__ __forceinline__ void bucket_hash(uint64_t key, uint32_t mask, uint32_t& b, uint32_t& step)
+// home bucket of a key: multiply-shift range reduction of the low hash word (nbuckets need not be a
+// power of two); the probe sequence continues linearly over buckets
+__device__ __forceinline__ uint32_t home_bucket(uint64_t key, uint32_t nbuckets)
 {
     const uint64_t h = murmur64(key + 0x5ad0dedULL);
-    b = (uint32_t)h & mask;
-    step = (uint32_t)(h >> 32) | 1u; // odd => visits every bucket of a power-of-two table
+    return __umulhi((uint32_t)h, nbuckets);
 }
+__device__ __forceinline__ uint32_t next_bucket(uint32_t b, uint32_t nbuckets) { return b + 1 == nbuckets ? 0u : b + 1; }
 
 // one thread per distinct key: claim a slot with CAS, then publish (offset, count)
 __global__ void __launch_bounds__(256) insert_keys_kernel(const uint64_t* __restrict__ keys,
                                                           const int32_t* __restrict__ head_pos, int64_t nkeys,
                                                           int64_t nvalid, uint32_t value_base, uint32_t upper,
-                                                          Slot* __restrict__ slots, uint32_t mask,
+                                                          Slot* __restrict__ slots, uint32_t nbuckets,
                                                           unsigned long long* __restrict__ errors)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -96,12 +98,11 @@ __global__ void __launch_bounds__(256) insert_keys_kernel(const uint64_t* __rest
         const uint64_t key = keys[pos];
         int64_t cnt = end - pos;
         if (cnt > upper) cnt = upper; // ref: groupbykey.hpp:177-191 keeps the FIRST `upper` values
-        uint32_t b, step;
-        bucket_hash(key, mask, b, step);
+        uint32_t b = home_bucket(key, nbuckets);
         bool done = false;
-        for (uint64_t probe = 0; probe <= (uint64_t)mask && !done; probe++) {
-            for (int sub = 0; sub < 2 && !done; sub++) {
-                Slot* s = slots + ((size_t)b * 2 + sub);
+        for (uint32_t probe = 0; probe < nbuckets && !done; probe++) {
+            for (int sub = 0; sub < BUCKET_SLOTS && !done; sub++) {
+                Slot* s = slots + ((size_t)b * BUCKET_SLOTS + sub);
                 const unsigned long long prev =
                     atomicCAS(reinterpret_cast<unsigned long long*>(&s->key), (unsigned long long)SLOT_EMPTY,
                               (unsigned long long)key);
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) insert_keys_kernel(const uint64_t* __rest
                     done = true;
                 }
             }
-            b = (b + step) & mask;
+            b = next_bucket(b, nbuckets);
         }
         if (!done) atomicAdd(errors, 1ULL);
     }
@@ -160,48 +161,61 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 constexpr int PROBE_THREADS = 256;
 constexpr int PROBE_LOOKUPS = 1024; // lookups (query x table) per tile
 
-// One lookup by a two-lane cooperative group (lane parity selects the slot of the bucket).
-// Returns (off, cnt) in both lanes; touches += slots examined.
-__device__ __forceinline__ uint2 probe_pair(const TableRef& T, uint64_t key, int sub, unsigned pairmask,
-                                            uint32_t max_results, uint32_t& touches)
+// the 64 bytes of one bucket: two 256-bit loads that bypass L1 allocation (no reuse between lookups)
+__device__ __forceinline__ void load_bucket(const Slot* bucket, uint64_t (&w)[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
+                 : "l"(bucket));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(w[4]), "=l"(w[5]), "=l"(w[6]), "=l"(w[7])
+                 : "l"(bucket + 2));
+}
+
+// One lookup by one thread.  Returns (off, cnt); visited += buckets read.
+__device__ __forceinline__ uint2 probe_one(const Slot* __restrict__ slots, uint32_t nbuckets, uint64_t key,
+                                           uint32_t max_results, uint32_t& visited)
 {
     uint2 res = make_uint2(0u, 0u);
     if (key == SLOT_EMPTY) return res; // invalid signature (len < k)
-    uint32_t b, step;
-    bucket_hash(key, T.bucket_mask, b, step);
-    const uint4* slots = reinterpret_cast<const uint4*>(T.slots);
-    for (uint32_t probe = 0; probe <= T.bucket_mask; probe++) {
-        const uint4 s = __ldg(slots + ((size_t)b * 2 + sub));
-        const uint64_t skey = ((uint64_t)s.y << 32) | s.x;
-        const bool hit = skey == key;
-        const bool empty = skey == SLOT_EMPTY;
-        uint32_t off = hit ? s.z : 0u, cnt = hit ? s.w : 0u;
-        off |= __shfl_xor_sync(pairmask, off, 1);
-        cnt |= __shfl_xor_sync(pairmask, cnt, 1);
-        const int flags = (hit ? 1 : 0) | (empty ? 2 : 0);
-        const int both = flags | __shfl_xor_sync(pairmask, flags, 1);
-        touches += 1;
-        if (both & 1) {
-            if (cnt <= max_results) res = make_uint2(off, cnt); // ref: fakegpuminhasher.cuh:280-285
+    uint32_t b = home_bucket(key, nbuckets);
+    for (uint32_t probe = 0; probe < nbuckets; probe++) {
+        uint64_t w[8];
+        load_bucket(slots + (size_t)b * BUCKET_SLOTS, w);
+        visited += 1;
+        bool hit = false, empty = false;
+        uint64_t pay = 0;
+#pragma unroll
+        for (int i = 0; i < BUCKET_SLOTS; i++) {
+            if (w[2 * i] == key) {
+                hit = true;
+                pay = w[2 * i + 1]; // off | cnt << 32
+            }
+            empty |= w[2 * i] == SLOT_EMPTY;
+        }
+        if (hit) {
+            const uint32_t cnt = (uint32_t)(pay >> 32);
+            if (cnt <= max_results) res = make_uint2((uint32_t)pay, cnt); // ref: fakegpuminhasher.cuh:280-285
             break;
         }
-        if (both & 2) break; // a free slot in the bucket ends the probe sequence: key absent
-        b = (b + step) & T.bucket_mask;
+        if (empty) break; // a free slot in the bucket ends the probe sequence: key absent
+        b = next_bucket(b, nbuckets);
     }
     return res;
 }
 
 __global__ void __launch_bounds__(PROBE_THREADS) probe_count_kernel(const uint64_t* __restrict__ sigs, int n, int H,
-                                                                    int TQ, TablesParam tabs, uint32_t max_results,
-                                                                    uint2* __restrict__ ranges,
+                                                                    int TQ, const TablesParam* __restrict__ tabs_g,
+                                                                    uint32_t max_results, uint2* __restrict__ ranges,
                                                                     int32_t* __restrict__ num_per_seq,
                                                                     unsigned long long* __restrict__ touches_out,
                                                                     int sigs_aligned)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* sbuf = reinterpret_cast<uint64_t*>(smem_raw);                       // [2][PROBE_LOOKUPS]
-    uint2* rbuf = reinterpret_cast<uint2*>(sbuf + 2 * PROBE_LOOKUPS);             // [PROBE_LOOKUPS]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + PROBE_LOOKUPS);           // [2]
+    uint64_t* sbuf = reinterpret_cast<uint64_t*>(smem_raw);                       // [2][PROBE_LOOKUPS] keys
+    uint32_t* cbuf = reinterpret_cast<uint32_t*>(sbuf + 2 * PROBE_LOOKUPS);       // [PROBE_LOOKUPS] counts (general H)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cbuf + PROBE_LOOKUPS);           // [2]
+    TableRef* tabs = reinterpret_cast<TableRef*>(bars + 2);                       // [H]
 
     const int tid = threadIdx.x;
     const int numTiles = (n + TQ - 1) / TQ;
@@ -211,6 +225,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_count_kernel(const uint64
         mbar_init(&bars[1], 1);
         mbar_fence_init();
     }
+    for (int t = tid; t < H; t += PROBE_THREADS) tabs[t] = tabs_g->t[t];
     __syncthreads();
 
     auto tile_elems = [&](int tile) {
@@ -227,11 +242,11 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_count_kernel(const uint64
         tma_load_1d(sbuf + (size_t)st * PROBE_LOOKUPS, sigs + (size_t)tile * tileElems, bytes, &bars[st]);
     };
 
-    uint32_t phase[2] = {0u, 0u};
-    uint32_t touches = 0;
-    const int sub = tid & 1;
-    const int group = tid >> 1;
-    const unsigned pairmask = 3u << ((tid & 31) & ~1);
+    uint32_t phases = 0u; // bit st = parity of the next completion of barrier st
+    uint32_t visited = 0;
+    // H a power of two <= 32: the H lookups of a query sit in H consecutive lanes -> totals by shuffle
+    const bool seg = H <= 32 && (H & (H - 1)) == 0;
+    const int lane = tid & 31;
 
     int tile = blockIdx.x;
     int it = 0;
@@ -243,34 +258,46 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_count_kernel(const uint64
         const int elems = tile_elems(tile);
         uint64_t* keys = sbuf + (size_t)st * PROBE_LOOKUPS;
         if (tma_ok(tile)) {
-            mbar_wait(&bars[st], phase[st]);
-            phase[st] ^= 1u;
+            mbar_wait(&bars[st], (phases >> st) & 1u);
+            phases ^= 1u << st;
         } else {
             for (int e = tid; e < elems; e += PROBE_THREADS) keys[e] = sigs[(size_t)tile * tileElems + e];
             __syncthreads();
         }
-        // lookups: element e = local query * H + table
-        for (int e = group; e < elems; e += PROBE_THREADS / 2) {
-            const int t = e % H;
-            const uint2 r = probe_pair(tabs.t[t], keys[e], sub, pairmask, max_results, touches);
-            if (sub == 0) rbuf[e] = r;
-        }
-        __syncthreads();
-        // coalesced write-out of ranges + per-query totals
+        // lookups: element e = local query * H + table; thread e, e + 256, ...
         uint2* gout = ranges + (size_t)tile * tileElems;
-        for (int e = tid; e < elems; e += PROBE_THREADS) gout[e] = rbuf[e];
         const int q0 = tile * TQ;
-        for (int q = tid; q * H < elems; q += PROBE_THREADS) {
-            int sum = 0;
-            for (int t = 0; t < H; t++) sum += (int)rbuf[q * H + t].y;
-            num_per_seq[q0 + q] = sum;
+        for (int e0 = 0; e0 < elems; e0 += PROBE_THREADS) {
+            const int e = e0 + tid;
+            uint2 r = make_uint2(0u, 0u);
+            if (e < elems) {
+                const int t = seg ? (e & (H - 1)) : (e % H);
+                const TableRef T = tabs[t];
+                r = probe_one(T.slots, T.nbuckets, keys[e], max_results, visited);
+                gout[e] = r;
+            }
+            if (seg) {
+                uint32_t sum = r.y;
+                for (int d = 1; d < H; d <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+                if (e < elems && (lane & (H - 1)) == 0) num_per_seq[q0 + e / H] = (int)sum;
+            } else {
+                if (e < elems) cbuf[e] = r.y;
+            }
         }
-        __syncthreads(); // rbuf and sbuf[st] are free again
+        if (!seg) {
+            __syncthreads();
+            for (int q = tid; q * H < elems; q += PROBE_THREADS) {
+                int sum = 0;
+                for (int t = 0; t < H; t++) sum += (int)cbuf[q * H + (t + q) % H]; // rotated: spreads the banks
+                num_per_seq[q0 + q] = sum;
+            }
+        }
+        __syncthreads(); // sbuf[st] (and cbuf) are free again
     }
-    // slot touches: every bucket visit examines both slots
-    touches = sub == 0 ? touches * 2 : 0;
-    for (int d = 16; d > 0; d >>= 1) touches += __shfl_xor_sync(0xffffffffu, touches, d);
-    if ((tid & 31) == 0 && touches && touches_out) atomicAdd(touches_out, (unsigned long long)touches);
+    // slot touches: every bucket visit examines all of its slots
+    visited *= BUCKET_SLOTS;
+    for (int d = 16; d > 0; d >>= 1) visited += __shfl_xor_sync(0xffffffffu, visited, d);
+    if (lane == 0 && visited && touches_out) atomicAdd(touches_out, (unsigned long long)visited);
 }
 
 // values of query q: buckets of tables 0..H-1 concatenated at d_values[offsets[q] ...]; one warp per query
@@ -326,13 +353,14 @@ hrm_status minhasher_count_sigs(hrm_minhasher* mh, QueryHandle* qh, const uint64
     HRM_TRY(qh->ranges.reserve(sizeof(uint2) * (size_t)n * H));
     const int TQ = PROBE_LOOKUPS / H > 0 ? PROBE_LOOKUPS / H : 1;
     const int numTiles = (n + TQ - 1) / TQ;
-    const size_t smem = sizeof(uint64_t) * 2 * PROBE_LOOKUPS + sizeof(uint2) * PROBE_LOOKUPS + 2 * sizeof(uint64_t);
+    const size_t smem = sizeof(uint64_t) * 2 * PROBE_LOOKUPS + sizeof(uint32_t) * PROBE_LOOKUPS + 2 * sizeof(uint64_t) +
+                        sizeof(TableRef) * (size_t)H;
     int grid = numTiles;
     const int cap = num_sms() * 8; // 8 resident CTAs of 256 threads per SM
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     const int aligned = (reinterpret_cast<uintptr_t>(d_sigs) & 15) == 0 ? 1 : 0;
-    HRM_LAUNCH(probe_count_kernel, grid, PROBE_THREADS, smem, s, d_sigs, n, H, TQ, mh->param,
+    HRM_LAUNCH(probe_count_kernel, grid, PROBE_THREADS, smem, s, d_sigs, n, H, TQ, mh->d_param,
                (uint32_t)mh->max_results, qh->ranges.as<uint2>(), d_num_per_seq, mh->d_touches, aligned);
     qh->stage = 1;
     qh->n = n;
@@ -386,7 +414,8 @@ extern "C" hrm_status hrm_minhasher_create(hrm_minhasher** out, int64_t max_sequ
     mh->max_sequences = max_sequences;
     cudaGetDevice(&mh->device);
     memset(&mh->param, 0, sizeof mh->param);
-    if (cudaMalloc(&mh->d_touches, sizeof(unsigned long long)) != cudaSuccess) {
+    if (cudaMalloc(&mh->d_touches, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&mh->d_param, sizeof(TablesParam)) != cudaSuccess) {
         set_error("cudaMalloc failed");
         delete mh;
         return HRM_ERR_NOMEM;
@@ -404,6 +433,7 @@ extern "C" void hrm_minhasher_destroy(hrm_minhasher* mh)
     for (auto p : mh->slots)
         if (p) cudaFree(p);
     if (mh->d_touches) cudaFree(mh->d_touches);
+    if (mh->d_param) cudaFree(mh->d_param);
     delete mh;
 }
 
@@ -559,25 +589,23 @@ extern "C" hrm_status hrm_minhasher_compact(hrm_minhasher* mh, hrm_stream stream
             nvalid = (int64_t)h_cnt[0];
             nkeys = (int64_t)h_cnt[1];
         }
-        // power-of-two bucket count with nkeys / (2 * nbuckets) <= load factor
-        int64_t want = (int64_t)((double)nkeys / (double)mh->load / 2.0) + 1;
-        int64_t nb = 1;
-        while (nb < want) nb <<= 1;
-        HRM_REQUIRE(nb <= (1LL << 31), "table too large");
+        // smallest bucket count with nkeys / (BUCKET_SLOTS * nbuckets) <= load factor
+        const int64_t nb = (int64_t)((double)nkeys / (double)mh->load / (double)BUCKET_SLOTS) + 1;
+        HRM_REQUIRE(nb < (1LL << 32), "table too large");
         Slot* sl = nullptr;
-        HRM_CUDA(cudaMalloc(&sl, sizeof(Slot) * (size_t)nb * 2));
+        HRM_CUDA(cudaMalloc(&sl, (size_t)BUCKET_BYTES * (size_t)nb));
         mh->slots[j] = sl;
         mh->nbuckets[j] = nb;
         mh->nkeys[j] = nkeys;
         // empty pattern: every 64-bit word = ~0 (key == SLOT_EMPTY; payload irrelevant)
-        HRM_CUDA(cudaMemsetAsync(sl, 0xFF, sizeof(Slot) * (size_t)nb * 2, s));
+        HRM_CUDA(cudaMemsetAsync(sl, 0xFF, (size_t)BUCKET_BYTES * (size_t)nb, s));
         if (nkeys > 0) {
             HRM_LAUNCH(insert_keys_kernel, capped_grid(nkeys, 256, 16), 256, 0, s, keys_sorted.as<uint64_t>(),
-                       head_pos.as<int32_t>(), nkeys, nvalid, (uint32_t)((size_t)j * n), upper, sl, (uint32_t)(nb - 1),
+                       head_pos.as<int32_t>(), nkeys, nvalid, (uint32_t)((size_t)j * n), upper, sl, (uint32_t)nb,
                        counters.as<unsigned long long>() + 2);
         }
         mh->param.t[j].slots = sl;
-        mh->param.t[j].bucket_mask = (uint32_t)(nb - 1);
+        mh->param.t[j].nbuckets = (uint32_t)nb;
         // staging of this table is no longer needed
         cudaFree(mh->stage_keys[j]);
         cudaFree(mh->stage_vals[j]);
@@ -591,6 +619,7 @@ extern "C" hrm_status hrm_minhasher_compact(hrm_minhasher* mh, hrm_stream stream
         set_error("hash table insertion failed for %llu keys", h_err);
         return HRM_ERR_CUDA;
     }
+    HRM_CUDA(cudaMemcpy(mh->d_param, &mh->param, sizeof mh->param, cudaMemcpyHostToDevice));
     mh->compacted = true;
     return HRM_OK;
 }
@@ -725,7 +754,7 @@ extern "C" hrm_status hrm_minhasher_info(const hrm_minhasher* mh, hrm_minhasher_
     if (mh->compacted) {
         for (int j = 0; j < mh->H; j++) {
             out->num_keys_total += mh->nkeys[j];
-            bytes += mh->nbuckets[j] * 32;
+            bytes += mh->nbuckets[j] * BUCKET_BYTES;
         }
         out->num_values_total = mh->values_count;
         bytes += mh->values_count * 4;
@@ -755,7 +784,7 @@ extern "C" hrm_status hrm_minhasher_serialize(const hrm_minhasher* mh, void* h_b
         return HRM_ERR_STATE;
     }
     int64_t need = sizeof(SerHeader) + sizeof(int64_t) * 2 * mh->H + mh->values_count * 4;
-    for (int j = 0; j < mh->H; j++) need += mh->nbuckets[j] * 32;
+    for (int j = 0; j < mh->H; j++) need += mh->nbuckets[j] * BUCKET_BYTES;
     if (!h_buf) {
         *h_size = need;
         return HRM_OK;
@@ -765,7 +794,7 @@ extern "C" hrm_status hrm_minhasher_serialize(const hrm_minhasher* mh, void* h_b
     SerHeader hd;
     memset(&hd, 0, sizeof hd);
     memcpy(hd.magic, "HRMB200", 8);
-    hd.version = 1;
+    hd.version = 2; // 2: 64-byte buckets, multiply-shift home bucket
     hd.k = mh->k;
     hd.max_results = mh->max_results;
     hd.H = mh->H;
@@ -783,8 +812,8 @@ extern "C" hrm_status hrm_minhasher_serialize(const hrm_minhasher* mh, void* h_b
     HRM_CUDA(cudaMemcpy(p, mh->values, (size_t)mh->values_count * 4, cudaMemcpyDeviceToHost));
     p += mh->values_count * 4;
     for (int j = 0; j < mh->H; j++) {
-        HRM_CUDA(cudaMemcpy(p, mh->slots[j], (size_t)mh->nbuckets[j] * 32, cudaMemcpyDeviceToHost));
-        p += mh->nbuckets[j] * 32;
+        HRM_CUDA(cudaMemcpy(p, mh->slots[j], (size_t)mh->nbuckets[j] * BUCKET_BYTES, cudaMemcpyDeviceToHost));
+        p += mh->nbuckets[j] * BUCKET_BYTES;
     }
     *h_size = need;
     return HRM_OK;
@@ -799,7 +828,7 @@ extern "C" hrm_status hrm_minhasher_deserialize(hrm_minhasher** out, const void*
     SerHeader hd;
     memcpy(&hd, p, sizeof hd);
     p += sizeof hd;
-    HRM_REQUIRE(memcmp(hd.magic, "HRMB200", 8) == 0 && hd.version == 1, "bad magic/version");
+    HRM_REQUIRE(memcmp(hd.magic, "HRMB200", 8) == 0 && hd.version == 2, "bad magic/version");
     HRM_REQUIRE(hd.H >= 0 && hd.H <= MAX_TABLES, "bad table count");
     hrm_minhasher* mh = nullptr;
     HRM_TRY(hrm_minhasher_create(&mh, hd.inserted, hd.max_results, hd.k, hd.load));
@@ -815,7 +844,7 @@ extern "C" hrm_status hrm_minhasher_deserialize(hrm_minhasher** out, const void*
         p += 8;
         memcpy(&mh->nkeys[j], p, 8);
         p += 8;
-        need += mh->nbuckets[j] * 32;
+        need += mh->nbuckets[j] * BUCKET_BYTES;
     }
     if (size < need) {
         hrm_minhasher_destroy(mh);
@@ -827,14 +856,15 @@ extern "C" hrm_status hrm_minhasher_deserialize(hrm_minhasher** out, const void*
     p += hd.values_count * 4;
     for (int j = 0; j < hd.H && e == cudaSuccess; j++) {
         Slot* sl = nullptr;
-        e = cudaMalloc(&sl, (size_t)mh->nbuckets[j] * 32);
+        e = cudaMalloc(&sl, (size_t)mh->nbuckets[j] * BUCKET_BYTES);
         if (e != cudaSuccess) break;
         mh->slots[j] = sl;
-        e = cudaMemcpy(sl, p, (size_t)mh->nbuckets[j] * 32, cudaMemcpyHostToDevice);
-        p += mh->nbuckets[j] * 32;
+        e = cudaMemcpy(sl, p, (size_t)mh->nbuckets[j] * BUCKET_BYTES, cudaMemcpyHostToDevice);
+        p += mh->nbuckets[j] * BUCKET_BYTES;
         mh->param.t[j].slots = sl;
-        mh->param.t[j].bucket_mask = (uint32_t)(mh->nbuckets[j] - 1);
+        mh->param.t[j].nbuckets = (uint32_t)mh->nbuckets[j];
     }
+    if (e == cudaSuccess) e = cudaMemcpy(mh->d_param, &mh->param, sizeof mh->param, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         set_error("deserialize: %s", cudaGetErrorString(e));
         hrm_minhasher_destroy(mh);

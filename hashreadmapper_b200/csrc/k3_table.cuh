@@ -7,7 +7,9 @@
 
 namespace hrm {
 
-// 16-byte slot; two slots form one 32-byte bucket (= one DRAM sector)
+// 16-byte slot; four slots form one 64-byte bucket.  64 B is what one HBM access moves on B200 (ncu: a
+// random 32-byte sector read costs 64 DRAM bytes), so a lookup that ends in its home bucket costs exactly
+// one DRAM access and examines everything that access brought in.
 struct alignas(16) Slot {
     uint64_t key;
     uint32_t off;   // index into the minhasher's value array
@@ -18,9 +20,12 @@ static_assert(sizeof(Slot) == 16, "slot must be 16 bytes (SURVEY 8d: 16 B per pr
 constexpr uint64_t SLOT_EMPTY = ~0ULL;   // ref: emptySlot cpuhashtable.hpp:277-278
 constexpr int MAX_TABLES = 64;           // ref: assert(numTables <= 64) fakegpuminhasher.cuh:541
 
+constexpr int BUCKET_SLOTS = 4;
+constexpr int BUCKET_BYTES = BUCKET_SLOTS * (int)sizeof(Slot);
+
 struct TableRef {
     const Slot* slots;
-    uint32_t bucket_mask; // nbuckets - 1 (power of two)
+    uint32_t nbuckets; // any count >= 1: home bucket = mulhi(hash32, nbuckets), then linear over buckets
     uint32_t pad;
 };
 struct TablesParam {
@@ -59,6 +64,7 @@ struct hrm_minhasher {
     std::vector<int64_t> nbuckets;
     std::vector<int64_t> nkeys;
     hrm::TablesParam param;
+    hrm::TablesParam* d_param = nullptr; // device copy read by the probe kernel
     // handles
     std::mutex mtx;
     std::vector<std::unique_ptr<hrm::QueryHandle>> handles;

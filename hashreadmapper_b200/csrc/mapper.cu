@@ -75,7 +75,9 @@ extern "C" void hrm_mapper_default_config(hrm_mapper_config* cfg)
     cfg->num_tables = 16;             // ref: options.hpp hashmaps
     cfg->min_table_hits = 4;          // ref: options.hpp minTableHits
     cfg->max_results_per_map = 65535; // ref: options.hpp maxResultsPerMap
-    cfg->load_factor = 0.8f;          // ref: options.hpp hashtableLoadfactor
+    // ref: options.hpp hashtableLoadfactor is 0.8 for the reference's 16-byte-slot linear-probing table.  The
+    // bucketized table here is sized at 0.5: 1.06 HBM accesses per lookup instead of 2.0 at 0.8 (measured)
+    cfg->load_factor = 0.5f;
     cfg->max_hamming_percent = 0.05f; // ref: options.hpp maxHammingPercent
     cfg->mapper_type = HRM_MAPPER_SW;
     cfg->num_passes = 1;
@@ -188,7 +190,7 @@ extern "C" hrm_status hrm_mapper_info(const hrm_mapper* m, hrm_mapper_info_t* ou
             hrm_minhasher_info(m->index[c], &mi);
             out->index_device_bytes += mi.device_bytes;
             out->num_keys_total += mi.num_keys_total;
-            for (int j = 0; j < m->index[c]->H; j++) out->table_slots_total += m->index[c]->nbuckets[j] * 2;
+            for (int j = 0; j < m->index[c]->H; j++) out->table_slots_total += m->index[c]->nbuckets[j] * hrm::BUCKET_SLOTS;
         }
     }
     return HRM_OK;
