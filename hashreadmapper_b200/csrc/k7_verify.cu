@@ -18,6 +18,7 @@
 // Work per alignment: ~(L+pad) x w cell updates forward, <= that backward, band x L for the trace.
 #include "pipeline.cuh"
 #include "core_sw.cuh"
+#include "core_swpair.cuh"
 
 namespace hrm {
 
@@ -269,6 +270,213 @@ __global__ void __launch_bounds__(256) sw_passes_kernel(Src src, int64_t n, int 
         }
         if (!ok) o.flag = Src::SKIP_FLAG;
         if (lane == 0) out[out_offset_items + e * out_stride_items] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel A2 (fused path): both alignments of a read in the halves of one register (core_swpair.cuh)
+// ------------------------------------------------------------------------------------------------
+// A group of G lanes owns one read: its two alignments (read and RC(read) against the same window) share
+// the reference column, so every DP instruction (VIMNMX3 / VIADDMNMX .S16x2) updates two cells.  Lane l of
+// the group keeps rows [l*R, l*R+R) of the frame in registers; the wavefront needs 3 shuffles per column.
+// The reverse pass runs both halves over the shared columns cmax..0, a half joining at its own end column.
+template <int G>
+__device__ __forceinline__ uint32_t group_max(uint32_t v)
+{
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, v, d, G);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+template <int G, int R>
+__global__ void __launch_bounds__(128) sw_pair_passes_kernel(PackedSrc src, int64_t nreads, int QP, int RP,
+                                                             hrm_alignment* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int PPW = 32 / G; // reads per warp
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gl = lane % G, gp = lane / G;
+    const size_t per_pair = (size_t)QP + RP + 8 * (size_t)RP;
+    unsigned char* pbase = smem + per_pair * (size_t)(wid * PPW + gp);
+    int8_t* sq = (int8_t*)pbase;               // oriented read, unconverted codes
+    int8_t* sr = sq + QP;                      // window, stage-V converted codes
+    uint32_t* cmW = (uint32_t*)(sr + RP);      // column maxima incl. word-mode pad rows (A lo, B hi)
+    uint32_t* cmB = cmW + RP;                  // ... incl. byte-mode pad rows
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int rtot = G * R;
+    PairWave<R> w;
+    for (int64_t rd0 = warp0 * PPW; rd0 < nreads; rd0 += nwarps * PPW) {
+        const int64_t rd = rd0 + gp;
+        bool ok = rd < nreads;
+        int L = 0, rl = 0, conv = 0;
+        __syncwarp();
+        if (ok) {
+            const hrm_mapped_read m = src.mapped[rd];
+            L = src.read_len[rd];
+            if (m.orientation == HRM_ORIENT_NONE || m.pass < 0 || m.pass >= src.VP.num_passes || L <= 0 || L > src.maxQ) {
+                ok = false;
+            } else {
+                const uint32_t* rw = src.VP.pass[m.pass].reads + rd * src.VP.pass[m.pass].read_pitch;
+                const int64_t clen = src.VP.pass[m.pass].G.chrom_len[m.chromosome_id];
+                const uint32_t* cw = src.VP.pass[m.pass].G.chrom_words[m.chromosome_id];
+                conv = src.VP.pass[m.pass].verify_conv;
+                int wl = (int)((m.position + src.VP.w < clen) ? src.VP.w : clen - m.position); // ref: mappinghandler.cu:434-440
+                if (wl > src.maxR) wl = src.maxR;
+                rl = wl;
+                const bool rcq = m.orientation == HRM_ORIENT_REVCOMP; // ref: mappinghandler.cu:420-423
+                for (int j = gl; j < L; j += G) sq[j] = (int8_t)(rcq ? 3 - (int)get_nuc(rw, L - 1 - j) : (int)get_nuc(rw, j));
+                for (int j = gl; j < wl; j += G) sr[j] = (int8_t)conv_code((int)get_nuc(cw, m.position + j), conv);
+            }
+        }
+        __syncwarp();
+        const int ml = L / 2 < 15 ? 15 : L / 2; // ref: mappinghandler.cu:453-454
+        const int top = pair_top(rtot, L);
+        // alignment 0: 3N(readsequence), alignment 1: 3N(RC(readsequence)) (ref: mappinghandler.cu:456-465)
+        auto qcode = [&](int half, int j) -> int { return conv_code(half ? 3 - (int)sq[L - 1 - j] : (int)sq[j], conv); };
+
+        // ---- forward pass -----------------------------------------------------------------------------
+        pair_wave_reset(w);
+        pair_build(w.L, gl * R, [&](int half, int g) -> int {
+            const int j = g - top;
+            if (!ok || j < 0) return PAIR_CODE_EMPTY;
+            if (j >= L) return PAIR_CODE_PAD;
+            return qcode(half, j);
+        });
+        const int ncolsF = ok ? rl : 0;
+        int nsteps = __reduce_max_sync(FULL, ncolsF > 0 ? ncolsF + G - 1 : 0);
+        for (int t = 0; t < nsteps; ++t) {
+            uint32_t recvS = __shfl_up_sync(FULL, w.outS, 1, G);
+            uint32_t recvF = __shfl_up_sync(FULL, w.outF, 1, G);
+            uint32_t recvC = __shfl_up_sync(FULL, w.outCm, 1, G);
+            if (gl == 0) {
+                recvS = 0u;
+                recvF = PX_TWOS;
+                recvC = 0u;
+            }
+            const int c = t - gl;
+            const int rc = (c >= 0 && c < ncolsF) ? (int)sr[c] : 0;
+            uint32_t a, b;
+            if (pair_wave_step(w, c, ncolsF, rc, PX_ONES, recvS, recvF, recvC, (uint32_t)c, a, b) && gl == G - 1) {
+                cmW[c] = a;
+                cmB[c] = b;
+            }
+        }
+        __syncwarp();
+        const uint32_t wordF[2] = {group_max<G>(pair_best_word(w.bestA, gl * R)),
+                                   group_max<G>(pair_best_word(w.bestB, gl * R))};
+        hrm_alignment o[2];
+        int score1[2], ref_end1[2], read_end1[2];
+        bool valid[2];
+        const bool samePad = pair_pad8(L) == pair_pad16(L);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            zero_alignment(o[h]);
+            const uint32_t word = wordF[h];
+            score1[h] = (int)(word >> 20);
+            ref_end1[h] = word ? 1023 - (int)((word >> 10) & 1023u) : -1;
+            const int g = 1023 - (int)(word & 1023u);
+            read_end1[h] = word ? ((g - top) < L - 1 ? (g - top) : L - 1) : 0;
+            valid[h] = ok && word != 0u;
+            // second best (ref: ssw.c:368-381 byte, :570-583 word): first column of the largest column maximum
+            // outside the mask around the end, left range first
+            const bool wordMode = score1[h] + 2 >= 255; // ref: ssw.c:329 byte overflow -> word pass (:846-849)
+            const uint32_t* cm = (wordMode || samePad) ? cmW : cmB;
+            unsigned k1 = 0, k2 = 0;
+            if (valid[h]) {
+                const int e1 = (ref_end1[h] - ml) > 0 ? (ref_end1[h] - ml) : 0;
+                const int e2 = (ref_end1[h] + ml) > rl ? rl : (ref_end1[h] + ml);
+                for (int c = gl; c < e1; c += G) {
+                    const unsigned key = (((cm[c] >> (16 * h)) & 0xFFFFu) << 16) | (unsigned)(0xFFFF - c);
+                    k1 = key > k1 ? key : k1;
+                }
+                for (int c = e2 + (wordMode ? 0 : 1) + gl; c < rl; c += G) {
+                    const unsigned key = (((cm[c] >> (16 * h)) & 0xFFFFu) << 16) | (unsigned)(0xFFFF - c);
+                    k2 = key > k2 ? key : k2;
+                }
+            }
+            k1 = group_max<G>(k1);
+            k2 = group_max<G>(k2);
+            int score2 = 0, ref2 = 0;
+            if ((k1 >> 16) > 0) {
+                score2 = (int)(k1 >> 16);
+                ref2 = 0xFFFF - (int)(k1 & 0xFFFFu);
+            }
+            if ((int)(k2 >> 16) > score2) {
+                score2 = (int)(k2 >> 16);
+                ref2 = 0xFFFF - (int)(k2 & 0xFFFFu);
+            }
+            if (ok) {
+                o[h].sw_score = score1[h];
+                o[h].ref_end = ref_end1[h];
+                o[h].query_end = read_end1[h];
+                o[h].sw_score_next_best = ml >= 15 ? score2 : 0;
+                o[h].ref_end_next_best = ml >= 15 ? ref2 : -1;
+                o[h].ref_begin = -1; // score 0 is undefined in the reference (ssw.c:220): deterministic convention
+                o[h].query_begin = -1;
+            }
+        }
+        // ---- reverse pass: reversed prefixes, both halves over the shared columns cmax .. 0 -----------
+        const int cmax = max(valid[0] ? ref_end1[0] : -1, valid[1] ? ref_end1[1] : -1);
+        const int ncolsR = cmax + 1;
+        __syncwarp();
+        pair_wave_reset(w);
+        pair_build(w.L, gl * R, [&](int half, int g) -> int {
+            if (!valid[half] || g > read_end1[half]) return PAIR_CODE_EMPTY;
+            return qcode(half, read_end1[half] - g);
+        });
+        bool done = !valid[0] && !valid[1];
+        bool doneA = !valid[0], doneB = !valid[1];
+        nsteps = __reduce_max_sync(FULL, ncolsR > 0 ? ncolsR + G - 1 : 0);
+        for (int t = 0; t < nsteps; ++t) {
+            uint32_t recvS = __shfl_up_sync(FULL, w.outS, 1, G);
+            uint32_t recvF = __shfl_up_sync(FULL, w.outF, 1, G);
+            uint32_t recvC = __shfl_up_sync(FULL, w.outCm, 1, G);
+            if (gl == 0) {
+                recvS = 0u;
+                recvF = PX_TWOS;
+                recvC = 0u;
+            }
+            const int j = t - gl;
+            int rc = 0;
+            uint32_t hmask = 0u;
+            if (j >= 0 && j < ncolsR) {
+                const int c = cmax - j;
+                rc = (int)sr[c];
+                hmask = ((valid[0] && c <= ref_end1[0]) ? 1u : 0u) | ((valid[1] && c <= ref_end1[1]) ? 0x10000u : 0u);
+            }
+            uint32_t a, b;
+            if (pair_wave_step(w, j, ncolsR, rc, hmask, recvS, recvF, recvC, (uint32_t)j, a, b) && gl == G - 1) {
+                if ((int)(b & 0xFFFFu) == score1[0]) doneA = true; // ref: ssw.c:339 stop at the first column reaching score1
+                if ((int)(b >> 16) == score1[1]) doneB = true;
+                done = doneA && doneB;
+            }
+            const int fin = __shfl_sync(FULL, (int)done, gp * G + G - 1);
+            if (__all_sync(FULL, fin)) break;
+        }
+        const uint32_t wordR[2] = {group_max<G>(pair_best_word(w.bestA, gl * R)),
+                                   group_max<G>(pair_best_word(w.bestB, gl * R))};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (valid[h]) {
+                const uint32_t word = wordR[h];
+                const int maxv = (int)(word >> 20);
+                const int j = 1023 - (int)((word >> 10) & 1023u);
+                int g = 1023 - (int)(word & 1023u);
+                if (g > read_end1[h]) g = read_end1[h];
+                o[h].ref_begin = cmax - j;
+                o[h].query_begin = read_end1[h] - g;
+                o[h].flag = score1[h] > maxv ? 2 : 0; // ref: ssw.c:890-893
+            }
+        }
+        if (rd < nreads) {
+            if (gl == 0) out[2 * rd] = o[0];
+            if (gl == 1) out[2 * rd + 1] = o[1];
+        }
     }
 }
 
@@ -616,14 +824,55 @@ __global__ void __launch_bounds__(256) record_header_kernel(VerifyParams VP, con
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// kernel A2 launcher; returns false when the batch does not fit the paired kernel's frames
+static bool launch_pair_passes(const PackedSrc& src, int64_t nreads, int QP, int RP, hrm_alignment* d_out, cudaStream_t s,
+                               hrm_status& st)
+{
+    st = HRM_OK;
+    const int maxQ = src.maxQ, w = src.maxR;
+    int G = 0;
+    if (pair_fits(4 * 40, maxQ, w)) G = 4;
+    else if (pair_fits(8 * 32, maxQ, w)) G = 8;
+    else return false;
+    const int ppw = 32 / G;
+    const size_t smem = ((size_t)QP + RP + 8 * (size_t)RP) * ppw * 4;
+    if (smem > 200 * 1024) return false;
+    int64_t blocks = HRM_SDIV(nreads, (int64_t)(ppw * 4));
+    const int64_t cap = (int64_t)num_sms() * 4;
+    if (blocks > cap) blocks = cap;
+    auto go = [&](auto kern) -> hrm_status {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        HRM_LAUNCH(kern, (unsigned)blocks, 128, smem, s, src, nreads, QP, RP, d_out);
+        return HRM_OK;
+    };
+    st = G == 4 ? go(sw_pair_passes_kernel<4, 40>) : go(sw_pair_passes_kernel<8, 32>);
+    return true;
+}
+
+template <class Src>
+static bool try_pair_passes(const Src&, int64_t, int, int, hrm_alignment*, int64_t, int64_t, cudaStream_t, hrm_status&)
+{
+    return false;
+}
+template <>
+bool try_pair_passes<PackedSrc>(const PackedSrc& src, int64_t n, int QP, int RP, hrm_alignment* d_out, int64_t out_stride,
+                                int64_t out_offset, cudaStream_t s, hrm_status& st)
+{
+    if (out_stride != 1 || out_offset != 0 || (n & 1)) return false;
+    return launch_pair_passes(src, n / 2, QP, RP, d_out, s, st);
+}
+
 template <class Src>
 static hrm_status run_sw(const Src& src, int64_t n, int maxQ, int maxR, hrm_alignment* d_out, int64_t out_stride,
                          int64_t out_offset, char* d_cigars, int64_t cigar_pitch, cudaStream_t s)
 {
     if (n == 0) return HRM_OK;
     const int QP = (int)align_up(maxQ > 16 ? maxQ : 16, 16), RP = (int)align_up(maxR > 16 ? maxR : 16, 16);
-    // kernel A
-    {
+    // kernel A: the paired SIMD kernel on the fused path, the generic warp-per-alignment kernel otherwise
+    hrm_status pst = HRM_OK;
+    if (try_pair_passes(src, n, QP, RP, d_out, out_stride, out_offset, s, pst)) {
+        HRM_TRY(pst);
+    } else {
         const size_t smemA = ((size_t)QP + RP + 4 * (size_t)RP) * 8;
         int64_t blocks = HRM_SDIV(n, (int64_t)8);
         const int64_t cap = (int64_t)num_sms() * 8;

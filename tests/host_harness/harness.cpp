@@ -5,10 +5,12 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#include <algorithm>
 #include "../../hashreadmapper_b200/csrc/core_pack.cuh"
 #include "../../hashreadmapper_b200/csrc/core_minhash.cuh"
 #include "../../hashreadmapper_b200/csrc/core_shd.cuh"
 #include "../../hashreadmapper_b200/csrc/core_sw.cuh"
+#include "../../hashreadmapper_b200/csrc/core_swpair.cuh"
 
 using namespace hrm;
 
@@ -83,3 +85,153 @@ int hh_myers(const char* q, int qlen, const char* t, int tlen)
 }
 
 } // extern "C"
+
+// ---- the paired SIMD passes (core_swpair.cuh), G lanes emulated one after the other -----------------
+namespace {
+struct PairOut {
+    int score, score2, ref_begin, ref_end, query_begin, query_end, ref2, flag;
+};
+
+template <int G, int R>
+void pair_passes_host(const int8_t* A, const int8_t* B, int L, const int8_t* ref, int rl, int ml, PairOut out[2])
+{
+    const int rtot = G * R, top = pair_top(rtot, L);
+    std::vector<PairWave<R>> w(G);
+    auto fwd_code = [&](int half, int g) {
+        const int j = g - top;
+        if (j < 0) return PAIR_CODE_EMPTY;
+        if (j >= L) return PAIR_CODE_PAD;
+        return (int)(half ? B[j] : A[j]);
+    };
+    for (int l = 0; l < G; l++) {
+        pair_wave_reset(w[l]);
+        pair_build(w[l].L, l * R, fwd_code);
+    }
+    std::vector<uint32_t> cmW(rl + 1), cmB(rl + 1);
+    auto run = [&](int ncols, auto colinfo, auto on_last) {
+        for (int t = 0; t < ncols + G - 1; t++) {
+            uint32_t oS[G], oF[G], oC[G];
+            for (int l = 0; l < G; l++) {
+                oS[l] = w[l].outS;
+                oF[l] = w[l].outF;
+                oC[l] = w[l].outCm;
+            }
+            bool stop = false;
+            for (int l = 0; l < G; l++) {
+                const int c = t - l;
+                int rc = 0;
+                uint32_t hmask = 0;
+                if (c >= 0 && c < ncols) colinfo(c, rc, hmask);
+                uint32_t a = 0, b = 0;
+                const bool did = pair_wave_step(w[l], c, ncols, rc, hmask, l ? oS[l - 1] : 0u, l ? oF[l - 1] : PX_TWOS,
+                                                l ? oC[l - 1] : 0u, (uint32_t)c, a, b);
+                if (did && l == G - 1) stop = on_last(c, a, b);
+            }
+            if (stop) break;
+        }
+    };
+    run(rl, [&](int c, int& rc, uint32_t& hm) { rc = ref[c]; hm = PX_ONES; },
+        [&](int c, uint32_t a, uint32_t b) { cmW[c] = a; cmB[c] = b; return false; });
+    int score1[2], ref_end1[2], read_end1[2];
+    const bool samePad = pair_pad8(L) == pair_pad16(L);
+    for (int h = 0; h < 2; h++) {
+        uint32_t word = 0;
+        for (int l = 0; l < G; l++) {
+            const uint32_t x = pair_best_word(h ? w[l].bestB : w[l].bestA, l * R);
+            word = x > word ? x : word;
+        }
+        score1[h] = (int)(word >> 20);
+        ref_end1[h] = word ? 1023 - (int)((word >> 10) & 1023u) : -1;
+        int g = 1023 - (int)(word & 1023u);
+        read_end1[h] = g - top < L - 1 ? g - top : L - 1;
+        PairOut& o = out[h];
+        o = PairOut{score1[h], 0, -1, ref_end1[h], -1, word ? read_end1[h] : 0, 0, 0};
+        o.ref2 = ml >= 15 ? 0 : -1;
+        if (!word) continue; // score 0: ref_end -1 (byte kernel's initial end), query_end 0, begins -1
+        const bool word_mode = score1[h] + 2 >= 255;
+        const std::vector<uint32_t>& cm = (word_mode || samePad) ? cmW : cmB;
+        auto val = [&](int c) { return (int)((cm[c] >> (16 * h)) & 0xFFFFu); };
+        int s2 = 0, r2 = 0;
+        const int e1 = ref_end1[h] - ml > 0 ? ref_end1[h] - ml : 0;
+        const int e2 = ref_end1[h] + ml > rl ? rl : ref_end1[h] + ml;
+        for (int c = 0; c < e1; c++)
+            if (val(c) > s2) {
+                s2 = val(c);
+                r2 = c;
+            }
+        for (int c = e2 + (word_mode ? 0 : 1); c < rl; c++)
+            if (val(c) > s2) {
+                s2 = val(c);
+                r2 = c;
+            }
+        o.score2 = ml >= 15 ? s2 : 0;
+        o.ref2 = ml >= 15 ? r2 : -1;
+    }
+    // reverse pass: both halves over the shared columns cmax .. 0
+    const bool vA = score1[0] > 0, vB = score1[1] > 0;
+    if (!vA && !vB) return;
+    const int cmax = std::max(vA ? ref_end1[0] : -1, vB ? ref_end1[1] : -1);
+    auto rev_code = [&](int half, int g) {
+        if (!(half ? vB : vA)) return PAIR_CODE_EMPTY;
+        const int nr = read_end1[half] + 1;
+        if (g >= nr) return PAIR_CODE_EMPTY;
+        return (int)(half ? B[read_end1[1] - g] : A[read_end1[0] - g]);
+    };
+    for (int l = 0; l < G; l++) {
+        pair_wave_reset(w[l]);
+        pair_build(w[l].L, l * R, rev_code);
+    }
+    bool doneA = !vA, doneB = !vB;
+    run(cmax + 1,
+        [&](int j, int& rc, uint32_t& hm) {
+            const int c = cmax - j;
+            rc = ref[c];
+            hm = ((vA && c <= ref_end1[0]) ? 1u : 0u) | ((vB && c <= ref_end1[1]) ? 0x10000u : 0u);
+        },
+        [&](int, uint32_t, uint32_t b) {
+            if ((int)(b & 0xFFFFu) == score1[0]) doneA = true;
+            if ((int)(b >> 16) == score1[1]) doneB = true;
+            return doneA && doneB;
+        });
+    for (int h = 0; h < 2; h++) {
+        if (!(h ? vB : vA)) continue;
+        uint32_t word = 0;
+        for (int l = 0; l < G; l++) {
+            const uint32_t x = pair_best_word(h ? w[l].bestB : w[l].bestA, l * R);
+            word = x > word ? x : word;
+        }
+        const int maxv = (int)(word >> 20);
+        const int j = 1023 - (int)((word >> 10) & 1023u);
+        int g = 1023 - (int)(word & 1023u);
+        const int nr = read_end1[h] + 1;
+        if (g > nr - 1) g = nr - 1;
+        out[h].ref_begin = cmax - j;
+        out[h].query_begin = read_end1[h] - g;
+        out[h].flag = score1[h] > maxv ? 2 : 0;
+    }
+}
+} // namespace
+
+extern "C" int hh_sw_pair(const int8_t* A, const int8_t* B, int L, const int8_t* ref, int rl, int ml, int G, int R,
+                          int* out16)
+{
+    PairOut o[2];
+    if (!pair_fits(G * R, L, rl)) return -1;
+    if (G == 4 && R == 40) pair_passes_host<4, 40>(A, B, L, ref, rl, ml, o);
+    else if (G == 8 && R == 32) pair_passes_host<8, 32>(A, B, L, ref, rl, ml, o);
+    else if (G == 4 && R == 32) pair_passes_host<4, 32>(A, B, L, ref, rl, ml, o);
+    else if (G == 2 && R == 33) pair_passes_host<2, 33>(A, B, L, ref, rl, ml, o);
+    else return -2;
+    for (int h = 0; h < 2; h++) {
+        int* p = out16 + 8 * h;
+        p[0] = o[h].score;
+        p[1] = o[h].score2;
+        p[2] = o[h].ref_begin;
+        p[3] = o[h].ref_end;
+        p[4] = o[h].query_begin;
+        p[5] = o[h].query_end;
+        p[6] = o[h].ref2;
+        p[7] = o[h].flag;
+    }
+    return 0;
+}
