@@ -79,6 +79,37 @@ void hh_sw_align(const char* query, int qlen, const char* ref, int rlen, int mas
     if (al->cigar_len < cigar_cap) cigar[al->cigar_len] = 0;
 }
 
+// band statistics of the trace-back stage (used by tools/band_stats.py to size the kernels)
+void hh_sw_band_stats(const char* query, int qlen, const char* ref, int rlen, int maskLen, int* out)
+{
+    SwAlignment al;
+    char cig[8];
+    hh_sw_align(query, qlen, ref, rlen, maskLen, &al, cig, 0);
+    out[0] = al.sw_score;
+    out[1] = al.ref_end - al.ref_begin + 1;
+    out[2] = al.query_end - al.query_begin + 1;
+    out[3] = out[4] = 0;
+    if (al.sw_score <= 0 || al.ref_begin < 0) return;
+    std::vector<int8_t> q(qlen + 1), r(rlen + 1);
+    for (int i = 0; i < qlen; i++) q[i] = sw_translate((unsigned char)query[i]);
+    for (int i = 0; i < rlen; i++) r[i] = sw_translate((unsigned char)ref[i]);
+    const int refLen = out[1], readLen = out[2], len = refLen > readLen ? refLen : readLen;
+    int band = refLen - readLen;
+    band = (band < 0 ? -band : band) + 1;
+    std::vector<int32_t> hb(2 * len + 32), eb(2 * len + 32), hc(2 * len + 32);
+    std::vector<uint8_t> dir((size_t)(2 * len + 3) * (readLen + 1));
+    int mx = 0, iters = 0;
+    do {
+        const int m = sw_banded_once(r.data() + al.ref_begin, q.data() + al.query_begin, refLen, readLen, band, hb.data(),
+                                     eb.data(), hc.data(), DirLinear{dir.data()}, 2 * band + 1);
+        mx = m > mx ? m : mx;
+        band *= 2;
+        iters++;
+    } while (mx < al.sw_score && band <= len);
+    out[3] = band / 2;
+    out[4] = iters;
+}
+
 int hh_myers(const char* q, int qlen, const char* t, int tlen)
 {
     return myers_nw((const unsigned char*)q, qlen, (const unsigned char*)t, tlen);
