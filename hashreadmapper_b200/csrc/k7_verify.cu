@@ -19,6 +19,8 @@
 #include "pipeline.cuh"
 #include "core_sw.cuh"
 #include "core_swpair.cuh"
+#include "core_swband.cuh"
+#include <stdlib.h>
 
 namespace hrm {
 
@@ -37,6 +39,21 @@ struct AsciiSrc { // function-level API: ASCII rows
     const int32_t* mask_len;
     int maxQ, maxR;
     static constexpr int SKIP_FLAG = 1; // sizes outside the limits: reported like a failed trace back
+    struct Item { // random access to the codes of one alignment (band kernels)
+        const char* q_;
+        const char* r_;
+        int ql, rl;
+        __device__ __forceinline__ int q(int i) const { return sw_translate((unsigned char)q_[i]); }
+        __device__ __forceinline__ int r(int j) const { return sw_translate((unsigned char)r_[j]); }
+    };
+    __device__ __forceinline__ bool open(int64_t e, Item& it) const
+    {
+        it.ql = qlen[e];
+        it.rl = rlen[e];
+        it.q_ = queries + e * qpitch;
+        it.r_ = refs + e * rpitch;
+        return !(it.ql < 0 || it.ql > maxQ || it.rl < 0 || it.rl > maxR);
+    }
     // returns false when the item must be skipped
     __device__ __forceinline__ bool load(int64_t e, int8_t* sq, int8_t* sr, int tid, int nthr, int& ql, int& rl,
                                          int& ml) const
@@ -64,6 +81,39 @@ struct PackedSrc { // fused path: item t = 2 * read + a
     const hrm_mapped_read* mapped;
     int maxQ, maxR;
     static constexpr int SKIP_FLAG = 0; // unmapped read: zero-initialised alignments (ref: mappinghandler.cu:548)
+    struct Item { // random access to the codes of one alignment (band kernels)
+        const uint32_t* rw;
+        const uint32_t* cw;
+        int64_t pos;
+        int ql, rl, conv;
+        bool rc;
+        __device__ __forceinline__ int q(int i) const
+        {
+            return conv_code(rc ? 3 - (int)get_nuc(rw, ql - 1 - i) : (int)get_nuc(rw, i), conv);
+        }
+        __device__ __forceinline__ int r(int j) const { return conv_code((int)get_nuc(cw, pos + j), conv); }
+    };
+    __device__ __forceinline__ bool open(int64_t t, Item& it) const
+    {
+        const int64_t rd = t >> 1;
+        const hrm_mapped_read m = mapped[rd];
+        const int L = read_len[rd];
+        it.ql = L;
+        it.rl = 0;
+        if (m.orientation == HRM_ORIENT_NONE || m.pass < 0 || m.pass >= VP.num_passes || L <= 0 || L > maxQ)
+            return false;
+        const VerifyPass& P = VP.pass[m.pass];
+        it.rw = P.reads + rd * P.read_pitch;
+        it.cw = P.G.chrom_words[m.chromosome_id];
+        const int64_t clen = P.G.chrom_len[m.chromosome_id];
+        int wl = (int)((m.position + VP.w < clen) ? VP.w : clen - m.position); // ref: mappinghandler.cu:434-440
+        if (wl > maxR) wl = maxR;
+        it.rl = wl;
+        it.pos = m.position;
+        it.conv = P.verify_conv;
+        it.rc = (m.orientation == HRM_ORIENT_REVCOMP) != ((t & 1) == 1);
+        return true;
+    }
     __device__ __forceinline__ bool load(int64_t t, int8_t* sq, int8_t* sr, int tid, int nthr, int& ql, int& rl,
                                          int& ml) const
     {
@@ -599,6 +649,175 @@ __device__ __forceinline__ int warp_banded(const int8_t* ref, const int8_t* read
     return 0;
 }
 
+// ---- work lists of the trace-back ladder ---------------------------------------------------------------
+// list c (c <= max_cls): alignments whose next band iteration has a band in [2^c, 2^(c+1)); list max_cls + 1:
+// everything the thread-per-alignment kernels cannot hold (kernel B3).  The band doubles after a failed
+// iteration, so an alignment visits each class at most once, in ascending order: one launch per class.
+struct BandLists {
+    int32_t* items;  // (max_cls + 2) lists of `cap` entries
+    int32_t* counts; // max_cls + 2
+    int64_t cap;
+    int max_cls;
+    int dir_rows; // rows the direction pool holds per alignment
+    __device__ __forceinline__ void push(int list, int32_t e) const
+    {
+        items[(int64_t)list * cap + atomicAdd(counts + list, 1)] = e;
+    }
+};
+
+// classifier: every alignment with a trace back to do goes to the list of its first band; the rest get their
+// terminating NUL (ref: ssw_align returns without a cigar when the score is 0 / banded_sw is never reached)
+__global__ void __launch_bounds__(256) sw_classify_kernel(const hrm_alignment* __restrict__ out, int64_t n,
+                                                          char* __restrict__ cigars, int64_t cigar_pitch, BandLists BL)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const hrm_alignment o = out[e];
+        if (o.flag == 1 || o.sw_score <= 0 || o.ref_begin < 0) {
+            if (o.cigar_len < cigar_pitch) cigars[e * cigar_pitch + o.cigar_len] = 0;
+            continue;
+        }
+        const int refLen = o.ref_end - o.ref_begin + 1, readLen = o.query_end - o.query_begin + 1;
+        int band = refLen - readLen;
+        band = (band < 0 ? -band : band) + 1;
+        const int c = sw_band_class(band);
+        BL.push(c <= BL.max_cls && readLen <= BL.dir_rows ? c : BL.max_cls + 1, (int32_t)e);
+    }
+}
+
+// ---- B2: one band iteration per alignment and class, one THREAD per alignment (core_swband.cuh) -------------
+// State of the row ((H, E) pairs, match masks of the window) in shared memory, word-interleaved over the
+// threads of the block (conflict free); direction nibbles in a global pool, word-interleaved over the lanes
+// of the warp (rows in lock step coalesce).  Success -> trace back + CIGAR in the same thread; a band that is
+// still too narrow -> next class.
+constexpr int BAND_TILE = 1024;
+template <class Src>
+__global__ void __launch_bounds__(128) sw_finish_band_kernel(Src src, BandLists BL, int cls, int band_max, int MW, int nw,
+                                                             uint32_t* __restrict__ dir_pool, int64_t dir_words_per_warp,
+                                                             hrm_alignment* __restrict__ out,
+                                                             char* __restrict__ cigars, int64_t cigar_pitch)
+{
+    extern __shared__ __align__(16) uint32_t smw[];
+    const int T = blockDim.x;
+    const int nstate = 2 * band_max + 3;
+    const BandState S{smw + threadIdx.x, T};
+    const BandMasks M{smw + (size_t)nstate * T + threadIdx.x, T, MW};
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const BandDirs D{dir_pool + (gtid >> 5) * dir_words_per_warp + (threadIdx.x & 31), 32, nw};
+    // Work of an item ~ rows x band cells and the lanes of a warp run rows and cells in lock step: every block
+    // takes a contiguous share of the list and sorts it tile-wise by (band, rows) in shared memory, so that the
+    // 32 items a warp holds at a time are nearly alike.
+    __shared__ unsigned long long tile[BAND_TILE];
+    __shared__ int next_group;
+    const int64_t total = BL.counts[cls];
+    const int32_t* list = BL.items + (int64_t)cls * BL.cap;
+    const int64_t share = HRM_SDIV(total, (int64_t)gridDim.x);
+    const int64_t share_lo = (int64_t)blockIdx.x * share;
+    const int64_t share_hi = (share_lo + share) < total ? (share_lo + share) : total;
+    for (int64_t tile0 = share_lo; tile0 < share_hi; tile0 += BAND_TILE) {
+    __syncthreads();
+    if (threadIdx.x == 0) next_group = 0;
+    for (int t = threadIdx.x; t < BAND_TILE; t += T) {
+        unsigned long long key = ~0ull;
+        if (tile0 + t < share_hi) {
+            const int32_t e = list[tile0 + t];
+            const hrm_alignment o = out[e];
+            const int refLen = o.ref_end - o.ref_begin + 1, readLen = o.query_end - o.query_begin + 1;
+            int band = refLen - readLen;
+            band = (band < 0 ? -band : band) + 1;
+            while (sw_band_class(band) < cls) band *= 2;
+            key = ((unsigned long long)(unsigned)band << 48) | ((unsigned long long)(unsigned)readLen << 32) | (unsigned)e;
+        }
+        tile[t] = key;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= BAND_TILE; k2 <<= 1)
+        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+            for (int t = threadIdx.x; t < BAND_TILE; t += T) {
+                const int p = t ^ j2;
+                if (p > t) {
+                    const unsigned long long a = tile[t], b = tile[p];
+                    if ((a > b) == ((t & k2) == 0)) {
+                        tile[t] = b;
+                        tile[p] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    const int ntile = (share_hi - tile0) < BAND_TILE ? (int)(share_hi - tile0) : BAND_TILE;
+    // warps pull groups of 32 neighbours, heaviest first (longest-processing-time order balances the warps)
+    while (true) {
+        int grp = 0;
+        if ((threadIdx.x & 31) == 0) grp = atomicAdd(&next_group, 1);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        const int it = ntile - 1 - (grp * 32 + (int)(threadIdx.x & 31));
+        if (grp * 32 >= ntile) break;
+        if (it < 0) continue;
+        const unsigned long long key = tile[it];
+        const int64_t e = (int64_t)(uint32_t)key;
+        hrm_alignment o = out[e];
+        const int refLen = o.ref_end - o.ref_begin + 1, readLen = o.query_end - o.query_begin + 1;
+        const int len = refLen > readLen ? refLen : readLen;
+        const int band = (int)(key >> 48); // the element of the doubling sequence in this class
+        typename Src::Item item;
+        if (band > band_max || readLen > BL.dir_rows || refLen > 32 * MW || !src.open(e, item)) {
+            BL.push(BL.max_cls + 1, (int32_t)e);
+            continue;
+        }
+        for (int c0 = 0; c0 < refLen; c0 += 32) { // match masks of the window sub-sequence
+            uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+            const int lim = (refLen - c0) < 32 ? (refLen - c0) : 32;
+            for (int t = 0; t < lim; t++) {
+                const int c = item.r(o.ref_begin + c0 + t);
+                m0 |= (uint32_t)(c == 0) << t;
+                m1 |= (uint32_t)(c == 1) << t;
+                m2 |= (uint32_t)(c == 2) << t;
+                m3 |= (uint32_t)(c == 3) << t;
+            }
+            const int w = c0 >> 5;
+            M.p[(int64_t)(0 * MW + w) * T] = m0;
+            M.p[(int64_t)(1 * MW + w) * T] = m1;
+            M.p[(int64_t)(2 * MW + w) * T] = m2;
+            M.p[(int64_t)(3 * MW + w) * T] = m3;
+        }
+        for (int w = HRM_SDIV(refLen, 32); w < MW; w++)
+            for (int c = 0; c < 4; c++) M.p[(int64_t)(c * MW + w) * T] = 0u;
+        const int qb = o.query_begin;
+        const int m = sw_band_iteration(M, [&](int i) -> int { return item.q(qb + i); }, refLen, readLen, band, S, D);
+        if (m < o.sw_score && band * 2 <= len) { // ref: while (max < score && band_width <= len), ssw.c:672
+            BL.push(sw_band_class(band * 2) <= BL.max_cls ? cls + 1 : BL.max_cls + 1, (int32_t)e);
+            continue;
+        }
+        uint32_t steps[(HRM_SW_MAX_QUERY + HRM_SW_MAX_REF) / 16 + 2];
+        int nsteps = sw_band_traceback(D, band, refLen, readLen, steps, (HRM_SW_MAX_QUERY + HRM_SW_MAX_REF) + 16);
+        SwAlignment al;
+        al.sw_score = o.sw_score;
+        al.sw_score_next_best = o.sw_score_next_best;
+        al.ref_begin = o.ref_begin;
+        al.ref_end = o.ref_end;
+        al.query_begin = o.query_begin;
+        al.query_end = o.query_end;
+        al.ref_end_next_best = o.ref_end_next_best;
+        al.mismatches = 0;
+        al.cigar_len = 0;
+        al.flag = o.flag;
+        if (nsteps < 0) { // ref: banded_sw failed -> flag 1, empty path (ssw.c:910)
+            al.flag = 1;
+            nsteps = 0;
+        }
+        char* cig = cigars + e * cigar_pitch;
+        sw_emit_steps([&](int i) -> int { return item.q(i); }, item.ql, [&](int j) -> int { return item.r(j); }, &al, steps,
+                      nsteps, cig, (int)cigar_pitch);
+        o.mismatches = al.mismatches;
+        o.flag = al.flag;
+        o.cigar_len = al.cigar_len;
+        out[e] = o;
+        if (o.cigar_len < cigar_pitch) cig[o.cigar_len] = 0;
+    }
+    }
+}
+
 // ---- B1 / B2: one THREAD per alignment -------------------------------------------------------------
 // The literal banded DP (core_sw.cuh: sw_banded_once) is most instruction-efficient with one alignment per
 // thread; what limits it is where its state lives.  B1 (BWMAX = 1): true alignments of substitution-only
@@ -614,8 +833,7 @@ __global__ void __launch_bounds__(128) sw_finish_thread_kernel(Src src, int64_t 
                                                                uint8_t* __restrict__ dir_pool,
                                                                hrm_alignment* __restrict__ out,
                                                                char* __restrict__ cigars, int64_t cigar_pitch,
-                                                               int32_t* __restrict__ worklist,
-                                                               int32_t* __restrict__ work_count)
+                                                               BandLists BL)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     int8_t* q = (int8_t*)(smem + (size_t)slice_bytes * threadIdx.x);
@@ -640,8 +858,12 @@ __global__ void __launch_bounds__(128) sw_finish_thread_kernel(Src src, int64_t 
         int band = refLen - readLen;
         band = (band < 0 ? -band : band) + 1;
         bool defer = band > BWMAX || readLen > dir_rows;
+        int defer_band = band; // the band the next stage has to run
         int ql = 0, rl = 0, ml = 0;
-        if (!defer) defer = !src.load(e, q, r, 0, 1, ql, rl, ml);
+        if (!defer && !src.load(e, q, r, 0, 1, ql, rl, ml)) {
+            defer = true;
+            defer_band = -1; // not loadable here: the general kernel decides
+        }
         if (!defer) {
             int32_t hb[2 * BWMAX + 3 + 8], eb[2 * BWMAX + 3 + 8], hc[2 * BWMAX + 3 + 8];
             int mx = 0;
@@ -654,6 +876,7 @@ __global__ void __launch_bounds__(128) sw_finish_thread_kernel(Src src, int64_t 
                     band *= 2;
                     if (band > BWMAX) {
                         defer = true;
+                        defer_band = band;
                         break;
                     }
                     continue;
@@ -666,7 +889,10 @@ __global__ void __launch_bounds__(128) sw_finish_thread_kernel(Src src, int64_t 
                 int nops;
                 if (SMEM_DIR) nops = sw_traceback(dlin, WD, 2 * band + 1, band, refLen, readLen, ops, lens, MAXOPS);
                 else nops = sw_traceback(dint, WD, 2 * band + 1, band, refLen, readLen, ops, lens, MAXOPS);
-                if (nops >= MAXOPS) defer = true; // may have been truncated: let the next stage redo it
+                if (nops >= MAXOPS) { // may have been truncated: the band kernel redoes this band without an op limit
+                    defer = true;
+                    defer_band = band;
+                }
                 if (!defer) {
                     SwAlignment al;
                     al.sw_score = o.sw_score;
@@ -692,7 +918,7 @@ __global__ void __launch_bounds__(128) sw_finish_thread_kernel(Src src, int64_t 
                 }
             }
         }
-        if (defer) worklist[atomicAdd(work_count, 1)] = (int32_t)e;
+        if (defer) BL.push(defer_band > 0 && readLen <= BL.dir_rows ? sw_band_class(defer_band) : BL.max_cls + 1, (int32_t)e);
     }
 }
 
@@ -894,18 +1120,28 @@ static hrm_status run_sw(const Src& src, int64_t n, int maxQ, int maxR, hrm_alig
         }
 #undef HRM_LAUNCH_A
     }
-    // kernel B1 (thread/alignment, band 1, on chip) -> B3 (warp/alignment, everything else)
+    // kernel B1 (thread/alignment, band 1, on chip) -> B2 ladder (thread/alignment, one launch per band class)
+    // -> B3 (warp/alignment, whatever is left)
     {
         HRM_REQUIRE(n < (1LL << 31), "too many alignments in one call");
-        Scratch wl;
-        HRM_TRY(wl.alloc(sizeof(int32_t) * (2 * (size_t)n + 8), s));
-        int32_t* count1 = wl.as<int32_t>();
-        int32_t* count2 = wl.as<int32_t>() + 1;
-        int32_t* list1 = wl.as<int32_t>() + 4;
-        int32_t* list2 = list1 + n;
-        HRM_CUDA(cudaMemsetAsync(count1, 0, 2 * sizeof(int32_t), s));
         const int maxQq = maxQ > 16 ? maxQ : 16;
-        {
+        const int maxLen = (maxQ > maxR ? maxQ : maxR) > 16 ? (maxQ > maxR ? maxQ : maxR) : 16;
+        BandLists BL;
+        BL.max_cls = sw_band_class(maxLen) < 8 ? sw_band_class(maxLen) : 8; // bands never exceed max(len)
+        BL.cap = n;
+        BL.dir_rows = maxQq;
+        const int nlists = BL.max_cls + 2;
+        Scratch wl;
+        HRM_TRY(wl.alloc(sizeof(int32_t) * ((size_t)nlists * (size_t)n + 64), s));
+        BL.counts = wl.as<int32_t>();
+        BL.items = wl.as<int32_t>() + 64;
+        HRM_CUDA(cudaMemsetAsync(BL.counts, 0, 64 * sizeof(int32_t), s));
+        static const bool use_b1 = getenv("HRM_SW_B1") != nullptr; // experiment switch: band-1 kernel in front
+        if (!use_b1) {
+            int64_t blocks = HRM_SDIV(n, (int64_t)256);
+            if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
+            HRM_LAUNCH(sw_classify_kernel, (unsigned)blocks, 256, 0, s, d_out, n, d_cigars, cigar_pitch, BL);
+        } else {
             int slice = (int)align_up(QP + RP + 3 * maxQq, 4) + 4; // odd number of words
             if (((slice / 4) & 1) == 0) slice += 4;
             const int threads = 128;
@@ -917,16 +1153,50 @@ static hrm_status run_sw(const Src& src, int64_t n, int maxQ, int maxR, hrm_alig
             if (smemS > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS);
             HRM_LAUNCH(kern, (unsigned)blocks, threads, smemS, s, src, n, (const int32_t*)nullptr,
                        (const int32_t*)nullptr, slice, QP, RP, maxQq, (uint8_t*)nullptr, d_out, d_cigars, cigar_pitch,
-                       list1, count1);
+                       BL);
         }
-        // (a thread-per-alignment stage for bands <= 16 with its state in local memory was measured slower than the
-        //  warp kernel on the gapped "other strand" alignments -- divergent band iterations; instantiate
-        //  sw_finish_thread_kernel<Src, 16, 128, true, false> between B1 and B3 to try it again)
-        (void)list2;
-        (void)count2;
-        int32_t* worklist = list1;
-        int32_t* work_count = count1;
-        const int maxLen = (maxQ > maxR ? maxQ : maxR) > 16 ? (maxQ > maxR ? maxQ : maxR) : 16;
+        // B2 ladder: geometry per class, one direction pool shared by the launches
+        struct ClassGeo {
+            int band_max, nw, threads;
+            size_t smem;
+            int64_t blocks, words_per_warp;
+        } geo[16];
+        const int MW = HRM_SDIV(maxR > 16 ? maxR : 16, 32);
+        const int64_t POOL_LIMIT = 768LL << 20;
+        int64_t pool_bytes = 256;
+        for (int c = 0; c <= BL.max_cls; c++) {
+            ClassGeo& g = geo[c];
+            g.band_max = (2 << c) - 1 < maxLen ? (2 << c) - 1 : maxLen;
+            g.nw = (2 * g.band_max + 8) / 8;
+            g.threads = 128;
+            const size_t per_thread = sizeof(uint32_t) * (size_t)(2 * g.band_max + 3 + 4 * MW);
+            while (per_thread * g.threads > 200 * 1024 && g.threads > 32) g.threads >>= 1;
+            g.smem = per_thread * g.threads;
+            HRM_REQUIRE(g.smem <= 200 * 1024, "band class does not fit shared memory");
+            int resident = (int)((220 * 1024) / (g.smem + 1024));
+            if (resident < 1) resident = 1;
+            if (resident > 2048 / g.threads) resident = 2048 / g.threads;
+            g.words_per_warp = (int64_t)BL.dir_rows * g.nw * 32;
+            g.blocks = HRM_SDIV(n, (int64_t)g.threads);
+            int64_t cap = (int64_t)num_sms() * resident;
+            const int64_t fit = POOL_LIMIT / (g.words_per_warp * 4 * (g.threads / 32));
+            if (cap > fit) cap = fit > 1 ? fit : 1;
+            if (g.blocks > cap) g.blocks = cap;
+            const int64_t need = g.blocks * (g.threads / 32) * g.words_per_warp * 4;
+            if (need > pool_bytes) pool_bytes = need;
+        }
+        Scratch pool;
+        HRM_TRY(pool.alloc((size_t)pool_bytes, s));
+        for (int c = 0; c <= BL.max_cls; c++) {
+            const ClassGeo& g = geo[c];
+            auto kern = sw_finish_band_kernel<Src>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            HRM_LAUNCH(kern, (unsigned)g.blocks, g.threads, g.smem, s, src, BL, c, g.band_max, MW, g.nw, pool.as<uint32_t>(),
+                       g.words_per_warp, d_out, d_cigars, cigar_pitch);
+        }
+        pool.release();
+        int32_t* worklist = BL.items + (int64_t)(BL.max_cls + 1) * BL.cap;
+        int32_t* work_count = BL.counts + BL.max_cls + 1;
         TracePool P;
         P.wmax = (int)align_up(2 * maxLen + 3 + 8 + 1, 4);
         P.maxops = 2 * maxLen + 8;

@@ -11,6 +11,7 @@
 #include "../../hashreadmapper_b200/csrc/core_shd.cuh"
 #include "../../hashreadmapper_b200/csrc/core_sw.cuh"
 #include "../../hashreadmapper_b200/csrc/core_swpair.cuh"
+#include "../../hashreadmapper_b200/csrc/core_swband.cuh"
 
 using namespace hrm;
 
@@ -108,6 +109,121 @@ void hh_sw_band_stats(const char* query, int qlen, const char* ref, int rlen, in
     } while (mx < al.sw_score && band <= len);
     out[3] = band / 2;
     out[4] = iters;
+}
+
+// the thread-per-alignment band ladder of k7_verify.cu (core_swband.cuh) on top of the scalar passes:
+// same begin/end search as hh_sw_align, then one sw_band_iteration per band of the doubling sequence
+void hh_sw_align_band(const char* query, int qlen, const char* ref, int rlen, int maskLen, SwAlignment* al,
+                      char* cigar, int cigar_cap, int stride)
+{
+    std::vector<int8_t> q(qlen + 1), r(rlen + 1);
+    for (int i = 0; i < qlen; i++) q[i] = sw_translate((unsigned char)query[i]);
+    for (int i = 0; i < rlen; i++) r[i] = sw_translate((unsigned char)ref[i]);
+    const int maxLen = (qlen > rlen ? qlen : rlen) + 16;
+    std::vector<int16_t> H(maxLen + 32), E(maxLen + 32), mc(maxLen + 32);
+    al->sw_score = al->sw_score_next_best = al->ref_begin = al->ref_end = al->query_begin = al->query_end = 0;
+    al->ref_end_next_best = al->mismatches = al->flag = al->cigar_len = 0;
+    if (cigar_cap > 0) cigar[0] = 0;
+    if (qlen <= 0) return;
+    bool word = false;
+    SwEnds b = sw_pass(r.data(), 0, rlen, q.data(), 0, 1, qlen, 16, 255, maskLen, H.data(), E.data(), mc.data());
+    if (b.score == 255) {
+        b = sw_pass(r.data(), 0, rlen, q.data(), 0, 1, qlen, 8, 65535, maskLen, H.data(), E.data(), mc.data());
+        word = true;
+    }
+    al->sw_score = b.score;
+    al->sw_score_next_best = maskLen >= 15 ? b.score2 : 0;
+    al->ref_end = b.ref;
+    al->query_end = b.read;
+    al->ref_end_next_best = maskLen >= 15 ? b.ref2 : -1;
+    if (b.score == 0 || b.ref < 0) {
+        al->ref_begin = -1;
+        al->query_begin = -1;
+        return;
+    }
+    const SwEnds br = sw_pass(r.data(), 1, b.ref + 1, q.data(), b.read, -1, b.read + 1, word ? 8 : 16,
+                              word ? b.score : (b.score & 255), maskLen, H.data(), E.data(), mc.data());
+    al->ref_begin = br.ref;
+    al->query_begin = b.read - br.read;
+    al->flag = b.score > br.score ? 2 : 0;
+    const int refLen = al->ref_end - al->ref_begin + 1, readLen = al->query_end - al->query_begin + 1;
+    const int len = refLen > readLen ? refLen : readLen;
+    int band = refLen - readLen;
+    band = (band < 0 ? -band : band) + 1;
+    const int MW = HRM_SDIV(refLen, 32);
+    std::vector<uint32_t> mk((size_t)4 * MW * stride + 1, 0xdeadbeefu);
+    BandMasks M{mk.data(), stride, MW};
+    M.clear();
+    for (int j = 0; j < refLen; j++) M.set(r[al->ref_begin + j], j);
+    auto qc = [&](int i) -> int { return q[al->query_begin + i]; };
+    std::vector<uint32_t> steps((qlen + rlen) / 16 + 4, 0xdeadbeefu);
+    int nsteps = -1;
+    int prev_class = -1;
+    while (true) {
+        const int cls = sw_band_class(band);
+        if (cls <= prev_class) std::abort(); // one iteration per class
+        prev_class = cls;
+        std::vector<uint32_t> st((size_t)(2 * band + 3) * stride + 1, 0xdeadbeefu);
+        const int nw = (2 * band + 8) / 8;
+        std::vector<uint32_t> dd((size_t)readLen * nw * stride + 1, 0xdeadbeefu);
+        BandState S{st.data(), stride};
+        BandDirs D{dd.data(), stride, nw};
+        const int m = sw_band_iteration(M, qc, refLen, readLen, band, S, D);
+        if (m < al->sw_score && band * 2 <= len) {
+            band *= 2;
+            continue;
+        }
+        nsteps = sw_band_traceback(D, band, refLen, readLen, steps.data(), (int)steps.size() * 16);
+        break;
+    }
+    if (nsteps < 0) {
+        al->flag = 1;
+        nsteps = 0;
+    }
+    sw_emit_steps([&](int i) -> int { return q[i]; }, qlen, [&](int j) -> int { return r[j]; }, al, steps.data(), nsteps,
+                  cigar, cigar_cap);
+    if (al->cigar_len < cigar_cap) cigar[al->cigar_len] = 0;
+}
+
+// cell-by-cell comparison of sw_band_iteration (diagonal coordinates) with the literal sw_banded_once for an
+// ARBITRARY band: returns the number of differing direction cells, +1000000 if the band maxima differ
+int hh_band_compare(const char* ref, int refLen, const char* read, int readLen, int band, int stride)
+{
+    std::vector<int8_t> q(readLen + 1), r(refLen + 1);
+    for (int i = 0; i < readLen; i++) q[i] = sw_translate((unsigned char)read[i]);
+    for (int i = 0; i < refLen; i++) r[i] = sw_translate((unsigned char)ref[i]);
+    const int width_d = 2 * band + 1;
+    std::vector<int32_t> hb(2 * band + 32), eb(2 * band + 32), hc(2 * band + 32);
+    std::vector<uint8_t> dir((size_t)width_d * readLen + 8);
+    const int m1 = sw_banded_once(r.data(), q.data(), refLen, readLen, band, hb.data(), eb.data(), hc.data(),
+                                  DirLinear{dir.data()}, width_d);
+    const int MW = HRM_SDIV(refLen, 32);
+    std::vector<uint32_t> mk((size_t)4 * MW * stride + 1, 0xdeadbeefu);
+    BandMasks M{mk.data(), stride, MW};
+    M.clear();
+    for (int j = 0; j < refLen; j++) M.set(r[j], j);
+    std::vector<uint32_t> st((size_t)(2 * band + 3) * stride + 1, 0xdeadbeefu);
+    const int nw = (2 * band + 8) / 8;
+    std::vector<uint32_t> dd((size_t)readLen * nw * stride + 1, 0xdeadbeefu);
+    BandState S{st.data(), stride};
+    BandDirs D{dd.data(), stride, nw};
+    const int m2 = sw_band_iteration(M, [&](int i) -> int { return q[i]; }, refLen, readLen, band, S, D);
+    int bad = m1 != m2 ? 1000000 : 0;
+    for (int i = 0; i < readLen; i++) {
+        const int xi = (i - band) > 0 ? (i - band) : 0;
+        const int beg = xi, end = (i + band) < (refLen - 1) ? (i + band) : (refLen - 1);
+        for (int j = beg; j <= end; j++) {
+            const uint8_t cell = dir[(size_t)width_d * i + (j - xi)];
+            const uint32_t nb = D.nibble(i, j - xi); // cell index within the row
+            const int dh = cell & 7;
+            // bit 3: not diagonal, bit 2: from E (only meaningful when bit 3), bit 1: E opened, bit 0: F opened
+            const uint32_t want_hi = dh == 1 ? 0u : ((dh == 2 || dh == 3) ? 12u : 8u);
+            const uint32_t want = want_hi | ((cell & 8) ? 2u : 0u) | ((cell & 16) ? 1u : 0u);
+            const uint32_t got = (nb & 8u) ? nb : (nb & 11u);
+            if (!(cell & 0x80) || got != want) bad++;
+        }
+    }
+    return bad;
 }
 
 int hh_myers(const char* q, int qlen, const char* t, int tlen)

@@ -119,6 +119,85 @@ def test_core_sw_and_myers(hh, port):
         assert hh.hh_myers(q, len(q), t, len(t)) == port.edit_distance_nw(q, t)
 
 
+def band_cases(seed, n):
+    """pairs that drive the band doubling of the trace back: junk local alignments in 3-letter alphabets,
+    long indels, and references much shorter than the read (band wider than half the reference -> the
+    reference's absolute-coordinate edge zeroing, ssw.c:635)"""
+    rng = random.Random(seed)
+    out = []
+    for it in range(n):
+        mode = it % 6
+        alpha = rng.choice(["AGT", "ACT", "AT", "ACGT", "AAT"])
+        if mode == 0:   # other-strand style: unrelated sequences
+            q, r = rs(rng, rng.choice([150, 250, 80]), alpha), rs(rng, rng.choice([128, 64, 256]), alpha)
+        elif mode == 1:  # one long deletion / insertion
+            G = rs(rng, 400, alpha)
+            p, gap = rng.randint(0, 100), rng.randint(1, 60)
+            r = G[p:p + 128]
+            q = (G[p:p + 40] + G[p + 40 + gap:p + 150 + gap]) if rng.random() < 0.5 else \
+                (G[p:p + 40] + rs(rng, gap, alpha) + G[p + 40:p + 110])
+        elif mode == 2:  # short reference, long read with an insertion: band > refLen / 2
+            G = rs(rng, 300, alpha)
+            rl = rng.randint(3, 40)
+            r = G[100:100 + rl]
+            cut = rng.randint(1, max(1, rl - 1))
+            q = G[100 - rng.randint(0, 20):100 + cut] + rs(rng, rng.randint(1, 80), alpha) + G[100 + cut:100 + rl + 10]
+        elif mode == 3:  # short read, long reference with a deletion
+            G = rs(rng, 400, alpha)
+            ql = rng.randint(6, 40)
+            cut = rng.randint(1, ql - 1)
+            q = G[50:50 + cut] + G[50 + cut + rng.randint(1, 90):][:ql - cut]
+            r = G[30:30 + rng.randint(60, 200)]
+        elif mode == 4:  # noisy copies with many small indels
+            G = rs(rng, 300, alpha)
+            r = G[50:50 + rng.choice([128, 100])]
+            q = mutate(rng, G[40:40 + rng.choice([150, 120])], 0.05, rng.choice([0.05, 0.1, 0.2])) or b"A"
+        else:            # low-complexity
+            r = rs(rng, rng.randint(5, 150), "AAAT")
+            q = rs(rng, rng.randint(5, 200), "AAT")
+        out.append((q or b"A", r or b"A", max(15, len(q) // 2)))
+    return out
+
+
+def test_core_sw_band_ladder(hh, port):
+    """core_swband.cuh (diagonal-coordinate band iteration, nibble directions, step-list CIGAR) against the
+    oracle's ssw_align, with strided state like the kernel's shared-memory slices"""
+    from oracle.pyoracle import Alignment
+    cases = ssw_cases(77, 1200) + band_cases(78, 3000)
+    wide = 0
+    for idx, (q, r, ml) in enumerate(cases):
+        al = Alignment()
+        cig = C.create_string_buffer(4096)
+        hh.hh_sw_align_band(q, len(q), r, len(r), ml, C.byref(al), cig, 4096, 1 + idx % 3)
+        want = port.ssw_align(q, r, ml)
+        assert (al.astuple(), cig.value.decode()) == want, (q, r, ml)
+        t = want[0]
+        if t[0] > 0 and t[2] >= 0:
+            wide += abs((t[3] - t[2]) - (t[5] - t[4])) + 1 > (t[3] - t[2] + 1) // 2
+    assert wide > 10  # the edge-zeroing regime was exercised
+
+
+def test_core_sw_band_cells(hh):
+    """every direction cell and the band maximum of sw_band_iteration against the literal banded row loop
+    (core_sw.cuh: sw_banded_once, itself pinned to the oracle) for ARBITRARY bands, including bands wider than
+    the reference where ssw.c:635 zeroes a valid cell"""
+    rng = random.Random(5)
+    killed = 0
+    for it in range(6000):
+        alpha = rng.choice(["AGT", "AT", "ACGT", "AAT", "A"])
+        refLen, readLen = rng.randint(1, 70), rng.randint(1, 90)
+        if it % 3 == 0:
+            refLen = rng.randint(1, 12)
+        band = rng.randint(1, 80) if it % 2 else rng.randint(1, 12)
+        r = rs(rng, refLen, alpha)
+        q = rs(rng, readLen, alpha)
+        if it % 4 == 0:  # related sequences: high scores along the last column
+            q = (r * 8)[:readLen]
+        killed += refLen <= 2 * band + 1 and readLen > refLen - band
+        assert hh.hh_band_compare(r, refLen, q, readLen, band, 1 + it % 3) == 0, (r, q, band)
+    assert killed > 500
+
+
 _CODE = {ord("A"): 0, ord("C"): 1, ord("G"): 2, ord("T"): 3, ord("N"): 4}
 _RC = {65: 84, 67: 71, 71: 67, 84: 65, 78: 78}
 
