@@ -64,6 +64,14 @@ class MapperInfo(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class CommInfo(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("bytes_sent", C.c_int64), ("bytes_received", C.c_int64),
+                ("exchanges", C.c_int64)]
+
+
+COMM_ID_BYTES = 128
+
+
 class BatchStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("num_reads", "num_probes", "num_slot_touches", "num_values",
                                          "num_candidates", "num_mapped", "num_kernel_launches")]
@@ -139,6 +147,13 @@ SIGNATURES = {
     "hrm_mapper_map_reads": (I32, [P, P, I64, P, I64, P, P, I64, C.POINTER(BatchStats), VP]),
     "hrm_mapper_set_profiling": (I32, [P, C.c_int]),
     "hrm_mapper_stage_times": (I32, [P, C.POINTER(C.c_float), C.POINTER(I32)]),
+    "hrm_comm_unique_id": (I32, [P, I64]),
+    "hrm_comm_create": (I32, [C.POINTER(P), C.c_int, C.c_int, P]),
+    "hrm_comm_destroy": (None, [P]),
+    "hrm_comm_info": (I32, [P, C.POINTER(CommInfo)]),
+    "hrm_key_owner": (C.c_int, [C.c_uint64, C.c_int]),
+    "hrm_minhasher_set_partition": (I32, [P, C.c_int, C.c_int]),
+    "hrm_mapper_set_partition": (I32, [P, P]),
     "hrm_sam_format": (I32, [P, P, P, I64, P, I64, P, I64, U32, P, C.c_int, P, I64, C.POINTER(I64)]),
 }
 

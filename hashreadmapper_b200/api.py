@@ -379,6 +379,45 @@ def default_config(**kw):
     return cfg
 
 
+class Comm:
+    """NCCL communicator of the key-partitioned index (hrm_comm_*).  The unique id is created on rank 0 and
+    broadcast with torch.distributed (any backend) when a process group exists."""
+
+    def __init__(self, rank=None, world=None, group=None):
+        import torch.distributed as dist
+        self.lib = L.load()
+        _dev()
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+        ident = np.zeros(L.COMM_ID_BYTES, dtype=np.uint8)
+        if rank == 0:
+            check(self.lib.hrm_comm_unique_id(_ptr(ident), ident.size))
+        if world > 1:
+            t = torch.from_numpy(ident)
+            if dist.get_backend(group) == "nccl":
+                t = t.cuda()
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            ident = t.cpu().numpy()
+        self.h = C.c_void_p()
+        check(self.lib.hrm_comm_create(C.byref(self.h), rank, world, _ptr(ident)))
+        self.rank, self.world = rank, world
+
+    def info(self):
+        info = L.CommInfo()
+        check(self.lib.hrm_comm_info(self.h, C.byref(info)))
+        return info
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.hrm_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def key_owner(key, world):
+    return L.load().hrm_key_owner(C.c_uint64(int(key)), int(world))
+
+
 class Mapper:
     def __init__(self, cfg=None):
         self.lib = L.load()
@@ -404,7 +443,12 @@ class Mapper:
         check(self.lib.hrm_mapper_info(self.h, C.byref(info)))
         return info
 
-    STAGES = ["pack", "minhash", "probe", "scan", "retrieve", "filter", "shd", "merge", "verify"]
+    STAGES = ["pack", "minhash", "probe", "scan", "retrieve", "filter", "shd", "merge", "verify", "route"]
+
+    def setPartition(self, comm):
+        """key-partitioned index over the ranks of `comm` (before setGenome); mapBatch becomes collective"""
+        self.comm = comm
+        check(self.lib.hrm_mapper_set_partition(self.h, comm.h if comm is not None else None))
 
     def setProfiling(self, enable=True):
         check(self.lib.hrm_mapper_set_profiling(self.h, int(enable)))

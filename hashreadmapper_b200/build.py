@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libhrm_b200.so")
 SOURCES = ["runtime.cu", "k1_pack.cu", "k2_minhash.cu", "k3_table.cu", "k4_collect.cu", "k5_shd.cu",
-           "k7_verify.cu", "store.cu", "mapper.cu", "sam.cu"]
+           "k7_verify.cu", "store.cu", "mapper.cu", "sam.cu", "partition.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
@@ -50,7 +50,7 @@ def build(force=False, verbose=False):
             with open(os.path.join(BUILD, src + ".ptxas.log"), "w") as f:
                 f.write(r.stderr)
             objs.append(obj)
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", LIB] + objs
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", LIB] + objs + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -15,6 +15,7 @@
 // (cp.async.bulk + mbarrier, double buffered); ranges written coalesced, per-query totals by warp shuffle.
 #include "k3_table.cuh"
 #include "core_minhash.cuh"
+#include "k3_probe.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <string.h>
 
@@ -31,7 +32,8 @@ __global__ void __launch_bounds__(256) stage_pairs_kernel(const uint64_t* __rest
                                                           int Hsig, int first_func, int k, const uint32_t* __restrict__ ids,
                                                           uint32_t first_id, int64_t at,
                                                           uint64_t* const* __restrict__ stage_keys,
-                                                          uint32_t* const* __restrict__ stage_vals)
+                                                          uint32_t* const* __restrict__ stage_vals, int part_rank,
+                                                          int part_world)
 {
     // thread per (table, sequence), sequence fastest => coalesced staging writes
     const int64_t total = n * H;
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(256) stage_pairs_kernel(const uint64_t* __rest
         const int64_t i = t - (int64_t)j * n;
         uint64_t key = sigs[i * Hsig + j];
         const bool ok = valid ? valid[i * Hsig + j] != 0 : key != ~0ULL;
-        if (!ok) key = invalid_key(k);
+        if (!ok || (part_world > 1 && (int)key_owner(key, (uint32_t)part_world) != part_rank)) key = invalid_key(k);
         stage_keys[first_func + j][at + i] = key;
         stage_vals[first_func + j][at + i] = ids ? ids[i] : first_id + (uint32_t)i;
     }
@@ -74,15 +76,6 @@ __global__ void __launch_bounds__(256) head_positions_kernel(const int32_t* __re
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         if (flags[i]) head_pos[excl[i]] = (int32_t)i;
 }
-
-// home bucket of a key: multiply-shift range reduction of the low hash word (nbuckets need not be a
-// power of two); the probe sequence continues linearly over buckets
-__device__ __forceinline__ uint32_t home_bucket(uint64_t key, uint32_t nbuckets)
-{
-    const uint64_t h = murmur64(key + 0x5ad0dedULL);
-    return __umulhi((uint32_t)h, nbuckets);
-}
-__device__ __forceinline__ uint32_t next_bucket(uint32_t b, uint32_t nbuckets) { return b + 1 == nbuckets ? 0u : b + 1; }
 
 // one thread per distinct key: claim a slot with CAS, then publish (offset, count)
 __global__ void __launch_bounds__(256) insert_keys_kernel(const uint64_t* __restrict__ keys,
@@ -161,49 +154,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase)
 constexpr int PROBE_THREADS = 256;
 constexpr int PROBE_LOOKUPS = 1024; // lookups (query x table) per tile
 
-// the 64 bytes of one bucket: two 256-bit loads that bypass L1 allocation (no reuse between lookups)
-__device__ __forceinline__ void load_bucket(const Slot* bucket, uint64_t (&w)[8])
-{
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
-                 : "l"(bucket));
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(w[4]), "=l"(w[5]), "=l"(w[6]), "=l"(w[7])
-                 : "l"(bucket + 2));
-}
-
-// One lookup by one thread.  Returns (off, cnt); visited += buckets read.
-__device__ __forceinline__ uint2 probe_one(const Slot* __restrict__ slots, uint32_t nbuckets, uint64_t key,
-                                           uint32_t max_results, uint32_t& visited)
-{
-    uint2 res = make_uint2(0u, 0u);
-    if (key == SLOT_EMPTY) return res; // invalid signature (len < k)
-    uint32_t b = home_bucket(key, nbuckets);
-    for (uint32_t probe = 0; probe < nbuckets; probe++) {
-        uint64_t w[8];
-        load_bucket(slots + (size_t)b * BUCKET_SLOTS, w);
-        visited += 1;
-        bool hit = false, empty = false;
-        uint64_t pay = 0;
-#pragma unroll
-        for (int i = 0; i < BUCKET_SLOTS; i++) {
-            if (w[2 * i] == key) {
-                hit = true;
-                pay = w[2 * i + 1]; // off | cnt << 32
-            }
-            empty |= w[2 * i] == SLOT_EMPTY;
-        }
-        if (hit) {
-            const uint32_t cnt = (uint32_t)(pay >> 32);
-            if (cnt <= max_results) res = make_uint2((uint32_t)pay, cnt); // ref: fakegpuminhasher.cuh:280-285
-            break;
-        }
-        if (empty) break; // a free slot in the bucket ends the probe sequence: key absent
-        b = next_bucket(b, nbuckets);
-    }
-    return res;
-}
-
 __global__ void __launch_bounds__(PROBE_THREADS) probe_count_kernel(const uint64_t* __restrict__ sigs, int n, int H,
                                                                     int TQ, const TablesParam* __restrict__ tabs_g,
                                                                     uint32_t max_results, uint2* __restrict__ ranges,
@@ -273,7 +223,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_count_kernel(const uint64
             if (e < elems) {
                 const int t = seg ? (e & (H - 1)) : (e % H);
                 const TableRef T = tabs[t];
-                r = probe_one(T.slots, T.nbuckets, keys[e], max_results, visited);
+                r = probe_bucket_sequence(T.slots, T.nbuckets, keys[e], max_results, visited);
                 gout[e] = r;
             }
             if (seg) {
@@ -476,7 +426,8 @@ static hrm_status stage_signatures(hrm_minhasher* mh, const uint64_t* d_sigs, co
     HRM_CUDA(cudaMemcpyAsync(kp.p, mh->stage_keys.data(), sizeof(uint64_t*) * mh->H, cudaMemcpyHostToDevice, s));
     HRM_CUDA(cudaMemcpyAsync(vp.p, mh->stage_vals.data(), sizeof(uint32_t*) * mh->H, cudaMemcpyHostToDevice, s));
     HRM_LAUNCH(stage_pairs_kernel, capped_grid(n * num_funcs, 256, 16), 256, 0, s, d_sigs, d_valid, n, num_funcs, Hsig,
-               first_func, mh->k, d_ids, first_id, mh->table_count[first_func], kp.as<uint64_t*>(), vp.as<uint32_t*>());
+               first_func, mh->k, d_ids, first_id, mh->table_count[first_func], kp.as<uint64_t*>(), vp.as<uint32_t*>(),
+               mh->part_rank, mh->part_world);
     // the pointer tables are pageable host memory: make sure the copies are done before returning
     HRM_CUDA(cudaStreamSynchronize(s));
     return HRM_OK;
@@ -529,6 +480,19 @@ extern "C" hrm_status hrm_minhasher_insert_signatures(hrm_minhasher* mh, const u
     HRM_TRY(stage_signatures(mh, d_sigs, d_valid, n, mh->H, 0, mh->H, d_ids, first_id, as_stream(stream)));
     for (int j = 0; j < mh->H; j++) mh->table_count[j] += n;
     mh->inserted = mh->table_count[0];
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_minhasher_set_partition(hrm_minhasher* mh, int rank, int world)
+{
+    HRM_REQUIRE(mh != nullptr && world >= 1 && rank >= 0 && rank < world, "args");
+    for (int j = 0; j < mh->H; j++)
+        if (mh->table_count[j] != 0 || mh->compacted) {
+            set_error("set_partition after insert");
+            return HRM_ERR_STATE;
+        }
+    mh->part_rank = rank;
+    mh->part_world = world;
     return HRM_OK;
 }
 

@@ -53,6 +53,7 @@ struct hrm_minhasher {
     bool compacted = false;
     bool finished = false;
     int device = 0;
+    int part_rank = 0, part_world = 1; // key partition: only keys owned by part_rank are inserted
     // build staging, one pair of device arrays per table
     std::vector<uint64_t*> stage_keys;
     std::vector<uint32_t*> stage_vals;

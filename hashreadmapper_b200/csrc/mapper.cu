@@ -13,6 +13,7 @@
 #include "pipeline.cuh"
 #include "k3_table.cuh"
 #include "mapper.hpp"
+#include "partition.cuh"
 #include <string.h>
 
 namespace hrm {
@@ -148,6 +149,7 @@ extern "C" hrm_status hrm_mapper_set_genome(hrm_mapper* m, const char* h_ascii, 
         hrm_minhasher* mh = nullptr;
         HRM_TRY(hrm_minhasher_create(&mh, m->num_windows, cfg.max_results_per_map, cfg.k, cfg.load_factor));
         m->index[gc] = mh;
+        if (m->comm) HRM_TRY(hrm_minhasher_set_partition(mh, comm_rank(m->comm), comm_world(m->comm)));
         const int added = hrm_minhasher_add_tables(mh, cfg.num_tables, nullptr, stream);
         if (added != cfg.num_tables) {
             set_error("not enough device memory for %d hash tables (got %d)", cfg.num_tables, added);
@@ -230,6 +232,16 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
     memset(&st, 0, sizeof st);
     st.num_reads = n;
     if (n == 0) {
+        if (m->comm) { // the routed query is collective: serve the other ranks' lookups
+            Scratch numoff, values;
+            HRM_TRY(numoff.alloc(sizeof(int32_t) * 4, s));
+            for (int p = 0; p < cfg.num_passes; p++) {
+                int64_t total = 0;
+                HRM_TRY(partitioned_query(m->comm, m->index[cfg.genome_conversion[p]], nullptr, 0, numoff.as<int32_t>(),
+                                          numoff.as<int32_t>() + 1, &total, values, m->timer, s));
+            }
+            HRM_CUDA(cudaStreamSynchronize(s));
+        }
         if (h_stats) *h_stats = st;
         return HRM_OK;
     }
@@ -266,29 +278,35 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
             T.end(s);
         }
         last_rc = rc;
-        // K3b probe -> per-read counts, scan -> offsets + total
-        T.begin(HRM_STAGE_PROBE, s);
-        HRM_TRY(minhasher_count_sigs(mh, qh, m->sigs.as<uint64_t>(), (int)n, m->num.as<int32_t>(), s));
-        T.end(s);
-        T.begin(HRM_STAGE_SCAN, s);
-        HRM_TRY(exclusive_scan_i32(m->num.as<int32_t>(), m->off.as<int32_t>(), n, d_tot, s));
+        hrm_mapped_read* passout = m->passres.as<hrm_mapped_read>();
+        Scratch values, cands;
         int64_t total = 0;
-        HRM_CUDA(cudaMemcpyAsync(&total, d_tot, sizeof total, cudaMemcpyDeviceToHost, s));
-        T.end(s);
-        HRM_CUDA(cudaStreamSynchronize(s)); // the one sync of this pass: sizes the candidate buffers
-        if (total > 0x7fffffffLL) {
-            set_error("candidate values of one batch exceed int: use smaller batches");
-            return HRM_ERR_OVERFLOW;
+        if (m->comm) {
+            // key-partitioned index: route the lookups to their owners, values come back in table order
+            HRM_TRY(partitioned_query(m->comm, mh, m->sigs.as<uint64_t>(), (int)n, m->num.as<int32_t>(),
+                                      m->off.as<int32_t>(), &total, values, T, s));
+        } else {
+            // K3b probe -> per-read counts, scan -> offsets + total
+            T.begin(HRM_STAGE_PROBE, s);
+            HRM_TRY(minhasher_count_sigs(mh, qh, m->sigs.as<uint64_t>(), (int)n, m->num.as<int32_t>(), s));
+            T.end(s);
+            T.begin(HRM_STAGE_SCAN, s);
+            HRM_TRY(exclusive_scan_i32(m->num.as<int32_t>(), m->off.as<int32_t>(), n, d_tot, s));
+            HRM_CUDA(cudaMemcpyAsync(&total, d_tot, sizeof total, cudaMemcpyDeviceToHost, s));
+            T.end(s);
+            HRM_CUDA(cudaStreamSynchronize(s)); // the one sync of this pass: sizes the candidate buffers
+            if (total > 0x7fffffffLL) {
+                set_error("candidate values of one batch exceed int: use smaller batches");
+                return HRM_ERR_OVERFLOW;
+            }
+            HRM_TRY(values.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
+            T.begin(HRM_STAGE_RETRIEVE, s);
+            if (total > 0) HRM_TRY(minhasher_retrieve(mh, qh, (int)n, values.as<uint32_t>(), m->off.as<int32_t>(), s));
+            T.end(s);
         }
         st.num_probes += n * H;
         st.num_values += total;
-        hrm_mapped_read* passout = m->passres.as<hrm_mapped_read>();
-        Scratch values, cands;
-        HRM_TRY(values.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
         HRM_TRY(cands.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
-        T.begin(HRM_STAGE_RETRIEVE, s);
-        if (total > 0) HRM_TRY(minhasher_retrieve(mh, qh, (int)n, values.as<uint32_t>(), m->off.as<int32_t>(), s));
-        T.end(s);
         qh->stage = 0;
         T.begin(HRM_STAGE_FILTER, s);
         // K4 sort + RLE + threshold, then dense candidate lists
@@ -408,6 +426,17 @@ extern "C" hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_as
     return HRM_OK;
 }
 
+
+extern "C" hrm_status hrm_mapper_set_partition(hrm_mapper* m, hrm_comm* comm)
+{
+    HRM_REQUIRE(m != nullptr, "mapper");
+    if (m->d_win_prefix != nullptr) {
+        set_error("hrm_mapper_set_partition must precede hrm_mapper_set_genome");
+        return HRM_ERR_STATE;
+    }
+    m->comm = comm;
+    return HRM_OK;
+}
 
 extern "C" hrm_status hrm_mapper_set_profiling(hrm_mapper* m, int enable)
 {

@@ -6,6 +6,7 @@
 #include <vector>
 
 struct hrm_minhasher;
+struct hrm_comm;
 
 namespace hrm {
 // CUDA-event spans around the stages of the fused path (enabled by hrm_mapper_set_profiling)
@@ -69,4 +70,5 @@ struct hrm_mapper {
     int64_t packed_pitch = 0;
     unsigned long long touches_seen[3] = {0, 0, 0};
     hrm::StageTimer timer;
+    hrm_comm* comm = nullptr; // key-partitioned index (partition.cu); not owned
 };

@@ -447,10 +447,41 @@ hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_ascii, int64_
 #define HRM_STAGE_SHD 6       /* K5 + per-read arg-min */
 #define HRM_STAGE_MERGE 7
 #define HRM_STAGE_VERIFY 8    /* K6/K7 */
-#define HRM_NUM_STAGES 9
+#define HRM_STAGE_ROUTE 9     /* key-partitioned index: routing + NCCL all-to-all exchanges */
+#define HRM_NUM_STAGES 10
 hrm_status hrm_mapper_set_profiling(hrm_mapper* m, int enable);
 hrm_status hrm_mapper_stage_times(hrm_mapper* m, float* h_ms /* [HRM_NUM_STAGES] */,
                                   int32_t* h_spans /* [HRM_NUM_STAGES], may be NULL */);
+
+/* ---- key-partitioned index over the GPUs of one box (BASELINE config 5) -------------
+ * ref: the reference's multi-GPU minhasher distributes whole tables (hash function j on GPU j mod G),
+ * broadcasts every query batch to all GPUs and gathers the results with cudaMemcpyPeerAsync
+ * (include/gpu/multigpuminhasher.cuh:257-333, :659-675, :724, :835-870).  Here every table is split by
+ * key, owner(key) = hrm_key_owner(key, G); one process per GPU; the (read, table) lookups of a batch are
+ * routed to their owners and the value lists come back with NCCL all-to-all (ncclSend/ncclRecv groups).
+ * Results are identical to the replicated index.
+ *
+ * Bootstrap: rank 0 calls hrm_comm_unique_id and ships the HRM_COMM_ID_BYTES bytes to the other ranks by
+ * whatever channel the application has (torch.distributed broadcast in the Python harness, a file, MPI);
+ * every rank then calls hrm_comm_create (collective).  hrm_mapper_set_partition must precede
+ * hrm_mapper_set_genome; afterwards hrm_map_batch is collective: all ranks call it once per batch
+ * (a rank without reads passes n = 0). */
+#define HRM_COMM_ID_BYTES 128
+typedef struct hrm_comm hrm_comm;
+typedef struct {
+    int32_t rank, world;
+    int64_t bytes_sent;      /* data-path bytes sent to other ranks since creation */
+    int64_t bytes_received;
+    int64_t exchanges;       /* all-to-all rounds */
+} hrm_comm_info_t;
+hrm_status hrm_comm_unique_id(void* out_id, int64_t capacity);
+hrm_status hrm_comm_create(hrm_comm** out, int rank, int world, const void* id_bytes);
+void hrm_comm_destroy(hrm_comm* c);
+hrm_status hrm_comm_info(const hrm_comm* c, hrm_comm_info_t* out);
+int hrm_key_owner(uint64_t key, int world);
+/* restricts a minhasher under construction to the keys owned by `rank` (call before the first insert) */
+hrm_status hrm_minhasher_set_partition(hrm_minhasher* mh, int rank, int world);
+hrm_status hrm_mapper_set_partition(hrm_mapper* m, hrm_comm* comm);
 
 /* ref: Mappinghandler::printtoSAM src/gpu/mappinghandler.cu:196-293 (SW mode).  Host-side text
  * formatting of n records into h_out (capacity cap); *h_written = bytes needed.  `with_header`

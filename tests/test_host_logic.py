@@ -339,6 +339,57 @@ def test_sharding_world_size_2_gloo(tmp_path):
     assert b"OK" in outs[0][0]
 
 
+ROUTE_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import hashreadmapper_b200 as hb
+from hashreadmapper_b200 import parallel
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
+lib = hb.load()
+H, nkeys = 5, 400
+rng = np.random.default_rng(7)                       # same tables on both ranks
+universe = rng.integers(0, 1 << 32, size=nkeys, dtype=np.uint64)
+tables = [dict() for _ in range(H)]
+for j in range(H):
+    for key in universe[rng.random(nkeys) < 0.6]:
+        tables[j][int(key)] = list(rng.integers(0, 10000, size=int(rng.integers(1, 6))))
+owner = lambda keys: np.array([lib.hrm_key_owner(int(k), 2) for k in keys], dtype=np.int64)
+shard = [{k: v for k, v in t.items() if lib.hrm_key_owner(k, 2) == rank} for t in tables]
+lookup = lambda keys, tabs: [shard[int(t)].get(int(k), []) for k, t in zip(keys, tabs)]
+rq = np.random.default_rng(100 + rank)               # different reads per rank; rank 1 also tests n = 0
+for n in ((37, 0) if rank == 1 else (11, 5)):
+    sigs = universe[rq.integers(0, nkeys, size=(n, H))]
+    if n:
+        sigs[0, 1] = np.uint64(0xFFFFFFFFFFFFFFFF)   # an invalid signature (read shorter than k)
+        sigs[n - 1, :] = rq.integers(1 << 40, 1 << 41, size=H, dtype=np.uint64)  # all misses
+    num, off, vals = parallel.routed_query_model(sigs, owner, lookup)
+    exp = [[v for j in range(H) for v in tables[j].get(int(sigs[i, j]), [])] for i in range(n)]
+    assert list(num) == [len(e) for e in exp]
+    assert list(off) == [0] + list(np.cumsum([len(e) for e in exp]))
+    assert list(vals) == [v for e in exp for v in e]
+owners = owner(universe)
+assert 0.35 < owners.mean() < 0.65                   # both shards populated
+print("OK")
+dist.destroy_process_group()
+"""
+
+
+def test_routed_query_world_size_2_gloo(tmp_path):
+    """message layout of the key-partitioned index (partition.cu) as a numpy + gloo model: two ranks with
+    different (and empty) batches, sharded tables; values come back in table order per read"""
+    script = tmp_path / "route_worker.py"
+    script.write_text(ROUTE_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE) for r in range(2)]
+    outs = [p.communicate(timeout=240) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e.decode()
+    assert b"OK" in outs[0][0] and b"OK" in outs[1][0]
+
+
 def test_adaptor_compiles_against_reference(tmp_path):
     """drop-in proof: B200Minhasher derives from the reference's abstract care::gpu::GpuMinhasher and is
     instantiable (every pure virtual overridden) -- compiled against the reference's own headers"""
