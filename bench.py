@@ -5,12 +5,15 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): 1 M synthetic 150 bp directional bisulfite reads (1 % substitution
-errors) against a 46 Mbp chr21-size synthetic reference, k=16, 16 hash tables, w=128, minTableHits=4,
-maxHammingPercent=0.05, SW verification with CIGAR.  A step = one pass of the whole hot path
-(K1 pack, K2 minhash, K3 probe, K4 collect, K5 SHD best window, K7 SW+CIGAR) over one 1 M-read batch
-per GPU, both 3N indexes (C->T and G->A) resident in HBM.  N > 1: weak scaling, every rank maps its
-own 1 M-read shard against its replica of the index; no data-path collective.
+Workload (BASELINE.json configs[2], the one its metric is quoted on -- "human-size 3N index"): 1 M synthetic
+150 bp directional bisulfite reads (1 % substitution errors) per GPU per step against a 3.1 Gbp synthetic
+reference with 24 GRCh38-like chromosome lengths, k=16, 16 hash tables, w=128, minTableHits=4,
+maxHammingPercent=0.05, SW verification with CIGAR; both 3N indexes (C->T and G->A, 27.4 M windows each)
+resident in HBM.  A step = one pass of the whole hot path (K1 pack, K2 minhash, K3 probe + retrieve, K4
+collect, K5 SHD best window, K7 SW+CIGAR) over one 1 M-read batch per GPU.  `--genome-bp 46000000` selects
+configs[1] (chr21-size reference).  N > 1: weak scaling, every rank maps its own 1 M-read shard against its
+replica of the index; no data-path collective; `--index partitioned` = configs[4], the
+key-partitioned index with NCCL all-to-all routing.
 
 One JSON line on stdout (rank 0).  `value` = reads/s with the reads already in HBM; `e2e` = the same
 through hrm_mapper_map_reads with pinned HOST buffers (H2D reads, D2H records + CIGARs inside the
@@ -102,9 +105,33 @@ class ClockSampler:
 
 def workload(args, rank):
     from hashreadmapper_b200 import synth
-    genome, off = synth.make_genome([args.genome_bp], seed=20240601)
+    if args.genome_bp >= (1 << 31) or args.chromosomes > 1:  # BASELINE configs[2]: GRCh38-like chromosome lengths
+        lengths = [int(x) for x in synth.human_like_lengths(args.genome_bp, max(args.chromosomes, 24))]
+    else:
+        lengths = [args.genome_bp]
+    genome, off = synth.make_genome(lengths, seed=20240601)
     reads, lens, truth = synth.make_reads(genome, off, args.reads, READ_LEN, error_rate=ERR, seed=20240602 + rank)
     return genome, off, reads, lens, truth
+
+
+def workload_name(reads, genome_bp, nchrom):
+    if reads == 1_000_000 and genome_bp == 3_100_000_000:
+        return ("1M x 150bp directional BS reads per GPU per step vs 3.1 Gbp human-size synthetic 3N index, 24 chromosomes "
+                "(BASELINE configs[2], batches of the 100M-read job)")
+    if reads == 1_000_000 and genome_bp == 46_000_000:
+        return "1M x 150bp directional BS reads vs 46 Mbp synthetic reference (BASELINE configs[1])"
+    return "%d x 150bp directional BS reads per step vs %.4g Mbp synthetic reference, %d chromosome(s)" % (
+        reads, genome_bp / 1e6, nchrom)
+
+
+def cpu_sample(args, n_reads):
+    """bounded sample of the workload for the CPU arm: S reads drawn from a `cpu_genome_bp` reference"""
+    from hashreadmapper_b200 import synth
+    sub_bp = min(args.genome_bp, args.cpu_genome_bp)
+    genome, off = synth.make_genome([sub_bp], seed=20240601)
+    S = min(args.cpu_sample, n_reads)
+    reads, lens, _ = synth.make_reads(genome, off, S, READ_LEN, error_rate=ERR, seed=20240602)
+    return genome, off, reads, lens, S, args.genome_bp / float(sub_bp)
 
 
 def reference_step(ref, port, genome_ct, genome_ga, off, reads, lens):
@@ -126,7 +153,8 @@ def run_reference(args, rank, world):
         return
     from oracle.pyoracle import Oracle, have_ref
     from hashreadmapper_b200 import synth
-    cfg = {"workload": "1M x 150bp directional BS reads vs 46 Mbp synthetic reference (BASELINE configs[1])",
+    nchrom = 24 if (args.genome_bp >= (1 << 31) or args.chromosomes > 1) else 1
+    cfg = {"workload": workload_name(args.reads, args.genome_bp, nchrom),
            "reads_per_gpu": args.reads, "genome_bp": args.genome_bp, "k": K_, "hashmaps": H_, "window": W_,
            "min_table_hits": T_, "passes": "C->T index + G->A index", "verification": "SW+CIGAR"}
     if not have_ref():
@@ -134,9 +162,7 @@ def run_reference(args, rank, world):
                           "(needs /root/reference at build time)"}))
         return
     ref, port = Oracle("ref"), Oracle("port")
-    genome, off = synth.make_genome([args.genome_bp], seed=20240601)
-    S = min(args.cpu_sample, args.reads)
-    reads, lens, _ = synth.make_reads(genome, off, S, READ_LEN, error_rate=ERR, seed=20240602)
+    genome, off, reads, lens, S, wscale = cpu_sample(args, args.reads)
     reads_ct = np.frombuffer(port.convert_ascii(reads.tobytes(), 1), dtype=np.uint8).reshape(reads.shape)
     g_ct, g_ga = port.convert_ascii(genome, 1), port.convert_ascii(genome, 2)
     cores = ref.lib.ref_num_threads()
@@ -152,17 +178,18 @@ def run_reference(args, rank, world):
     per = acc / args.steps
     # fixed part: streaming + sketching all windows (times[1]); the rest scales with the number of reads
     scale = args.reads / S
-    full_s = per[1] + scale * (per[0] + per[2] + per[3])
+    full_s = wscale * per[1] + scale * (per[0] + per[2] + per[3])
     value = args.reads / full_s
     line = {"metric": "reads mapped/sec", "value": value, "unit": "reads/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer", "data": "synthetic",
-            "config": dict(cfg, reference_sample_reads=S),
+            "config": dict(cfg, reference_sample_reads=S, reference_sample_genome_bp=min(args.genome_bp, args.cpu_genome_bp)),
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "reference",
-                             "sample": ("%d of %d reads per step against the full reference; window streaming (%.2f s) "
-                                        "counted once, per-read stages (%.2f s) scaled x%.1f to the full workload; "
-                                        "measured on the sample alone: %.0f reads/s"
-                                        % (S, args.reads, per[1], per[0] + per[2] + per[3], scale, S / (ms / 1e3))),
+                             "sample": ("%d of %d reads per step against %.0f Mbp of reference; window streaming "
+                                        "(%.2f s) scaled x%.1f to %.0f Mbp and counted once per step, per-read stages "
+                                        "(%.2f s) scaled x%.1f to the full batch; measured on the sample alone: %.0f reads/s"
+                                        % (S, args.reads, min(args.genome_bp, args.cpu_genome_bp) / 1e6, per[1], wscale,
+                                           args.genome_bp / 1e6, per[0] + per[2] + per[3], scale, S / (ms / 1e3))),
                              "stage_seconds_per_step": {"reads_build": per[0], "windows_query_filter": per[1],
                                                         "shd": per[2], "verify_ssw": per[3]}},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -177,10 +204,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
-    ap.add_argument("--genome-bp", type=int, default=46_000_000)
+    ap.add_argument("--genome-bp", type=int, default=3_100_000_000)
+    ap.add_argument("--cpu-genome-bp", type=int, default=46_000_000,
+                    help="reference bases the CPU baseline streams (window streaming is scaled to --genome-bp)")
     ap.add_argument("--cpu-sample", type=int, default=50_000, help="reads in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--load-factor", type=float, default=None, help="hash-table load factor (default: the library's)")
+    ap.add_argument("--chromosomes", type=int, default=1, help="> 1: GRCh38-like chromosome lengths (configs[2])")
+    ap.add_argument("--index", default="replicated", choices=["replicated", "partitioned"],
+                    help="partitioned: key-partitioned tables, lookups routed with NCCL all-to-all (configs[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,8 +238,12 @@ def main():
     if args.load_factor:
         cfg.load_factor = args.load_factor
     mp = api.Mapper(cfg)
+    comm = None
+    if args.index == "partitioned":
+        comm = api.Comm()
+        mp.setPartition(comm)
     t0 = time.perf_counter()
-    mp.setGenome(genome, off, ["chrS"])
+    mp.setGenome(genome, off, ["chr%d" % (i + 1) for i in range(len(off) - 1)])
     torch.cuda.synchronize()
     index_s = time.perf_counter() - t0
     info = mp.info()
@@ -288,7 +324,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * n * args.steps / e2e_s
     n_mapped = int((rec_np["mapped"]["orientation"] != 3).sum())
-    ok = (rec_np["mapped"]["orientation"] != 3) & (rec_np["mapped"]["position"] + rec_np["mapped"]["shift"] == truth["pos"])
+    ok = ((rec_np["mapped"]["orientation"] != 3) & (rec_np["mapped"]["chromosome_id"] == truth["chrom"]) &
+          (rec_np["mapped"]["position"] + rec_np["mapped"]["shift"] == truth["pos"]))
     h2d = n * reads.shape[1] + n * 4
     d2h = n * hb.RECORD_DTYPE.itemsize + 2 * n * CIG
 
@@ -297,6 +334,7 @@ def main():
             dist.destroy_process_group()
         return
 
+    wl_name = workload_name(n, args.genome_bp, len(off) - 1)
     # ---- roofline of the hash-probe kernel (K3b) -----------------------------------------------------
     peak, peak_src = peaks()
     probe_ms, probe_spans = stages["probe"]
@@ -315,7 +353,8 @@ def main():
             traffic = None
     stage_ms = {k: v[0] / args.steps for k, v in stages.items()}
     stage_sum = sum(stage_ms.values())
-    roofline = {"kernel": "hrm::probe_count_kernel (K3b hash probe)", "bound": "hbm", "achieved": achieved,
+    roofline = {"kernel": "hrm::probe_count_kernel (K3b hash probe)" if comm is None else
+                          "hrm::probe_keys_kernel (K3b hash probe of routed keys, owner side)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": probe_launch_ms,
                 "launches_per_step": launches_per_step_probe,
@@ -327,10 +366,11 @@ def main():
     line = {"metric": "reads mapped/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/u64 integer", "data": "synthetic",
-            "config": {"workload": "1M x 150bp directional BS reads vs 46 Mbp synthetic reference (BASELINE configs[1])",
-                       "reads_per_gpu": n, "genome_bp": args.genome_bp, "k": K_, "hashmaps": H_, "window": W_,
+            "config": {"workload": wl_name, "reads_per_gpu": n, "genome_bp": args.genome_bp, "k": K_, "hashmaps": H_, "window": W_,
                        "min_table_hits": T_, "passes": "C->T index + G->A index", "verification": "SW+CIGAR",
-                       "load_factor": float(cfg.load_factor), "parallelism": "reads sharded x%d, index replicated" % world,
+                       "load_factor": float(cfg.load_factor),
+                       "parallelism": ("reads sharded x%d, index replicated" % world) if comm is None else
+                                      ("reads sharded x%d, index key-partitioned x%d, NCCL all-to-all" % (world, world)),
                        "l2": "inputs larger than L2 (reads %.0f MB + index %.0f MB per GPU)"
                              % (reads.nbytes / 1e6, info.index_device_bytes / 1e6),
                        "index_build_s": index_s, "windows": int(info.num_windows),
@@ -344,35 +384,40 @@ def main():
             "mapped_fraction": n_mapped / n, "mapped_at_true_locus_fraction": float(ok.sum()) / max(n_mapped, 1),
             "candidates_per_read": st.num_candidates / n, "values_per_read": st.num_values / n,
             "clocks": clocks}
+    if comm is not None:
+        ci = comm.info()
+        line["exchange"] = {"backend": "NCCL ncclSend/ncclRecv groups", "bytes_sent_rank0": int(ci.bytes_sent),
+                            "exchanges_rank0": int(ci.exchanges)}
 
     # ---- CPU baseline: the reference's own functions on this box's host cores (rank 0, N = 1) -------
     if world == 1 and not args.no_cpu_baseline:
         try:
             from oracle.pyoracle import Oracle, have_ref
             port = Oracle("port")
-            S = min(args.cpu_sample, n)
-            r_ct = np.frombuffer(port.convert_ascii(reads[:S].tobytes(), 1), dtype=np.uint8).reshape(S, -1)
-            g_ct, g_ga = port.convert_ascii(genome, 1), port.convert_ascii(genome, 2)
+            g_s, off_s, r_s, l_s, S, wscale = cpu_sample(args, n)
+            r_ct = np.frombuffer(port.convert_ascii(r_s.tobytes(), 1), dtype=np.uint8).reshape(S, -1)
+            g_ct, g_ga = port.convert_ascii(g_s, 1), port.convert_ascii(g_s, 2)
             if have_ref():
                 ref = Oracle("ref")
                 t0 = time.perf_counter()
-                per, nm = reference_step(ref, port, g_ct, g_ga, off, r_ct, lens[:S])
+                per, nm = reference_step(ref, port, g_ct, g_ga, off_s, r_ct, l_s)
                 wall = time.perf_counter() - t0
                 scale = n / S
-                full_s = per[1] + scale * (per[0] + per[2] + per[3])
+                full_s = wscale * per[1] + scale * (per[0] + per[2] + per[3])
                 line["cpu_baseline"] = {
                     "value": n / full_s, "unit": "reads/s", "cores": int(ref.lib.ref_num_threads()), "kind": "reference",
-                    "sample": ("%d of %d reads against the full reference, both 3N passes, %.1f s wall; window "
-                               "streaming (%.2f s) counted once, per-read stages (%.2f s) scaled x%.1f; measured on the "
-                               "sample alone: %.0f reads/s" % (S, n, wall, per[1], per[0] + per[2] + per[3], scale,
-                                                               S / wall)),
+                    "sample": ("%d of %d reads against %.0f Mbp of reference, both 3N passes, %.1f s wall; window "
+                               "streaming (%.2f s) scaled x%.1f to %.0f Mbp, per-read stages (%.2f s) scaled x%.1f; "
+                               "measured on the sample alone: %.0f reads/s"
+                               % (S, n, min(args.genome_bp, args.cpu_genome_bp) / 1e6, wall, per[1], wscale,
+                                  args.genome_bp / 1e6, per[0] + per[2] + per[3], scale, S / wall)),
                     "stage_seconds": {"reads_build": per[0], "windows_query_filter": per[1], "shd": per[2],
                                       "verify_ssw": per[3]}}
             else:
                 S2 = min(S, 5000)
                 t0 = time.perf_counter()
                 for g in (g_ct, g_ga):
-                    port.map_pass_refdir(g, off, r_ct[:S2], lens[:S2])
+                    port.map_pass_refdir(g, off_s, r_ct[:S2], l_s[:S2])
                 wall = time.perf_counter() - t0
                 line["cpu_baseline"] = {"value": S2 / wall, "unit": "reads/s", "cores": 1, "kind": "port",
                                         "sample": "%d reads, seeding+SHD only (scalar oracle port, no SSW)" % S2}

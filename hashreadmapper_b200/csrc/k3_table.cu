@@ -317,11 +317,11 @@ hrm_status minhasher_count_sigs(hrm_minhasher* mh, QueryHandle* qh, const uint64
     return HRM_OK;
 }
 
-hrm_status minhasher_retrieve(hrm_minhasher* mh, QueryHandle* qh, int n, uint32_t* d_values,
+hrm_status minhasher_retrieve(hrm_minhasher* mh, QueryHandle* qh, int64_t first, int n, uint32_t* d_values,
                               const int32_t* d_offsets, cudaStream_t s)
 {
     if (n == 0) return HRM_OK;
-    HRM_LAUNCH(retrieve_kernel, capped_grid((int64_t)n * 32, 256, 16), 256, 0, s, qh->ranges.as<uint2>(), n, mh->H,
+    HRM_LAUNCH(retrieve_kernel, capped_grid((int64_t)n * 32, 256, 16), 256, 0, s, qh->ranges.as<uint2>() + first * mh->H, n, mh->H,
                mh->values, d_offsets, d_values);
     return HRM_OK;
 }
@@ -700,7 +700,7 @@ extern "C" hrm_status hrm_minhasher_retrieve(hrm_minhasher* mh, int handle, int 
         return HRM_OK;
     }
     HRM_TRY(exclusive_scan_i32(d_num_per_seq, d_offsets, n, nullptr, s));
-    return minhasher_retrieve(mh, qh, n, d_values, d_offsets, s);
+    return minhasher_retrieve(mh, qh, 0, n, d_values, d_offsets, s);
 }
 
 extern "C" hrm_status hrm_minhasher_info(const hrm_minhasher* mh, hrm_minhasher_info_t* out)

@@ -77,7 +77,8 @@ namespace hrm {
 // device-side pieces used by the fused mapper
 hrm_status minhasher_count_sigs(hrm_minhasher* mh, QueryHandle* qh, const uint64_t* d_sigs, int n,
                                 int32_t* d_num_per_seq, cudaStream_t s);
-hrm_status minhasher_retrieve(hrm_minhasher* mh, QueryHandle* qh, int n, uint32_t* d_values,
+// values of queries [first, first + n) of the last count; d_offsets: n + 1 offsets relative to d_values
+hrm_status minhasher_retrieve(hrm_minhasher* mh, QueryHandle* qh, int64_t first, int n, uint32_t* d_values,
                               const int32_t* d_offsets, cudaStream_t s);
 QueryHandle* minhasher_handle(hrm_minhasher* mh, int id);
 hrm_status minhash_rows(const uint32_t* d_seq2bit, int64_t pitch_words, const int32_t* d_lengths, int64_t n, int k,

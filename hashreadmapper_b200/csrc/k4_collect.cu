@@ -2,53 +2,44 @@
 // ref: GpuSegmentedUniqueByCount::unique include/gpu/cuda_unique_by_count.cuh:33-215 (cub segmented
 //      radix sort + ~9 thrust launches) via GpuMinhashQueryFilter::keepDistinctByFrequency
 //      include/gpu/minhashqueryfilter.cuh:239-278; keepDistinct :217-236 (minTableHits <= 1).
-// Here: one warp per segment sorts in shared memory with a normalised bitonic network (all
-// compare-exchanges ascending, so virtual +inf padding needs no storage), detects run heads and
-// keeps a head iff the element minHits-1 places further is equal (sorted => multiplicity >= minHits).
-// Segments above 256 ids go to a block-per-segment kernel (shared memory up to 8192 ids, in-place
-// in global memory beyond that).  Then one scan and one gather compact the lists.
+// Here (minHits >= 2, the mapper's case): multiplicities are COUNTED, not sorted out -- every id of a
+// segment goes into an open-addressing table in shared memory (atomicCAS on the id, atomicAdd on its
+// count; one warp per segment up to 256 ids, one block per segment above, ids hashed into several
+// passes when the segment exceeds the table), the few ids that reach minHits are collected and only
+// those are sorted: O(ids) work instead of O(ids log^2 ids).  At human-genome scale a read retrieves
+// ~4000 ids per pass of which 1-3 survive.  minHits <= 1 (keepDistinct), and any segment whose
+// survivors overflow the shared list, take the sort path: normalised bitonic network (all
+// compare-exchanges ascending, so virtual +inf padding needs no storage), run heads, threshold by
+// looking minHits-1 places ahead.  Then one scan and one gather compact the lists.
 // Traffic: 4 B read + <= 4 B written per candidate id, plus 8 B per segment.
 #include "runtime.cuh"
+#include "k4_sort.cuh"
 
 namespace hrm {
 
 constexpr int K4_WARP_CAP = 256;    // ids per segment handled by one warp
 constexpr int K4_BLOCK_CAP = 8192;  // ids per segment sorted in shared memory by one block
 constexpr int K4_THREADS = 256;
+constexpr int K4_WARP_SLOTS = 512;   // counting-table slots of a warp (load <= 0.5)
+constexpr int K4_BLOCK_SLOTS = 8192; // counting-table slots of a block
+constexpr int K4_BLOCK_FILL = 5120;  // ids hashed into one pass of the block table (load <= 0.63)
+constexpr int K4_SURV_CAP = 1024;    // survivors a block can hold before it falls back to the sort path
+constexpr int K4_MAX_GROUPS = 512;   // hash groups of one segment (segments up to 2.6 M ids are counted)
+constexpr uint32_t K4_EMPTY = 0xFFFFFFFFu;
 
-__device__ __forceinline__ void cmpswap(uint32_t* s, int lo, int hi)
-{
-    const uint32_t a = s[lo], b = s[hi];
-    if (a > b) {
-        s[lo] = b;
-        s[hi] = a;
-    }
-}
+__device__ __forceinline__ uint32_t k4_hash(uint32_t v) { return v * 0x9E3779B1u; }
 
-// normalised bitonic sort of cnt elements by `nthreads` cooperating threads (tid in [0,nthreads))
-template <bool BLOCK>
-__device__ __forceinline__ void bitonic_sort(uint32_t* s, int cnt, int tid, int nthreads)
+// counts one id; slots = power of two.  The id 0xFFFFFFFF (the empty marker) is counted by the caller.
+__device__ __forceinline__ void k4_count(uint32_t* keys, uint32_t* cnts, uint32_t mask, int shift, uint32_t v)
 {
-    int npow = 1;
-    while (npow < cnt) npow <<= 1;
-    const int half = npow >> 1;
-    for (int k = 2; k <= npow; k <<= 1) {
-        const int hk = k >> 1;
-        for (int i = tid; i < half; i += nthreads) {
-            const int blk = i / hk, r = i - blk * hk;
-            const int lo = blk * k + r, hi = blk * k + k - 1 - r;
-            if (hi < cnt) cmpswap(s, lo, hi);
+    uint32_t h = k4_hash(v) >> shift;
+    while (true) {
+        const uint32_t prev = atomicCAS(&keys[h], K4_EMPTY, v);
+        if (prev == K4_EMPTY || prev == v) {
+            atomicAdd(&cnts[h], 1u);
+            return;
         }
-        if (BLOCK) __syncthreads();
-        else __syncwarp();
-        for (int j = k >> 2; j >= 1; j >>= 1) {
-            for (int i = tid; i < half; i += nthreads) {
-                const int lo = 2 * j * (i / j) + (i % j), hi = lo + j;
-                if (hi < cnt) cmpswap(s, lo, hi);
-            }
-            if (BLOCK) __syncthreads();
-            else __syncwarp();
-        }
+        h = (h + 1) & mask;
     }
 }
 
@@ -69,8 +60,12 @@ __global__ void __launch_bounds__(K4_THREADS) filter_small_kernel(uint32_t* __re
                                                                   int32_t* __restrict__ big_count)
 {
     __shared__ uint32_t sm[K4_THREADS / 32][K4_WARP_CAP];
+    __shared__ uint32_t hk[K4_THREADS / 32][K4_WARP_SLOTS];
+    __shared__ uint32_t hc[K4_THREADS / 32][K4_WARP_SLOTS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* s = sm[wid];
+    uint32_t* keys = hk[wid];
+    uint32_t* cnts = hc[wid];
     const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
     for (int seg = warp0; seg < n; seg += nwarps) {
@@ -85,6 +80,45 @@ __global__ void __launch_bounds__(K4_THREADS) filter_small_kernel(uint32_t* __re
                 big_list[atomicAdd(big_count, 1)] = seg;
                 new_counts[seg] = 0; // filled in by the block kernel
             }
+            continue;
+        }
+        if (min_hits >= 2) {
+            // count multiplicities in a table of >= 2 * cnt slots, collect the ids that reach min_hits, sort those
+            int slots = 32, shift = 27;
+            while (slots < 2 * cnt) {
+                slots <<= 1;
+                shift--;
+            }
+            for (int i = lane; i < slots; i += 32) {
+                keys[i] = K4_EMPTY;
+                cnts[i] = 0u;
+            }
+            __syncwarp();
+            int nff = 0;
+            for (int i = lane; i < cnt; i += 32) {
+                const uint32_t v = values[b + i];
+                if (v == K4_EMPTY) nff++;
+                else k4_count(keys, cnts, (uint32_t)slots - 1u, shift, v);
+            }
+            nff = __reduce_add_sync(0xffffffffu, nff);
+            __syncwarp();
+            int ns = 0;
+            for (int base = 0; base < slots; base += 32) {
+                const int i = base + lane;
+                const bool keep = cnts[i] >= (uint32_t)min_hits;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) s[ns + __popc(m & ((1u << lane) - 1u))] = keys[i]; // ns <= cnt / min_hits < K4_WARP_CAP
+                ns += __popc(m);
+            }
+            if (nff >= min_hits) { // the largest id sorts last
+                if (lane == 0) s[ns] = K4_EMPTY;
+                ns++;
+            }
+            __syncwarp();
+            if (ns > 1) bitonic_sort<false>(s, ns, lane, 32);
+            for (int i = lane; i < ns; i += 32) values[b + i] = s[i];
+            if (lane == 0) new_counts[seg] = ns;
+            __syncwarp();
             continue;
         }
         for (int i = lane; i < cnt; i += 32) s[i] = values[b + i];
@@ -103,13 +137,145 @@ __global__ void __launch_bounds__(K4_THREADS) filter_small_kernel(uint32_t* __re
     }
 }
 
+// block per large segment, counting version (min_hits >= 2).  A segment that exceeds one table fill is first
+// partitioned by hash group into `scratch` (histogram, scan, scatter -- O(ids)), then every group is counted on
+// its own; survivors are collected in shared memory, sorted and written to the front of the segment once all
+// groups are done.  A segment with more survivors than the list holds, more groups than the histogram, or a
+// wildly skewed group goes to the sort kernel through sort_list.
+__global__ void __launch_bounds__(K4_THREADS) filter_count_kernel(uint32_t* __restrict__ values,
+                                                                  uint32_t* __restrict__ scratch,
+                                                                  const int32_t* __restrict__ offsets, int min_hits,
+                                                                  int32_t* __restrict__ new_counts,
+                                                                  const int32_t* __restrict__ big_list,
+                                                                  const int32_t* __restrict__ big_count,
+                                                                  int32_t* __restrict__ sort_list,
+                                                                  int32_t* __restrict__ sort_count)
+{
+    extern __shared__ uint32_t k4_dyn[];
+    uint32_t* keys = k4_dyn;                              // [K4_BLOCK_SLOTS]
+    uint32_t* cnts = keys + K4_BLOCK_SLOTS;               // [K4_BLOCK_SLOTS]
+    uint32_t* surv = cnts + K4_BLOCK_SLOTS;               // [K4_SURV_CAP]
+    int* ghist = reinterpret_cast<int*>(surv + K4_SURV_CAP); // [K4_MAX_GROUPS] ids per group
+    int* gpos = ghist + K4_MAX_GROUPS;                    // [K4_MAX_GROUPS] start, then running position
+    __shared__ int s_ns, s_nff, s_bad;
+    const int tid = threadIdx.x;
+    const int nbig = *big_count;
+    for (int bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+        const int seg = big_list[bi];
+        const int b = offsets[seg];
+        const int cnt = offsets[seg + 1] - b;
+        uint32_t* g = values + b;
+        const int groups = HRM_SDIV(cnt, K4_BLOCK_FILL);
+        if (tid == 0) {
+            s_ns = 0;
+            s_nff = 0;
+            s_bad = groups > K4_MAX_GROUPS ? 1 : 0;
+        }
+        const uint32_t* src = g;
+        if (groups > 1 && groups <= K4_MAX_GROUPS) { // partition by hash group into scratch
+            for (int i = tid; i < groups; i += K4_THREADS) ghist[i] = 0;
+            __syncthreads();
+            int nff = 0;
+            for (int i = tid; i < cnt; i += K4_THREADS) {
+                const uint32_t v = g[i];
+                if (v == K4_EMPTY) nff++;
+                else atomicAdd(&ghist[(int)((k4_hash(v) & 0xFFFFu) * (uint32_t)groups >> 16)], 1);
+            }
+            if (nff) atomicAdd(&s_nff, nff);
+            __syncthreads();
+            if (tid < 32) { // exclusive scan of the histogram by one warp
+                int carry = 0;
+                for (int base = 0; base < groups; base += 32) {
+                    const int i = base + tid;
+                    const int x = i < groups ? ghist[i] : 0;
+                    int incl = x;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (tid >= d) incl += o;
+                    }
+                    if (i < groups) {
+                        gpos[i] = carry + incl - x;
+                        if (x > K4_BLOCK_SLOTS - K4_BLOCK_SLOTS / 8) s_bad = 1; // skewed group: would clog the table
+                    }
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+            }
+            __syncthreads();
+            uint32_t* dst = scratch + b;
+            for (int i = tid; i < cnt; i += K4_THREADS) {
+                const uint32_t v = g[i];
+                if (v != K4_EMPTY) dst[atomicAdd(&gpos[(int)((k4_hash(v) & 0xFFFFu) * (uint32_t)groups >> 16)], 1)] = v;
+            }
+            __syncthreads(); // gpos[p] is now the END of group p; the scattered ids are visible to the block
+            src = dst;
+        } else {
+            __syncthreads();
+        }
+        bool bad = s_bad != 0;
+        for (int p = 0; p < groups && !bad; p++) {
+            int lo = 0, hi = cnt;
+            if (groups > 1) {
+                hi = gpos[p];
+                lo = hi - ghist[p];
+            }
+            const int np = hi - lo;
+            int slots = 512, shift = 32 - 9; // table of >= 1.6 * np slots
+            while (slots < K4_BLOCK_SLOTS && 5 * slots < 8 * np) {
+                slots <<= 1;
+                shift--;
+            }
+            for (int i = tid; i < slots; i += K4_THREADS) {
+                keys[i] = K4_EMPTY;
+                cnts[i] = 0u;
+            }
+            __syncthreads();
+            int nff = 0;
+            for (int i0 = lo; i0 < hi; i0 += K4_THREADS * 4) { // four independent loads in flight before the atomics
+                uint32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = i0 + u * K4_THREADS + tid;
+                    v[u] = i < hi ? src[i] : K4_EMPTY;
+                    if (i < hi && v[u] == K4_EMPTY) nff++; // only when groups == 1
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (v[u] != K4_EMPTY) k4_count(keys, cnts, (uint32_t)slots - 1u, shift, v[u]);
+            }
+            if (nff) atomicAdd(&s_nff, nff);
+            __syncthreads();
+            for (int i = tid; i < slots; i += K4_THREADS)
+                if (cnts[i] >= (uint32_t)min_hits) {
+                    const int at = atomicAdd(&s_ns, 1);
+                    if (at < K4_SURV_CAP) surv[at] = keys[i];
+                }
+            __syncthreads();
+            bad = s_ns >= K4_SURV_CAP; // keeps one slot free for the id 0xFFFFFFFF
+            __syncthreads();
+        }
+        if (bad) {
+            if (tid == 0) sort_list[atomicAdd(sort_count, 1)] = seg;
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0 && s_nff >= min_hits) surv[s_ns++] = K4_EMPTY;
+        __syncthreads();
+        const int ns = s_ns;
+        if (ns > 1) bitonic_sort<true>(surv, ns, tid, K4_THREADS);
+        for (int i = tid; i < ns; i += K4_THREADS) g[i] = surv[i];
+        if (tid == 0) new_counts[seg] = ns;
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(K4_THREADS) filter_large_kernel(uint32_t* __restrict__ values,
                                                                   const int32_t* __restrict__ offsets, int min_hits,
                                                                   int32_t* __restrict__ new_counts,
                                                                   const int32_t* __restrict__ big_list,
                                                                   const int32_t* __restrict__ big_count)
 {
-    extern __shared__ uint32_t sdata[]; // K4_BLOCK_CAP ids
+    extern __shared__ uint32_t k4_dyn[];
+    uint32_t* sdata = k4_dyn; // K4_BLOCK_CAP ids
     __shared__ int wsum[K4_THREADS / 32];
     __shared__ int s_out;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -195,8 +361,8 @@ static unsigned k4_grid(int64_t threads_wanted, int waves)
 
 // Sort+filter every segment in place (kept heads at the front of each segment), write the new
 // counts and their exclusive scan.  d_new_offsets: n+1.  d_total64: device int64.
-hrm_status filter_segments(uint32_t* d_values, const int32_t* d_offsets, int n, int min_hits, int32_t* d_new_counts,
-                           int32_t* d_new_offsets, int64_t* d_total64, cudaStream_t s)
+hrm_status filter_segments(uint32_t* d_values, uint32_t* d_scratch, const int32_t* d_offsets, int n, int min_hits,
+                           int32_t* d_new_counts, int32_t* d_new_offsets, int64_t* d_total64, cudaStream_t s)
 {
     if (n == 0) return exclusive_scan_i32(d_new_counts, d_new_offsets, 0, d_total64, s);
     Scratch big;
@@ -211,6 +377,25 @@ hrm_status filter_segments(uint32_t* d_values, const int32_t* d_offsets, int n, 
         cudaFuncSetAttribute(filter_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(sizeof(uint32_t) * K4_BLOCK_CAP));
         attr_set = true;
+    }
+    if (min_hits >= 2) { // counting kernel first; what it cannot hold goes on to the sort kernel
+        Scratch srt;
+        HRM_TRY(srt.alloc(sizeof(int32_t) * ((size_t)n + 1), s));
+        int32_t* sort_count = srt.as<int32_t>();
+        int32_t* sort_list = srt.as<int32_t>() + 1;
+        HRM_CUDA(cudaMemsetAsync(sort_count, 0, sizeof(int32_t), s));
+        const size_t smem_count = sizeof(uint32_t) * (2 * K4_BLOCK_SLOTS + K4_SURV_CAP + 2 * K4_MAX_GROUPS);
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            cudaFuncSetAttribute(filter_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count);
+            attr2_set = true;
+        }
+        HRM_LAUNCH(filter_count_kernel, (unsigned)(num_sms() * 3), K4_THREADS, smem_count, s, d_values, d_scratch, d_offsets,
+                   min_hits,
+                   d_new_counts, big_list, big_count, sort_list, sort_count);
+        HRM_LAUNCH(filter_large_kernel, (unsigned)(num_sms() * 2), K4_THREADS, sizeof(uint32_t) * K4_BLOCK_CAP, s, d_values,
+                   d_offsets, min_hits, d_new_counts, sort_list, sort_count);
+        return exclusive_scan_i32(d_new_counts, d_new_offsets, n, d_total64, s);
     }
     HRM_LAUNCH(filter_large_kernel, (unsigned)(num_sms() * 2), K4_THREADS, sizeof(uint32_t) * K4_BLOCK_CAP, s, d_values,
                d_offsets, min_hits, d_new_counts, big_list, big_count);
@@ -240,10 +425,16 @@ extern "C" hrm_status hrm_filter_by_frequency(uint32_t* d_values, int32_t* d_num
         if (h_total) *h_total = 0;
         return HRM_OK;
     }
-    Scratch newoff, tot;
+    Scratch newoff, tot, part;
     HRM_TRY(newoff.alloc(sizeof(int32_t) * ((size_t)n + 1), s));
     HRM_TRY(tot.alloc(sizeof(int64_t), s));
-    HRM_TRY(filter_segments(d_values, d_offsets, n, min_hits, d_num_per_seq, newoff.as<int32_t>(), tot.as<int64_t>(), s));
+    int32_t total_in = 0; // ref: the reference sizes its temporaries from the host-known total too (main_gpu.cu:225)
+    HRM_CUDA(cudaMemcpyAsync(&total_in, d_offsets + n, sizeof total_in, cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    HRM_REQUIRE(total_in >= 0, "offsets[n] is negative");
+    HRM_TRY(part.alloc(sizeof(uint32_t) * (size_t)(total_in > 0 ? total_in : 1), s));
+    HRM_TRY(filter_segments(d_values, part.as<uint32_t>(), d_offsets, n, min_hits, d_num_per_seq, newoff.as<int32_t>(),
+                            tot.as<int64_t>(), s));
     int64_t total = 0;
     HRM_CUDA(cudaMemcpyAsync(&total, tot.p, sizeof total, cudaMemcpyDeviceToHost, s));
     HRM_CUDA(cudaStreamSynchronize(s)); // ref: main_gpu.cu:266-275 synchronises for the total too

@@ -1,0 +1,524 @@
+// k4_fused.cu -- K3b value retrieval + K4 candidate collection in one step, for the replicated index.
+// ref: FakeGpuMinhasher::retrieveValues include/gpu/fakegpuminhasher.cuh:312-392 (copy every bucket of every
+//      query into one list) followed by GpuMinhashQueryFilter::keepDistinctByFrequency
+//      include/gpu/minhashqueryfilter.cuh:239-278 -> GpuSegmentedUniqueByCount::unique
+//      include/gpu/cuda_unique_by_count.cuh:33-215 (segmented radix sort + run-length count + threshold).
+// Result per read: the ascending list of ids that occur in at least minTableHits of its H buckets -- the same
+// list the reference builds.  How: the H buckets of a read are never copied.  Every bucket is an ascending id
+// list inside the index (stable sort at build time), so
+//   * multiplicities are counted in a shared-memory table straight from the index (atomicCAS on the id,
+//     atomicAdd on its count);
+//   * a read with more ids than one table holds is cut into id RANGES: a range is a contiguous piece of each
+//     bucket (binary search), ranges are visited in ascending order, so their sorted survivors concatenate
+//     into the sorted result;
+//   * the L = min(2, minTableHits - 2) LARGEST buckets are not enumerated at all: an id with multiplicity >=
+//     minTableHits still reaches minTableHits - L in the other buckets, and only ids that do are looked up in
+//     the big buckets (binary search).  Bucket sizes are heavy-tailed on a 3-letter genome (T-rich k-mers), so
+//     this removes a large share of the ids.
+// At human-genome scale a read retrieves ~4000 ids per pass and keeps 1-3; this path moves each id once
+// (index -> shared memory) instead of index -> value list -> partition scratch -> table.
+// Anything that does not fit (more than COLLECT_FINAL_CAP survivors for one read, output space exhausted,
+// minTableHits < 2) is reported through the overflow flag and the caller reruns the batch on the general
+// path (retrieve + filter_segments).
+#include "pipeline.cuh"
+#include "k3_table.cuh"
+#include "k4_sort.cuh"
+#include <stdlib.h>
+
+namespace hrm {
+
+constexpr int COLLECT_THREADS = 256;
+constexpr int COLLECT_WARP_SLOTS = 512;
+constexpr int COLLECT_WARP_CAP = 256;   // ids per read handled by one warp
+constexpr int COLLECT_FINAL_CAP = 1024; // survivors per read the block kernel can hold
+constexpr int COLLECT_MLP = 4;         // independent id loads a thread keeps in flight
+constexpr int COLLECT_CHUNK = 16;       // id ranges whose bucket boundaries are searched together
+constexpr uint32_t COLLECT_EMPTY = 0xFFFFFFFFu;
+
+struct CollectParams {
+    const uint2* ranges;        // [n][H] (value offset, count) of the last probe
+    const uint32_t* table_values;
+    int n, H, min_hits;
+    uint32_t id_space;          // ids are < id_space
+    uint32_t* out;              // candidate lists, allocated from `cursor`
+    unsigned long long out_cap;
+    unsigned long long* cursor;
+    int2* lists;                // per read: (start in out, count)
+    int* overflow;
+    int32_t* big_list;
+    int32_t* big_count;
+    int warp_cap;               // reads with more ids go to the block kernel
+    int slots;                  // table slots of the block kernel (power of two)
+    int fill;                   // target ids per range
+    unsigned long long* stats;  // [0] ids enumerated, [1] ids skipped (largest buckets), [2] ranges
+};
+
+__device__ __forceinline__ uint32_t collect_hash(uint32_t v) { return v * 0x9E3779B1u; }
+
+// Counting table.  PACKED (ids < 2^26): one word per slot, id << 6 | count (count <= 63 >= any number of hash
+// tables), so an id costs ONE atomic -- the CAS that claims the slot or the add that bumps it.  Otherwise two
+// words per slot (id, count).  A slot is empty iff its (first) word is all ones.
+constexpr int COLLECT_PACK_BITS = 6;
+template <bool PACKED>
+struct CountTable {
+    uint32_t* w;  // PACKED: [slots]; else ids [cap] followed by counts [cap]
+    int cap;      // allocated slots (power of two)
+    __device__ __forceinline__ void clear_all(int tid, int nthr) const
+    {
+        for (int i = tid; i < cap; i += nthr) {
+            w[i] = COLLECT_EMPTY;
+            if (!PACKED) w[cap + i] = 0u;
+        }
+    }
+    __device__ __forceinline__ void count(uint32_t mask, int shift, uint32_t v) const
+    {
+        uint32_t h = collect_hash(v) >> shift;
+        if (PACKED) {
+            while (true) {
+                uint32_t cur = w[h];
+                if (cur == COLLECT_EMPTY) {
+                    cur = atomicCAS(&w[h], COLLECT_EMPTY, (v << COLLECT_PACK_BITS) | 1u);
+                    if (cur == COLLECT_EMPTY) return;
+                }
+                if ((cur >> COLLECT_PACK_BITS) == v) {
+                    atomicAdd(&w[h], 1u);
+                    return;
+                }
+                h = (h + 1) & mask;
+            }
+        } else {
+            while (true) {
+                const uint32_t prev = atomicCAS(&w[h], COLLECT_EMPTY, v);
+                if (prev == COLLECT_EMPTY || prev == v) {
+                    atomicAdd(&w[cap + h], 1u);
+                    return;
+                }
+                h = (h + 1) & mask;
+            }
+        }
+    }
+    // reads slot i and leaves it empty; returns false for an empty slot
+    __device__ __forceinline__ bool take(int i, uint32_t& id, uint32_t& cnt) const
+    {
+        const uint32_t x = w[i];
+        if (x == COLLECT_EMPTY) return false;
+        w[i] = COLLECT_EMPTY;
+        if (PACKED) {
+            id = x >> COLLECT_PACK_BITS;
+            cnt = x & ((1u << COLLECT_PACK_BITS) - 1u);
+        } else {
+            id = x;
+            cnt = w[cap + i];
+            w[cap + i] = 0u;
+        }
+        return true;
+    }
+};
+
+// first position in [lo, hi) of the ascending list p whose id is >= key
+__device__ __forceinline__ int collect_lower_bound(const uint32_t* __restrict__ p, int lo, int hi, uint32_t key)
+{
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p + mid) < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void collect_sort_warp(uint32_t* s, int cnt, int lane)
+{
+    // odd-even transposition is enough for the handful of survivors a warp sees
+    for (int round = 0; round < cnt; round++) {
+        for (int i = 2 * lane + (round & 1); i + 1 < cnt; i += 64) {
+            const uint32_t a = s[i], b = s[i + 1];
+            if (a > b) {
+                s[i] = b;
+                s[i + 1] = a;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- warp per read ---------------------------------------------------------------------------------
+template <bool PACKED>
+__global__ void __launch_bounds__(COLLECT_THREADS) collect_small_kernel(CollectParams P)
+{
+    __shared__ uint32_t hw[COLLECT_THREADS / 32][(PACKED ? 1 : 2) * COLLECT_WARP_SLOTS];
+    __shared__ uint32_t srt[COLLECT_THREADS / 32][COLLECT_WARP_CAP / 2 + 1];
+    __shared__ int pre[COLLECT_THREADS / 32][MAX_TABLES + 1];
+    __shared__ uint32_t offv[COLLECT_THREADS / 32][MAX_TABLES];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const CountTable<PACKED> tab{hw[wid], COLLECT_WARP_SLOTS};
+    uint32_t* s = srt[wid];
+    const int H = P.H;
+    const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+    unsigned long long enumerated = 0;
+    tab.clear_all(lane, 32); // a read leaves the slots it used empty again
+    __syncwarp();
+    for (int rd = warp0; rd < P.n; rd += nwarps) {
+        int total = 0;
+        for (int t0 = 0; t0 < H; t0 += 32) {
+            const int t = t0 + lane;
+            const uint2 r = t < H ? P.ranges[(int64_t)rd * H + t] : make_uint2(0u, 0u);
+            int incl = (int)r.y;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (t < H) {
+                pre[wid][t] = total + incl - (int)r.y;
+                offv[wid][t] = r.x;
+            }
+            total += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) pre[wid][H] = total;
+        __syncwarp();
+        if (total <= P.warp_cap) enumerated += (unsigned long long)(lane == 0 ? total : 0);
+        if (total < P.min_hits) {
+            if (lane == 0) P.lists[rd] = make_int2(0, 0);
+            __syncwarp();
+            continue;
+        }
+        if (total > P.warp_cap) {
+            if (lane == 0) P.big_list[atomicAdd(P.big_count, 1)] = rd;
+            __syncwarp();
+            continue;
+        }
+        int slots = 32, shift = 27;
+        while (slots < 2 * total) {
+            slots <<= 1;
+            shift--;
+        }
+        for (int e0 = 0; e0 < total; e0 += 32 * COLLECT_MLP) {
+            uint32_t v[COLLECT_MLP];
+#pragma unroll
+            for (int u = 0; u < COLLECT_MLP; u++) {
+                const int e = e0 + u * 32 + lane;
+                v[u] = COLLECT_EMPTY;
+                if (e < total) {
+                    int lo = 0, hi = H; // bucket t with pre[t] <= e < pre[t + 1]
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (pre[wid][mid] <= e) lo = mid;
+                        else hi = mid;
+                    }
+                    v[u] = __ldg(P.table_values + offv[wid][lo] + (e - pre[wid][lo]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < COLLECT_MLP; u++)
+                if (v[u] != COLLECT_EMPTY) tab.count((uint32_t)slots - 1u, shift, v[u]);
+        }
+        __syncwarp();
+        int ns = 0;
+        for (int base = 0; base < slots; base += 32) {
+            uint32_t id = 0, c = 0;
+            const bool keep = tab.take(base + lane, id, c) && c >= (uint32_t)P.min_hits;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) s[ns + __popc(m & ((1u << lane) - 1u))] = id; // ns <= total / min_hits <= warp_cap / 2
+            ns += __popc(m);
+        }
+        __syncwarp();
+        if (ns > 1) collect_sort_warp(s, ns, lane);
+        unsigned long long start = 0;
+        if (lane == 0 && ns > 0) start = atomicAdd(P.cursor, (unsigned long long)ns);
+        start = __shfl_sync(0xffffffffu, start, 0);
+        if (start + (unsigned long long)ns > P.out_cap) {
+            if (lane == 0) *P.overflow = 1;
+            ns = 0;
+        }
+        for (int i = lane; i < ns; i += 32) P.out[start + i] = s[i];
+        if (lane == 0) P.lists[rd] = make_int2((int)start, ns);
+        __syncwarp();
+    }
+    if (lane == 0 && enumerated && P.stats) atomicAdd(P.stats, enumerated);
+}
+
+// ---- block per read ----------------------------------------------------------------------------------
+template <bool PACKED>
+__global__ void __launch_bounds__(COLLECT_THREADS) collect_big_kernel(CollectParams P)
+{
+    extern __shared__ uint32_t cdyn[];
+    const int S = P.slots;
+    const CountTable<PACKED> tab{cdyn, S};
+    uint32_t* cand = cdyn + (PACKED ? 1 : 2) * S; // [S / 2] ids that reached the reduced threshold in the enumerated buckets
+    uint32_t* ccnt = cand + S / 2;                 // [S / 2] their counts
+    uint32_t* fin = ccnt + S / 2;                  // [COLLECT_FINAL_CAP] survivors of the read, ascending
+    __shared__ uint32_t offv[MAX_TABLES];
+    __shared__ int cntv[MAX_TABLES];
+    __shared__ int skip[MAX_TABLES];
+    __shared__ int bnd[(COLLECT_CHUNK + 1) * MAX_TABLES]; // bucket positions of the range boundaries of a chunk
+    __shared__ int gtot[COLLECT_CHUNK];                   // ids per range of the chunk
+    __shared__ int gpre[COLLECT_CHUNK * (MAX_TABLES + 1)]; // per range: exclusive prefix of its bucket pieces
+    __shared__ int s_ncand, s_gfin, s_nfin, s_bad;
+    __shared__ unsigned long long s_start;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, H = P.H, T = P.min_hits;
+    const int L = T - 2 < 2 ? (T - 2 < 0 ? 0 : T - 2) : 2; // buckets not enumerated
+    const int thr = T - L;                                  // >= 2 for T >= 2
+    const int nbig = *P.big_count;
+    unsigned long long st_enum = 0, st_skip = 0, st_ranges = 0;
+    tab.clear_all(tid, COLLECT_THREADS); // every range leaves the slots it used empty again
+    if (tid == 0) {
+        s_ncand = 0;
+        s_gfin = 0;
+    }
+    __syncthreads();
+    for (int bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+        const int rd = P.big_list[bi];
+        if (tid < H) {
+            const uint2 r = P.ranges[(int64_t)rd * H + tid];
+            offv[tid] = r.x;
+            cntv[tid] = (int)r.y;
+            skip[tid] = 0;
+        }
+        if (tid == 0) {
+            s_nfin = 0;
+            s_bad = 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int l = 0; l < L; l++) { // the L largest buckets
+                int best = -1;
+                for (int t = 0; t < H; t++)
+                    if (!skip[t] && (best < 0 || cntv[t] > cntv[best])) best = t;
+                if (best >= 0 && cntv[best] > 0) skip[best] = 1;
+            }
+        }
+        __syncthreads();
+        int64_t E = 0, SK = 0;
+        for (int t = 0; t < H; t++) {
+            if (skip[t]) SK += cntv[t];
+            else E += cntv[t];
+        }
+        const int64_t nranges = E > 0 ? HRM_SDIV(E, (int64_t)P.fill) : 1;
+        const uint64_t width = ((uint64_t)P.id_space + (uint64_t)nranges - 1) / (uint64_t)nranges;
+        if (tid == 0) {
+            st_enum += (unsigned long long)E;
+            st_skip += (unsigned long long)SK;
+            st_ranges += (unsigned long long)nranges;
+        }
+        bool bad = false; // block-uniform copy of s_bad (read only after a barrier)
+        for (int64_t g0 = 0; g0 < nranges && !bad; g0 += COLLECT_CHUNK) {
+            const int ng = (int)((nranges - g0) < COLLECT_CHUNK ? (nranges - g0) : COLLECT_CHUNK);
+            // boundaries of ranges g0 .. g0 + ng in every enumerated bucket, all searches in flight together
+            for (int x = tid; x < (ng + 1) * H; x += COLLECT_THREADS) {
+                const int g = x / H, t = x - g * H;
+                int pos = 0;
+                if (!skip[t]) {
+                    const uint64_t key = (uint64_t)(g0 + g) * width;
+                    pos = key >= (uint64_t)P.id_space ? cntv[t]
+                                                       : collect_lower_bound(P.table_values + offv[t], 0, cntv[t], (uint32_t)key);
+                }
+                bnd[g * MAX_TABLES + t] = pos;
+            }
+            __syncthreads();
+            if (tid < ng) {
+                int tot = 0;
+                for (int t = 0; t < H; t++) {
+                    gpre[tid * (MAX_TABLES + 1) + t] = tot; // flat index of the first id of bucket t inside range tid
+                    tot += bnd[(tid + 1) * MAX_TABLES + t] - bnd[tid * MAX_TABLES + t];
+                }
+                gpre[tid * (MAX_TABLES + 1) + H] = tot;
+                gtot[tid] = tot;
+            }
+            __syncthreads();
+            for (int g = 0; g < ng && !bad; g++) {
+                const int gtotal = gtot[g];
+                if (gtotal < thr) continue;
+                if (8 * gtotal > 7 * S) { // ids far from uniform: this range would clog the table
+                    bad = true;
+                    break;
+                }
+                int slots = 64, shift = 32 - 6;
+                while (slots < S && 5 * slots < 8 * gtotal) {
+                    slots <<= 1;
+                    shift--;
+                }
+                // the range's ids as one flat sequence (balanced over the block whatever the bucket sizes);
+                // COLLECT_MLP independent loads per thread are issued before the first atomic, so a thread waits for
+                // DRAM once per batch instead of once per id
+                const int* gp = gpre + g * (MAX_TABLES + 1);
+                int tcur = 0;
+                for (int e0 = 0; e0 < gtotal; e0 += COLLECT_THREADS * COLLECT_MLP) {
+                    uint32_t v[COLLECT_MLP];
+#pragma unroll
+                    for (int u = 0; u < COLLECT_MLP; u++) {
+                        const int e = e0 + u * COLLECT_THREADS + tid;
+                        v[u] = COLLECT_EMPTY;
+                        if (e < gtotal) {
+                            while (gp[tcur + 1] <= e) tcur++; // bucket with gp[t] <= e < gp[t + 1]; e only grows
+                            v[u] = __ldg(P.table_values + offv[tcur] + bnd[g * MAX_TABLES + tcur] + (e - gp[tcur]));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < COLLECT_MLP; u++)
+                        if (v[u] != COLLECT_EMPTY) tab.count((uint32_t)slots - 1u, shift, v[u]);
+                }
+                __syncthreads();
+                for (int i = tid; i < slots; i += COLLECT_THREADS) { // collect + leave the table empty
+                    uint32_t id = 0, c = 0;
+                    if (tab.take(i, id, c) && c >= (uint32_t)thr) {
+                        const int at = atomicAdd(&s_ncand, 1); // <= gtotal / thr <= S / 2
+                        cand[at] = id;
+                        ccnt[at] = c;
+                    }
+                }
+                __syncthreads();
+                const int ncand = s_ncand;
+                if (ncand == 0) continue; // the common case: nothing in this id range reaches the threshold
+                const int base = s_nfin;
+                for (int c = tid; c < ncand; c += COLLECT_THREADS) {
+                    const uint32_t id = cand[c];
+                    uint32_t m = ccnt[c];
+                    for (int t = 0; t < H && m < (uint32_t)T; t++) {
+                        if (!skip[t]) continue;
+                        const uint32_t* p = P.table_values + offv[t];
+                        const int pos = collect_lower_bound(p, 0, cntv[t], id);
+                        if (pos < cntv[t] && __ldg(p + pos) == id) m++;
+                    }
+                    if (m >= (uint32_t)T) {
+                        const int at = base + atomicAdd(&s_gfin, 1);
+                        if (at < COLLECT_FINAL_CAP) fin[at] = id;
+                        else s_bad = 1;
+                    }
+                }
+                __syncthreads();
+                bad = s_bad != 0;
+                const int gf = s_gfin;
+                // sort this range's survivors; ranges ascend, so the read's list stays sorted
+                if (!bad && gf > 1) bitonic_sort<true>(fin + base, gf, tid, COLLECT_THREADS);
+                __syncthreads();
+                if (tid == 0) {
+                    s_nfin = base + (bad ? 0 : gf);
+                    s_ncand = 0;
+                    s_gfin = 0;
+                }
+                __syncthreads();
+            }
+        }
+        if (bad) {
+            __syncthreads();
+            tab.clear_all(tid, COLLECT_THREADS); // the aborted range may have left ids behind
+            if (tid == 0) {
+                *P.overflow = 1;
+                P.lists[rd] = make_int2(0, 0);
+                s_ncand = 0;
+                s_gfin = 0;
+            }
+            __syncthreads();
+            continue;
+        }
+        __syncthreads();
+        const int ns = s_nfin;
+        if (tid == 0) {
+            unsigned long long start = 0;
+            if (ns > 0) start = atomicAdd(P.cursor, (unsigned long long)ns);
+            if (start + (unsigned long long)ns > P.out_cap) {
+                *P.overflow = 1;
+                start = ~0ull;
+            }
+            s_start = start;
+        }
+        __syncthreads();
+        const unsigned long long start = s_start;
+        if (start != ~0ull) {
+            for (int i = tid; i < ns; i += COLLECT_THREADS) P.out[start + i] = fin[i];
+            if (tid == 0) P.lists[rd] = make_int2((int)start, ns);
+        } else if (tid == 0) {
+            P.lists[rd] = make_int2(0, 0);
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && P.stats) {
+        if (st_enum) atomicAdd(P.stats, st_enum);
+        if (st_skip) atomicAdd(P.stats + 1, st_skip);
+        if (st_ranges) atomicAdd(P.stats + 2, st_ranges);
+    }
+}
+
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    if (!v) return dflt;
+    const int x = atoi(v);
+    return x > 0 ? x : dflt;
+}
+
+// Candidate lists of n reads from the bucket ranges of the last probe.  d_lists: n (start, count) pairs into
+// d_out (capacity out_cap ids).  *h_overflow != 0: rerun on the general path.  Synchronises once.
+hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, int n, int min_hits, uint32_t id_space,
+                              uint32_t* d_out, int64_t out_cap, int2* d_lists, int64_t* h_total, int* h_overflow,
+                              int64_t* h_stats3, cudaStream_t s)
+{
+    *h_overflow = 0;
+    *h_total = 0;
+    if (n == 0) return HRM_OK;
+    HRM_REQUIRE(min_hits >= 2 && id_space < 0xFFFFFFFFu, "collect_candidates needs minTableHits >= 2");
+    static const int warp_cap = env_int("HRM_COLLECT_WARP_CAP", COLLECT_WARP_CAP) < COLLECT_WARP_CAP
+                                    ? env_int("HRM_COLLECT_WARP_CAP", COLLECT_WARP_CAP)
+                                    : COLLECT_WARP_CAP;
+    static const int slots_env = env_int("HRM_COLLECT_SLOTS", 2048);
+    int slots = 64;
+    while (slots < slots_env && slots < 16384) slots <<= 1;
+    static const int fill_env = env_int("HRM_COLLECT_FILL", 0);
+    const int fill = fill_env > 0 ? fill_env : (slots * 3) / 8; // expected ids per range: 3/8 of the table, 7/8 tolerated
+    Scratch ctl, big;
+    HRM_TRY(ctl.alloc(sizeof(unsigned long long) * 8, s));
+    HRM_TRY(big.alloc(sizeof(int32_t) * ((size_t)n + 1), s));
+    HRM_CUDA(cudaMemsetAsync(ctl.p, 0, sizeof(unsigned long long) * 8, s));
+    HRM_CUDA(cudaMemsetAsync(big.p, 0, sizeof(int32_t), s));
+    CollectParams P;
+    P.ranges = qh->ranges.as<uint2>();
+    P.table_values = mh->values;
+    P.n = n;
+    P.H = mh->H;
+    P.min_hits = min_hits;
+    P.id_space = id_space;
+    P.out = d_out;
+    P.out_cap = (unsigned long long)out_cap;
+    P.cursor = ctl.as<unsigned long long>();
+    P.overflow = reinterpret_cast<int*>(ctl.as<unsigned long long>() + 1);
+    P.stats = ctl.as<unsigned long long>() + 2;
+    P.lists = d_lists;
+    P.big_count = big.as<int32_t>();
+    P.big_list = big.as<int32_t>() + 1;
+    P.warp_cap = warp_cap;
+    P.slots = slots;
+    P.fill = fill;
+    int64_t g = HRM_SDIV((int64_t)n * 32, (int64_t)COLLECT_THREADS);
+    if (g > (int64_t)num_sms() * 16) g = (int64_t)num_sms() * 16;
+    static const bool allow_packed = env_int("HRM_COLLECT_UNPACKED", 0) == 0;
+    const bool packed = allow_packed && id_space < (1u << (32 - COLLECT_PACK_BITS)) - 1u && mh->H < (1 << COLLECT_PACK_BITS);
+    const size_t smem = sizeof(uint32_t) * ((size_t)((packed ? 1 : 2) + 1) * slots + COLLECT_FINAL_CAP);
+    // one wave of resident blocks, each loops over the list of big reads
+    int resident = 1;
+    if (packed) {
+        HRM_LAUNCH(collect_small_kernel<true>, (unsigned)g, COLLECT_THREADS, 0, s, P);
+        cudaFuncSetAttribute(collect_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, collect_big_kernel<true>, COLLECT_THREADS, smem));
+        HRM_LAUNCH(collect_big_kernel<true>, (unsigned)(num_sms() * (resident > 0 ? resident : 1)), COLLECT_THREADS, smem, s,
+                   P);
+    } else {
+        HRM_LAUNCH(collect_small_kernel<false>, (unsigned)g, COLLECT_THREADS, 0, s, P);
+        cudaFuncSetAttribute(collect_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, collect_big_kernel<false>, COLLECT_THREADS, smem));
+        HRM_LAUNCH(collect_big_kernel<false>, (unsigned)(num_sms() * (resident > 0 ? resident : 1)), COLLECT_THREADS, smem, s,
+                   P);
+    }
+    unsigned long long h[8];
+    HRM_CUDA(cudaMemcpyAsync(h, ctl.p, sizeof h, cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s)); // the one sync of the pass: overflow flag + candidate total
+    *h_total = (int64_t)h[0];
+    *h_overflow = (int)(h[1] & 0xFFFFFFFFull);
+    if (h_stats3) {
+        h_stats3[0] = (int64_t)h[2];
+        h_stats3[1] = (int64_t)h[3];
+        h_stats3[2] = (int64_t)h[4];
+    }
+    return HRM_OK;
+}
+
+} // namespace hrm

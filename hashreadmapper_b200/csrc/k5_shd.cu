@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(256) extended_windows_kernel(const uint32_t* _
 __global__ void __launch_bounds__(256) best_window_kernel(const uint32_t* __restrict__ reads, int64_t read_pitch,
                                                           const int32_t* __restrict__ read_len, int64_t n,
                                                           const uint32_t* __restrict__ cand_windows,
-                                                          const int32_t* __restrict__ cand_offsets, GenomeDev G,
+                                                          const int32_t* __restrict__ cand_offsets,
+                                                          const int2* __restrict__ cand_lists, GenomeDev G,
                                                           const int64_t* __restrict__ win_prefix, int k, int w,
                                                           float rate, int pass, hrm_mapped_read* __restrict__ out)
 {
@@ -166,7 +167,15 @@ __global__ void __launch_bounds__(256) best_window_kernel(const uint32_t* __rest
     const int stride_bases = w - k + 1;
     for (int64_t r = warp0; r < n; r += nwarps) {
         const int Lc = read_len[r];
-        const int cb = cand_offsets[r], ce = cand_offsets[r + 1];
+        int cb, ce; // the read's candidate list: dense offsets (K4) or (start, count) (fused collection)
+        if (cand_lists) {
+            const int2 l = cand_lists[r];
+            cb = l.x;
+            ce = l.x + l.y;
+        } else {
+            cb = cand_offsets[r];
+            ce = cand_offsets[r + 1];
+        }
         hrm_mapped_read best;
         best.orientation = HRM_ORIENT_NONE;
         best.hamming_distance = 0;
@@ -222,11 +231,11 @@ static unsigned warp_grid(int64_t nwarps_wanted, int waves)
 hrm_status best_windows(const uint32_t* d_reads, int64_t read_pitch, const int32_t* d_read_len, int64_t n,
                         const uint32_t* d_cand_windows, const int32_t* d_cand_offsets, const hrm_genome* g,
                         const int64_t* d_win_prefix, int k, int w, float rate, int pass, hrm_mapped_read* d_out,
-                        cudaStream_t s)
+                        cudaStream_t s, const int2* d_cand_lists)
 {
     if (n == 0) return HRM_OK;
     HRM_LAUNCH(best_window_kernel, warp_grid(n, 32), 256, 0, s, d_reads, read_pitch, d_read_len, n, d_cand_windows,
-               d_cand_offsets, g->dev(), d_win_prefix, k, w, rate, pass, d_out);
+               d_cand_offsets, d_cand_lists, g->dev(), d_win_prefix, k, w, rate, pass, d_out);
     return HRM_OK;
 }
 

@@ -15,6 +15,8 @@
 #include "mapper.hpp"
 #include "partition.cuh"
 #include <string.h>
+#include <stdlib.h>
+#include <vector>
 
 namespace hrm {
 
@@ -105,6 +107,11 @@ extern "C" hrm_status hrm_mapper_create(hrm_mapper** out, const hrm_mapper_confi
     }
     auto* m = new hrm_mapper;
     m->cfg = *cfg;
+    if (const char* cf = getenv("HRM_COLLECT")) m->use_fused = atoi(cf) != 0; // 0: general retrieve + filter path only
+    if (const char* vb = getenv("HRM_VALUE_BUDGET")) { // test hook: forces the range splitting at small sizes
+        const long long v = atoll(vb);
+        if (v > 0 && v < m->value_budget) m->value_budget = v;
+    }
     *out = m;
     return HRM_OK;
 }
@@ -279,57 +286,113 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
         }
         last_rc = rc;
         hrm_mapped_read* passout = m->passres.as<hrm_mapped_read>();
-        Scratch values, cands;
-        int64_t total = 0;
+        // K4 + K5 of reads [lo, lo + cnt): values in table order at `values`, offsets in m->off[0 .. cnt]
+        auto filter_and_select = [&](int64_t lo, int64_t cnt, int64_t total, Scratch& values) -> hrm_status {
+            Scratch cands;
+            HRM_TRY(cands.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
+            T.begin(HRM_STAGE_FILTER, s);
+            // K4 count / sort + threshold, then dense candidate lists (cands doubles as K4's partition space first)
+            HRM_TRY(filter_segments(values.as<uint32_t>(), cands.as<uint32_t>(), m->off.as<int32_t>(), (int)cnt,
+                                    cfg.min_table_hits, m->num.as<int32_t>() + lo, m->newoff.as<int32_t>(), d_tot + 1, s));
+            HRM_TRY(compact_segments(values.as<uint32_t>(), m->off.as<int32_t>(), m->newoff.as<int32_t>(), (int)cnt,
+                                     cands.as<uint32_t>(), s));
+            T.end(s);
+            // K5 + per-read arg-min
+            T.begin(HRM_STAGE_SHD, s);
+            HRM_TRY(best_windows(reads + lo * m->packed_pitch, m->packed_pitch, d_lengths + lo, cnt, cands.as<uint32_t>(),
+                                 m->newoff.as<int32_t>(), m->genome[gc], m->d_win_prefix, cfg.k, cfg.window_size,
+                                 cfg.max_hamming_percent, p, passout + lo, s));
+            T.end(s);
+            st.num_values += total;
+            if (h_stats) {
+                int64_t ftotal = 0;
+                HRM_CUDA(cudaMemcpyAsync(&ftotal, d_tot + 1, sizeof ftotal, cudaMemcpyDeviceToHost, s));
+                HRM_CUDA(cudaStreamSynchronize(s));
+                st.num_candidates += ftotal;
+            }
+            return HRM_OK;
+        };
         if (m->comm) {
             // key-partitioned index: route the lookups to their owners, values come back in table order
+            Scratch values;
+            int64_t total = 0;
             HRM_TRY(partitioned_query(m->comm, mh, m->sigs.as<uint64_t>(), (int)n, m->num.as<int32_t>(),
                                       m->off.as<int32_t>(), &total, values, T, s));
+            HRM_TRY(filter_and_select(0, n, total, values));
         } else {
-            // K3b probe -> per-read counts, scan -> offsets + total
+            // K3b probe of the whole batch -> per-read counts and bucket ranges
             T.begin(HRM_STAGE_PROBE, s);
             HRM_TRY(minhasher_count_sigs(mh, qh, m->sigs.as<uint64_t>(), (int)n, m->num.as<int32_t>(), s));
             T.end(s);
-            T.begin(HRM_STAGE_SCAN, s);
-            HRM_TRY(exclusive_scan_i32(m->num.as<int32_t>(), m->off.as<int32_t>(), n, d_tot, s));
-            HRM_CUDA(cudaMemcpyAsync(&total, d_tot, sizeof total, cudaMemcpyDeviceToHost, s));
-            T.end(s);
-            HRM_CUDA(cudaStreamSynchronize(s)); // the one sync of this pass: sizes the candidate buffers
-            if (total > 0x7fffffffLL) {
-                set_error("candidate values of one batch exceed int: use smaller batches");
-                return HRM_ERR_OVERFLOW;
+            // fused retrieval + collection straight from the index (k4_fused.cu); falls through to the general
+            // path when a read or the output does not fit its bounds
+            bool collected = false;
+            if (m->use_fused && cfg.min_table_hits >= 2 && m->num_windows < 0xFFFFFFFFLL) {
+                Scratch cands, lists;
+                const int64_t cap = n * 32 > (1 << 16) ? n * 32 : (1 << 16);
+                HRM_REQUIRE(cap < (1LL << 31), "batch too large for int candidate offsets");
+                HRM_TRY(cands.alloc(sizeof(uint32_t) * (size_t)cap, s));
+                HRM_TRY(lists.alloc(sizeof(int2) * (size_t)n, s));
+                int64_t ctotal = 0, cst[3] = {0, 0, 0};
+                int overflow = 0;
+                T.begin(HRM_STAGE_FILTER, s);
+                HRM_TRY(collect_candidates(mh, qh, (int)n, cfg.min_table_hits, (uint32_t)m->num_windows, cands.as<uint32_t>(),
+                                           cap, lists.as<int2>(), &ctotal, &overflow, cst, s));
+                T.end(s);
+                if (!overflow) {
+                    T.begin(HRM_STAGE_SHD, s);
+                    HRM_TRY(best_windows(reads, m->packed_pitch, d_lengths, n, cands.as<uint32_t>(), nullptr, m->genome[gc],
+                                         m->d_win_prefix, cfg.k, cfg.window_size, cfg.max_hamming_percent, p, passout, s,
+                                         lists.as<int2>()));
+                    T.end(s);
+                    st.num_values += cst[0] + cst[1];
+                    st.num_candidates += ctotal;
+                    m->collect_enumerated += cst[0];
+                    m->collect_skipped += cst[1];
+                    collected = true;
+                }
             }
-            HRM_TRY(values.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
-            T.begin(HRM_STAGE_RETRIEVE, s);
-            if (total > 0) HRM_TRY(minhasher_retrieve(mh, qh, (int)n, values.as<uint32_t>(), m->off.as<int32_t>(), s));
-            T.end(s);
+            // ranges of reads whose candidate values fit the budget (int offsets, bounded scratch): scan -> offsets +
+            // total (one host sync per range: sizes the buffers), retrieve, K4, K5.  A batch normally is one range;
+            // at human-genome scale (thousands of values per read) it is halved until the ranges fit.
+            struct Range {
+                int64_t lo, cnt;
+            };
+            std::vector<Range> todo;
+            if (!collected) todo.push_back({0, n});
+            while (!todo.empty()) {
+                const Range r = todo.back();
+                todo.pop_back();
+                int64_t total = 0;
+                T.begin(HRM_STAGE_SCAN, s);
+                HRM_TRY(exclusive_scan_i32(m->num.as<int32_t>() + r.lo, m->off.as<int32_t>(), r.cnt, d_tot, s));
+                HRM_CUDA(cudaMemcpyAsync(&total, d_tot, sizeof total, cudaMemcpyDeviceToHost, s));
+                T.end(s);
+                HRM_CUDA(cudaStreamSynchronize(s));
+                if (total > m->value_budget) {
+                    if (r.cnt == 1) {
+                        set_error("one read retrieves more candidate values than the value budget");
+                        return HRM_ERR_OVERFLOW;
+                    }
+                    const int64_t half = r.cnt / 2;
+                    todo.push_back({r.lo + half, r.cnt - half}); // processed second
+                    todo.push_back({r.lo, half});
+                    continue;
+                }
+                Scratch values;
+                HRM_TRY(values.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
+                T.begin(HRM_STAGE_RETRIEVE, s);
+                if (total > 0)
+                    HRM_TRY(minhasher_retrieve(mh, qh, r.lo, (int)r.cnt, values.as<uint32_t>(), m->off.as<int32_t>(), s));
+                T.end(s);
+                HRM_TRY(filter_and_select(r.lo, r.cnt, total, values));
+            }
         }
         st.num_probes += n * H;
-        st.num_values += total;
-        HRM_TRY(cands.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
         qh->stage = 0;
-        T.begin(HRM_STAGE_FILTER, s);
-        // K4 sort + RLE + threshold, then dense candidate lists
-        HRM_TRY(filter_segments(values.as<uint32_t>(), m->off.as<int32_t>(), (int)n, cfg.min_table_hits,
-                                m->num.as<int32_t>(), m->newoff.as<int32_t>(), d_tot + 1, s));
-        HRM_TRY(compact_segments(values.as<uint32_t>(), m->off.as<int32_t>(), m->newoff.as<int32_t>(), (int)n,
-                                 cands.as<uint32_t>(), s));
-        T.end(s);
-        // K5 + per-read arg-min
-        T.begin(HRM_STAGE_SHD, s);
-        HRM_TRY(best_windows(reads, m->packed_pitch, d_lengths, n, cands.as<uint32_t>(), m->newoff.as<int32_t>(),
-                             m->genome[gc], m->d_win_prefix, cfg.k, cfg.window_size, cfg.max_hamming_percent, p,
-                             passout, s));
-        T.end(s);
         T.begin(HRM_STAGE_MERGE, s);
         HRM_LAUNCH(merge_pass_kernel, mgrid(n), 256, 0, s, d_out, passout, n, p == 0 ? 1 : 0);
         T.end(s);
-        if (h_stats) {
-            int64_t ftotal = 0;
-            HRM_CUDA(cudaMemcpyAsync(&ftotal, d_tot + 1, sizeof ftotal, cudaMemcpyDeviceToHost, s));
-            HRM_CUDA(cudaStreamSynchronize(s));
-            st.num_candidates += ftotal;
-        }
     }
     if (h_stats) {
         HRM_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s));

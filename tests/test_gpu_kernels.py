@@ -185,6 +185,36 @@ def test_k4_filter_by_frequency(cuda, port, min_hits):
     assert (seg == exp_seg).all()
 
 
+def test_k4_filter_counting_edge_cases(cuda, port):
+    """counting path of K4: the id 0xFFFFFFFF (the table's empty marker), one id repeated, all distinct,
+    segments around the warp/block/multi-pass boundaries, human-scale segments with 1-3 survivors"""
+    rng = np.random.RandomState(99)
+    segs = []
+    for n in (1, 3, 4, 5, 255, 256, 257, 600, 5119, 5120, 5121, 12000, 30000):
+        segs.append(np.full(n, 0xFFFFFFFF, np.uint32))                       # only the marker value
+        segs.append(np.full(n, 12345, np.uint32))                            # one id
+        segs.append(rng.permutation(n).astype(np.uint32) * 7919)             # all distinct
+        mixed = rng.randint(0, 1 << 31, size=n).astype(np.uint32) * 2        # random + planted survivors
+        for v, reps in ((0xFFFFFFFF, 4), (0xFFFFFFFE, 5), (0, 4), (77, 3), (2 ** 31 + 5, 16)):
+            if n >= 40:
+                mixed[rng.choice(n, reps, replace=False)] = v
+        segs.append(mixed)
+    rng.shuffle(segs)
+    sizes = [len(x) for x in segs]
+    offs = np.zeros(len(sizes) + 1, np.int64)
+    offs[1:] = np.cumsum(sizes)
+    vals = np.concatenate(segs)
+    for min_hits in (4, 2):
+        ev, eo = port.filter_by_frequency(vals, offs, min_hits)
+        dv = tt(cuda, vals.view(np.int32))
+        dnum = tt(cuda, np.array(sizes, np.int32))
+        doff = tt(cuda, offs.astype(np.int32))
+        total = cuda.filter_by_frequency(dv, dnum, doff, min_hits)
+        assert total == len(ev)
+        assert (doff.cpu().numpy().astype(np.int64) == eo).all()
+        assert (as_u32(dv)[:total] == ev).all()
+
+
 # ---- S2 / S3 -------------------------------------------------------------------------------------
 def test_s2_extended_windows(cuda, port):
     rng = random.Random(8)

@@ -154,6 +154,28 @@ def test_properties_at_scale(cuda, port):
     o2, _ = mp.mapBatch(d_reads[half:].contiguous(), d_lens[half:].contiguous())
     cat = np.concatenate([o1.cpu().numpy(), o2.cpu().numpy()])
     assert (cat == out.cpu().numpy()).all()
+    # the general path (retrieve + K4 over value lists; HRM_COLLECT=0) against the default fused collection, and
+    # candidate values beyond the value budget: the batch is halved into ranges of reads (human-genome scale
+    # retrieves thousands of values per read); results and counters must not depend on path or split
+    import os
+    os.environ["HRM_COLLECT"] = "0"
+    try:
+        mp_gen = cuda.Mapper(cuda.directional_config())
+        os.environ["HRM_VALUE_BUDGET"] = str(int(st.num_values // 2 // 7))
+        mp_split = cuda.Mapper(cuda.directional_config())
+    finally:
+        os.environ.pop("HRM_VALUE_BUDGET", None)
+        del os.environ["HRM_COLLECT"]
+    mp_gen.setGenome(genome, off)
+    mp_split.setGenome(genome, off)
+    outg, stg = mp_gen.mapBatch(d_reads, d_lens)
+    out3, st3 = mp_split.mapBatch(d_reads, d_lens)
+    assert (outg.cpu().numpy() == out.cpu().numpy()).all()
+    assert (out3.cpu().numpy() == out.cpu().numpy()).all()
+    for s_ in (stg, st3):
+        assert (s_.num_values, s_.num_candidates, s_.num_mapped) == (st.num_values, st.num_candidates, st.num_mapped)
+    assert st3.num_kernel_launches > stg.num_kernel_launches  # it did split
+    del mp_split, mp_gen
     # a sample against the oracle's reference-direction pipeline restricted to that sample
     idx = np.arange(0, len(lens), 400)
     passes = []
@@ -163,3 +185,36 @@ def test_properties_at_scale(cuda, port):
         passes.append(port.map_pass_refdir(g, off, r, lens[idx])[0])
     exp, which = merge(passes)
     check_mapped(a[idx], exp, which)
+
+
+@pytest.mark.parametrize("min_hits", [4, 2, 3])
+def test_fused_collection_paths(cuda, tmp_path, min_hits):
+    """K3b retrieval + K4 fused (k4_fused.cu): warp path, block path, many id ranges per read, tiny tables, skipped
+    largest buckets -- all against the general retrieve + filter path, on a low-complexity genome with planted
+    repeats (large buckets, many survivors)"""
+    import os
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "collect_worker.py")
+    variants = {"general": {"HRM_COLLECT": "0"},
+                "default": {},
+                "block": {"HRM_COLLECT_WARP_CAP": "8"},
+                "ranges": {"HRM_COLLECT_WARP_CAP": "8", "HRM_COLLECT_SLOTS": "256", "HRM_COLLECT_FILL": "40"},
+                "tiny": {"HRM_COLLECT_WARP_CAP": "4", "HRM_COLLECT_SLOTS": "64", "HRM_COLLECT_FILL": "12"},
+                "unpacked": {"HRM_COLLECT_UNPACKED": "1"},
+                "unpacked_ranges": {"HRM_COLLECT_UNPACKED": "1", "HRM_COLLECT_WARP_CAP": "8", "HRM_COLLECT_SLOTS": "128",
+                                    "HRM_COLLECT_FILL": "30"}}
+    res, logs = {}, {}
+    for name, env in variants.items():
+        path = str(tmp_path / (name + ".npy"))
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, worker, path, str(min_hits)], capture_output=True, text=True, env=e,
+                           timeout=600)
+        assert r.returncode == 0, name + ": " + r.stdout + r.stderr
+        res[name] = np.load(path)
+        logs[name] = r.stdout.strip().splitlines()[-1]
+    assert (res["general"][:, 0] != 3).mean() > 0.5
+    for name in variants:
+        assert (res[name] == res["general"]).all(), name
+        assert logs[name] == logs["general"], (name, logs[name], logs["general"])
