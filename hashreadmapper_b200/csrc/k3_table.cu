@@ -18,6 +18,7 @@
 #include "k3_probe.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <string.h>
+#include <stdlib.h>
 
 namespace hrm {
 
@@ -251,8 +252,8 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_count_kernel(const uint64
 }
 
 // values of query q: buckets of tables 0..H-1 concatenated at d_values[offsets[q] ...]; one warp per query
-__global__ void __launch_bounds__(256) retrieve_kernel(const uint2* __restrict__ ranges, int n, int H,
-                                                       const uint32_t* __restrict__ table_values,
+__global__ void __launch_bounds__(256) retrieve_kernel(const uint2* __restrict__ ranges, int64_t rq, int64_t rt, int n,
+                                                       int H, const uint32_t* __restrict__ table_values,
                                                        const int32_t* __restrict__ offsets,
                                                        uint32_t* __restrict__ out)
 {
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(256) retrieve_kernel(const uint2* __restrict__
         int64_t w = offsets[q];
         for (int t0 = 0; t0 < H; t0 += 32) {
             const int t = t0 + lane;
-            const uint2 r = t < H ? ranges[q * H + t] : make_uint2(0u, 0u);
+            const uint2 r = t < H ? ranges[q * rq + t * rt] : make_uint2(0u, 0u);
             // exclusive prefix of counts over the lanes
             int incl = (int)r.y;
             for (int d = 1; d < 32; d <<= 1) {
@@ -314,6 +315,151 @@ hrm_status minhasher_count_sigs(hrm_minhasher* mh, QueryHandle* qh, const uint64
                (uint32_t)mh->max_results, qh->ranges.as<uint2>(), d_num_per_seq, mh->d_touches, aligned);
     qh->stage = 1;
     qh->n = n;
+    qh->tm = false;
+    qh->rq = H;
+    qh->rt = 1;
+    return HRM_OK;
+}
+
+// ---- table-major probe -----------------------------------------------------------------------------
+// [n][H] -> [H][n]; block = 64 queries, staged through shared memory so that both sides are coalesced
+__global__ void __launch_bounds__(256) transpose_sigs_kernel(const uint64_t* __restrict__ sigs, int n, int H,
+                                                             uint64_t* __restrict__ sigs_tm)
+{
+    extern __shared__ uint64_t tsm[]; // [64][H + 1]
+    const int nblk = (n + 63) / 64;
+    for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
+        const int q0 = b * 64;
+        const int nq = (n - q0) < 64 ? (n - q0) : 64;
+        for (int e = threadIdx.x; e < nq * H; e += blockDim.x) tsm[(e / H) * (H + 1) + (e % H)] = sigs[(size_t)q0 * H + e];
+        __syncthreads();
+        for (int e = threadIdx.x; e < nq * H; e += blockDim.x) {
+            const int t = e / nq, q = e - t * nq;
+            sigs_tm[(size_t)t * n + q0 + q] = tsm[q * (H + 1) + t];
+        }
+        __syncthreads();
+    }
+}
+
+// Same lookup as probe_count_kernel, tiles in table-major order: tile = (table t, 1024 consecutive queries).
+// Keys of a tile are contiguous in sigs_tm -> one TMA bulk copy per tile, double buffered; ranges written
+// coalesced at ranges_tm[t * n + q].
+__global__ void __launch_bounds__(PROBE_THREADS) probe_tm_kernel(const uint64_t* __restrict__ sigs_tm, int n, int H,
+                                                                 const TablesParam* __restrict__ tabs_g,
+                                                                 uint32_t max_results, uint2* __restrict__ ranges_tm,
+                                                                 unsigned long long* __restrict__ touches_out)
+{
+    __shared__ __align__(16) uint64_t sbuf[2][PROBE_LOOKUPS];
+    __shared__ __align__(8) uint64_t bars[2];
+    const int tid = threadIdx.x;
+    const int tilesPerTable = (n + PROBE_LOOKUPS - 1) / PROBE_LOOKUPS;
+    const int64_t numTiles = (int64_t)tilesPerTable * H;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto q0_of = [&](int64_t tile) { return (int)(tile % tilesPerTable) * PROBE_LOOKUPS; };
+    auto t_of = [&](int64_t tile) { return (int)(tile / tilesPerTable); };
+    auto elems_of = [&](int64_t tile) {
+        const int q0 = q0_of(tile);
+        return (n - q0) < PROBE_LOOKUPS ? (n - q0) : PROBE_LOOKUPS;
+    };
+    auto src_of = [&](int64_t tile) { return sigs_tm + (size_t)t_of(tile) * n + q0_of(tile); };
+    auto tma_ok = [&](int64_t tile) {
+        return ((reinterpret_cast<uintptr_t>(src_of(tile)) & 15) == 0) && ((elems_of(tile) * 8) % 16 == 0);
+    };
+    auto issue = [&](int64_t tile, int st) {
+        const uint32_t bytes = (uint32_t)elems_of(tile) * 8u;
+        mbar_expect_tx(&bars[st], bytes);
+        tma_load_1d(sbuf[st], src_of(tile), bytes, &bars[st]);
+    };
+    uint32_t phases = 0u, visited = 0;
+    int64_t tile = blockIdx.x;
+    int it = 0;
+    if (tid == 0 && tile < numTiles && tma_ok(tile)) issue(tile, 0);
+    for (; tile < numTiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        const int64_t next = tile + gridDim.x;
+        if (tid == 0 && next < numTiles && tma_ok(next)) issue(next, st ^ 1);
+        const int elems = elems_of(tile);
+        uint64_t* keys = sbuf[st];
+        if (tma_ok(tile)) {
+            mbar_wait(&bars[st], (phases >> st) & 1u);
+            phases ^= 1u << st;
+        } else {
+            const uint64_t* src = src_of(tile);
+            for (int e = tid; e < elems; e += PROBE_THREADS) keys[e] = src[e];
+            __syncthreads();
+        }
+        const TableRef T = tabs_g->t[t_of(tile)];
+        uint2* gout = ranges_tm + (size_t)t_of(tile) * n + q0_of(tile);
+        for (int e = tid; e < elems; e += PROBE_THREADS)
+            gout[e] = probe_bucket_sequence(T.slots, T.nbuckets, keys[e], max_results, visited);
+        __syncthreads(); // sbuf[st] is free again
+    }
+    visited *= BUCKET_SLOTS;
+    for (int d = 16; d > 0; d >>= 1) visited += __shfl_xor_sync(0xffffffffu, visited, d);
+    if ((tid & 31) == 0 && visited && touches_out) atomicAdd(touches_out, (unsigned long long)visited);
+}
+
+__global__ void __launch_bounds__(256) totals_tm_kernel(const uint2* __restrict__ ranges_tm, int n, int H,
+                                                        int32_t* __restrict__ num_per_seq)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) {
+        int sum = 0;
+        for (int t = 0; t < H; t++) sum += (int)ranges_tm[(size_t)t * n + q].y;
+        num_per_seq[q] = sum;
+    }
+}
+
+bool minhasher_wants_table_major(const hrm_minhasher* mh)
+{
+    // Measured on B200 (profiles/README.md): with all H tables in flight at once a human-size index (2.5 GB of
+    // buckets per conversion) is probed at 27 % of the HBM copy peak, table by table at 78 %; a chr21-size
+    // index (143 MB) goes from 65 % to 85 %.  HRM_PROBE_TM=0 selects the query-major kernel.
+    static const int forced = getenv("HRM_PROBE_TM") ? atoi(getenv("HRM_PROBE_TM")) : -1;
+    (void)mh;
+    return forced != 0;
+}
+
+hrm_status minhasher_tm_prepare(hrm_minhasher* mh, QueryHandle* qh, const uint64_t* d_sigs, int n, cudaStream_t s)
+{
+    const int H = mh->H;
+    HRM_TRY(qh->sigs_tm.reserve(sizeof(uint64_t) * (size_t)n * H));
+    HRM_TRY(qh->ranges.reserve(sizeof(uint2) * (size_t)n * H));
+    if (n == 0) return HRM_OK;
+    const size_t smem = sizeof(uint64_t) * 64 * (size_t)(H + 1);
+    HRM_LAUNCH(transpose_sigs_kernel, capped_grid((int64_t)((n + 63) / 64) * 256, 256, 8), 256, smem, s, d_sigs, n, H,
+               qh->sigs_tm.as<uint64_t>());
+    return HRM_OK;
+}
+
+hrm_status minhasher_tm_probe(hrm_minhasher* mh, QueryHandle* qh, int n, cudaStream_t s)
+{
+    const int H = mh->H;
+    if (n > 0) {
+        const int64_t numTiles = (int64_t)((n + PROBE_LOOKUPS - 1) / PROBE_LOOKUPS) * H;
+        int64_t grid = numTiles;
+        const int64_t cap = (int64_t)num_sms() * 8;
+        if (grid > cap) grid = cap;
+        HRM_LAUNCH(probe_tm_kernel, (unsigned)grid, PROBE_THREADS, 0, s, qh->sigs_tm.as<uint64_t>(), n, H, mh->d_param,
+                   (uint32_t)mh->max_results, qh->ranges.as<uint2>(), mh->d_touches);
+    }
+    qh->stage = 1;
+    qh->n = n;
+    qh->tm = true;
+    qh->rq = 1;
+    qh->rt = n;
+    return HRM_OK;
+}
+
+hrm_status minhasher_tm_totals(hrm_minhasher* mh, QueryHandle* qh, int n, int32_t* d_num_per_seq, cudaStream_t s)
+{
+    if (n == 0) return HRM_OK;
+    HRM_LAUNCH(totals_tm_kernel, capped_grid(n, 256, 16), 256, 0, s, qh->ranges.as<uint2>(), n, mh->H, d_num_per_seq);
     return HRM_OK;
 }
 
@@ -321,7 +467,8 @@ hrm_status minhasher_retrieve(hrm_minhasher* mh, QueryHandle* qh, int64_t first,
                               const int32_t* d_offsets, cudaStream_t s)
 {
     if (n == 0) return HRM_OK;
-    HRM_LAUNCH(retrieve_kernel, capped_grid((int64_t)n * 32, 256, 16), 256, 0, s, qh->ranges.as<uint2>() + first * mh->H, n, mh->H,
+    HRM_LAUNCH(retrieve_kernel, capped_grid((int64_t)n * 32, 256, 16), 256, 0, s, qh->ranges.as<uint2>() + first * qh->rq,
+               qh->rq, qh->rt, n, mh->H,
                mh->values, d_offsets, d_values);
     return HRM_OK;
 }

@@ -34,7 +34,10 @@ struct TablesParam {
 
 struct QueryHandle {
     GrowBuf sigs;    // [n][H] u64 (when hashing inside count)
-    GrowBuf ranges;  // [n][H] uint2 (off, cnt)
+    GrowBuf ranges;  // uint2 (off, cnt): [n][H], or [H][n] after a table-major probe (tm)
+    GrowBuf sigs_tm; // [H][n] u64: signatures transposed for the table-major probe
+    bool tm = false; // layout of `ranges`
+    int64_t rq = 0, rt = 0; // index of (query q, table t) in `ranges` = q * rq + t * rt
     GrowBuf misc;    // totals
     int stage = 0;   // 0 none, 1 counted
     int n = 0;
@@ -77,6 +80,12 @@ namespace hrm {
 // device-side pieces used by the fused mapper
 hrm_status minhasher_count_sigs(hrm_minhasher* mh, QueryHandle* qh, const uint64_t* d_sigs, int n,
                                 int32_t* d_num_per_seq, cudaStream_t s);
+// table-major probe for indexes far larger than L2 / the TLB reach (k3_table.cu): all lookups of table 0, then table
+// 1, ... so that the lookups in flight share one table.  Three steps so that the caller can time the probe alone.
+bool minhasher_wants_table_major(const hrm_minhasher* mh);
+hrm_status minhasher_tm_prepare(hrm_minhasher* mh, QueryHandle* qh, const uint64_t* d_sigs, int n, cudaStream_t s);
+hrm_status minhasher_tm_probe(hrm_minhasher* mh, QueryHandle* qh, int n, cudaStream_t s);
+hrm_status minhasher_tm_totals(hrm_minhasher* mh, QueryHandle* qh, int n, int32_t* d_num_per_seq, cudaStream_t s);
 // values of queries [first, first + n) of the last count; d_offsets: n + 1 offsets relative to d_values
 hrm_status minhasher_retrieve(hrm_minhasher* mh, QueryHandle* qh, int64_t first, int n, uint32_t* d_values,
                               const int32_t* d_offsets, cudaStream_t s);

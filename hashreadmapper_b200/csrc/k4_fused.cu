@@ -36,7 +36,8 @@ constexpr int COLLECT_CHUNK = 16;       // id ranges whose bucket boundaries are
 constexpr uint32_t COLLECT_EMPTY = 0xFFFFFFFFu;
 
 struct CollectParams {
-    const uint2* ranges;        // [n][H] (value offset, count) of the last probe
+    const uint2* ranges;        // (value offset, count) of the last probe; (q, t) at q * rq + t * rt
+    int64_t rq, rt;
     const uint32_t* table_values;
     int n, H, min_hits;
     uint32_t id_space;          // ids are < id_space
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_small_kernel(CollectP
         int total = 0;
         for (int t0 = 0; t0 < H; t0 += 32) {
             const int t = t0 + lane;
-            const uint2 r = t < H ? P.ranges[(int64_t)rd * H + t] : make_uint2(0u, 0u);
+            const uint2 r = t < H ? P.ranges[(int64_t)rd * P.rq + (int64_t)t * P.rt] : make_uint2(0u, 0u);
             int incl = (int)r.y;
             for (int d = 1; d < 32; d <<= 1) {
                 const int o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_big_kernel(CollectPar
     for (int bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
         const int rd = P.big_list[bi];
         if (tid < H) {
-            const uint2 r = P.ranges[(int64_t)rd * H + tid];
+            const uint2 r = P.ranges[(int64_t)rd * P.rq + (int64_t)tid * P.rt];
             offv[tid] = r.x;
             cntv[tid] = (int)r.y;
             skip[tid] = 0;
@@ -472,6 +473,8 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     HRM_CUDA(cudaMemsetAsync(big.p, 0, sizeof(int32_t), s));
     CollectParams P;
     P.ranges = qh->ranges.as<uint2>();
+    P.rq = qh->rq;
+    P.rt = qh->rt;
     P.table_values = mh->values;
     P.n = n;
     P.H = mh->H;

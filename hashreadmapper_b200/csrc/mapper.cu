@@ -321,9 +321,22 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
             HRM_TRY(filter_and_select(0, n, total, values));
         } else {
             // K3b probe of the whole batch -> per-read counts and bucket ranges
-            T.begin(HRM_STAGE_PROBE, s);
-            HRM_TRY(minhasher_count_sigs(mh, qh, m->sigs.as<uint64_t>(), (int)n, m->num.as<int32_t>(), s));
-            T.end(s);
+            if (minhasher_wants_table_major(mh)) {
+                // index far larger than L2: probe table by table (transpose + totals are booked under "scan")
+                T.begin(HRM_STAGE_SCAN, s);
+                HRM_TRY(minhasher_tm_prepare(mh, qh, m->sigs.as<uint64_t>(), (int)n, s));
+                T.end(s);
+                T.begin(HRM_STAGE_PROBE, s);
+                HRM_TRY(minhasher_tm_probe(mh, qh, (int)n, s));
+                T.end(s);
+                T.begin(HRM_STAGE_SCAN, s);
+                HRM_TRY(minhasher_tm_totals(mh, qh, (int)n, m->num.as<int32_t>(), s));
+                T.end(s);
+            } else {
+                T.begin(HRM_STAGE_PROBE, s);
+                HRM_TRY(minhasher_count_sigs(mh, qh, m->sigs.as<uint64_t>(), (int)n, m->num.as<int32_t>(), s));
+                T.end(s);
+            }
             // fused retrieval + collection straight from the index (k4_fused.cu); falls through to the general
             // path when a read or the output does not fit its bounds
             bool collected = false;

@@ -201,6 +201,8 @@ def test_fused_collection_paths(cuda, tmp_path, min_hits):
                 "block": {"HRM_COLLECT_WARP_CAP": "8"},
                 "ranges": {"HRM_COLLECT_WARP_CAP": "8", "HRM_COLLECT_SLOTS": "256", "HRM_COLLECT_FILL": "40"},
                 "tiny": {"HRM_COLLECT_WARP_CAP": "4", "HRM_COLLECT_SLOTS": "64", "HRM_COLLECT_FILL": "12"},
+                "probe_qm": {"HRM_PROBE_TM": "0"},  # query-major probe ([n][H] signatures and ranges) + fused collection
+                "probe_qm_general": {"HRM_PROBE_TM": "0", "HRM_COLLECT": "0"},
                 "unpacked": {"HRM_COLLECT_UNPACKED": "1"},
                 "unpacked_ranges": {"HRM_COLLECT_UNPACKED": "1", "HRM_COLLECT_WARP_CAP": "8", "HRM_COLLECT_SLOTS": "128",
                                     "HRM_COLLECT_FILL": "30"}}
