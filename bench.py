@@ -340,8 +340,9 @@ def main():
     probe_ms, probe_spans = stages["probe"]
     probe_launch_ms = probe_ms / max(probe_spans, 1)
     launches_per_step_probe = probe_spans / args.steps
-    P = st.num_slot_touches / cfg.num_passes          # slots examined per probe launch
-    Q = n
+    launches = max(launches_per_step_probe, 1.0)
+    P = st.num_slot_touches / launches                # slots examined per probe launch
+    Q = n * cfg.num_passes / launches                 # queries per probe launch
     alg_bytes = 16.0 * P + (8.0 * H_ + 4.0) * Q       # 16 B per slot touch + signatures in + count out
     achieved = alg_bytes / (probe_launch_ms / 1e3) / 1e9 if probe_launch_ms > 0 else 0.0
     traffic = None
@@ -353,7 +354,7 @@ def main():
             traffic = None
     stage_ms = {k: v[0] / args.steps for k, v in stages.items()}
     stage_sum = sum(stage_ms.values())
-    roofline = {"kernel": "hrm::probe_count_kernel (K3b hash probe)" if comm is None else
+    roofline = {"kernel": "hrm::probe_tm_kernel (K3b hash probe, table-major)" if comm is None else
                           "hrm::probe_keys_kernel (K3b hash probe of routed keys, owner side)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": probe_launch_ms,
@@ -383,6 +384,8 @@ def main():
             "stages_ms_per_step": stage_ms, "stages_unaccounted_ms": ms_per_step - stage_sum,
             "mapped_fraction": n_mapped / n, "mapped_at_true_locus_fraction": float(ok.sum()) / max(n_mapped, 1),
             "candidates_per_read": st.num_candidates / n, "values_per_read": st.num_values / n,
+            "collect_ids_skipped_fraction": (float(mp.info().collect_ids_skipped) /
+                                             max(1, mp.info().collect_ids_skipped + mp.info().collect_ids_counted)),
             "clocks": clocks}
     if comm is not None:
         ci = comm.info()

@@ -61,7 +61,7 @@ class MapperConfig(C.Structure):
 class MapperInfo(C.Structure):
     _fields_ = [("num_windows", C.c_int64), ("index_device_bytes", C.c_int64), ("genome_device_bytes", C.c_int64),
                 ("num_keys_total", C.c_int64), ("table_slots_total", C.c_int64), ("num_passes", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("collect_ids_counted", C.c_int64), ("collect_ids_skipped", C.c_int64)]
 
 
 class CommInfo(C.Structure):

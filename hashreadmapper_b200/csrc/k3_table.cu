@@ -68,6 +68,20 @@ __global__ void __launch_bounds__(256) mark_heads_kernel(const uint64_t* __restr
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(valid_count, local);
 }
 
+// number of pairs with a valid key
+__global__ void __launch_bounds__(256) count_valid_kernel(const uint64_t* __restrict__ keys, int64_t n, uint64_t inv,
+                                                          unsigned long long* __restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long local = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t key = keys[i];
+        local += (key != inv && key != SLOT_EMPTY) ? 1 : 0;
+    }
+    for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
 // head_pos[u] = index of the first pair of distinct key u
 __global__ void __launch_bounds__(256) head_positions_kernel(const int32_t* __restrict__ flags,
                                                              const int32_t* __restrict__ excl, int64_t n,
@@ -659,16 +673,33 @@ extern "C" hrm_status hrm_minhasher_compact(hrm_minhasher* mh, hrm_stream stream
     mh->slots.assign(H, nullptr);
     mh->nbuckets.assign(H, 0);
     mh->nkeys.assign(H, 0);
-    mh->values_count = (int64_t)H * n;
+    // values: only the pairs with a valid key are kept (a key-partitioned table stages the keys of other ranks
+    // as invalid, so its value array shrinks with the number of ranks like its slots do)
+    std::vector<int64_t> vbase(H + 1, 0);
+    {
+        Scratch vc;
+        HRM_TRY(vc.alloc(sizeof(unsigned long long) * (size_t)(H > 0 ? H : 1), s));
+        HRM_CUDA(cudaMemsetAsync(vc.p, 0, sizeof(unsigned long long) * (size_t)(H > 0 ? H : 1), s));
+        const uint64_t inv0 = mh->k < 32 ? (1ULL << (2 * mh->k)) : ~0ULL;
+        for (int j = 0; j < H && n > 0; j++)
+            HRM_LAUNCH(count_valid_kernel, capped_grid(n, 256, 16), 256, 0, s, mh->stage_keys[j], n, inv0,
+                       vc.as<unsigned long long>() + j);
+        std::vector<unsigned long long> hv((size_t)(H > 0 ? H : 1), 0);
+        HRM_CUDA(cudaMemcpyAsync(hv.data(), vc.p, sizeof(unsigned long long) * hv.size(), cudaMemcpyDeviceToHost, s));
+        HRM_CUDA(cudaStreamSynchronize(s));
+        for (int j = 0; j < H; j++) vbase[j + 1] = vbase[j] + (int64_t)hv[j];
+    }
+    mh->values_count = vbase[H];
     HRM_CUDA(cudaMalloc(&mh->values, sizeof(uint32_t) * (size_t)(mh->values_count > 0 ? mh->values_count : 1)));
     const uint16_t bs = (uint16_t)mh->max_results; // ref: BucketSize(maxValuesPerKey) groupbykey.hpp:178
     const uint32_t upper = bs < 65535 ? bs : 65535;
     const int end_bit = mh->k < 32 ? 2 * mh->k + 1 : 64;
     const uint64_t inv = mh->k < 32 ? (1ULL << (2 * mh->k)) : ~0ULL;
 
-    Scratch keys_sorted, flags, excl, head_pos, cub_tmp, counters;
+    Scratch keys_sorted, vals_sorted, flags, excl, head_pos, cub_tmp, counters;
     const size_t nn = (size_t)(n > 0 ? n : 1);
     HRM_TRY(keys_sorted.alloc(sizeof(uint64_t) * nn, s));
+    HRM_TRY(vals_sorted.alloc(sizeof(uint32_t) * nn, s));
     HRM_TRY(flags.alloc(sizeof(int32_t) * nn, s));
     HRM_TRY(excl.alloc(sizeof(int32_t) * (nn + 1), s));
     HRM_TRY(head_pos.alloc(sizeof(int32_t) * (nn + 1), s));
@@ -681,7 +712,7 @@ extern "C" hrm_status hrm_minhasher_compact(hrm_minhasher* mh, hrm_stream stream
     }
     for (int j = 0; j < H; j++) {
         int64_t nkeys = 0, nvalid = 0;
-        uint32_t* vals_out = mh->values + (size_t)j * n;
+        uint32_t* vals_out = vals_sorted.as<uint32_t>();
         if (n > 0) {
             HRM_REQUIRE(n < (1LL << 31), "at most 2^31-1 sequences per table");
             HRM_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, mh->stage_keys[j], keys_sorted.as<uint64_t>(),
@@ -699,6 +730,10 @@ extern "C" hrm_status hrm_minhasher_compact(hrm_minhasher* mh, hrm_stream stream
             HRM_CUDA(cudaStreamSynchronize(s));
             nvalid = (int64_t)h_cnt[0];
             nkeys = (int64_t)h_cnt[1];
+            HRM_REQUIRE(nvalid == vbase[j + 1] - vbase[j], "compact: valid pair count changed");
+            if (nvalid > 0) // valid keys sort first: their values are the prefix
+                HRM_CUDA(cudaMemcpyAsync(mh->values + vbase[j], vals_out, sizeof(uint32_t) * (size_t)nvalid,
+                                         cudaMemcpyDeviceToDevice, s));
         }
         // smallest bucket count with nkeys / (BUCKET_SLOTS * nbuckets) <= load factor
         const int64_t nb = (int64_t)((double)nkeys / (double)mh->load / (double)BUCKET_SLOTS) + 1;
@@ -712,7 +747,7 @@ extern "C" hrm_status hrm_minhasher_compact(hrm_minhasher* mh, hrm_stream stream
         HRM_CUDA(cudaMemsetAsync(sl, 0xFF, (size_t)BUCKET_BYTES * (size_t)nb, s));
         if (nkeys > 0) {
             HRM_LAUNCH(insert_keys_kernel, capped_grid(nkeys, 256, 16), 256, 0, s, keys_sorted.as<uint64_t>(),
-                       head_pos.as<int32_t>(), nkeys, nvalid, (uint32_t)((size_t)j * n), upper, sl, (uint32_t)nb,
+                       head_pos.as<int32_t>(), nkeys, nvalid, (uint32_t)vbase[j], upper, sl, (uint32_t)nb,
                        counters.as<unsigned long long>() + 2);
         }
         mh->param.t[j].slots = sl;

@@ -107,6 +107,10 @@ extern "C" hrm_status hrm_mapper_create(hrm_mapper** out, const hrm_mapper_confi
     }
     auto* m = new hrm_mapper;
     m->cfg = *cfg;
+    if (const char* pc = getenv("HRM_PART_CHUNK")) { // test hook: chunked collective query at small sizes
+        const long long v = atoll(pc);
+        if (v > 0) m->part_chunk = v;
+    }
     if (const char* cf = getenv("HRM_COLLECT")) m->use_fused = atoi(cf) != 0; // 0: general retrieve + filter path only
     if (const char* vb = getenv("HRM_VALUE_BUDGET")) { // test hook: forces the range splitting at small sizes
         const long long v = atoll(vb);
@@ -192,6 +196,8 @@ extern "C" hrm_status hrm_mapper_info(const hrm_mapper* m, hrm_mapper_info_t* ou
     memset(out, 0, sizeof *out);
     out->num_windows = m->num_windows;
     out->num_passes = m->cfg.num_passes;
+    out->collect_ids_counted = m->collect_enumerated;
+    out->collect_ids_skipped = m->collect_skipped;
     for (int c = 0; c < 3; c++) {
         if (m->genome[c]) out->genome_device_bytes += m->genome[c]->device_bytes();
         if (m->index[c]) {
@@ -238,15 +244,24 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
     hrm_batch_stats st;
     memset(&st, 0, sizeof st);
     st.num_reads = n;
+    // key-partitioned index: the routed query is collective and bounded per call, so every rank runs the same number
+    // of chunks of at most part_chunk reads (a rank that has run out of reads serves the others' lookups with n = 0)
+    int64_t part_chunks = 1;
+    if (m->comm) {
+        int64_t nmax = n;
+        HRM_TRY(comm_max_i64(m->comm, &nmax, s));
+        part_chunks = nmax > 0 ? HRM_SDIV(nmax, m->part_chunk) : 1;
+    }
     if (n == 0) {
-        if (m->comm) { // the routed query is collective: serve the other ranks' lookups
+        if (m->comm) {
             Scratch numoff, values;
             HRM_TRY(numoff.alloc(sizeof(int32_t) * 4, s));
-            for (int p = 0; p < cfg.num_passes; p++) {
-                int64_t total = 0;
-                HRM_TRY(partitioned_query(m->comm, m->index[cfg.genome_conversion[p]], nullptr, 0, numoff.as<int32_t>(),
-                                          numoff.as<int32_t>() + 1, &total, values, m->timer, s));
-            }
+            for (int p = 0; p < cfg.num_passes; p++)
+                for (int64_t c = 0; c < part_chunks; c++) {
+                    int64_t total = 0;
+                    HRM_TRY(partitioned_query(m->comm, m->index[cfg.genome_conversion[p]], nullptr, 0,
+                                              numoff.as<int32_t>(), numoff.as<int32_t>() + 1, &total, values, m->timer, s));
+                }
             HRM_CUDA(cudaStreamSynchronize(s));
         }
         if (h_stats) *h_stats = st;
@@ -314,11 +329,15 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
         };
         if (m->comm) {
             // key-partitioned index: route the lookups to their owners, values come back in table order
-            Scratch values;
-            int64_t total = 0;
-            HRM_TRY(partitioned_query(m->comm, mh, m->sigs.as<uint64_t>(), (int)n, m->num.as<int32_t>(),
-                                      m->off.as<int32_t>(), &total, values, T, s));
-            HRM_TRY(filter_and_select(0, n, total, values));
+            for (int64_t c = 0; c < part_chunks; c++) {
+                const int64_t lo = c * m->part_chunk < n ? c * m->part_chunk : n;
+                const int64_t cnt = (n - lo) < m->part_chunk ? (n - lo) : m->part_chunk;
+                Scratch values;
+                int64_t total = 0;
+                HRM_TRY(partitioned_query(m->comm, mh, m->sigs.as<uint64_t>() + lo * H, (int)cnt, m->num.as<int32_t>() + lo,
+                                          m->off.as<int32_t>(), &total, values, T, s));
+                if (cnt > 0) HRM_TRY(filter_and_select(lo, cnt, total, values));
+            }
         } else {
             // K3b probe of the whole batch -> per-read counts and bucket ranges
             if (minhasher_wants_table_major(mh)) {

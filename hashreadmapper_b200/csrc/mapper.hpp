@@ -73,5 +73,6 @@ struct hrm_mapper {
     int64_t value_budget = 1LL << 30; // candidate values retrieved per range of reads (int offsets, 8 B scratch each)
     bool use_fused = true;            // K3b retrieval + K4 fused (k4_fused.cu) on the replicated index
     int64_t collect_enumerated = 0, collect_skipped = 0; // ids counted / skipped (largest buckets) by the fused path
+    int64_t part_chunk = 1 << 17;     // reads per routed query of the key-partitioned index
     hrm_comm* comm = nullptr; // key-partitioned index (partition.cu); not owned
 };

@@ -25,6 +25,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <string.h>
+#include <vector>
 
 namespace hrm {
 
@@ -93,6 +94,21 @@ struct hrm_comm {
 };
 
 namespace hrm {
+
+// max over the ranks of one host value (collective; synchronises the stream)
+hrm_status comm_max_i64(hrm_comm* c, int64_t* v, cudaStream_t s)
+{
+    Scratch buf;
+    HRM_TRY(buf.alloc(sizeof(int64_t) * (size_t)(c->world + 1), s));
+    int64_t* d = buf.as<int64_t>();
+    HRM_CUDA(cudaMemcpyAsync(d, v, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    HRM_NCCL(c->api, c->api->AllGather(d, d + 1, 1, ncclInt64, c->comm, s));
+    std::vector<int64_t> h((size_t)c->world);
+    HRM_CUDA(cudaMemcpyAsync(h.data(), d + 1, sizeof(int64_t) * h.size(), cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    for (int64_t x : h) *v = x > *v ? x : *v;
+    return HRM_OK;
+}
 
 int comm_rank(const hrm_comm* c) { return c ? c->rank : 0; }
 int comm_world(const hrm_comm* c) { return c ? c->world : 1; }

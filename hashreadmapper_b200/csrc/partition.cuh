@@ -9,6 +9,7 @@ struct hrm_comm;
 namespace hrm {
 int comm_rank(const hrm_comm* c);
 int comm_world(const hrm_comm* c);
+hrm_status comm_max_i64(hrm_comm* c, int64_t* v, cudaStream_t s);
 // count + retrieve of one batch through the partitioned tables (collective over the communicator):
 // d_num_per_seq [n], d_offsets [n + 1], `values` allocated to *h_total entries in table order
 hrm_status partitioned_query(hrm_comm* c, hrm_minhasher* mh, const uint64_t* d_sigs, int n, int32_t* d_num_per_seq,

@@ -388,6 +388,8 @@ typedef struct {
     int64_t table_slots_total;
     int32_t num_passes;
     int32_t reserved;
+    int64_t collect_ids_counted;  /* fused collection, since creation: ids counted in shared memory */
+    int64_t collect_ids_skipped;  /* ... ids of the largest buckets that were only looked up */
 } hrm_mapper_info_t;
 hrm_status hrm_mapper_info(const hrm_mapper* m, hrm_mapper_info_t* out);
 

@@ -38,7 +38,9 @@ def main():
     rep = api.Mapper(api.directional_config())
     rep.setGenome(genome, off)
     comm = api.Comm()
+    os.environ["HRM_PART_CHUNK"] = "3000"  # several collective chunks per batch, uneven over the ranks
     par = api.Mapper(api.directional_config())
+    del os.environ["HRM_PART_CHUNK"]
     par.setPartition(comm)
     par.setGenome(genome, off)
     ri, pi = rep.info(), par.info()
