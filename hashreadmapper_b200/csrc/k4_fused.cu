@@ -27,7 +27,8 @@
 
 namespace hrm {
 
-constexpr int COLLECT_THREADS = 256;
+constexpr int COLLECT_THREADS = 256;     // warp-per-read kernel
+constexpr int COLLECT_BIG_THREADS = 256; // block-per-read kernel (128 and 512 threads measured slower: 247 and 148 ms vs 96 ms per 1M reads)
 constexpr int COLLECT_WARP_SLOTS = 512;
 constexpr int COLLECT_WARP_CAP = 256;   // ids per read handled by one warp
 constexpr int COLLECT_FINAL_CAP = 1024; // survivors per read the block kernel can hold
@@ -125,6 +126,48 @@ __device__ __forceinline__ int collect_lower_bound(const uint32_t* __restrict__ 
         else hi = mid;
     }
     return lo;
+}
+
+// The same for a bucket of cnt ids spread over [0, id_space): window ids of a bucket are close to uniform, so
+// the answer lies within a few sqrt(cnt) of cnt * key / id_space.  One probe at the estimate, a gallop away from
+// it, then the bisection of a bracket that sits in one or two sectors: 3-4 dependent DRAM accesses instead of
+// log2(cnt).  Any distribution is handled (the gallop doubles), uniformity only makes it fast.
+__device__ __forceinline__ int collect_lower_bound_interp(const uint32_t* __restrict__ p, int cnt, uint32_t key,
+                                                          uint32_t id_space)
+{
+    if (cnt <= 0 || key == 0u) return 0;
+    int lo = 0, hi = cnt; // the answer is in [lo, hi]
+    int pos = (int)(((uint64_t)key * (uint64_t)cnt) / (uint64_t)id_space);
+    pos = pos >= cnt ? cnt - 1 : pos;
+    int step = 8;
+    while (step * step < cnt) step <<= 1; // ~ sqrt(cnt), at least one sector
+    if (__ldg(p + pos) < key) {
+        lo = pos + 1;
+        while (true) {
+            const int nx = lo + step - 1;
+            if (nx >= cnt) break;
+            if (__ldg(p + nx) < key) {
+                lo = nx + 1;
+                step <<= 1;
+            } else {
+                hi = nx;
+                break;
+            }
+        }
+    } else {
+        hi = pos;
+        while (true) {
+            const int nx = hi - step;
+            if (nx < 0) break;
+            if (__ldg(p + nx) < key) {
+                lo = nx + 1;
+                break;
+            }
+            hi = nx;
+            step <<= 1;
+        }
+    }
+    return collect_lower_bound(p, lo, hi, key);
 }
 
 __device__ __forceinline__ void collect_sort_warp(uint32_t* s, int cnt, int lane)
@@ -240,7 +283,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_small_kernel(CollectP
 
 // ---- block per read ----------------------------------------------------------------------------------
 template <bool PACKED>
-__global__ void __launch_bounds__(COLLECT_THREADS) collect_big_kernel(CollectParams P)
+__global__ void __launch_bounds__(COLLECT_BIG_THREADS) collect_big_kernel(CollectParams P)
 {
     extern __shared__ uint32_t cdyn[];
     const int S = P.slots;
@@ -261,7 +304,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_big_kernel(CollectPar
     const int thr = T - L;                                  // >= 2 for T >= 2
     const int nbig = *P.big_count;
     unsigned long long st_enum = 0, st_skip = 0, st_ranges = 0;
-    tab.clear_all(tid, COLLECT_THREADS); // every range leaves the slots it used empty again
+    tab.clear_all(tid, COLLECT_BIG_THREADS); // every range leaves the slots it used empty again
     if (tid == 0) {
         s_ncand = 0;
         s_gfin = 0;
@@ -305,13 +348,14 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_big_kernel(CollectPar
         for (int64_t g0 = 0; g0 < nranges && !bad; g0 += COLLECT_CHUNK) {
             const int ng = (int)((nranges - g0) < COLLECT_CHUNK ? (nranges - g0) : COLLECT_CHUNK);
             // boundaries of ranges g0 .. g0 + ng in every enumerated bucket, all searches in flight together
-            for (int x = tid; x < (ng + 1) * H; x += COLLECT_THREADS) {
+            for (int x = tid; x < (ng + 1) * H; x += COLLECT_BIG_THREADS) {
                 const int g = x / H, t = x - g * H;
                 int pos = 0;
                 if (!skip[t]) {
                     const uint64_t key = (uint64_t)(g0 + g) * width;
-                    pos = key >= (uint64_t)P.id_space ? cntv[t]
-                                                       : collect_lower_bound(P.table_values + offv[t], 0, cntv[t], (uint32_t)key);
+                    pos = key >= (uint64_t)P.id_space
+                              ? cntv[t]
+                              : collect_lower_bound_interp(P.table_values + offv[t], cntv[t], (uint32_t)key, P.id_space);
                 }
                 bnd[g * MAX_TABLES + t] = pos;
             }
@@ -343,11 +387,11 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_big_kernel(CollectPar
                 // DRAM once per batch instead of once per id
                 const int* gp = gpre + g * (MAX_TABLES + 1);
                 int tcur = 0;
-                for (int e0 = 0; e0 < gtotal; e0 += COLLECT_THREADS * COLLECT_MLP) {
+                for (int e0 = 0; e0 < gtotal; e0 += COLLECT_BIG_THREADS * COLLECT_MLP) {
                     uint32_t v[COLLECT_MLP];
 #pragma unroll
                     for (int u = 0; u < COLLECT_MLP; u++) {
-                        const int e = e0 + u * COLLECT_THREADS + tid;
+                        const int e = e0 + u * COLLECT_BIG_THREADS + tid;
                         v[u] = COLLECT_EMPTY;
                         if (e < gtotal) {
                             while (gp[tcur + 1] <= e) tcur++; // bucket with gp[t] <= e < gp[t + 1]; e only grows
@@ -359,7 +403,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_big_kernel(CollectPar
                         if (v[u] != COLLECT_EMPTY) tab.count((uint32_t)slots - 1u, shift, v[u]);
                 }
                 __syncthreads();
-                for (int i = tid; i < slots; i += COLLECT_THREADS) { // collect + leave the table empty
+                for (int i = tid; i < slots; i += COLLECT_BIG_THREADS) { // collect + leave the table empty
                     uint32_t id = 0, c = 0;
                     if (tab.take(i, id, c) && c >= (uint32_t)thr) {
                         const int at = atomicAdd(&s_ncand, 1); // <= gtotal / thr <= S / 2
@@ -371,13 +415,13 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_big_kernel(CollectPar
                 const int ncand = s_ncand;
                 if (ncand == 0) continue; // the common case: nothing in this id range reaches the threshold
                 const int base = s_nfin;
-                for (int c = tid; c < ncand; c += COLLECT_THREADS) {
+                for (int c = tid; c < ncand; c += COLLECT_BIG_THREADS) {
                     const uint32_t id = cand[c];
                     uint32_t m = ccnt[c];
                     for (int t = 0; t < H && m < (uint32_t)T; t++) {
                         if (!skip[t]) continue;
                         const uint32_t* p = P.table_values + offv[t];
-                        const int pos = collect_lower_bound(p, 0, cntv[t], id);
+                        const int pos = collect_lower_bound_interp(p, cntv[t], id, P.id_space);
                         if (pos < cntv[t] && __ldg(p + pos) == id) m++;
                     }
                     if (m >= (uint32_t)T) {
@@ -390,7 +434,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_big_kernel(CollectPar
                 bad = s_bad != 0;
                 const int gf = s_gfin;
                 // sort this range's survivors; ranges ascend, so the read's list stays sorted
-                if (!bad && gf > 1) bitonic_sort<true>(fin + base, gf, tid, COLLECT_THREADS);
+                if (!bad && gf > 1) bitonic_sort<true>(fin + base, gf, tid, COLLECT_BIG_THREADS);
                 __syncthreads();
                 if (tid == 0) {
                     s_nfin = base + (bad ? 0 : gf);
@@ -402,7 +446,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_big_kernel(CollectPar
         }
         if (bad) {
             __syncthreads();
-            tab.clear_all(tid, COLLECT_THREADS); // the aborted range may have left ids behind
+            tab.clear_all(tid, COLLECT_BIG_THREADS); // the aborted range may have left ids behind
             if (tid == 0) {
                 *P.overflow = 1;
                 P.lists[rd] = make_int2(0, 0);
@@ -426,7 +470,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_big_kernel(CollectPar
         __syncthreads();
         const unsigned long long start = s_start;
         if (start != ~0ull) {
-            for (int i = tid; i < ns; i += COLLECT_THREADS) P.out[start + i] = fin[i];
+            for (int i = tid; i < ns; i += COLLECT_BIG_THREADS) P.out[start + i] = fin[i];
             if (tid == 0) P.lists[rd] = make_int2((int)start, ns);
         } else if (tid == 0) {
             P.lists[rd] = make_int2(0, 0);
@@ -501,15 +545,15 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     if (packed) {
         HRM_LAUNCH(collect_small_kernel<true>, (unsigned)g, COLLECT_THREADS, 0, s, P);
         cudaFuncSetAttribute(collect_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, collect_big_kernel<true>, COLLECT_THREADS, smem));
-        HRM_LAUNCH(collect_big_kernel<true>, (unsigned)(num_sms() * (resident > 0 ? resident : 1)), COLLECT_THREADS, smem, s,
-                   P);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, collect_big_kernel<true>, COLLECT_BIG_THREADS, smem));
+        HRM_LAUNCH(collect_big_kernel<true>, (unsigned)(num_sms() * (resident > 0 ? resident : 1)), COLLECT_BIG_THREADS, smem,
+                   s, P);
     } else {
         HRM_LAUNCH(collect_small_kernel<false>, (unsigned)g, COLLECT_THREADS, 0, s, P);
         cudaFuncSetAttribute(collect_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, collect_big_kernel<false>, COLLECT_THREADS, smem));
-        HRM_LAUNCH(collect_big_kernel<false>, (unsigned)(num_sms() * (resident > 0 ? resident : 1)), COLLECT_THREADS, smem, s,
-                   P);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, collect_big_kernel<false>, COLLECT_BIG_THREADS, smem));
+        HRM_LAUNCH(collect_big_kernel<false>, (unsigned)(num_sms() * (resident > 0 ? resident : 1)), COLLECT_BIG_THREADS,
+                   smem, s, P);
     }
     unsigned long long h[8];
     HRM_CUDA(cudaMemcpyAsync(h, ctl.p, sizeof h, cudaMemcpyDeviceToHost, s));
