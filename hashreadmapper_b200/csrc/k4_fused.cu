@@ -29,8 +29,6 @@ namespace hrm {
 
 constexpr int COLLECT_THREADS = 256;     // warp-per-read kernel
 constexpr int COLLECT_BIG_THREADS = 256; // block-per-read kernel (128 and 512 threads measured slower: 247 and 148 ms vs 96 ms per 1M reads)
-constexpr int COLLECT_WARP_SLOTS = 512;
-constexpr int COLLECT_WARP_CAP = 256;   // ids per read handled by one warp
 constexpr int COLLECT_FINAL_CAP = 1024; // survivors per read the block kernel can hold
 constexpr int COLLECT_MLP = 4;         // independent id loads a thread keeps in flight
 constexpr int COLLECT_CHUNK = 16;       // id ranges whose bucket boundaries are searched together
@@ -49,7 +47,8 @@ struct CollectParams {
     int* overflow;
     int32_t* big_list;
     int32_t* big_count;
-    int warp_cap;               // reads with more ids go to the block kernel
+    int warp_cap;               // reads with more ids go straight to the block kernel (test hook)
+    int warp_slots;             // table slots of a warp (power of two)
     int slots;                  // table slots of the block kernel (power of two)
     int fill;                   // target ids per range
     unsigned long long* stats;  // [0] ids enumerated, [1] ids skipped (largest buckets), [2] ranges
@@ -186,99 +185,232 @@ __device__ __forceinline__ void collect_sort_warp(uint32_t* s, int cnt, int lane
 }
 
 // ---- warp per read ---------------------------------------------------------------------------------
-template <bool PACKED>
-__global__ void __launch_bounds__(COLLECT_THREADS) collect_small_kernel(CollectParams P)
+// The whole scheme (skip the L largest buckets, id ranges, count, look the survivors up in the big buckets) run by
+// ONE WARP per read on its own slice of shared memory: no block barriers, and an SM keeps as many reads in flight
+// as it has resident warps, which is what hides the DRAM latency of a path that is a chain of dependent accesses
+// (bucket ranges -> range boundaries -> ids -> big-bucket lookups).  Reads whose ids are far from uniform or that
+// keep more survivors than the slice holds go to the block kernel through big_list.
+constexpr int COLLECT_WCHUNK = 4;   // id ranges whose boundaries a warp searches together
+constexpr int COLLECT_WCAND = 256;  // ids reaching the reduced threshold per range a warp can hold
+constexpr int COLLECT_WFIN = 256;   // survivors per read a warp can hold
+constexpr int COLLECT_WMLP = 8;     // independent id loads per lane
+
+__host__ __device__ inline size_t collect_warp_slice_words(int slots, int H, bool packed)
 {
-    __shared__ uint32_t hw[COLLECT_THREADS / 32][(PACKED ? 1 : 2) * COLLECT_WARP_SLOTS];
-    __shared__ uint32_t srt[COLLECT_THREADS / 32][COLLECT_WARP_CAP / 2 + 1];
-    __shared__ int pre[COLLECT_THREADS / 32][MAX_TABLES + 1];
-    __shared__ uint32_t offv[COLLECT_THREADS / 32][MAX_TABLES];
+    return (size_t)(packed ? 1 : 2) * slots + 2 * COLLECT_WCAND + COLLECT_WFIN + 3 * (size_t)H +
+           (size_t)(COLLECT_WCHUNK + 1) * H + (size_t)H + 1;
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(COLLECT_THREADS) collect_warp_kernel(CollectParams P)
+{
+    extern __shared__ uint32_t wdyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const CountTable<PACKED> tab{hw[wid], COLLECT_WARP_SLOTS};
-    uint32_t* s = srt[wid];
-    const int H = P.H;
+    const int H = P.H, T = P.min_hits, SW = P.warp_slots;
+    uint32_t* base = wdyn + (size_t)wid * collect_warp_slice_words(SW, H, PACKED);
+    const CountTable<PACKED> tab{base, SW};
+    uint32_t* cand = base + (PACKED ? 1 : 2) * SW; // [WCAND]
+    uint32_t* ccnt = cand + COLLECT_WCAND;          // [WCAND]
+    uint32_t* fin = ccnt + COLLECT_WCAND;           // [WFIN]
+    uint32_t* offv = fin + COLLECT_WFIN;            // [H]
+    int* cntv = reinterpret_cast<int*>(offv + H);   // [H]
+    int* skipf = cntv + H;                          // [H]
+    int* bnd = skipf + H;                           // [(WCHUNK + 1) * H]
+    int* gpre = bnd + (COLLECT_WCHUNK + 1) * H;     // [H + 1]
+    const int L = T - 2 < 2 ? (T - 2 < 0 ? 0 : T - 2) : 2; // buckets not enumerated
+    const int thr = T - L;
     const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
-    unsigned long long enumerated = 0;
-    tab.clear_all(lane, 32); // a read leaves the slots it used empty again
+    unsigned long long st_enum = 0, st_skip = 0, st_ranges = 0;
+    tab.clear_all(lane, 32); // a range leaves the slots it used empty again
     __syncwarp();
     for (int rd = warp0; rd < P.n; rd += nwarps) {
+        // bucket ranges of the read
         int total = 0;
         for (int t0 = 0; t0 < H; t0 += 32) {
             const int t = t0 + lane;
             const uint2 r = t < H ? P.ranges[(int64_t)rd * P.rq + (int64_t)t * P.rt] : make_uint2(0u, 0u);
-            int incl = (int)r.y;
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += o;
-            }
             if (t < H) {
-                pre[wid][t] = total + incl - (int)r.y;
-                offv[wid][t] = r.x;
+                offv[t] = r.x;
+                cntv[t] = (int)r.y;
+                skipf[t] = 0;
             }
-            total += __shfl_sync(0xffffffffu, incl, 31);
+            total += __reduce_add_sync(0xffffffffu, (int)r.y);
         }
-        if (lane == 0) pre[wid][H] = total;
         __syncwarp();
-        if (total <= P.warp_cap) enumerated += (unsigned long long)(lane == 0 ? total : 0);
-        if (total < P.min_hits) {
-            if (lane == 0) P.lists[rd] = make_int2(0, 0);
-            __syncwarp();
+        if (total < T) {
+            if (lane == 0) {
+                P.lists[rd] = make_int2(0, 0);
+                st_enum += (unsigned long long)total;
+            }
             continue;
         }
-        if (total > P.warp_cap) {
+        if (total > P.warp_cap) { // test hook / safety valve: straight to the block kernel
             if (lane == 0) P.big_list[atomicAdd(P.big_count, 1)] = rd;
+            continue;
+        }
+        // the L largest buckets are looked up, not enumerated
+        int skipped = 0;
+        for (int l = 0; l < L; l++) {
+            unsigned best = 0u; // (count << 8 | table) of the lane's best candidate
+            for (int t = lane; t < H; t += 32)
+                if (!skipf[t] && cntv[t] > 0) {
+                    const unsigned key = ((unsigned)cntv[t] << 8) | (unsigned)(255 - t); // ties: lowest table
+                    best = key > best ? key : best;
+                }
+            best = __reduce_max_sync(0xffffffffu, best);
+            if (best == 0u) break;
+            const int t = 255 - (int)(best & 255u);
+            if (lane == 0) skipf[t] = 1;
+            skipped += (int)(best >> 8);
+            __syncwarp();
+        }
+        const int E = total - skipped;
+        const int fill = (3 * SW) / 8;
+        const int nranges = E > 0 ? (E + fill - 1) / fill : 1;
+        const uint64_t width = ((uint64_t)P.id_space + (uint64_t)nranges - 1) / (uint64_t)nranges;
+        if (lane == 0) {
+            st_enum += (unsigned long long)E;
+            st_skip += (unsigned long long)skipped;
+            st_ranges += (unsigned long long)nranges;
+        }
+        int nfin = 0;
+        bool bad = false;
+        for (int g0 = 0; g0 < nranges && !bad; g0 += COLLECT_WCHUNK) {
+            const int ng = (nranges - g0) < COLLECT_WCHUNK ? (nranges - g0) : COLLECT_WCHUNK;
+            for (int x = lane; x < (ng + 1) * H; x += 32) { // range boundaries, all searches of the chunk in flight
+                const int g = x / H, t = x - g * H;
+                int pos = 0;
+                if (!skipf[t]) {
+                    const uint64_t key = (uint64_t)(g0 + g) * width;
+                    pos = key >= (uint64_t)P.id_space
+                              ? cntv[t]
+                              : collect_lower_bound_interp(P.table_values + offv[t], cntv[t], (uint32_t)key, P.id_space);
+                }
+                bnd[g * H + t] = pos;
+            }
+            __syncwarp();
+            for (int g = 0; g < ng && !bad; g++) {
+                int gtotal = 0; // flat prefix of the range's bucket pieces
+                for (int t0 = 0; t0 < H; t0 += 32) {
+                    const int t = t0 + lane;
+                    const int len = t < H ? bnd[(g + 1) * H + t] - bnd[g * H + t] : 0;
+                    int incl = len;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += o;
+                    }
+                    if (t < H) gpre[t] = gtotal + incl - len;
+                    gtotal += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) gpre[H] = gtotal;
+                __syncwarp();
+                if (gtotal < thr) continue;
+                if (8 * gtotal > 7 * SW) { // ids far from uniform: this range would clog the table
+                    bad = true;
+                    break;
+                }
+                int slots = 64, shift = 32 - 6;
+                while (slots < SW && 5 * slots < 8 * gtotal) {
+                    slots <<= 1;
+                    shift--;
+                }
+                int tcur = 0;
+                for (int e0 = 0; e0 < gtotal; e0 += 32 * COLLECT_WMLP) {
+                    uint32_t v[COLLECT_WMLP];
+#pragma unroll
+                    for (int u = 0; u < COLLECT_WMLP; u++) {
+                        const int e = e0 + u * 32 + lane;
+                        v[u] = COLLECT_EMPTY;
+                        if (e < gtotal) {
+                            while (gpre[tcur + 1] <= e) tcur++; // bucket with gpre[t] <= e < gpre[t + 1]; e only grows
+                            v[u] = __ldg(P.table_values + offv[tcur] + bnd[g * H + tcur] + (e - gpre[tcur]));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < COLLECT_WMLP; u++)
+                        if (v[u] != COLLECT_EMPTY) tab.count((uint32_t)slots - 1u, shift, v[u]);
+                }
+                __syncwarp();
+                int ncand = 0;
+                for (int i0 = 0; i0 < slots; i0 += 32) { // collect + leave the table empty
+                    uint32_t id = 0, c = 0;
+                    const bool keep = tab.take(i0 + lane, id, c) && c >= (uint32_t)thr;
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (m) {
+                        const int at = ncand + __popc(m & ((1u << lane) - 1u));
+                        if (keep && at < COLLECT_WCAND) {
+                            cand[at] = id;
+                            ccnt[at] = c;
+                        }
+                        ncand += __popc(m);
+                    }
+                }
+                __syncwarp();
+                if (ncand == 0) continue; // the common case: nothing in this id range reaches the threshold
+                if (ncand > COLLECT_WCAND) {
+                    bad = true;
+                    break;
+                }
+                int gf = 0;
+                for (int c0 = 0; c0 < ncand; c0 += 32) {
+                    const int c = c0 + lane;
+                    bool keep = false;
+                    uint32_t id = 0;
+                    if (c < ncand) {
+                        id = cand[c];
+                        uint32_t m = ccnt[c];
+                        for (int t = 0; t < H && m < (uint32_t)T; t++) {
+                            if (!skipf[t]) continue;
+                            const uint32_t* p = P.table_values + offv[t];
+                            const int pos = collect_lower_bound_interp(p, cntv[t], id, P.id_space);
+                            if (pos < cntv[t] && __ldg(p + pos) == id) m++;
+                        }
+                        keep = m >= (uint32_t)T;
+                    }
+                    const unsigned m2 = __ballot_sync(0xffffffffu, keep);
+                    const int at = nfin + gf + __popc(m2 & ((1u << lane) - 1u));
+                    if (keep && at < COLLECT_WFIN) fin[at] = id;
+                    gf += __popc(m2);
+                }
+                __syncwarp();
+                if (nfin + gf > COLLECT_WFIN) {
+                    bad = true;
+                    break;
+                }
+                // ranges ascend, so sorting each range's survivors keeps the read's list sorted
+                if (gf > 1) collect_sort_warp(fin + nfin, gf, lane);
+                nfin += gf;
+            }
+        }
+        if (bad) { // the aborted range may have left ids behind; the block kernel redoes the read
+            __syncwarp();
+            tab.clear_all(lane, 32);
+            if (lane == 0) {
+                P.big_list[atomicAdd(P.big_count, 1)] = rd;
+                st_enum -= (unsigned long long)E; // counted again there
+                st_skip -= (unsigned long long)skipped;
+                st_ranges -= (unsigned long long)nranges;
+            }
             __syncwarp();
             continue;
         }
-        int slots = 32, shift = 27;
-        while (slots < 2 * total) {
-            slots <<= 1;
-            shift--;
-        }
-        for (int e0 = 0; e0 < total; e0 += 32 * COLLECT_MLP) {
-            uint32_t v[COLLECT_MLP];
-#pragma unroll
-            for (int u = 0; u < COLLECT_MLP; u++) {
-                const int e = e0 + u * 32 + lane;
-                v[u] = COLLECT_EMPTY;
-                if (e < total) {
-                    int lo = 0, hi = H; // bucket t with pre[t] <= e < pre[t + 1]
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (pre[wid][mid] <= e) lo = mid;
-                        else hi = mid;
-                    }
-                    v[u] = __ldg(P.table_values + offv[wid][lo] + (e - pre[wid][lo]));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < COLLECT_MLP; u++)
-                if (v[u] != COLLECT_EMPTY) tab.count((uint32_t)slots - 1u, shift, v[u]);
-        }
-        __syncwarp();
-        int ns = 0;
-        for (int base = 0; base < slots; base += 32) {
-            uint32_t id = 0, c = 0;
-            const bool keep = tab.take(base + lane, id, c) && c >= (uint32_t)P.min_hits;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (keep) s[ns + __popc(m & ((1u << lane) - 1u))] = id; // ns <= total / min_hits <= warp_cap / 2
-            ns += __popc(m);
-        }
-        __syncwarp();
-        if (ns > 1) collect_sort_warp(s, ns, lane);
         unsigned long long start = 0;
-        if (lane == 0 && ns > 0) start = atomicAdd(P.cursor, (unsigned long long)ns);
+        if (lane == 0 && nfin > 0) start = atomicAdd(P.cursor, (unsigned long long)nfin);
         start = __shfl_sync(0xffffffffu, start, 0);
-        if (start + (unsigned long long)ns > P.out_cap) {
+        if (start + (unsigned long long)nfin > P.out_cap) {
             if (lane == 0) *P.overflow = 1;
-            ns = 0;
+            nfin = 0;
         }
-        for (int i = lane; i < ns; i += 32) P.out[start + i] = s[i];
-        if (lane == 0) P.lists[rd] = make_int2((int)start, ns);
+        for (int i = lane; i < nfin; i += 32) P.out[start + i] = fin[i];
+        if (lane == 0) P.lists[rd] = make_int2((int)start, nfin);
         __syncwarp();
     }
-    if (lane == 0 && enumerated && P.stats) atomicAdd(P.stats, enumerated);
+    if (lane == 0 && P.stats) {
+        if (st_enum) atomicAdd(P.stats, st_enum);
+        if (st_skip) atomicAdd(P.stats + 1, st_skip);
+        if (st_ranges) atomicAdd(P.stats + 2, st_ranges);
+    }
 }
 
 // ---- block per read ----------------------------------------------------------------------------------
@@ -502,9 +634,10 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     *h_total = 0;
     if (n == 0) return HRM_OK;
     HRM_REQUIRE(min_hits >= 2 && id_space < 0xFFFFFFFFu, "collect_candidates needs minTableHits >= 2");
-    static const int warp_cap = env_int("HRM_COLLECT_WARP_CAP", COLLECT_WARP_CAP) < COLLECT_WARP_CAP
-                                    ? env_int("HRM_COLLECT_WARP_CAP", COLLECT_WARP_CAP)
-                                    : COLLECT_WARP_CAP;
+    static const int warp_cap = env_int("HRM_COLLECT_WARP_CAP", 0x7fffffff);
+    static const int wslots_env = env_int("HRM_COLLECT_WARP_SLOTS", 1024);
+    int wslots = 64;
+    while (wslots < wslots_env && wslots < 8192) wslots <<= 1;
     static const int slots_env = env_int("HRM_COLLECT_SLOTS", 2048);
     int slots = 64;
     while (slots < slots_env && slots < 16384) slots <<= 1;
@@ -533,23 +666,30 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     P.big_count = big.as<int32_t>();
     P.big_list = big.as<int32_t>() + 1;
     P.warp_cap = warp_cap;
+    P.warp_slots = wslots;
     P.slots = slots;
     P.fill = fill;
-    int64_t g = HRM_SDIV((int64_t)n * 32, (int64_t)COLLECT_THREADS);
-    if (g > (int64_t)num_sms() * 16) g = (int64_t)num_sms() * 16;
     static const bool allow_packed = env_int("HRM_COLLECT_UNPACKED", 0) == 0;
     const bool packed = allow_packed && id_space < (1u << (32 - COLLECT_PACK_BITS)) - 1u && mh->H < (1 << COLLECT_PACK_BITS);
     const size_t smem = sizeof(uint32_t) * ((size_t)((packed ? 1 : 2) + 1) * slots + COLLECT_FINAL_CAP);
+    // warp kernel: 2 warps per block so that the slices of many blocks fill the SM's shared memory
+    const int wthreads = 64;
+    const size_t wsmem = sizeof(uint32_t) * collect_warp_slice_words(wslots, mh->H, packed) * (wthreads / 32);
+    int wres = 1;
     // one wave of resident blocks, each loops over the list of big reads
     int resident = 1;
     if (packed) {
-        HRM_LAUNCH(collect_small_kernel<true>, (unsigned)g, COLLECT_THREADS, 0, s, P);
+        cudaFuncSetAttribute(collect_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wres, collect_warp_kernel<true>, wthreads, wsmem));
+        HRM_LAUNCH(collect_warp_kernel<true>, (unsigned)(num_sms() * (wres > 0 ? wres : 1)), wthreads, wsmem, s, P);
         cudaFuncSetAttribute(collect_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, collect_big_kernel<true>, COLLECT_BIG_THREADS, smem));
         HRM_LAUNCH(collect_big_kernel<true>, (unsigned)(num_sms() * (resident > 0 ? resident : 1)), COLLECT_BIG_THREADS, smem,
                    s, P);
     } else {
-        HRM_LAUNCH(collect_small_kernel<false>, (unsigned)g, COLLECT_THREADS, 0, s, P);
+        cudaFuncSetAttribute(collect_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wres, collect_warp_kernel<false>, wthreads, wsmem));
+        HRM_LAUNCH(collect_warp_kernel<false>, (unsigned)(num_sms() * (wres > 0 ? wres : 1)), wthreads, wsmem, s, P);
         cudaFuncSetAttribute(collect_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, collect_big_kernel<false>, COLLECT_BIG_THREADS, smem));
         HRM_LAUNCH(collect_big_kernel<false>, (unsigned)(num_sms() * (resident > 0 ? resident : 1)), COLLECT_BIG_THREADS,

@@ -198,6 +198,8 @@ def test_fused_collection_paths(cuda, tmp_path, min_hits):
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "collect_worker.py")
     variants = {"general": {"HRM_COLLECT": "0"},
                 "default": {},
+                "warp_ranges": {"HRM_COLLECT_WARP_SLOTS": "64"},   # many id ranges per read in the warp kernel
+                "warp_ranges_unpacked": {"HRM_COLLECT_WARP_SLOTS": "128", "HRM_COLLECT_UNPACKED": "1"},
                 "block": {"HRM_COLLECT_WARP_CAP": "8"},
                 "ranges": {"HRM_COLLECT_WARP_CAP": "8", "HRM_COLLECT_SLOTS": "256", "HRM_COLLECT_FILL": "40"},
                 "tiny": {"HRM_COLLECT_WARP_CAP": "4", "HRM_COLLECT_SLOTS": "64", "HRM_COLLECT_FILL": "12"},

@@ -1,10 +1,15 @@
 set -x
-for S in 2048 4096; do
-HRM_COLLECT_SLOTS=$S python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_g$S.err | grep '^{' > gpurun_out/bench_g$S.json; echo rc=$?
+python -m pytest tests -m gpu -x -q -k "fused or scale or small" 2>&1 | tail -3
+for S in 512 256; do
+HRM_COLLECT_WARP_SLOTS=$S python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_w$S.err | grep '^{' > gpurun_out/bench_w$S.json; echo rc=$?
+HRM_COLLECT_WARP_SLOTS=$S python bench.py --genome-bp 46000000 --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_wc$S.err | grep '^{' > gpurun_out/bench_wc$S.json; echo rc=$?
 done
 python - <<PY
 import json
-for f in ("bench_g2048","bench_g4096"):
-    d=json.load(open("gpurun_out/%s.json"%f))
-    print(f, d["value"], d["e2e"]["value"], d["stages_ms_per_step"]["filter"])
+for f in ("bench_w512","bench_w256","bench_wc512","bench_wc256"):
+    try:
+        d=json.load(open("gpurun_out/%s.json"%f))
+        print(f, d["value"], d["e2e"]["value"], d["stages_ms_per_step"]["filter"], d["stages_ms_per_step"]["shd"])
+    except Exception as e:
+        print(f, "failed", e)
 PY
