@@ -71,7 +71,8 @@ struct CountTable {
             if (!PACKED) w[cap + i] = 0u;
         }
     }
-    __device__ __forceinline__ void count(uint32_t mask, int shift, uint32_t v) const
+    // counts one id and returns its new count
+    __device__ __forceinline__ uint32_t count(uint32_t mask, int shift, uint32_t v) const
     {
         uint32_t h = collect_hash(v) >> shift;
         if (PACKED) {
@@ -79,23 +80,43 @@ struct CountTable {
                 uint32_t cur = w[h];
                 if (cur == COLLECT_EMPTY) {
                     cur = atomicCAS(&w[h], COLLECT_EMPTY, (v << COLLECT_PACK_BITS) | 1u);
-                    if (cur == COLLECT_EMPTY) return;
+                    if (cur == COLLECT_EMPTY) return 1u;
                 }
-                if ((cur >> COLLECT_PACK_BITS) == v) {
-                    atomicAdd(&w[h], 1u);
-                    return;
-                }
+                if ((cur >> COLLECT_PACK_BITS) == v)
+                    return (atomicAdd(&w[h], 1u) & ((1u << COLLECT_PACK_BITS) - 1u)) + 1u;
                 h = (h + 1) & mask;
             }
         } else {
             while (true) {
                 const uint32_t prev = atomicCAS(&w[h], COLLECT_EMPTY, v);
-                if (prev == COLLECT_EMPTY || prev == v) {
-                    atomicAdd(&w[cap + h], 1u);
-                    return;
-                }
+                if (prev == COLLECT_EMPTY || prev == v) return atomicAdd(&w[cap + h], 1u) + 1u;
                 h = (h + 1) & mask;
             }
+        }
+    }
+    // count of an id that is in the table
+    __device__ __forceinline__ uint32_t lookup(uint32_t mask, int shift, uint32_t v) const
+    {
+        uint32_t h = collect_hash(v) >> shift;
+        while (true) {
+            const uint32_t cur = w[h];
+            if (cur == COLLECT_EMPTY) return 0u;
+            if (PACKED) {
+                if ((cur >> COLLECT_PACK_BITS) == v) return cur & ((1u << COLLECT_PACK_BITS) - 1u);
+            } else if (cur == v) {
+                return w[cap + h];
+            }
+            h = (h + 1) & mask;
+        }
+    }
+    // empties slots [0, n), n a multiple of 128: 128-bit stores
+    __device__ __forceinline__ void clear_prefix(int n, int tid, int nthr) const
+    {
+        uint4* p = reinterpret_cast<uint4*>(w);
+        for (int i = tid; i < n / 4; i += nthr) p[i] = make_uint4(COLLECT_EMPTY, COLLECT_EMPTY, COLLECT_EMPTY, COLLECT_EMPTY);
+        if (!PACKED) {
+            uint4* q = reinterpret_cast<uint4*>(w + cap);
+            for (int i = tid; i < n / 4; i += nthr) q[i] = make_uint4(0u, 0u, 0u, 0u);
         }
     }
     // reads slot i and leaves it empty; returns false for an empty slot
@@ -136,8 +157,9 @@ __device__ __forceinline__ int collect_lower_bound_interp(const uint32_t* __rest
 {
     if (cnt <= 0 || key == 0u) return 0;
     int lo = 0, hi = cnt; // the answer is in [lo, hi]
-    int pos = (int)(((uint64_t)key * (uint64_t)cnt) / (uint64_t)id_space);
-    pos = pos >= cnt ? cnt - 1 : pos;
+    // the estimate only steers the search: single precision is enough and avoids a 64-bit division
+    int pos = (int)(((float)key / (float)id_space) * (float)cnt);
+    pos = pos >= cnt ? cnt - 1 : (pos < 0 ? 0 : pos);
     int step = 8;
     while (step * step < cnt) step <<= 1; // ~ sqrt(cnt), at least one sector
     if (__ldg(p + pos) < key) {
@@ -197,14 +219,15 @@ constexpr int COLLECT_WMLP = 8;     // independent id loads per lane
 
 __host__ __device__ inline size_t collect_warp_slice_words(int slots, int H, bool packed)
 {
-    return (size_t)(packed ? 1 : 2) * slots + 2 * COLLECT_WCAND + COLLECT_WFIN + 3 * (size_t)H +
-           (size_t)(COLLECT_WCHUNK + 1) * H + (size_t)H + 1;
+    const size_t w = (size_t)(packed ? 1 : 2) * slots + 2 * COLLECT_WCAND + COLLECT_WFIN + 3 * (size_t)H +
+                     (size_t)(COLLECT_WCHUNK + 1) * H + (size_t)H + 2;
+    return (w + 3) & ~(size_t)3; // slices stay 16-byte aligned (128-bit table clears)
 }
 
 template <bool PACKED>
 __global__ void __launch_bounds__(COLLECT_THREADS) collect_warp_kernel(CollectParams P)
 {
-    extern __shared__ uint32_t wdyn[];
+    extern __shared__ __align__(16) uint32_t wdyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int H = P.H, T = P.min_hits, SW = P.warp_slots;
     uint32_t* base = wdyn + (size_t)wid * collect_warp_slice_words(SW, H, PACKED);
@@ -217,12 +240,14 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_warp_kernel(CollectPa
     int* skipf = cntv + H;                          // [H]
     int* bnd = skipf + H;                           // [(WCHUNK + 1) * H]
     int* gpre = bnd + (COLLECT_WCHUNK + 1) * H;     // [H + 1]
+    int* wcount = gpre + H + 1;                     // candidates of the current range
     const int L = T - 2 < 2 ? (T - 2 < 0 ? 0 : T - 2) : 2; // buckets not enumerated
     const int thr = T - L;
     const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
     unsigned long long st_enum = 0, st_skip = 0, st_ranges = 0;
     tab.clear_all(lane, 32); // a range leaves the slots it used empty again
+    if (lane == 0) *wcount = 0;
     __syncwarp();
     for (int rd = warp0; rd < P.n; rd += nwarps) {
         // bucket ranges of the read
@@ -310,7 +335,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_warp_kernel(CollectPa
                     bad = true;
                     break;
                 }
-                int slots = 64, shift = 32 - 6;
+                int slots = 128, shift = 32 - 7;
                 while (slots < SW && 5 * slots < 8 * gtotal) {
                     slots <<= 1;
                     shift--;
@@ -329,23 +354,20 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_warp_kernel(CollectPa
                     }
 #pragma unroll
                     for (int u = 0; u < COLLECT_WMLP; u++)
-                        if (v[u] != COLLECT_EMPTY) tab.count((uint32_t)slots - 1u, shift, v[u]);
+                        if (v[u] != COLLECT_EMPTY && tab.count((uint32_t)slots - 1u, shift, v[u]) == (uint32_t)thr) {
+                            // the id just reached the reduced threshold: a candidate (once per id)
+                            const int at = atomicAdd(wcount, 1);
+                            if (at < COLLECT_WCAND) cand[at] = v[u];
+                        }
                 }
                 __syncwarp();
-                int ncand = 0;
-                for (int i0 = 0; i0 < slots; i0 += 32) { // collect + leave the table empty
-                    uint32_t id = 0, c = 0;
-                    const bool keep = tab.take(i0 + lane, id, c) && c >= (uint32_t)thr;
-                    const unsigned m = __ballot_sync(0xffffffffu, keep);
-                    if (m) {
-                        const int at = ncand + __popc(m & ((1u << lane) - 1u));
-                        if (keep && at < COLLECT_WCAND) {
-                            cand[at] = id;
-                            ccnt[at] = c;
-                        }
-                        ncand += __popc(m);
-                    }
-                }
+                const int ncand = *wcount;
+                __syncwarp();
+                if (ncand > 0 && ncand <= COLLECT_WCAND)
+                    for (int c = lane; c < ncand; c += 32) ccnt[c] = tab.lookup((uint32_t)slots - 1u, shift, cand[c]);
+                if (lane == 0) *wcount = 0;
+                __syncwarp();
+                tab.clear_prefix(slots, lane, 32); // leave the table empty (128-bit stores; slots >= 128)
                 __syncwarp();
                 if (ncand == 0) continue; // the common case: nothing in this id range reaches the threshold
                 if (ncand > COLLECT_WCAND) {
@@ -386,6 +408,7 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_warp_kernel(CollectPa
         if (bad) { // the aborted range may have left ids behind; the block kernel redoes the read
             __syncwarp();
             tab.clear_all(lane, 32);
+            if (lane == 0) *wcount = 0;
             if (lane == 0) {
                 P.big_list[atomicAdd(P.big_count, 1)] = rd;
                 st_enum -= (unsigned long long)E; // counted again there
@@ -636,7 +659,7 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     HRM_REQUIRE(min_hits >= 2 && id_space < 0xFFFFFFFFu, "collect_candidates needs minTableHits >= 2");
     static const int warp_cap = env_int("HRM_COLLECT_WARP_CAP", 0x7fffffff);
     static const int wslots_env = env_int("HRM_COLLECT_WARP_SLOTS", 1024);
-    int wslots = 64;
+    int wslots = 128;
     while (wslots < wslots_env && wslots < 8192) wslots <<= 1;
     static const int slots_env = env_int("HRM_COLLECT_SLOTS", 2048);
     int slots = 64;
