@@ -340,7 +340,9 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_warp_kernel(CollectPa
                     slots <<= 1;
                     shift--;
                 }
-                int tcur = 0;
+                // flat index e -> bucket piece: pbase + e is the id's position while e < pnext (e only grows per lane)
+                int tcur = 0, pnext = 0;
+                int64_t pbase = 0;
                 for (int e0 = 0; e0 < gtotal; e0 += 32 * COLLECT_WMLP) {
                     uint32_t v[COLLECT_WMLP];
 #pragma unroll
@@ -348,8 +350,12 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_warp_kernel(CollectPa
                         const int e = e0 + u * 32 + lane;
                         v[u] = COLLECT_EMPTY;
                         if (e < gtotal) {
-                            while (gpre[tcur + 1] <= e) tcur++; // bucket with gpre[t] <= e < gpre[t + 1]; e only grows
-                            v[u] = __ldg(P.table_values + offv[tcur] + bnd[g * H + tcur] + (e - gpre[tcur]));
+                            if (e >= pnext) {
+                                while (gpre[tcur + 1] <= e) tcur++;
+                                pnext = gpre[tcur + 1];
+                                pbase = (int64_t)offv[tcur] + bnd[g * H + tcur] - gpre[tcur];
+                            }
+                            v[u] = __ldg(P.table_values + pbase + e);
                         }
                     }
 #pragma unroll
