@@ -111,6 +111,10 @@ extern "C" hrm_status hrm_mapper_create(hrm_mapper** out, const hrm_mapper_confi
         const long long v = atoll(pc);
         if (v > 0) m->part_chunk = v;
     }
+    if (const char* ec = getenv("HRM_E2E_CHUNK")) { // reads per pipelined chunk of hrm_mapper_map_reads
+        const long long v = atoll(ec);
+        if (v > 0) m->e2e_chunk = v;
+    }
     if (const char* cf = getenv("HRM_COLLECT")) m->use_fused = atoi(cf) != 0; // 0: general retrieve + filter path only
     if (const char* vb = getenv("HRM_VALUE_BUDGET")) { // test hook: forces the range splitting at small sizes
         const long long v = atoll(vb);
@@ -128,6 +132,8 @@ extern "C" void hrm_mapper_destroy(hrm_mapper* m)
         if (m->genome[c]) hrm_genome_destroy(m->genome[c]);
     }
     if (m->d_win_prefix) cudaFree(m->d_win_prefix);
+    for (auto e : m->copy_events) cudaEventDestroy(e);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     delete m;
 }
 
@@ -496,6 +502,8 @@ extern "C" hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_as
     cudaStream_t s = as_stream(stream);
     if (n == 0) {
         if (h_stats) memset(h_stats, 0, sizeof *h_stats);
+        // key-partitioned index: the call is collective, a rank without reads still serves the others' lookups
+        if (m->comm) return hrm_map_batch(m, nullptr, ascii_pitch, nullptr, 0, nullptr, nullptr, stream);
         return HRM_OK;
     }
     Scratch d_ascii, d_len, d_mapped, d_rec, d_cig;
@@ -504,18 +512,58 @@ extern "C" hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_as
     HRM_TRY(d_mapped.alloc(sizeof(hrm_mapped_read) * (size_t)n, s));
     HRM_TRY(d_rec.alloc(sizeof(hrm_read_record) * (size_t)n, s));
     HRM_TRY(d_cig.alloc((size_t)(2 * n * cigar_pitch), s));
-    HRM_CUDA(cudaMemcpyAsync(d_ascii.p, h_reads_ascii, (size_t)(n * ascii_pitch), cudaMemcpyHostToDevice, s));
-    HRM_CUDA(cudaMemcpyAsync(d_len.p, h_lengths, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
     hrm_batch_stats st;
     memset(&st, 0, sizeof st);
-    HRM_TRY(hrm_map_batch(m, d_ascii.as<char>(), ascii_pitch, d_len.as<int32_t>(), n, d_mapped.as<hrm_mapped_read>(),
-                          h_stats ? &st : nullptr, stream));
-    HRM_TRY(hrm_verify_batch(m, d_ascii.as<char>(), ascii_pitch, d_len.as<int32_t>(), n,
-                             d_mapped.as<hrm_mapped_read>(), d_rec.as<hrm_read_record>(), d_cig.as<char>(), cigar_pitch,
-                             h_stats ? &st : nullptr, stream));
-    HRM_CUDA(cudaMemcpyAsync(h_records, d_rec.p, sizeof(hrm_read_record) * (size_t)n, cudaMemcpyDeviceToHost, s));
-    if (h_cigars)
-        HRM_CUDA(cudaMemcpyAsync(h_cigars, d_cig.p, (size_t)(2 * n * cigar_pitch), cudaMemcpyDeviceToHost, s));
+    // Chunks of reads pipelined over a second stream: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 run
+    // under the kernels of chunk c (reads are independent, so chunking does not change any result).  The
+    // key-partitioned index keeps one chunk: its routed queries are collective and every rank must issue the same
+    // sequence of them.
+    const int64_t chunk = m->comm ? n : m->e2e_chunk;
+    const int nchunks = (int)HRM_SDIV(n, chunk);
+    if (!m->copy_stream) HRM_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = m->copy_stream;
+    while ((int)m->copy_events.size() < 2 * nchunks + 1) {
+        cudaEvent_t e;
+        HRM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        m->copy_events.push_back(e);
+    }
+    cudaEvent_t ev_ready = m->copy_events[2 * nchunks]; // the device buffers exist (allocated in order on s)
+    HRM_CUDA(cudaEventRecord(ev_ready, s));
+    HRM_CUDA(cudaStreamWaitEvent(cs, ev_ready, 0));
+    for (int c = 0; c < nchunks; c++) {
+        const int64_t lo = (int64_t)c * chunk, cnt = (n - lo) < chunk ? (n - lo) : chunk;
+        HRM_CUDA(cudaMemcpyAsync(d_ascii.as<char>() + lo * ascii_pitch, h_reads_ascii + lo * ascii_pitch,
+                                 (size_t)(cnt * ascii_pitch), cudaMemcpyHostToDevice, cs));
+        HRM_CUDA(cudaMemcpyAsync(d_len.as<int32_t>() + lo, h_lengths + lo, sizeof(int32_t) * (size_t)cnt,
+                                 cudaMemcpyHostToDevice, cs));
+        HRM_CUDA(cudaEventRecord(m->copy_events[2 * c], cs));
+    }
+    for (int c = 0; c < nchunks; c++) {
+        const int64_t lo = (int64_t)c * chunk, cnt = (n - lo) < chunk ? (n - lo) : chunk;
+        HRM_CUDA(cudaStreamWaitEvent(s, m->copy_events[2 * c], 0));
+        hrm_batch_stats cst;
+        memset(&cst, 0, sizeof cst);
+        HRM_TRY(hrm_map_batch(m, d_ascii.as<char>() + lo * ascii_pitch, ascii_pitch, d_len.as<int32_t>() + lo, cnt,
+                              d_mapped.as<hrm_mapped_read>() + lo, h_stats ? &cst : nullptr, stream));
+        HRM_TRY(hrm_verify_batch(m, d_ascii.as<char>() + lo * ascii_pitch, ascii_pitch, d_len.as<int32_t>() + lo, cnt,
+                                 d_mapped.as<hrm_mapped_read>() + lo, d_rec.as<hrm_read_record>() + lo,
+                                 d_cig.as<char>() + 2 * lo * cigar_pitch, cigar_pitch, h_stats ? &cst : nullptr, stream));
+        st.num_reads += cst.num_reads;
+        st.num_probes += cst.num_probes;
+        st.num_slot_touches += cst.num_slot_touches;
+        st.num_values += cst.num_values;
+        st.num_candidates += cst.num_candidates;
+        st.num_mapped += cst.num_mapped;
+        st.num_kernel_launches += cst.num_kernel_launches;
+        HRM_CUDA(cudaEventRecord(m->copy_events[2 * c + 1], s));
+        HRM_CUDA(cudaStreamWaitEvent(cs, m->copy_events[2 * c + 1], 0));
+        HRM_CUDA(cudaMemcpyAsync(h_records + lo, d_rec.as<hrm_read_record>() + lo, sizeof(hrm_read_record) * (size_t)cnt,
+                                 cudaMemcpyDeviceToHost, cs));
+        if (h_cigars)
+            HRM_CUDA(cudaMemcpyAsync(h_cigars + 2 * lo * cigar_pitch, d_cig.as<char>() + 2 * lo * cigar_pitch,
+                                     (size_t)(2 * cnt * cigar_pitch), cudaMemcpyDeviceToHost, cs));
+    }
+    HRM_CUDA(cudaStreamSynchronize(cs));
     HRM_CUDA(cudaStreamSynchronize(s));
     if (h_stats) *h_stats = st;
     return HRM_OK;

@@ -74,5 +74,11 @@ struct hrm_mapper {
     bool use_fused = true;            // K3b retrieval + K4 fused (k4_fused.cu) on the replicated index
     int64_t collect_enumerated = 0, collect_skipped = 0; // ids counted / skipped (largest buckets) by the fused path
     int64_t part_chunk = 1 << 17;     // reads per routed query of the key-partitioned index
+    // reads per pipelined chunk of hrm_mapper_map_reads (copies of neighbouring chunks under compute).  Default: one
+    // chunk -- measured on B200 at 1 M reads: 8.05 M reads/s as one chunk, 6.44 M in chunks of 262 144, 5.08 M in
+    // chunks of 131 072 (per-chunk launch and sync overheads cost more than the 8 ms of hidden PCIe copies)
+    int64_t e2e_chunk = 1LL << 40;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_events;
     hrm_comm* comm = nullptr; // key-partitioned index (partition.cu); not owned
 };

@@ -37,13 +37,16 @@ def check_mapped(got, exp, which):
     assert (got["pass"] == which).all()
 
 
-@pytest.mark.parametrize("conf", ["single_none", "single_ct", "directional", "nondirectional"])
+@pytest.mark.parametrize("conf", ["single_none", "single_ct", "directional", "nondirectional", "config4"])
 def test_map_and_verify_small(cuda, port, conf):
     import torch
     genome, off = synth.make_genome([60000, 25013], seed=11)
-    nondir = conf == "nondirectional"
+    nondir = conf in ("nondirectional", "config4")
     reads, lens, truth = synth.make_reads(genome, off, 3000, 150, error_rate=0.02 if conf != "single_none" else 0.0,
                                           nondirectional=nondir, seed=12)
+    if conf == "config4":  # BASELINE configs[3]: non-directional library, 250 bp reads, 3 % errors of which 10 % indels
+        reads, lens, truth = synth.make_reads(genome, off, 2000, 250, error_rate=0.03, indel_frac=0.1,
+                                              nondirectional=True, seed=14)
     if conf == "single_none":  # plain 4-letter mapping of unconverted reads (the reference as shipped)
         reads, lens, truth = synth.make_reads(genome, off, 3000, 150, error_rate=0.01, conversion_rate=0.0, seed=12)
     # a few junk / short reads
@@ -51,7 +54,8 @@ def test_map_and_verify_small(cuda, port, conf):
     lens[7] = 12
     lens[9] = 40
     cfg = {"single_none": cuda.default_config(), "single_ct": cuda.default_config(),
-           "directional": cuda.directional_config(), "nondirectional": cuda.nondirectional_config()}[conf]
+           "directional": cuda.directional_config(), "nondirectional": cuda.nondirectional_config(),
+           "config4": cuda.nondirectional_config()}[conf]
     if conf == "single_ct":
         cfg.read_conversion[0] = cfg.genome_conversion[0] = cfg.verify_conversion[0] = 1
     mp = cuda.Mapper(cfg)
@@ -65,7 +69,8 @@ def test_map_and_verify_small(cuda, port, conf):
         passes.append(res)
     exp, which = merge(passes)
     nmapped_exp = int((exp["orientation"] != 3).sum())
-    assert nmapped_exp > (1200 if conf == "single_ct" else 2400)  # one strand only maps on the C->T index alone
+    # one strand only maps on the C->T index alone; 3 % errors over 250 bp exceed the 5 % Hamming threshold more often
+    assert nmapped_exp > {"single_ct": 1200, "config4": 600}.get(conf, 2400)
     d_reads = torch.from_numpy(reads).cuda()
     d_lens = torch.from_numpy(lens).cuda()
     out, st = mp.mapBatch(d_reads, d_lens)
