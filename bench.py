@@ -5,13 +5,14 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[2], the one its metric is quoted on -- "human-size 3N index"): 1 M synthetic
+Workload (BASELINE.json configs[2], the one its metric is quoted on -- "human-size 3N index"): 4 M synthetic
 150 bp directional bisulfite reads (1 % substitution errors) per GPU per step against a 3.1 Gbp synthetic
 reference with 24 GRCh38-like chromosome lengths, k=16, 16 hash tables, w=128, minTableHits=4,
 maxHammingPercent=0.05, SW verification with CIGAR; both 3N indexes (C->T and G->A, 27.4 M windows each)
 resident in HBM.  A step = one pass of the whole hot path (K1 pack, K2 minhash, K3 probe + retrieve, K4
-collect, K5 SHD best window, K7 SW+CIGAR) over one 1 M-read batch per GPU.  `--genome-bp 46000000` selects
-configs[1] (chr21-size reference).  N > 1: weak scaling, every rank maps its own 1 M-read shard against its
+collect, K5 SHD best window, K7 SW+CIGAR) over one 4 M-read batch per GPU (`--reads`; measured on B200: 8.6 M
+reads/s with 1 M-read batches, 9.0 M with 2 M, 9.2 M with 4 M -- fixed per-batch costs).  `--genome-bp 46000000`
+selects configs[1] (chr21-size reference).  N > 1: weak scaling, every rank maps its own 4 M-read shard against its
 replica of the index; no data-path collective; `--index partitioned` = configs[4], the
 key-partitioned index with NCCL all-to-all routing.
 
@@ -110,18 +111,27 @@ def workload(args, rank):
     else:
         lengths = [args.genome_bp]
     genome, off = synth.make_genome(lengths, seed=20240601)
-    reads, lens, truth = synth.make_reads(genome, off, args.reads, READ_LEN, error_rate=ERR, seed=20240602 + rank)
+    parts, at, piece = [], 0, 0
+    while at < args.reads:  # pieces of 1 M reads bound the generator's temporaries
+        cnt = min(1_000_000, args.reads - at)
+        parts.append(synth.make_reads(genome, off, cnt, READ_LEN, error_rate=ERR, seed=20240602 + rank + 1000 * piece))
+        at += cnt
+        piece += 1
+    reads = np.concatenate([p[0] for p in parts])
+    lens = np.concatenate([p[1] for p in parts])
+    truth = {k: np.concatenate([p[2][k] for p in parts]) for k in parts[0][2]}
     return genome, off, reads, lens, truth
 
 
 def workload_name(reads, genome_bp, nchrom):
-    if reads == 1_000_000 and genome_bp == 3_100_000_000:
-        return ("1M x 150bp directional BS reads per GPU per step vs 3.1 Gbp human-size synthetic 3N index, 24 chromosomes "
-                "(BASELINE configs[2], batches of the 100M-read job)")
-    if reads == 1_000_000 and genome_bp == 46_000_000:
-        return "1M x 150bp directional BS reads vs 46 Mbp synthetic reference (BASELINE configs[1])"
-    return "%d x 150bp directional BS reads per step vs %.4g Mbp synthetic reference, %d chromosome(s)" % (
-        reads, genome_bp / 1e6, nchrom)
+    rd = "%gM" % (reads / 1e6) if reads % 100_000 == 0 else str(reads)
+    if genome_bp == 3_100_000_000:
+        return ("%s x 150bp directional BS reads per GPU per step vs 3.1 Gbp human-size synthetic 3N index, 24 chromosomes "
+                "(BASELINE configs[2]: batches of the 100M-read job)" % rd)
+    if genome_bp == 46_000_000:
+        return "%s x 150bp directional BS reads per GPU per step vs 46 Mbp synthetic reference (BASELINE configs[1])" % rd
+    return "%s x 150bp directional BS reads per step vs %.4g Mbp synthetic reference, %d chromosome(s)" % (
+        rd, genome_bp / 1e6, nchrom)
 
 
 def cpu_sample(args, n_reads):
@@ -203,7 +213,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
+    ap.add_argument("--reads", type=int, default=4_000_000, help="reads per GPU per step (one batch)")
     ap.add_argument("--genome-bp", type=int, default=3_100_000_000)
     ap.add_argument("--cpu-genome-bp", type=int, default=46_000_000,
                     help="reference bases the CPU baseline streams (window streaming is scaled to --genome-bp)")
