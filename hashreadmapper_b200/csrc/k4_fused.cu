@@ -215,7 +215,7 @@ __device__ __forceinline__ void collect_sort_warp(uint32_t* s, int cnt, int lane
 constexpr int COLLECT_WCHUNK = 4;   // id ranges whose boundaries a warp searches together
 constexpr int COLLECT_WCAND = 128;  // ids reaching the reduced threshold per range a warp can hold
 constexpr int COLLECT_WFIN = 128;   // survivors per read a warp can hold
-constexpr int COLLECT_WMLP = 8;     // independent id loads per lane
+constexpr int COLLECT_WMLP = 4;     // independent id loads per lane
 
 __host__ __device__ inline size_t collect_warp_slice_words(int slots, int H, bool packed)
 {

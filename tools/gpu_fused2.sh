@@ -1,5 +1,4 @@
 set -x
-python -m pytest tests -m gpu -x -q -k "fused or scale" 2>&1 | tail -3 > gpurun_out/pt.txt; cat gpurun_out/pt.txt
 python bench.py --reads 1000000 --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_x.err | grep '^{' > gpurun_out/bench_x.json; echo rc=$?
 python - <<PY
 import json
