@@ -1,4 +1,5 @@
 set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/r1_pytest_gpu.txt; cat gpurun_out/r1_pytest_gpu.txt
 python bench.py --steps 5 --warmup 3 2>gpurun_out/r1_bench_human.err | grep '^{' > gpurun_out/r1_bench_human.json; echo rc=$?
 python bench.py --genome-bp 46000000 --reads 1000000 --steps 5 --warmup 3 2>gpurun_out/r1_bench_chr21.err | grep '^{' > gpurun_out/r1_bench_chr21.json; echo rc=$?
 python bench.py --impl reference --steps 2 --warmup 1 2>gpurun_out/r1_bench_reference.err | grep '^{' > gpurun_out/r1_bench_reference.json; echo rc=$?
