@@ -4,18 +4,19 @@
 //      StripedSmithWaterman::Aligner::Align src/ssw_cpp.cpp:361-400, ssw_align src/ssw.c:818-922
 //      (sw_sse2_byte :197-386, sw_sse2_word :412-588, banded_sw :590-774), edlibAlign src/edlib.cpp:1474.
 //
-// Two kernels per batch of alignments:
-//  A. sw_passes_kernel -- one WARP per alignment.  The forward and the reverse DP pass run as an
-//     anti-diagonal wavefront: lane l owns R consecutive read rows (H, E in registers), processes
-//     reference column t-l at step t and hands the bottom H/F of its strip plus the running column
-//     maximum (with its first row) to lane l+1 by warp shuffle.  Lane 31 sees every finished column:
-//     it tracks score / first end column / smallest end row exactly like the striped SSE2 kernels and
-//     stores the per-column maxima (with the byte-mode and the word-mode pad rows) in shared memory
-//     for the second-best scan.  Inputs are built on the fly from the packed read and the packed
-//     genome (stage-V 3N conversion applied on the codes): no ASCII, no host prep loop.
-//  B. sw_finish_kernel -- one THREAD per alignment: the reference's banded trace back restated
-//     literally (core_sw.cuh: sw_banded) on the small begin..end rectangle, then the =/X/I/D/S CIGAR.
-// Work per alignment: ~(L+pad) x w cell updates forward, <= that backward, band x L for the trace.
+// Per batch of alignments:
+//  A. passes -- score, ends, begins, second best.  Fused path: sw_pair_passes_kernel, 4 lanes per read, both
+//     alignments of a read in the s16x2 halves of every register (core_swpair.cuh, DPX VIMNMX3 / VIADDMNMX),
+//     anti-diagonal wavefront, forward + reverse pass.  Function-level API (ASCII rows, any size up to 512):
+//     sw_passes_kernel, one warp per alignment, 32-bit cells.  Inputs are built on the fly from the packed read
+//     and the packed genome (stage-V 3N conversion applied on the codes): no ASCII, no host prep loop.
+//  B. trace back + CIGAR -- the reference's banded_sw doubles its band until the banded score reaches the
+//     alignment score.  sw_classify_kernel puts every alignment on the list of its first band's class
+//     [2^c, 2^(c+1)); sw_finish_band_kernel runs ONE band iteration per alignment and class, one thread per
+//     alignment (core_swband.cuh), and either finishes the alignment (trace back, =/X/I/D/S string) or hands it to
+//     the next class; one launch per class, ascending.  sw_finish_kernel (one warp per alignment, the literal
+//     band arrays) takes what exceeds the ladder's limits.
+// Work per alignment: ~(L+pad) x w cell updates forward, <= that backward, rows x (2 band + 1) per band iteration.
 #include "pipeline.cuh"
 #include "core_sw.cuh"
 #include "core_swpair.cuh"
