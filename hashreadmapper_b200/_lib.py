@@ -113,6 +113,8 @@ SIGNATURES = {
     "hrm_minhasher_info": (I32, [P, C.POINTER(MinhasherInfo)]),
     "hrm_minhasher_serialize": (I32, [P, P, C.POINTER(I64)]),
     "hrm_minhasher_deserialize": (I32, [C.POINTER(P), P, I64]),
+    "hrm_minhasher_write_reference_format": (I32, [P, P, C.POINTER(I64)]),
+    "hrm_minhasher_read_reference_format": (I32, [C.POINTER(P), P, I64, C.c_int]),
     "hrm_filter_by_frequency": (I32, [P, P, P, C.c_int, C.c_int, C.POINTER(I64), VP]),
     "hrm_segment_ids": (I32, [P, C.c_int, I64, P, VP]),
     "hrm_readstore_create_from_ascii": (I32, [C.POINTER(P), P, I64, P, I64, C.c_int, VP]),

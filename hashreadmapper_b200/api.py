@@ -186,6 +186,27 @@ class Minhasher:
         return self
 
 
+    def writeToStream(self, path):
+        """the reference's own file format (ref: FakeGpuMinhasher::writeToStream fakegpuminhasher.cuh:498-510)"""
+        size = C.c_int64(0)
+        check(self.lib.hrm_minhasher_write_reference_format(self.h, None, C.byref(size)))
+        buf = np.empty(size.value, dtype=np.uint8)
+        check(self.lib.hrm_minhasher_write_reference_format(self.h, _ptr(buf), C.byref(size)))
+        buf[:size.value].tofile(path)
+        return int(size.value)
+
+    @classmethod
+    def loadFromStream(cls, path, num_maps_upper_limit=-1):
+        """ref: FakeGpuMinhasher::loadFromStream fakegpuminhasher.cuh:512-532; returns the minhasher"""
+        self = cls.__new__(cls)
+        self.lib = L.load()
+        _dev()
+        self.h = C.c_void_p()
+        buf = np.fromfile(path, dtype=np.uint8)
+        check(self.lib.hrm_minhasher_read_reference_format(C.byref(self.h), _ptr(buf), buf.size, num_maps_upper_limit))
+        return self
+
+
 # ---- K4 ----------------------------------------------------------------------------------------
 def filter_by_frequency(values, num_per_seq, offsets, min_hits):
     """in place; returns new total (values[:total] valid)"""

@@ -19,6 +19,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <iterator>
 
 #include "hrm_b200.h"
 
@@ -111,23 +112,21 @@ public:
     int getKmerSize() const noexcept override { return info().k; }
     bool hasGpuTables() const noexcept override { return true; }
 
+    // the reference's own file format (fakegpuminhasher.cuh:498-532): files are interchangeable with
+    // FakeGpuMinhasher's --save-hashtables-to / --load-hashtables-from
     void writeToStream(std::ostream& os) const override
     {
         int64_t size = 0;
-        hrm_check(hrm_minhasher_serialize(mh_, nullptr, &size));
+        hrm_check(hrm_minhasher_write_reference_format(mh_, nullptr, &size));
         std::vector<char> buf((std::size_t)size);
-        hrm_check(hrm_minhasher_serialize(mh_, buf.data(), &size));
-        os.write(reinterpret_cast<const char*>(&size), sizeof size);
+        hrm_check(hrm_minhasher_write_reference_format(mh_, buf.data(), &size));
         os.write(buf.data(), size);
     }
-    int loadFromStream(std::ifstream& is, int /*numMapsUpperLimit*/) override
+    int loadFromStream(std::ifstream& is, int numMapsUpperLimit) override
     {
-        int64_t size = 0;
-        is.read(reinterpret_cast<char*>(&size), sizeof size);
-        std::vector<char> buf((std::size_t)size);
-        is.read(buf.data(), size);
+        const std::vector<char> buf((std::istreambuf_iterator<char>(is)), std::istreambuf_iterator<char>());
         hrm_minhasher* fresh = nullptr;
-        hrm_check(hrm_minhasher_deserialize(&fresh, buf.data(), size));
+        hrm_check(hrm_minhasher_read_reference_format(&fresh, buf.data(), (int64_t)buf.size(), numMapsUpperLimit));
         hrm_minhasher_destroy(mh_);
         mh_ = fresh;
         return info().num_tables;

@@ -22,6 +22,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <string.h>
 #include <stdlib.h>
+#include <algorithm>
 
 namespace hrm {
 
@@ -1017,6 +1018,267 @@ extern "C" hrm_status hrm_minhasher_deserialize(hrm_minhasher** out, const void*
     if (e != cudaSuccess) {
         set_error("deserialize: %s", cudaGetErrorString(e));
         hrm_minhasher_destroy(mh);
+        return HRM_ERR_CUDA;
+    }
+    mh->compacted = true;
+    mh->finished = true;
+    *out = mh;
+    return HRM_OK;
+}
+
+// ---- the reference's own file format (--save-hashtables-to / --load-hashtables-from) ----------------------
+// ref: FakeGpuMinhasher::writeToStream / loadFromStream include/gpu/fakegpuminhasher.cuh:498-532:
+//        int kmerSize, int resultsPerMapThreshold, float loadfactor, int numTables, then per table
+//      CpuReadOnlyMultiValueHashTable::writeToStream include/cpuhashtable.hpp:624-646:
+//        size_t nValues, u32 values[nValues] (grouped by ascending key, truncated buckets already cut), then
+//      AoSCpuSingleValueHashTable::writeToStream :217-229:
+//        float load, size_t numKeys, size_t maxProbes, size_t size, size_t capacity, size_t elements,
+//        Data storage[capacity], Data = pair<u64 key, pair<u32 offset, u16 count>> (16 bytes, 2 padding bytes),
+//        empty slot = {~0, {0, 0}} (:277-278), capacity = size_t(float(size) / load) (:60-64), keys inserted in
+//        ascending order at murmur64(key) % capacity with linear probing (:96-124, built at :524-544).
+// The tables of this library are bucketised differently, so writing re-inserts every key on the host exactly
+// as the reference does and reading re-inserts every stored key into 64-byte buckets on the device.
+namespace {
+struct RefSlot {
+    uint64_t key;
+    uint32_t off;
+    uint16_t cnt;
+    uint16_t pad;
+};
+static_assert(sizeof(RefSlot) == 16, "reference Data is 16 bytes");
+
+struct KeyEntry {
+    uint64_t key;
+    uint32_t off, cnt;
+};
+
+template <class T>
+void put(std::vector<char>& out, const T& v)
+{
+    const char* p = reinterpret_cast<const char*>(&v);
+    out.insert(out.end(), p, p + sizeof(T));
+}
+template <class T>
+bool get(const char*& p, const char* end, T& v)
+{
+    if (end - p < (ptrdiff_t)sizeof(T)) return false;
+    memcpy(&v, p, sizeof(T));
+    p += sizeof(T);
+    return true;
+}
+
+// explicit (key, offset, count) entries into the bucketised device table
+__global__ void __launch_bounds__(256) insert_entries_kernel(const KeyEntry* __restrict__ entries, int64_t n,
+                                                             uint32_t value_base, Slot* __restrict__ slots,
+                                                             uint32_t nbuckets, unsigned long long* __restrict__ errors)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += stride) {
+        const KeyEntry en = entries[u];
+        uint32_t b = home_bucket(en.key, nbuckets);
+        bool done = false;
+        for (uint32_t probe = 0; probe < nbuckets && !done; probe++) {
+            for (int sub = 0; sub < BUCKET_SLOTS && !done; sub++) {
+                Slot* s = slots + ((size_t)b * BUCKET_SLOTS + sub);
+                const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long*>(&s->key),
+                                                          (unsigned long long)SLOT_EMPTY, (unsigned long long)en.key);
+                if (prev == SLOT_EMPTY) {
+                    s->off = value_base + en.off;
+                    s->cnt = en.cnt;
+                    done = true;
+                }
+            }
+            b = next_bucket(b, nbuckets);
+        }
+        if (!done) atomicAdd(errors, 1ULL);
+    }
+}
+} // namespace
+
+extern "C" hrm_status hrm_minhasher_write_reference_format(const hrm_minhasher* mh, void* h_buf, int64_t* h_size)
+{
+    HRM_REQUIRE(mh != nullptr && h_size != nullptr, "args");
+    if (!mh->compacted) {
+        set_error("write_reference_format before compact");
+        return HRM_ERR_STATE;
+    }
+    std::vector<char> out;
+    put(out, (int32_t)mh->k);
+    put(out, (int32_t)mh->max_results);
+    put(out, (float)mh->load);
+    put(out, (int32_t)mh->H);
+    std::vector<uint32_t> hvalues((size_t)(mh->values_count > 0 ? mh->values_count : 1));
+    if (mh->values_count > 0)
+        HRM_CUDA(cudaMemcpy(hvalues.data(), mh->values, (size_t)mh->values_count * 4, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < mh->H; j++) {
+        std::vector<Slot> hs((size_t)mh->nbuckets[j] * BUCKET_SLOTS);
+        HRM_CUDA(cudaMemcpy(hs.data(), mh->slots[j], hs.size() * sizeof(Slot), cudaMemcpyDeviceToHost));
+        std::vector<KeyEntry> keys;
+        keys.reserve((size_t)mh->nkeys[j]);
+        for (const Slot& s : hs)
+            if (s.key != SLOT_EMPTY) keys.push_back({s.key, s.off, s.cnt});
+        std::sort(keys.begin(), keys.end(), [](const KeyEntry& a, const KeyEntry& b) { return a.key < b.key; });
+        // values grouped by ascending key, each bucket cut to its stored count (ref: groupbykey.hpp:177-191)
+        std::vector<uint32_t> vals;
+        std::vector<uint32_t> newoff(keys.size());
+        for (size_t u = 0; u < keys.size(); u++) {
+            newoff[u] = (uint32_t)vals.size();
+            vals.insert(vals.end(), hvalues.begin() + keys[u].off, hvalues.begin() + keys[u].off + keys[u].cnt);
+        }
+        put(out, (uint64_t)vals.size());
+        if (!vals.empty()) out.insert(out.end(), (const char*)vals.data(), (const char*)(vals.data() + vals.size()));
+        // the key -> (offset, count) table exactly as AoSCpuSingleValueHashTable builds it
+        const uint64_t size = keys.size();
+        const uint64_t capacity = (uint64_t)((float)size / mh->load); // float arithmetic, as `capacity(size/load)`
+        std::vector<RefSlot> storage((size_t)capacity, RefSlot{~0ULL, 0u, 0, 0});
+        uint64_t maxProbes = 0;
+        if (!keys.empty()) HRM_REQUIRE(capacity >= size, "load factor above 1");
+        for (size_t u = 0; u < keys.size(); u++) {
+            HRM_REQUIRE(keys[u].cnt <= 65535u, "bucket count exceeds the reference's 16-bit BucketSize");
+            uint64_t pos = murmur64(keys[u].key) % capacity, probes = 0;
+            while (storage[pos].key != ~0ULL) {
+                pos = pos + 1 == capacity ? 0 : pos + 1;
+                probes++;
+            }
+            storage[pos] = RefSlot{keys[u].key, newoff[u], (uint16_t)keys[u].cnt, 0};
+            maxProbes = probes > maxProbes ? probes : maxProbes;
+        }
+        put(out, (float)mh->load);
+        put(out, (uint64_t)size);      // numKeys
+        put(out, (uint64_t)maxProbes);
+        put(out, (uint64_t)size);      // size
+        put(out, (uint64_t)capacity);
+        put(out, (uint64_t)storage.size());
+        if (!storage.empty())
+            out.insert(out.end(), (const char*)storage.data(), (const char*)(storage.data() + storage.size()));
+    }
+    if (!h_buf) {
+        *h_size = (int64_t)out.size();
+        return HRM_OK;
+    }
+    HRM_REQUIRE(*h_size >= (int64_t)out.size(), "buffer too small");
+    memcpy(h_buf, out.data(), out.size());
+    *h_size = (int64_t)out.size();
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_minhasher_read_reference_format(hrm_minhasher** out, const void* h_buf, int64_t size,
+                                                          int max_tables)
+{
+    HRM_REQUIRE(out != nullptr && h_buf != nullptr && size >= 16, "args");
+    *out = nullptr;
+    HRM_TRY(ensure_device());
+    const char* p = (const char*)h_buf;
+    const char* end = p + size;
+    int32_t k = 0, thr = 0, H = 0;
+    float load = 0.f;
+    HRM_REQUIRE(get(p, end, k) && get(p, end, thr) && get(p, end, load) && get(p, end, H), "truncated header");
+    HRM_REQUIRE(k >= 1 && k <= 32 && H >= 0 && H <= MAX_TABLES && load > 0.f && load <= 1.f, "bad header");
+    if (max_tables >= 0 && H > max_tables) H = max_tables; // ref: loadFromStream(is, numMapsUpperLimit)
+    // first pass over the image: table extents
+    struct Ext {
+        const uint32_t* vals;
+        uint64_t nvals;
+        const RefSlot* storage;
+        uint64_t elements;
+    };
+    std::vector<Ext> ext((size_t)H);
+    int64_t total_vals = 0, max_inserted = 0;
+    for (int j = 0; j < H; j++) {
+        uint64_t nvals = 0, numKeys = 0, maxProbes = 0, sz = 0, cap = 0, elements = 0;
+        float tl = 0.f;
+        HRM_REQUIRE(get(p, end, nvals) && (uint64_t)(end - p) >= nvals * 4, "truncated values");
+        ext[j].vals = (const uint32_t*)p;
+        ext[j].nvals = nvals;
+        p += nvals * 4;
+        HRM_REQUIRE(get(p, end, tl) && get(p, end, numKeys) && get(p, end, maxProbes) && get(p, end, sz) &&
+                        get(p, end, cap) && get(p, end, elements),
+                    "truncated table header");
+        HRM_REQUIRE((uint64_t)(end - p) >= elements * sizeof(RefSlot), "truncated table storage");
+        ext[j].storage = (const RefSlot*)p;
+        ext[j].elements = elements;
+        p += elements * sizeof(RefSlot);
+        total_vals += (int64_t)nvals;
+        max_inserted = (int64_t)nvals > max_inserted ? (int64_t)nvals : max_inserted;
+    }
+    HRM_REQUIRE(total_vals < (1LL << 32), "value offsets must fit 32 bits");
+    hrm_minhasher* mh = nullptr;
+    HRM_TRY(hrm_minhasher_create(&mh, max_inserted, thr, k, load));
+    mh->H = H;
+    mh->inserted = max_inserted;
+    mh->values_count = total_vals;
+    mh->slots.assign(H, nullptr);
+    mh->nbuckets.assign(H, 0);
+    mh->nkeys.assign(H, 0);
+    mh->table_count.assign(H, max_inserted);
+    auto fail = [&](const char* what, cudaError_t e) {
+        set_error("read_reference_format: %s: %s", what, cudaGetErrorString(e));
+        hrm_minhasher_destroy(mh);
+        return e == cudaErrorMemoryAllocation ? HRM_ERR_NOMEM : HRM_ERR_CUDA;
+    };
+    cudaError_t e = cudaMalloc(&mh->values, (size_t)(total_vals > 0 ? total_vals : 1) * 4);
+    if (e != cudaSuccess) return fail("values", e);
+    unsigned long long* d_err = nullptr;
+    e = cudaMalloc(&d_err, sizeof(unsigned long long));
+    if (e != cudaSuccess) return fail("counter", e);
+    cudaMemset(d_err, 0, sizeof(unsigned long long));
+    int64_t vbase = 0;
+    for (int j = 0; j < H; j++) {
+        std::vector<KeyEntry> keys;
+        for (uint64_t i = 0; i < ext[j].elements; i++) {
+            RefSlot s;
+            memcpy(&s, ext[j].storage + i, sizeof s);
+            if (s.key == ~0ULL && s.off == 0u && s.cnt == 0) continue; // ref: emptySlot cpuhashtable.hpp:277-278
+            if ((uint64_t)s.off + s.cnt > ext[j].nvals) {
+                cudaFree(d_err);
+                hrm_minhasher_destroy(mh);
+                set_error("read_reference_format: value range of a key exceeds the value array");
+                return HRM_ERR_INVALID;
+            }
+            keys.push_back({s.key, s.off, s.cnt});
+        }
+        if (ext[j].nvals > 0) {
+            std::vector<uint32_t> tmp(ext[j].nvals); // the image need not be 4-byte aligned
+            memcpy(tmp.data(), ext[j].vals, ext[j].nvals * 4);
+            e = cudaMemcpy(mh->values + vbase, tmp.data(), ext[j].nvals * 4, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) break;
+        }
+        const int64_t nb = (int64_t)((double)keys.size() / (double)mh->load / (double)BUCKET_SLOTS) + 1;
+        Slot* sl = nullptr;
+        e = cudaMalloc(&sl, (size_t)BUCKET_BYTES * (size_t)nb);
+        if (e != cudaSuccess) break;
+        mh->slots[j] = sl;
+        mh->nbuckets[j] = nb;
+        mh->nkeys[j] = (int64_t)keys.size();
+        mh->param.t[j].slots = sl;
+        mh->param.t[j].nbuckets = (uint32_t)nb;
+        e = cudaMemset(sl, 0xFF, (size_t)BUCKET_BYTES * (size_t)nb);
+        if (e != cudaSuccess) break;
+        if (!keys.empty()) {
+            KeyEntry* d_keys = nullptr;
+            e = cudaMalloc(&d_keys, keys.size() * sizeof(KeyEntry));
+            if (e != cudaSuccess) break;
+            e = cudaMemcpy(d_keys, keys.data(), keys.size() * sizeof(KeyEntry), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                insert_entries_kernel<<<capped_grid((int64_t)keys.size(), 256, 16), 256>>>(d_keys, (int64_t)keys.size(),
+                                                                                          (uint32_t)vbase, sl, (uint32_t)nb,
+                                                                                          d_err);
+                g_launches.fetch_add(1);
+                e = cudaDeviceSynchronize();
+            }
+            cudaFree(d_keys);
+            if (e != cudaSuccess) break;
+        }
+        vbase += (int64_t)ext[j].nvals;
+    }
+    unsigned long long h_err = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&h_err, d_err, sizeof h_err, cudaMemcpyDeviceToHost);
+    cudaFree(d_err);
+    if (e == cudaSuccess) e = cudaMemcpy(mh->d_param, &mh->param, sizeof mh->param, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail("tables", e);
+    if (h_err != 0) {
+        hrm_minhasher_destroy(mh);
+        set_error("read_reference_format: %llu keys could not be inserted", h_err);
         return HRM_ERR_CUDA;
     }
     mh->compacted = true;

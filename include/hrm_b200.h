@@ -180,6 +180,18 @@ hrm_status hrm_minhasher_info(const hrm_minhasher* mh, hrm_minhasher_info_t* out
 hrm_status hrm_minhasher_serialize(const hrm_minhasher* mh, void* h_buf, int64_t* h_size);
 hrm_status hrm_minhasher_deserialize(hrm_minhasher** out, const void* h_buf, int64_t size);
 
+/* The reference's own on-disk format (`--save-hashtables-to` / `--load-hashtables-from`):
+ * ref: FakeGpuMinhasher::writeToStream / loadFromStream include/gpu/fakegpuminhasher.cuh:498-532,
+ *      CpuReadOnlyMultiValueHashTable::writeToStream / loadFromStream include/cpuhashtable.hpp:624-646,
+ *      AoSCpuSingleValueHashTable::writeToStream / loadFromStream :217-244.
+ * write: the byte stream the reference would save for tables with these contents (every key re-inserted into
+ * the reference's linear-probing layout on the host); h_buf == NULL returns the size in *h_size.
+ * read: builds device tables from such a stream; max_tables >= 0 limits the number of tables loaded
+ * (ref: numMapsUpperLimit). */
+hrm_status hrm_minhasher_write_reference_format(const hrm_minhasher* mh, void* h_buf, int64_t* h_size);
+hrm_status hrm_minhasher_read_reference_format(hrm_minhasher** out, const void* h_buf, int64_t size,
+                                               int max_tables);
+
 /* ------------------------------------------------------------------------------------------
  * K4 -- candidate collection: per segment sort ascending, run-length count, keep ids whose
  * multiplicity >= min_hits (min_hits <= 1: plain distinct).

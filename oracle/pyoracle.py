@@ -173,6 +173,24 @@ class Oracle:
                                 _p(num, C.c_int32), _p(off, C.c_int64), _p(vals, C.c_uint32))
         return num, off, vals[:total]
 
+    def tables_save(self, handle, path, k, loadfactor=0.8):
+        """reference only: the reference's own writeToStream of every table (hash-table file format)"""
+        assert self.kind == "ref"
+        self.lib.ref_tables_save.restype = C.c_int
+        rc = self.lib.ref_tables_save(handle[0], str(path).encode(), int(k), C.c_float(loadfactor))
+        assert rc == 0, rc
+
+    def tables_load(self, path):
+        """reference only: the reference's own loadFromStream -> (handle, k, loadfactor)"""
+        assert self.kind == "ref"
+        self.lib.ref_tables_load.restype = C.c_void_p
+        k, lf = C.c_int(0), C.c_float(0)
+        h = self.lib.ref_tables_load(str(path).encode(), C.byref(k), C.byref(lf))
+        assert h, "the reference could not load " + str(path)
+        hh = C.c_void_p(h)
+        # number of tables: stored in the handle; query functions take it from there, python needs it for shapes
+        return (hh, None), k.value, lf.value
+
     # ---- C1 (port only; the reference implementation is CUDA-only) ----
     def filter_by_frequency(self, values, offsets, min_hits):
         values = np.ascontiguousarray(values, dtype=np.uint32)

@@ -19,6 +19,7 @@
 #include <config.hpp>
 #include <sequencehelpers.hpp>
 #include <helpers/hashers.cuh>
+#include <fstream>
 #include <cpuhashtable.hpp>
 #include <groupbykey.hpp>
 #include <ssw_cpp.h>
@@ -179,6 +180,46 @@ int64_t ref_tables_query(void* p, const uint64_t* qsigs, const uint8_t* qvalid, 
         }
     }
     return total;
+}
+
+// ---- hash-table files (--save-hashtables-to / --load-hashtables-from): the per-table stream functions are the
+// reference's own (cpuhashtable.hpp:624-646 -> :217-244); the four header fields are written as
+// FakeGpuMinhasher::writeToStream does (fakegpuminhasher.cuh:498-510; that class needs a GPU build) ----
+int ref_tables_save(void* p, const char* path, int kmerSize, float loadfactor)
+{
+    auto* T = (RefTables*)p;
+    std::ofstream os(path, std::ios::binary);
+    if (!os) return -1;
+    const int thr = T->maxResultsPerMap, numTables = T->H;
+    os.write(reinterpret_cast<const char*>(&kmerSize), sizeof(int));
+    os.write(reinterpret_cast<const char*>(&thr), sizeof(int));
+    os.write(reinterpret_cast<const char*>(&loadfactor), sizeof(float));
+    os.write(reinterpret_cast<const char*>(&numTables), sizeof(int));
+    for (const auto& t : T->t) t->writeToStream(os);
+    return os.good() ? 0 : -2;
+}
+
+void* ref_tables_load(const char* path, int* kmerSize, float* loadfactor)
+{
+    std::ifstream is(path, std::ios::binary);
+    if (!is) return nullptr;
+    auto* T = new RefTables;
+    int numMaps = 0;
+    is.read(reinterpret_cast<char*>(kmerSize), sizeof(int));
+    is.read(reinterpret_cast<char*>(&T->maxResultsPerMap), sizeof(int));
+    is.read(reinterpret_cast<char*>(loadfactor), sizeof(float));
+    is.read(reinterpret_cast<char*>(&numMaps), sizeof(int));
+    T->H = numMaps;
+    for (int i = 0; i < numMaps; i++) {
+        auto ptr = std::make_unique<RefTables::Table>();
+        ptr->loadFromStream(is);
+        T->t.push_back(std::move(ptr));
+    }
+    if (!is.good()) {
+        delete T;
+        return nullptr;
+    }
+    return T;
 }
 
 // ---- V2: the reference's SSW (src/ssw.c, src/ssw_cpp.cpp) ----

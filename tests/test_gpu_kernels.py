@@ -139,6 +139,59 @@ def test_k3_minhasher_reference_direction(cuda, port, cap):
     port.tables_free(T)
 
 
+@pytest.mark.parametrize("cap", [65535, 3])
+def test_k3_reference_hashtable_files(cuda, port, ref, tmp_path, cap):
+    """the reference's own hash-table file format (--save-hashtables-to / --load-hashtables-from), both ways:
+    (a) tables built on the GPU, written by hrm_minhasher_write_reference_format, loaded by the REFERENCE's
+    loadFromStream and queried by the reference; (b) tables built and written by the reference's code, read by
+    hrm_minhasher_read_reference_format and queried on the GPU"""
+    rng = random.Random(501 + cap)
+    k, H, w = 16, 8, 128
+    g = rs(rng, 20000, "AGT")
+    reads = []
+    for _ in range(900):
+        p = rng.randint(0, len(g) - 150)
+        reads.append(mutate(rng, g[p:p + 150], 0.01, 0)[:150])
+    reads += [b"ACGT"] + [reads[0]] * 6
+    enc = pack_rows(port, reads, 10)
+    lens = np.array([len(r) for r in reads], np.int32)
+    rsig, rval = port.minhash_batch(enc, lens, k, H)
+    stride = w - k + 1
+    wins = [g[i * stride:i * stride + w] for i in range((len(g) + stride - 1) // stride)] + [rs(rng, 128)]
+    qenc = pack_rows(port, wins, 8)
+    qlens = np.array([len(x) for x in wins], np.int32)
+    qsig, qval = port.minhash_batch(qenc, qlens, k, H)
+    # (a) GPU tables -> file -> the reference loads and answers
+    mh = cuda.Minhasher(len(reads), cap, k, 0.8)
+    assert mh.addHashTables(H, list(range(H))) == H
+    mh.insert(tt(cuda, enc.view(np.int32)), tt(cuda, lens), None, 0)
+    mh.compact()
+    path_a = tmp_path / "ours.tables"
+    assert mh.writeToStream(str(path_a)) == path_a.stat().st_size
+    Ta, k_a, lf_a = ref.tables_load(path_a)
+    assert k_a == k and abs(lf_a - 0.8) < 1e-6
+    Tref = ref.tables_build(rsig, rval, None, cap, 0.8, 1)
+    na, oa, va = ref.tables_query(Ta, qsig, qval)
+    nr, orf, vr = ref.tables_query(Tref, qsig, qval)
+    assert (na == nr).all() and (oa == orf).all() and (va == vr).all() and len(vr) > 100
+    # (b) the reference's tables -> its own writeToStream -> read here -> queried on the GPU
+    path_b = tmp_path / "ref.tables"
+    ref.tables_save(Tref, path_b, k, 0.8)
+    mh2 = cuda.Minhasher.loadFromStream(str(path_b))
+    info = mh2.getInfo()
+    assert info.k == k and info.num_tables == H and info.max_results_per_map == cap
+    h2 = mh2.makeMinhasherHandle()
+    _query_both(cuda, port, mh2, h2, port.tables_build(rsig, rval, None, cap), qenc, qlens, k, H)
+    # and a file of ours read back by ourselves
+    mh3 = cuda.Minhasher.loadFromStream(str(path_a), 5)  # numMapsUpperLimit
+    assert mh3.getInfo().num_tables == 5
+    # byte-identical where the format leaves no freedom: same size, same header, same values and key tables
+    a, b = np.fromfile(path_a, dtype=np.uint8), np.fromfile(path_b, dtype=np.uint8)
+    assert a.size == b.size and (a[:16] == b[:16]).all()
+    ref.tables_free(Ta)
+    ref.tables_free(Tref)
+
+
 def test_k3_empty_and_all_miss(cuda, port):
     rng = random.Random(5)
     k, H = 16, 4
