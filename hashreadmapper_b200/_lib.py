@@ -149,6 +149,7 @@ SIGNATURES = {
     "hrm_mapper_map_reads": (I32, [P, P, I64, P, I64, P, P, I64, C.POINTER(BatchStats), VP]),
     "hrm_mapper_set_profiling": (I32, [P, C.c_int]),
     "hrm_mapper_stage_times": (I32, [P, C.POINTER(C.c_float), C.POINTER(I32)]),
+    "hrm_ingest_reads": (I32, [P, I64, I64, I32, P, I64, P, P, I64, C.POINTER(I64), C.POINTER(I32), VP]),
     "hrm_comm_unique_id": (I32, [P, I64]),
     "hrm_comm_create": (I32, [C.POINTER(P), C.c_int, C.c_int, P]),
     "hrm_comm_destroy": (None, [P]),

@@ -207,6 +207,21 @@ class Minhasher:
         return self
 
 
+# ---- read ingestion --------------------------------------------------------------------------------
+def ingest_reads(text: torch.Tensor, pitch, max_reads, first_read_id=0, carry_replaced=0):
+    """FASTQ / FASTA text (uint8 tensor on the device, whole records) -> (rows [n, pitch] u8, lengths [n] i32,
+    ambiguous [n] u8, carry for the next chunk).  ref: readlibraryio.hpp:288-326 +
+    chunkedreadstorageconstruction.hpp:70-95"""
+    lib = L.load()
+    rows = torch.zeros((max_reads, pitch), dtype=torch.uint8, device=text.device)
+    lens = torch.zeros((max_reads,), dtype=torch.int32, device=text.device)
+    amb = torch.zeros((max_reads,), dtype=torch.uint8, device=text.device)
+    n, carry = C.c_int64(0), C.c_int32(0)
+    check(lib.hrm_ingest_reads(_ptr(text), text.numel(), first_read_id, carry_replaced, _ptr(rows), pitch, _ptr(lens),
+                               _ptr(amb), max_reads, C.byref(n), C.byref(carry), _stream()))
+    return rows[:n.value], lens[:n.value], amb[:n.value], carry.value
+
+
 # ---- K4 ----------------------------------------------------------------------------------------
 def filter_by_frequency(values, num_per_seq, offsets, min_hits):
     """in place; returns new total (values[:total] valid)"""

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libhrm_b200.so")
 SOURCES = ["runtime.cu", "k1_pack.cu", "k2_minhash.cu", "k3_table.cu", "k4_collect.cu", "k4_fused.cu", "k5_shd.cu",
-           "k7_verify.cu", "store.cu", "mapper.cu", "sam.cu", "partition.cu"]
+           "k7_verify.cu", "store.cu", "mapper.cu", "sam.cu", "partition.cu", "ingest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]

@@ -1,0 +1,191 @@
+// ingest.cu -- read ingestion on the device: FASTQ / FASTA text -> ASCII rows ready for K1.
+// ref: forEachReadInFile include/readlibraryio.hpp:288-326 (kseqpp parser, one host thread),
+//      constructChunkedReadStorageFromFiles include/chunkedreadstorageconstruction.hpp:31-502: one parser thread
+//      fills batches of fileParserMaxBatchsize = 65536 reads (:107), encoder threads run preprocessSequence (:70-95)
+//      on every read of a batch -- a c g t -> upper case, every other character that is not A C G T is replaced by
+//      "ACGT"[Ncount], Ncount = (Ncount + 1) % 4, with Ncount = 0 at the START OF EVERY BATCH (:277) -- and record
+//      the ids of reads that contained such characters (:293-297).
+// Here: the text of a chunk is in device memory; line starts come from one flag + scan + scatter pass, a record
+// is 4 lines (FASTQ, first byte '@') or 2 lines (FASTA, first byte '>'; sequences on one line), the cyclic
+// replacement index of a read is an exclusive scan of the per-read counts of replaced characters, rebased at
+// every 65536th read of the file.  One warp per read copies and normalises its sequence.
+// Traffic: the text once for the flags, once for the copy; 4 B per byte for the scan (chunks are bounded).
+#include "runtime.cuh"
+
+namespace hrm {
+
+constexpr int INGEST_BATCH = 65536; // ref: fileParserMaxBatchsize chunkedreadstorageconstruction.hpp:107
+
+__device__ __forceinline__ bool ingest_valid_base(unsigned char c)
+{
+    return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'a' || c == 'c' || c == 'g' || c == 't';
+}
+
+__global__ void __launch_bounds__(256) newline_flags_kernel(const char* __restrict__ text, int64_t n,
+                                                            int32_t* __restrict__ flags)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) flags[i] = text[i] == '\n';
+}
+
+// line_start[l + 1] = position after the l-th newline; line_start[0] = 0
+__global__ void __launch_bounds__(256) line_starts_kernel(const char* __restrict__ text, int64_t n,
+                                                          const int32_t* __restrict__ excl,
+                                                          int64_t* __restrict__ line_start)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (i == 0) line_start[0] = 0;
+        if (text[i] == '\n') line_start[excl[i] + 1] = i + 1;
+    }
+}
+
+// per read: sequence extent, length, number of characters that will be replaced; format errors
+__global__ void __launch_bounds__(256) record_extents_kernel(const char* __restrict__ text, int64_t nbytes,
+                                                             const int64_t* __restrict__ line_start, int64_t nlines,
+                                                             int lines_per_record, int64_t nreads, int64_t pitch,
+                                                             int64_t* __restrict__ seq_begin, int32_t* __restrict__ len,
+                                                             int32_t* __restrict__ ninvalid, int* __restrict__ error)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const char head = lines_per_record == 4 ? '@' : '>';
+    for (int64_t r = warp0; r < nreads; r += nwarps) {
+        const int64_t l0 = r * lines_per_record;
+        const int64_t hb = line_start[l0], sb = line_start[l0 + 1];
+        int64_t se = (l0 + 2 <= nlines ? line_start[l0 + 2] - 1 : nbytes); // newline of the sequence line (or EOF)
+        if (se > sb && text[se - 1] == '\r') se--;
+        const int64_t L = se - sb;
+        if (lane == 0) {
+            if (text[hb] != head) atomicExch(error, 1);            // not a record start: multi-line or damaged input
+            if (lines_per_record == 4 && (l0 + 2 >= nlines + 1 || text[line_start[l0 + 2]] != '+')) atomicExch(error, 1);
+            if (L > pitch) atomicExch(error, 2);                    // row too short
+            seq_begin[r] = sb;
+            len[r] = (int32_t)L;
+        }
+        int bad = 0;
+        for (int64_t i = sb + lane; i < se; i += 32) bad += !ingest_valid_base((unsigned char)text[i]);
+        bad = __reduce_add_sync(0xffffffffu, bad);
+        if (lane == 0) ninvalid[r] = bad;
+    }
+}
+
+__global__ void __launch_bounds__(256) copy_reads_kernel(const char* __restrict__ text,
+                                                         const int64_t* __restrict__ seq_begin,
+                                                         const int32_t* __restrict__ len,
+                                                         const int32_t* __restrict__ ninvalid,
+                                                         const int32_t* __restrict__ invalid_excl, int64_t nreads,
+                                                         int64_t first_read_id, int carry, char* __restrict__ rows,
+                                                         int64_t pitch, uint8_t* __restrict__ ambiguous)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < nreads; r += nwarps) {
+        // replaced characters before this read inside its batch of 65536 reads of the FILE
+        const int64_t in_batch = (first_read_id + r) % INGEST_BATCH;
+        const int64_t batch_first = r - in_batch; // negative: the batch began in an earlier chunk (carry applies)
+        int running = batch_first >= 0 ? invalid_excl[r] - invalid_excl[batch_first] : invalid_excl[r] + carry;
+        const int64_t sb = seq_begin[r];
+        const int L = len[r];
+        char* row = rows + r * pitch;
+        for (int i0 = 0; i0 < L; i0 += 32) {
+            const int i = i0 + lane;
+            unsigned char c = i < L ? (unsigned char)text[sb + i] : (unsigned char)'A';
+            const bool bad = !ingest_valid_base(c);
+            const unsigned m = __ballot_sync(0xffffffffu, bad);
+            if (bad) c = (unsigned char)("ACGT"[(running + __popc(m & ((1u << lane) - 1u))) & 3]);
+            else if (c >= 'a') c = (unsigned char)(c - 32);
+            if (i < L) row[i] = (char)c;
+            running += __popc(m);
+        }
+        for (int64_t i = L + lane; i < pitch; i += 32) row[i] = 0;
+        if (lane == 0 && ambiguous) ambiguous[r] = ninvalid[r] > 0 ? 1 : 0;
+    }
+}
+
+static unsigned igrid(int64_t items)
+{
+    int64_t g = HRM_SDIV(items, (int64_t)256);
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+} // namespace hrm
+
+using namespace hrm;
+
+extern "C" hrm_status hrm_ingest_reads(const char* d_text, int64_t nbytes, int64_t first_read_id,
+                                       int32_t carry_replaced, char* d_rows, int64_t pitch, int32_t* d_lengths,
+                                       uint8_t* d_ambiguous, int64_t max_reads, int64_t* h_num_reads,
+                                       int32_t* h_carry_replaced_out, hrm_stream stream)
+{
+    HRM_TRY(ensure_device());
+    HRM_REQUIRE(nbytes >= 0 && nbytes < (1LL << 31), "text chunks are limited to 2 GiB");
+    HRM_REQUIRE(pitch > 0 && max_reads >= 0 && h_num_reads != nullptr && first_read_id >= 0, "args");
+    *h_num_reads = 0;
+    if (h_carry_replaced_out) *h_carry_replaced_out = carry_replaced;
+    if (nbytes == 0) return HRM_OK;
+    HRM_REQUIRE(d_text != nullptr && d_rows != nullptr && d_lengths != nullptr, "buffers");
+    cudaStream_t s = as_stream(stream);
+    Scratch flags, excl, tot, first;
+    HRM_TRY(flags.alloc(sizeof(int32_t) * (size_t)nbytes, s));
+    HRM_TRY(excl.alloc(sizeof(int32_t) * ((size_t)nbytes + 1), s));
+    HRM_TRY(tot.alloc(sizeof(int64_t) * 2, s));
+    HRM_TRY(first.alloc(16, s));
+    HRM_LAUNCH(newline_flags_kernel, igrid(nbytes), 256, 0, s, d_text, nbytes, flags.as<int32_t>());
+    HRM_TRY(exclusive_scan_i32(flags.as<int32_t>(), excl.as<int32_t>(), nbytes, tot.as<int64_t>(), s));
+    int64_t nlines = 0;
+    char head[2] = {0, 0};
+    HRM_CUDA(cudaMemcpyAsync(&nlines, tot.p, sizeof nlines, cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaMemcpyAsync(head, d_text, 1, cudaMemcpyDeviceToHost, s));
+    char last = 0;
+    HRM_CUDA(cudaMemcpyAsync(&last, d_text + nbytes - 1, 1, cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    HRM_REQUIRE(head[0] == '@' || head[0] == '>', "not FASTQ ('@') or FASTA ('>') text");
+    const int lpr = head[0] == '@' ? 4 : 2;
+    const int64_t total_lines = nlines + (last != '\n' ? 1 : 0); // a last line without newline still counts
+    HRM_REQUIRE(total_lines % lpr == 0, "incomplete record (or multi-line sequences: not supported on the device)");
+    const int64_t nreads = total_lines / lpr;
+    HRM_REQUIRE(nreads <= max_reads, "more reads in the text than max_reads");
+    if (nreads == 0) return HRM_OK;
+    Scratch lstart, sbeg, ninv, invx, err;
+    HRM_TRY(lstart.alloc(sizeof(int64_t) * ((size_t)nlines + 2), s));
+    HRM_TRY(sbeg.alloc(sizeof(int64_t) * (size_t)nreads, s));
+    HRM_TRY(ninv.alloc(sizeof(int32_t) * (size_t)nreads, s));
+    HRM_TRY(invx.alloc(sizeof(int32_t) * ((size_t)nreads + 1), s));
+    HRM_TRY(err.alloc(sizeof(int) + sizeof(int64_t), s));
+    HRM_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int) + sizeof(int64_t), s));
+    HRM_LAUNCH(line_starts_kernel, igrid(nbytes), 256, 0, s, d_text, nbytes, excl.as<int32_t>(), lstart.as<int64_t>());
+    HRM_LAUNCH(record_extents_kernel, igrid(nreads * 32), 256, 0, s, d_text, nbytes, lstart.as<int64_t>(), nlines, lpr,
+               nreads, pitch, sbeg.as<int64_t>(), d_lengths, ninv.as<int32_t>(), err.as<int>());
+    HRM_TRY(exclusive_scan_i32(ninv.as<int32_t>(), invx.as<int32_t>(), nreads, nullptr, s));
+    int h_err = 0;
+    HRM_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof h_err, cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    if (h_err == 1) {
+        set_error("malformed record (header / '+' line missing, or multi-line sequences)");
+        return HRM_ERR_INVALID;
+    }
+    if (h_err == 2) {
+        set_error("a sequence is longer than the row pitch");
+        return HRM_ERR_INVALID;
+    }
+    HRM_LAUNCH(copy_reads_kernel, igrid(nreads * 32), 256, 0, s, d_text, sbeg.as<int64_t>(), d_lengths, ninv.as<int32_t>(),
+               invx.as<int32_t>(), nreads, first_read_id, carry_replaced & 3, d_rows, pitch, d_ambiguous);
+    // replaced characters of the (unfinished) last batch, for the next chunk
+    const int64_t last_in_batch = (first_read_id + nreads) % INGEST_BATCH; // reads of that batch inside this chunk
+    int32_t tail[2] = {0, 0};
+    const int64_t last_first = nreads - last_in_batch;
+    HRM_CUDA(cudaMemcpyAsync(&tail[0], invx.as<int32_t>() + nreads, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (last_first > 0)
+        HRM_CUDA(cudaMemcpyAsync(&tail[1], invx.as<int32_t>() + last_first, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    if (h_carry_replaced_out)
+        *h_carry_replaced_out = last_in_batch == 0 ? 0 : (last_first >= 0 ? (tail[0] - tail[1]) & 3 : (tail[0] + carry_replaced) & 3);
+    *h_num_reads = nreads;
+    return HRM_OK;
+}

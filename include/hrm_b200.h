@@ -467,6 +467,22 @@ hrm_status hrm_mapper_set_profiling(hrm_mapper* m, int enable);
 hrm_status hrm_mapper_stage_times(hrm_mapper* m, float* h_ms /* [HRM_NUM_STAGES] */,
                                   int32_t* h_spans /* [HRM_NUM_STAGES], may be NULL */);
 
+/* ---- read ingestion on the device -------------------------------------------------------
+ * ref: forEachReadInFile include/readlibraryio.hpp:288-326 (kseqpp, one host parser thread) and the encoder
+ * threads of constructChunkedReadStorageFromFiles include/chunkedreadstorageconstruction.hpp:70-95,:273-314:
+ * a c g t -> upper case, every other non-ACGT character -> "ACGT"[Ncount++ % 4] with Ncount = 0 at the start of
+ * every batch of 65536 reads of the file, reads with such characters recorded as ambiguous.
+ * d_text: FASTQ (4-line records) or FASTA (2-line records) text of whole records in device memory, < 2 GiB per
+ * call.  Output: ASCII rows (d_rows, `pitch` bytes each, zero padded) + lengths, exactly what the reference hands to
+ * encodeSequence2Bit and what hrm_encode_2bit / hrm_map_batch / hrm_readstore_create_from_ascii take.
+ * first_read_id: id of the first read of the text within its file; carry_replaced: replaced-character count
+ * carried from the previous chunk of the same batch (0 at a multiple of 65536 reads); *h_carry_replaced_out: the
+ * value to pass with the next chunk.  d_ambiguous (may be NULL): 1 per read with replaced characters. */
+hrm_status hrm_ingest_reads(const char* d_text, int64_t nbytes, int64_t first_read_id, int32_t carry_replaced,
+                            char* d_rows, int64_t pitch, int32_t* d_lengths, uint8_t* d_ambiguous,
+                            int64_t max_reads, int64_t* h_num_reads, int32_t* h_carry_replaced_out,
+                            hrm_stream stream);
+
 /* ---- key-partitioned index over the GPUs of one box (BASELINE config 5) -------------
  * ref: the reference's multi-GPU minhasher distributes whole tables (hash function j on GPU j mod G),
  * broadcasts every query batch to all GPUs and gathers the results with cudaMemcpyPeerAsync

@@ -191,6 +191,18 @@ class Oracle:
         # number of tables: stored in the handle; query functions take it from there, python needs it for shapes
         return (hh, None), k.value, lf.value
 
+    def read_file(self, path, pitch, cap):
+        """reference only: sequences of a FASTA/FASTQ file as the reference's own parser yields them
+        (forEachReadInFile, readlibraryio.hpp:288-326) -> (rows [n, pitch] u8 unmodified, lengths)"""
+        assert self.kind == "ref"
+        rows = np.zeros((cap, pitch), dtype=np.uint8)
+        lens = np.zeros(cap, dtype=np.int32)
+        self.lib.ref_read_file.restype = C.c_int64
+        n = self.lib.ref_read_file(str(path).encode(), _p(rows, C.c_char), C.c_int64(pitch), _p(lens, C.c_int32),
+                                   C.c_int64(cap))
+        assert 0 <= n <= cap, n
+        return rows[:n], lens[:n]
+
     # ---- C1 (port only; the reference implementation is CUDA-only) ----
     def filter_by_frequency(self, values, offsets, min_hits):
         values = np.ascontiguousarray(values, dtype=np.uint32)
@@ -275,3 +287,42 @@ def ref_cpu_pipeline(ref: "Oracle", genome: bytes, chrom_off, reads: np.ndarray,
                              out.ctypes.data_as(C.c_void_p), sw.ctypes.data_as(C.c_void_p) if sw is not None else None,
                              ed.ctypes.data_as(C.c_void_p), _p(times, C.c_double))
     return out, sw, ed, times
+
+
+# ---- 8f-1 read ingestion: restatement (TEST INFRASTRUCTURE) ------------------------------------------------
+def preprocess_reads_model(seqs, first_read_id=0, carry=0):
+    """ref: preprocessSequence include/chunkedreadstorageconstruction.hpp:70-95 as driven by the encoder thread
+    (:273-314): a c g t -> upper case; any other character that is not A C G T -> "ACGT"[Ncount], Ncount =
+    (Ncount + 1) % 4; Ncount = 0 at the start of every batch of 65536 reads (fileParserMaxBatchsize :107).
+    seqs: list of bytes.  Returns (list of bytes, ambiguous flags, Ncount after the last read)."""
+    out, amb = [], []
+    ncount = carry & 3
+    for i, s in enumerate(seqs):
+        if (first_read_id + i) % 65536 == 0:
+            ncount = 0
+        b = bytearray(s)
+        bad = False
+        for j, c in enumerate(b):
+            if c in b"ACGT":
+                continue
+            if c in b"acgt":
+                b[j] = c - 32
+            else:
+                b[j] = b"ACGT"[ncount]
+                ncount = (ncount + 1) % 4
+                bad = True
+        out.append(bytes(b))
+        amb.append(bad)
+    return out, amb, ncount
+
+
+def parse_records_model(text):
+    """4-line FASTQ / 2-line FASTA records -> list of sequence lines (what kseqpp yields for such files)"""
+    lines = text.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    if not lines:
+        return []
+    lpr = 4 if lines[0][:1] == b"@" else 2
+    assert len(lines) % lpr == 0
+    return [lines[i + 1].rstrip(b"\r") for i in range(0, len(lines), lpr)]

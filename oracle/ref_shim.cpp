@@ -21,6 +21,7 @@
 #include <helpers/hashers.cuh>
 #include <fstream>
 #include <cpuhashtable.hpp>
+#include <readlibraryio.hpp>
 #include <groupbykey.hpp>
 #include <ssw_cpp.h>
 #include <edlib.h>
@@ -220,6 +221,22 @@ void* ref_tables_load(const char* path, int* kmerSize, float* loadfactor)
         return nullptr;
     }
     return T;
+}
+
+// ---- read files: the reference's own parser (forEachReadInFile include/readlibraryio.hpp:288-326, kseqpp) ----
+// rows: cap rows of `pitch` bytes; returns the number of reads in the file (rows beyond cap are not written)
+int64_t ref_read_file(const char* path, char* rows, int64_t pitch, int32_t* lens, int64_t cap)
+{
+    int64_t n = 0;
+    care::forEachReadInFile(std::string(path), [&](auto /*readNumber*/, auto& read) {
+        if (n < cap) {
+            const int64_t L = (int64_t)read.sequence.size();
+            lens[n] = (int32_t)L;
+            memcpy(rows + n * pitch, read.sequence.data(), (size_t)(L < pitch ? L : pitch));
+        }
+        n++;
+    });
+    return n;
 }
 
 // ---- V2: the reference's SSW (src/ssw.c, src/ssw_cpp.cpp) ----

@@ -363,3 +363,57 @@ def test_v3_edit_distance(cuda, port):
     d = cuda.edit_distance(tt(cuda, qa), tt(cuda, ql), tt(cuda, ta), tt(cuda, tl)).cpu().numpy()
     for i in range(len(qs)):
         assert int(d[i]) == port.edit_distance_nw(qs[i], ts[i]), i
+
+
+# ---- 8f-1 read ingestion ---------------------------------------------------------------------------
+def test_ingest_reads(cuda, tmp_path):
+    """FASTQ / FASTA text -> normalised ASCII rows on the device, against the restatement of the reference's
+    reader + preprocessSequence (65536-read replacement cycle, ambiguous flags, chunk carry, error paths)"""
+    import torch
+    import hashreadmapper_b200 as hb
+    from oracle.pyoracle import parse_records_model, preprocess_reads_model
+    rng = random.Random(21)
+
+    def make(fmt, n, maxlen, trailing_newline=True):
+        recs = []
+        for i in range(n):
+            sq = "".join(rng.choice("ACGTACGTACGTNacgtnR") for _ in range(rng.randint(1, maxlen)))
+            recs.append("@r%d x\n%s\n+\n%s\n" % (i, sq, "I" * len(sq)) if fmt == "fastq" else ">r%d\n%s\n" % (i, sq))
+        text = "".join(recs).encode()
+        return text if trailing_newline else text[:-1]
+
+    def run(text, pitch, first=0, carry=0, cap=None):
+        t = torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy()).cuda()
+        return cuda.ingest_reads(t, pitch, cap or text.count(b"\n") + 1, first, carry)
+
+    for fmt, n, maxlen, nl in (("fastq", 3000, 150, True), ("fasta", 2000, 100, False), ("fastq", 70000, 24, True),
+                               ("fastq", 1, 5, False)):
+        text = make(fmt, n, maxlen, nl)
+        seqs = parse_records_model(text)
+        exp, amb, carry_exp = preprocess_reads_model(seqs)
+        rows, lens, a, carry = run(text, 160)
+        assert rows.shape[0] == n and (lens.cpu().numpy() == [len(x) for x in exp]).all()
+        r = rows.cpu().numpy()
+        for i in (list(range(min(n, 400))) + list(range(max(0, n - 400), n)) + list(range(65400, min(n, 65700)))):
+            assert bytes(r[i, :len(exp[i])]) == exp[i], i
+            assert not r[i, len(exp[i]):].any()
+        assert (a.cpu().numpy().astype(bool) == np.array(amb)).all()
+        assert carry == (carry_exp if n % 65536 else 0)
+    # two chunks of one file: the second starts inside a batch and continues its replacement cycle
+    text = make("fastq", 5000, 60)
+    seqs = parse_records_model(text)
+    exp, amb, _ = preprocess_reads_model(seqs)
+    cut = len(b"\n".join(text.split(b"\n")[:4 * 1234])) + 1
+    r1, l1, a1, c1 = run(text[:cut], 64)
+    r2, l2, a2, c2 = run(text[cut:], 64, first=1234, carry=c1)
+    both = np.concatenate([r1.cpu().numpy(), r2.cpu().numpy()])
+    assert both.shape[0] == 5000
+    for i in range(5000):
+        assert bytes(both[i, :len(exp[i])]) == exp[i], i
+    # rows feed K1 directly
+    enc = cuda.encode_2bit(r1, l1)
+    assert enc.shape[0] == 1234
+    # error paths: multi-line FASTA, row too short, garbage
+    for bad in (b">a\nACGT\nACGT\n>b\nAC\n", b"@a\n" + b"A" * 100 + b"\n+\n" + b"I" * 100 + b"\n", b"hello\n"):
+        with pytest.raises(hb.HrmError):
+            run(bad, 64)

@@ -191,3 +191,35 @@ def test_ref_whole_pipeline(port, ref):
             for a, qq in enumerate((q, qrc)):
                 ea, _ = port.ssw_align(qq, r, max(15, int(lens[i]) // 2))
                 assert ea == tuple(int(sw[i][a][n]) for n in sw.dtype.names[:9])
+
+
+def test_read_ingestion_model_against_reference_parser(ref, tmp_path):
+    """8f-1: the record parsing model against the reference's own file reader (kseqpp through forEachReadInFile);
+    the character normalisation is a restatement of a lambda that cannot be linked (cited in pyoracle)"""
+    import random
+    from oracle.pyoracle import parse_records_model, preprocess_reads_model
+    rng = random.Random(12)
+    for fmt in ("fastq", "fasta"):
+        seqs = ["".join(rng.choice("ACGTNacgtnRY-") for _ in range(rng.randint(1, 120))) for _ in range(700)]
+        recs = []
+        for i, sq in enumerate(seqs):
+            if fmt == "fastq":
+                recs.append("@r%d extra words\n%s\n+\n%s\n" % (i, sq, "I" * len(sq)))
+            else:
+                recs.append(">r%d\n%s\n" % (i, sq))
+        text = "".join(recs).encode()
+        path = tmp_path / ("reads." + fmt)
+        path.write_bytes(text)
+        rows, lens = ref.read_file(path, 128, 1000)
+        got = [bytes(rows[i, :lens[i]]) for i in range(len(lens))]
+        assert got == parse_records_model(text) == [s.encode() for s in seqs]
+        norm, amb, _ = preprocess_reads_model(got)
+        assert all(set(x) <= set(b"ACGT") for x in norm) and len(norm) == 700
+        # the replacement cycle: k-th replaced character of the batch becomes "ACGT"[k % 4]
+        k = 0
+        for raw, fixed, a in zip(got, norm, amb):
+            for c0, c1 in zip(raw, fixed):
+                if c0 not in b"ACGTacgt":
+                    assert c1 == b"ACGT"[k % 4]
+                    k += 1
+            assert a == any(c not in b"ACGTacgt" for c in raw)
