@@ -5,11 +5,12 @@
 //      on every read of a batch -- a c g t -> upper case, every other character that is not A C G T is replaced by
 //      "ACGT"[Ncount], Ncount = (Ncount + 1) % 4, with Ncount = 0 at the START OF EVERY BATCH (:277) -- and record
 //      the ids of reads that contained such characters (:293-297).
-// Here: the text of a chunk is in device memory; line starts come from one flag + scan + scatter pass, a record
+// Here: the text of a chunk is in device memory; line starts come from two passes over the text (newlines per
+// 1 KiB tile by byte-SIMD compare, scan of the tile counts, positions written tile by tile), a record
 // is 4 lines (FASTQ, first byte '@') or 2 lines (FASTA, first byte '>'; sequences on one line), the cyclic
 // replacement index of a read is an exclusive scan of the per-read counts of replaced characters, rebased at
 // every 65536th read of the file.  One warp per read copies and normalises its sequence.
-// Traffic: the text once for the flags, once for the copy; 4 B per byte for the scan (chunks are bounded).
+// Traffic: the text three times (count, positions, copy), rows once.
 #include "runtime.cuh"
 
 namespace hrm {
@@ -21,22 +22,71 @@ __device__ __forceinline__ bool ingest_valid_base(unsigned char c)
     return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'a' || c == 'c' || c == 'g' || c == 't';
 }
 
-__global__ void __launch_bounds__(256) newline_flags_kernel(const char* __restrict__ text, int64_t n,
-                                                            int32_t* __restrict__ flags)
+constexpr int INGEST_TILE = 1024; // text bytes per warp-tile of the line index
+
+// newlines of byte j of the 4 bytes in w, as 0x00 / 0xFF per byte
+__device__ __forceinline__ uint32_t newline_mask4(uint32_t w) { return __vcmpeq4(w, 0x0A0A0A0Au); }
+
+// bytes [t * TILE, (t + 1) * TILE) of the text: lane l owns bytes [32 l, 32 l + 32) of the tile
+__device__ __forceinline__ int tile_lane_newlines(const char* __restrict__ text, int64_t n, int64_t tile, int lane,
+                                                  uint32_t (&m)[8])
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) flags[i] = text[i] == '\n';
+    const int64_t base = tile * INGEST_TILE + 32 * lane;
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int64_t at = base + 4 * q;
+        uint32_t w = 0u;
+        if (at + 4 <= n) {
+            w = *reinterpret_cast<const uint32_t*>(text + at); // the text buffer is 4-byte aligned (device allocation)
+        } else {
+            for (int j = 0; j < 4; j++)
+                if (at + j < n) w |= (uint32_t)(unsigned char)text[at + j] << (8 * j);
+        }
+        m[q] = newline_mask4(w) & 0x01010101u;
+        cnt += __popc(m[q]);
+    }
+    return cnt;
 }
 
-// line_start[l + 1] = position after the l-th newline; line_start[0] = 0
-__global__ void __launch_bounds__(256) line_starts_kernel(const char* __restrict__ text, int64_t n,
-                                                          const int32_t* __restrict__ excl,
+// pass 1: newlines per tile
+__global__ void __launch_bounds__(256) tile_newlines_kernel(const char* __restrict__ text, int64_t n, int64_t ntiles,
+                                                            int32_t* __restrict__ tile_count)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = warp0; t < ntiles; t += nwarps) {
+        uint32_t m[8];
+        const int c = __reduce_add_sync(0xffffffffu, tile_lane_newlines(text, n, t, lane, m));
+        if (lane == 0) tile_count[t] = c;
+    }
+}
+
+// pass 2: line_start[l + 1] = position after the l-th newline; line_start[0] = 0
+__global__ void __launch_bounds__(256) line_starts_kernel(const char* __restrict__ text, int64_t n, int64_t ntiles,
+                                                          const int32_t* __restrict__ tile_excl,
                                                           int64_t* __restrict__ line_start)
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        if (i == 0) line_start[0] = 0;
-        if (text[i] == '\n') line_start[excl[i] + 1] = i + 1;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    if (warp0 == 0 && lane == 0) line_start[0] = 0;
+    for (int64_t t = warp0; t < ntiles; t += nwarps) {
+        uint32_t m[8];
+        const int c = tile_lane_newlines(text, n, t, lane, m);
+        int incl = c;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        int64_t line = (int64_t)tile_excl[t] + (incl - c); // newlines before this lane's bytes
+        const int64_t base = t * INGEST_TILE + 32 * lane;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (m[q] & (1u << (8 * j))) line_start[++line] = base + 4 * q + j + 1;
     }
 }
 
@@ -131,13 +181,14 @@ extern "C" hrm_status hrm_ingest_reads(const char* d_text, int64_t nbytes, int64
     if (nbytes == 0) return HRM_OK;
     HRM_REQUIRE(d_text != nullptr && d_rows != nullptr && d_lengths != nullptr, "buffers");
     cudaStream_t s = as_stream(stream);
-    Scratch flags, excl, tot, first;
-    HRM_TRY(flags.alloc(sizeof(int32_t) * (size_t)nbytes, s));
-    HRM_TRY(excl.alloc(sizeof(int32_t) * ((size_t)nbytes + 1), s));
+    HRM_REQUIRE((reinterpret_cast<uintptr_t>(d_text) & 3) == 0, "d_text must be 4-byte aligned");
+    Scratch tcount, texcl, tot;
+    const int64_t ntiles = HRM_SDIV(nbytes, (int64_t)INGEST_TILE);
+    HRM_TRY(tcount.alloc(sizeof(int32_t) * (size_t)ntiles, s));
+    HRM_TRY(texcl.alloc(sizeof(int32_t) * ((size_t)ntiles + 1), s));
     HRM_TRY(tot.alloc(sizeof(int64_t) * 2, s));
-    HRM_TRY(first.alloc(16, s));
-    HRM_LAUNCH(newline_flags_kernel, igrid(nbytes), 256, 0, s, d_text, nbytes, flags.as<int32_t>());
-    HRM_TRY(exclusive_scan_i32(flags.as<int32_t>(), excl.as<int32_t>(), nbytes, tot.as<int64_t>(), s));
+    HRM_LAUNCH(tile_newlines_kernel, igrid(ntiles * 32), 256, 0, s, d_text, nbytes, ntiles, tcount.as<int32_t>());
+    HRM_TRY(exclusive_scan_i32(tcount.as<int32_t>(), texcl.as<int32_t>(), ntiles, tot.as<int64_t>(), s));
     int64_t nlines = 0;
     char head[2] = {0, 0};
     HRM_CUDA(cudaMemcpyAsync(&nlines, tot.p, sizeof nlines, cudaMemcpyDeviceToHost, s));
@@ -159,7 +210,8 @@ extern "C" hrm_status hrm_ingest_reads(const char* d_text, int64_t nbytes, int64
     HRM_TRY(invx.alloc(sizeof(int32_t) * ((size_t)nreads + 1), s));
     HRM_TRY(err.alloc(sizeof(int) + sizeof(int64_t), s));
     HRM_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int) + sizeof(int64_t), s));
-    HRM_LAUNCH(line_starts_kernel, igrid(nbytes), 256, 0, s, d_text, nbytes, excl.as<int32_t>(), lstart.as<int64_t>());
+    HRM_LAUNCH(line_starts_kernel, igrid(ntiles * 32), 256, 0, s, d_text, nbytes, ntiles, texcl.as<int32_t>(),
+               lstart.as<int64_t>());
     HRM_LAUNCH(record_extents_kernel, igrid(nreads * 32), 256, 0, s, d_text, nbytes, lstart.as<int64_t>(), nlines, lpr,
                nreads, pitch, sbeg.as<int64_t>(), d_lengths, ninv.as<int32_t>(), err.as<int>());
     HRM_TRY(exclusive_scan_i32(ninv.as<int32_t>(), invx.as<int32_t>(), nreads, nullptr, s));
