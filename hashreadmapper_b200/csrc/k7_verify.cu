@@ -1057,9 +1057,10 @@ static bool launch_pair_passes(const PackedSrc& src, int64_t nreads, int QP, int
 {
     st = HRM_OK;
     const int maxQ = src.maxQ, w = src.maxR;
-    int G = 0;
-    if (pair_fits(4 * 40, maxQ, w)) G = 4;
-    else if (pair_fits(8 * 32, maxQ, w)) G = 8;
+    int G = 0, R = 0; // frames: 4 x 40 rows (reads up to 152 bp), 8 x 32 (up to 248), 8 x 34 (up to 264: 250 bp reads)
+    if (pair_fits(4 * 40, maxQ, w)) G = 4, R = 40;
+    else if (pair_fits(8 * 32, maxQ, w)) G = 8, R = 32;
+    else if (pair_fits(8 * 34, maxQ, w)) G = 8, R = 34;
     else return false;
     const int ppw = 32 / G;
     const size_t smem = ((size_t)QP + RP + 8 * (size_t)RP) * ppw * 4;
@@ -1072,7 +1073,8 @@ static bool launch_pair_passes(const PackedSrc& src, int64_t nreads, int QP, int
         HRM_LAUNCH(kern, (unsigned)blocks, 128, smem, s, src, nreads, QP, RP, d_out);
         return HRM_OK;
     };
-    st = G == 4 ? go(sw_pair_passes_kernel<4, 40>) : go(sw_pair_passes_kernel<8, 32>);
+    st = G == 4 ? go(sw_pair_passes_kernel<4, 40>)
+                : (R == 32 ? go(sw_pair_passes_kernel<8, 32>) : go(sw_pair_passes_kernel<8, 34>));
     return true;
 }
 

@@ -366,6 +366,7 @@ extern "C" int hh_sw_pair(const int8_t* A, const int8_t* B, int L, const int8_t*
     if (!pair_fits(G * R, L, rl)) return -1;
     if (G == 4 && R == 40) pair_passes_host<4, 40>(A, B, L, ref, rl, ml, o);
     else if (G == 8 && R == 32) pair_passes_host<8, 32>(A, B, L, ref, rl, ml, o);
+    else if (G == 8 && R == 34) pair_passes_host<8, 34>(A, B, L, ref, rl, ml, o);
     else if (G == 4 && R == 32) pair_passes_host<4, 32>(A, B, L, ref, rl, ml, o);
     else if (G == 2 && R == 33) pair_passes_host<2, 33>(A, B, L, ref, rl, ml, o);
     else return -2;
