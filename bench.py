@@ -114,7 +114,9 @@ def workload(args, rank):
     parts, at, piece = [], 0, 0
     while at < args.reads:  # pieces of 1 M reads bound the generator's temporaries
         cnt = min(1_000_000, args.reads - at)
-        parts.append(synth.make_reads(genome, off, cnt, READ_LEN, error_rate=ERR, seed=20240602 + rank + 1000 * piece))
+        parts.append(synth.make_reads(genome, off, cnt, args.read_len, error_rate=args.error_rate,
+                                      indel_frac=args.indel_frac, nondirectional=args.nondirectional,
+                                      seed=20240602 + rank + 1000 * piece))
         at += cnt
         piece += 1
     reads = np.concatenate([p[0] for p in parts])
@@ -123,15 +125,15 @@ def workload(args, rank):
     return genome, off, reads, lens, truth
 
 
-def workload_name(reads, genome_bp, nchrom):
+def workload_name(reads, genome_bp, nchrom, shape="150bp directional BS reads"):
     rd = "%gM" % (reads / 1e6) if reads % 100_000 == 0 else str(reads)
     if genome_bp == 3_100_000_000:
-        return ("%s x 150bp directional BS reads per GPU per step vs 3.1 Gbp human-size synthetic 3N index, 24 chromosomes "
-                "(BASELINE configs[2]: batches of the 100M-read job)" % rd)
+        return ("%s x %s per GPU per step vs 3.1 Gbp human-size synthetic 3N index, 24 chromosomes "
+                "(BASELINE configs[2]: batches of the 100M-read job)" % (rd, shape))
     if genome_bp == 46_000_000:
-        return "%s x 150bp directional BS reads per GPU per step vs 46 Mbp synthetic reference (BASELINE configs[1])" % rd
-    return "%s x 150bp directional BS reads per step vs %.4g Mbp synthetic reference, %d chromosome(s)" % (
-        rd, genome_bp / 1e6, nchrom)
+        tag = "BASELINE configs[1]" if shape == "150bp directional BS reads" else "read shape of BASELINE configs[3]"
+        return "%s x %s per GPU per step vs 46 Mbp synthetic reference (%s)" % (rd, shape, tag)
+    return "%s x %s per step vs %.4g Mbp synthetic reference, %d chromosome(s)" % (rd, shape, genome_bp / 1e6, nchrom)
 
 
 def cpu_sample(args, n_reads):
@@ -140,7 +142,8 @@ def cpu_sample(args, n_reads):
     sub_bp = min(args.genome_bp, args.cpu_genome_bp)
     genome, off = synth.make_genome([sub_bp], seed=20240601)
     S = min(args.cpu_sample, n_reads)
-    reads, lens, _ = synth.make_reads(genome, off, S, READ_LEN, error_rate=ERR, seed=20240602)
+    reads, lens, _ = synth.make_reads(genome, off, S, args.read_len, error_rate=args.error_rate,
+                                      indel_frac=args.indel_frac, seed=20240602)
     return genome, off, reads, lens, S, args.genome_bp / float(sub_bp)
 
 
@@ -220,6 +223,12 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=50_000, help="reads in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--load-factor", type=float, default=None, help="hash-table load factor (default: the library's)")
+    ap.add_argument("--read-len", type=int, default=READ_LEN)
+    ap.add_argument("--error-rate", type=float, default=ERR)
+    ap.add_argument("--indel-frac", type=float, default=0.0, help="fraction of the errors that are 1-bp indels")
+    ap.add_argument("--nondirectional", action="store_true",
+                    help="non-directional library: G->A reads too, four 3N passes (BASELINE configs[3] with --read-len 250 "
+                         "--error-rate 0.03 --indel-frac 0.1)")
     ap.add_argument("--chromosomes", type=int, default=1, help="> 1: GRCh38-like chromosome lengths (configs[2])")
     ap.add_argument("--index", default="replicated", choices=["replicated", "partitioned"],
                     help="partitioned: key-partitioned tables, lookups routed with NCCL all-to-all (configs[4])")
@@ -244,7 +253,7 @@ def main():
 
     genome, off, reads, lens, truth = workload(args, rank)
     n = len(lens)
-    cfg = api.directional_config()
+    cfg = api.nondirectional_config() if args.nondirectional else api.directional_config()
     if args.load_factor:
         cfg.load_factor = args.load_factor
     mp = api.Mapper(cfg)
@@ -344,7 +353,10 @@ def main():
             dist.destroy_process_group()
         return
 
-    wl_name = workload_name(n, args.genome_bp, len(off) - 1)
+    shape = "%dbp %s BS reads" % (args.read_len, "non-directional" if args.nondirectional else "directional")
+    if args.error_rate != ERR or args.indel_frac:
+        shape += " (%.3g %% errors, %.3g %% of them indels)" % (100 * args.error_rate, 100 * args.indel_frac)
+    wl_name = workload_name(n, args.genome_bp, len(off) - 1, shape)
     # ---- roofline of the hash-probe kernel (K3b) -----------------------------------------------------
     peak, peak_src = peaks()
     probe_ms, probe_spans = stages["probe"]
@@ -378,7 +390,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/u64 integer", "data": "synthetic",
             "config": {"workload": wl_name, "reads_per_gpu": n, "genome_bp": args.genome_bp, "k": K_, "hashmaps": H_, "window": W_,
-                       "min_table_hits": T_, "passes": "C->T index + G->A index", "verification": "SW+CIGAR",
+                       "min_table_hits": T_, "passes": "C->T index + G->A index" if not args.nondirectional else
+                       "C->T and G->A reads x C->T and G->A index (4 passes)", "verification": "SW+CIGAR",
                        "load_factor": float(cfg.load_factor),
                        "parallelism": ("reads sharded x%d, index replicated" % world) if comm is None else
                                       ("reads sharded x%d, index key-partitioned x%d, NCCL all-to-all" % (world, world)),
