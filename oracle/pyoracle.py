@@ -326,3 +326,89 @@ def parse_records_model(text):
     lpr = 4 if lines[0][:1] == b"@" else 2
     assert len(lines) % lpr == 0
     return [lines[i + 1].rstrip(b"\r") for i in range(0, len(lines), lpr)]
+
+
+# ---- V4 + O1: recalculation, alignment choice, MAPQ, SAM text (TEST INFRASTRUCTURE) --------------------------
+REF_SAM_SO = os.path.join(HERE, "_ref", "libhrm_ref_sam.so")
+SAM_FIELDS_DTYPE = np.dtype([("sw_score", "<i4", 2), ("sw_score_next_best", "<i4", 2), ("num_conversions", "<i4", 2),
+                             ("chosen", "<i4"), ("flag", "<i4"), ("mapq", "<i4"), ("window_length", "<i4"),
+                             ("pos", "<i8")])
+_COMP = bytes.maketrans(b"ACGT", b"TGCA")
+
+
+def have_ref_sam():
+    return os.path.exists(REF_SAM_SO)
+
+
+def _names_array(names):
+    return (C.c_char_p * len(names))(*[n if isinstance(n, bytes) else n.encode() for n in names])
+
+
+def port_sam_format(port, genomes, chrom_off, names, reads, read_len, mapped, passes, verify_conv, w=128,
+                    first_read_id=0, with_header=True):
+    """oracle/hrm_oracle.c: orc_sam_format.  genomes[p]: converted genome bytes of pass p; reads[p]: converted read
+    rows (uint8 [n, pitch]) of pass p; mapped: MAPPED_DTYPE [n]; passes: int32 [n] (pass of each hit).
+    -> (sam bytes, SAM_FIELDS_DTYPE [n])"""
+    assert port.kind == "port"
+    chrom_off = np.ascontiguousarray(chrom_off, dtype=np.int64)
+    read_len = np.ascontiguousarray(read_len, dtype=np.int32)
+    mapped = np.ascontiguousarray(mapped)
+    passes = np.ascontiguousarray(passes, dtype=np.int32)
+    vc = np.ascontiguousarray(verify_conv, dtype=np.int32)
+    n = read_len.shape[0]
+    reads = [np.ascontiguousarray(r, dtype=np.uint8) for r in reads]
+    gp = (C.c_char_p * len(genomes))(*genomes)
+    rp = (C.c_void_p * len(reads))(*[r.ctypes.data for r in reads])
+    fields = np.zeros(n, dtype=SAM_FIELDS_DTYPE)
+    fn = port.lib.orc_sam_format
+    fn.restype = C.c_int64
+    args = [gp, _p(chrom_off, C.c_int64), chrom_off.shape[0] - 1, _names_array(names), rp, reads[0].shape[1],
+            _p(read_len, C.c_int32), C.c_int64(n), mapped.ctypes.data_as(C.c_void_p), _p(passes, C.c_int32),
+            _p(vc, C.c_int32), w, C.c_uint32(first_read_id), int(with_header)]
+    size = fn(*args, None, C.c_int64(0), None)
+    out = C.create_string_buffer(size)
+    fn(*args, out, C.c_int64(size), fields.ctypes.data_as(C.c_void_p))
+    return out.raw[:size], fields
+
+
+def ref_mapping_sam(genome, chrom_off, names, reads, read_len, mapped, w=128, threads=4, tmp_prefix=None):
+    """The reference's own Mappinghandler::go (SW mode) on these inputs (oracle/ref_shim_sam.cpp), single pass:
+    genome / reads as the reference would be given them.  -> (sam bytes, per-read int32 [n, 8]:
+    sw_score0, next_best0, sw_score1, next_best1, num_conversions0, num_conversions1, flag, flag_rc)"""
+    import tempfile
+    lib = C.CDLL(REF_SAM_SO)
+    chrom_off = np.ascontiguousarray(chrom_off, dtype=np.int64)
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    read_len = np.ascontiguousarray(read_len, dtype=np.int32)
+    mapped = np.ascontiguousarray(mapped)
+    n = read_len.shape[0]
+    per = np.zeros((n, 8), dtype=np.int32)
+    with tempfile.TemporaryDirectory() as d:
+        prefix = os.path.join(d, "out") if tmp_prefix is None else tmp_prefix
+        rc = lib.ref_mapping_sam(genome, _p(chrom_off, C.c_int64), chrom_off.shape[0] - 1, _names_array(names),
+                                 _p(reads, C.c_char), reads.shape[1], _p(read_len, C.c_int32), C.c_int64(n),
+                                 mapped.ctypes.data_as(C.c_void_p), w, threads, prefix.encode(),
+                                 per.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("ref_mapping_sam failed: %d" % rc)
+        with open(prefix + ".SAM", "rb") as f:
+            sam = f.read()
+    return sam, per
+
+
+def complement_ascii(b):
+    return bytes(b).translate(_COMP)
+
+
+def sam_complement_text_columns(sam):
+    """complements the RNEXT (window) and SEQ columns of the record lines of a SAM text (the G->A mirror of
+    oracle/hrm_oracle.c: orc_sam_record)"""
+    out = []
+    for ln in sam.split(b"\n"):
+        if ln and not ln.startswith(b"@"):
+            c = ln.split(b"\t")
+            c[6] = c[6].translate(_COMP)
+            c[9] = c[9].translate(_COMP)
+            ln = b"\t".join(c)
+        out.append(ln)
+    return b"\n".join(out)

@@ -223,3 +223,74 @@ def test_read_ingestion_model_against_reference_parser(ref, tmp_path):
                     assert c1 == b"ACGT"[k % 4]
                     k += 1
             assert a == any(c not in b"ACGTacgt" for c in raw)
+
+
+# ---- V4 + O1: recalculation, alignment choice, MAPQ and the SAM text -------------------------------------------
+GOLD_SAM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_sam_v1.json")
+
+
+@pytest.fixture(scope="module")
+def gold_sam():
+    with open(GOLD_SAM) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", ["ct150", "ga150", "ct250", "none100"])
+def test_golden_sam(port, gold_sam, name):
+    """the port's SAM text against the golden made by the reference's own Mappinghandler (byte for byte, by hash),
+    its per-read recalculated scores / conversion counts / flags, and a few literal lines"""
+    import hashlib
+    import samcase
+    from oracle import pyoracle as po
+    g = gold_sam["cases"][name]
+    case = samcase.make(port, name)
+    sam, F = samcase.port_sam(po, port, case)
+    per = np.array(g["per_read"], dtype=np.int64)
+    m = case["mapped"]["orientation"] != 3
+    assert (F["sw_score"][:, 0] == per[:, 0]).all() and (F["sw_score_next_best"][:, 0] == per[:, 1]).all()
+    assert (F["sw_score"][:, 1] == per[:, 2]).all() and (F["sw_score_next_best"][:, 1] == per[:, 3]).all()
+    assert (F["num_conversions"] == per[:, 4:6]).all()
+    assert (F["chosen"] == (per[:, 0] < per[:, 2])).all()
+    assert (F["flag"][m] == np.where(F["chosen"] == 0, per[:, 6], per[:, 7])[m]).all()
+    n = len(case["lens"])
+    rec = sam.split(b"\n")[n + 2:]
+    for i, ln in g["lines"].items():
+        assert rec[int(i)].decode() == ln
+    assert len(sam) == g["bytes"] and hashlib.sha256(sam).hexdigest() == g["sha256"]
+    # every branch is present in the fixture
+    assert F["chosen"].sum() > 0 and (~m).sum() > 0
+    if case["conv"]:
+        assert F["num_conversions"].sum() > 0
+        assert (F["sw_score_next_best"] > 60000).any()  # the uint16 wrap of the reference's score fields
+
+
+@pytest.mark.parametrize("name", ["ct150", "ga150"])
+def test_ref_sam_live(port, name):
+    """the same comparison against the reference's Mappinghandler run now (fresh seeds through case edits)"""
+    import samcase
+    from oracle import pyoracle as po
+    if not po.have_ref_sam():
+        pytest.skip("oracle/_ref/libhrm_ref_sam.so not built (needs /root/reference)")
+    case = samcase.make(port, name, w=128)
+    # move the hits around once more so that the live run is not the golden run
+    rng = np.random.RandomState(5)
+    mp = case["mapped"]
+    idx = np.nonzero(mp["orientation"] != 3)[0]
+    flip = idx[rng.rand(len(idx)) < 0.2]
+    mp["orientation"][flip] = 3 - mp["orientation"][flip]
+    sam_p, F = samcase.port_sam(po, port, case)
+    sam_r, per = samcase.reference_sam(po, case)
+    assert sam_p == sam_r
+    assert (F["num_conversions"] == per[:, 4:6]).all()
+
+
+def test_mapq_u16(port):
+    """MAPQ (mapqfkt mappinghandler.cu:184-193): finite cases against the closed form, the out-of-range conversions
+    against what the compiled reference prints (4)"""
+    import math
+    f = port.lib.orc_mapq_u16
+    f.restype = np.ctypeslib.ctypes.c_uint32
+    assert f(0, 0) == 4 and f(300, 0) == 4 and f(220, 65456) == 4 and f(100, 250) == 4
+    for s1, s2 in ((300, 150), (300, 299), (300, 1), (65300, 20), (250, 249), (40, 38)):
+        v = -4.343 * math.log(1 - abs(s1 - s2) / s1)
+        assert f(s1, s2) == min(254, int(int(v) + 4.99))
