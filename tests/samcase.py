@@ -12,7 +12,8 @@ CASES = {
     "ct150": ([40007, 21013], 1200, 150, 0.02, 0.0, 1, 31),
     "ga150": ([30011, 9001], 900, 150, 0.02, 0.0, 2, 32),
     "ct250": ([50021], 700, 250, 0.03, 0.1, 1, 33),
-    "none100": ([20011], 500, 100, 0.01, 0.0, 0, 34),
+    # the reference as shipped: unconverted reads and genome seed the hit, stage V converts C->T (conv 0 below)
+    "none100": ([20011], 500, 100, 0.03, 0.0, 0, 34),
 }
 NAMES = ["chrA", "chrB", "chrC"]
 
@@ -56,7 +57,7 @@ def make(port, name, w=128, k=16):
     mapped["hammingDistance"][unm] = 0
     mapped["shift"][unm] = 0
     return {"genome": g, "off": off, "names": NAMES[:len(lengths)], "reads": r, "lens": lens, "mapped": mapped,
-            "conv": conv, "w": w}
+            "conv": conv if conv else 1, "w": w}
 
 
 def reference_sam(po, case):
