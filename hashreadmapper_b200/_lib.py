@@ -84,6 +84,13 @@ MAPPED_DTYPE = np.dtype([("orientation", "<i4"), ("hamming_distance", "<i4"), ("
 ALIGN_DTYPE = np.dtype([(n, "<i4") for n, _ in Alignment._fields_])
 RECORD_DTYPE = np.dtype([("mapped", MAPPED_DTYPE), ("alignments", ALIGN_DTYPE, (2,)), ("edit_distance", "<i4", (2,)),
                          ("window_length", "<i4"), ("mask_len", "<i4")])
+SAM_FIELDS_DTYPE = np.dtype([("sw_score", "<i4", (2,)), ("sw_score_next_best", "<i4", (2,)),
+                             ("num_conversions", "<i4", (2,)), ("chosen", "<i4"), ("flag", "<i4"), ("mapq", "<i4"),
+                             ("window_length", "<i4"), ("pos", "<i8")])
+SAM_HD = b"@HD\tVN:1.4\n"
+SAM_PG_CO = b"@PG\tHashreadmapper\tID:1.0@CO: QNAME\tFLAG\tRNAME\tPOS\tMAPQ\tCIGAR\tRNEXT\tPNEXT\tTLEN\tSEQ\tQUAL\tTAG\n"
+SAM_SQ_LINES, SAM_RECORDS = 0, 1
+assert SAM_FIELDS_DTYPE.itemsize == 48
 assert MAPPED_DTYPE.itemsize == C.sizeof(MappedRead) == 32
 assert RECORD_DTYPE.itemsize == C.sizeof(ReadRecord)
 
@@ -158,6 +165,10 @@ SIGNATURES = {
     "hrm_minhasher_set_partition": (I32, [P, C.c_int, C.c_int]),
     "hrm_mapper_set_partition": (I32, [P, P]),
     "hrm_sam_format": (I32, [P, P, P, I64, P, I64, P, I64, U32, P, C.c_int, P, I64, C.POINTER(I64)]),
+    "hrm_sam_fields_batch": (I32, [P, P, I64, P, I64, P, P, I64, P, VP]),
+    "hrm_sam_format_device": (I32, [P, P, I64, P, I64, P, P, I64, U32, P, C.c_int, P, I64, C.POINTER(I64), VP]),
+    "hrm_mapper_map_reads_sam": (I32, [P, P, I64, P, I64, U32, P, P, I64, C.POINTER(I64), P, I64, C.POINTER(I64), P, P,
+                                       I64, C.POINTER(BatchStats), VP]),
 }
 
 _lib = None

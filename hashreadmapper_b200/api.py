@@ -526,9 +526,55 @@ class Mapper:
                                             _ptr(cigars), cigar_pitch, C.byref(st), _stream()))
         return records, cigars, st
 
+    def _names(self):
+        return (C.c_char_p * len(self.chrom_names))(*[s.encode() for s in self.chrom_names])
+
+    def samFields(self, reads_ascii, lengths, records, cigars):
+        """V4 on the device (recalculated scores, conversion counts, chosen alignment, FLAG, MAPQ, POS):
+        device tensors in -> numpy SAM_FIELDS_DTYPE [n]"""
+        n, pitch = reads_ascii.shape
+        out = torch.empty((n, L.SAM_FIELDS_DTYPE.itemsize // 4), dtype=torch.int32, device=reads_ascii.device)
+        check(self.lib.hrm_sam_fields_batch(self.h, _ptr(reads_ascii), pitch, _ptr(lengths), n, _ptr(records),
+                                            _ptr(cigars), cigars.shape[1], _ptr(out), _stream()))
+        return out.cpu().numpy().view(L.SAM_FIELDS_DTYPE).reshape(n)
+
+    def samFormatDevice(self, reads_ascii, lengths, records, cigars, part, first_read_id=0):
+        """text of one part (L.SAM_SQ_LINES / L.SAM_RECORDS) as a device uint8 tensor"""
+        n, pitch = reads_ascii.shape
+        written = C.c_int64(0)
+        args = (self.h, _ptr(reads_ascii), pitch, _ptr(lengths), n, _ptr(records), _ptr(cigars), cigars.shape[1],
+                first_read_id, self._names(), part)
+        check(self.lib.hrm_sam_format_device(*args, None, 0, C.byref(written), _stream()))
+        out = torch.empty((max(written.value, 1),), dtype=torch.uint8, device=reads_ascii.device)
+        check(self.lib.hrm_sam_format_device(*args, _ptr(out), written.value, C.byref(written), _stream()))
+        return out[:written.value]
+
+    def mapReadsSam(self, reads_ascii: np.ndarray, lengths: np.ndarray, first_read_id=0, cigar_pitch=128,
+                    rec_out=None, sq_out=None, want_records=False):
+        """host reads in, SAM text out (the @SQ lines and the record lines of these reads), end to end on the device.
+        -> (sq bytes view, record bytes view, stats[, records, cigars])"""
+        n, pitch = reads_ascii.shape
+        bound = n * (96 + cigar_pitch + self.cfg.window_size + pitch)
+        if rec_out is None:
+            rec_out = np.empty(bound, dtype=np.uint8)
+        if sq_out is None:
+            sq_out = np.empty(n * 40 + 16, dtype=np.uint8)
+        records = np.empty(n, dtype=L.RECORD_DTYPE) if want_records else None
+        cigars = np.empty((2 * n, cigar_pitch), dtype=np.uint8) if want_records else None
+        st = L.BatchStats()
+        sqw, recw = C.c_int64(0), C.c_int64(0)
+        check(self.lib.hrm_mapper_map_reads_sam(self.h, _ptr(reads_ascii), pitch, _ptr(lengths), n, first_read_id,
+                                                self._names(), _ptr(sq_out), sq_out.size, C.byref(sqw), _ptr(rec_out),
+                                                rec_out.size, C.byref(recw), _ptr(records) if want_records else None,
+                                                _ptr(cigars) if want_records else None, cigar_pitch, C.byref(st),
+                                                _stream()))
+        if want_records:
+            return sq_out[:sqw.value], rec_out[:recw.value], st, records, cigars
+        return sq_out[:sqw.value], rec_out[:recw.value], st
+
     def samFormat(self, records, cigars, reads_ascii, lengths, first_read_id=0, with_header=True):
         n = len(records)
-        names = (C.c_char_p * len(self.chrom_names))(*[s.encode() for s in self.chrom_names])
+        names = self._names()
         written = C.c_int64(0)
         check(self.lib.hrm_sam_format(self.h, _ptr(records), _ptr(cigars), cigars.shape[1], _ptr(reads_ascii),
                                       reads_ascii.shape[1], _ptr(lengths), n, first_read_id, names, int(with_header),

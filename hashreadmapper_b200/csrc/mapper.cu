@@ -146,7 +146,6 @@ extern "C" hrm_status hrm_mapper_set_genome(hrm_mapper* m, const char* h_ascii, 
     const hrm_mapper_config& cfg = m->cfg;
     m->n_chrom = n_chrom;
     m->chrom_off.assign(h_chrom_offsets, h_chrom_offsets + n_chrom + 1);
-    m->host_genome.assign(h_ascii + h_chrom_offsets[0], (size_t)(h_chrom_offsets[n_chrom] - h_chrom_offsets[0]));
     const int64_t stride = cfg.window_size - cfg.k + 1;
     std::vector<int64_t> prefix(n_chrom + 1, 0);
     for (int c = 0; c < n_chrom; c++) {
@@ -218,8 +217,8 @@ extern "C" hrm_status hrm_mapper_info(const hrm_mapper* m, hrm_mapper_info_t* ou
 }
 
 // packs the batch once per distinct read conversion used by the passes
-static hrm_status pack_batch(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch, const int32_t* d_lengths,
-                             int64_t n, hrm_stream stream)
+hrm_status hrm::mapper_pack_batch(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch, const int32_t* d_lengths,
+                                  int64_t n, hrm_stream stream)
 {
     const hrm_mapper_config& cfg = m->cfg;
     m->packed_pitch = ascii_pitch / 16;
@@ -282,7 +281,7 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
             }
     StageTimer& T = m->timer;
     T.begin(HRM_STAGE_PACK, s);
-    HRM_TRY(pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
+    HRM_TRY(mapper_pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
     T.end(s);
     HRM_TRY(m->sigs.reserve(sizeof(uint64_t) * (size_t)n * H));
     HRM_TRY(m->num.reserve(sizeof(int32_t) * ((size_t)n + 1)));
@@ -466,7 +465,7 @@ extern "C" hrm_status hrm_verify_batch(hrm_mapper* m, const char* d_reads_ascii,
     if (n == 0) return HRM_OK;
     const hrm_mapper_config& cfg = m->cfg;
     m->timer.begin(HRM_STAGE_VERIFY, s);
-    HRM_TRY(pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
+    HRM_TRY(mapper_pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
     HRM_TRY(m->misc.reserve(64));
     int* d_maxlen = m->misc.as<int>() + 8;
     HRM_CUDA(cudaMemsetAsync(d_maxlen, 0, sizeof(int), s));
@@ -566,6 +565,73 @@ extern "C" hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_as
     HRM_CUDA(cudaStreamSynchronize(cs));
     HRM_CUDA(cudaStreamSynchronize(s));
     if (h_stats) *h_stats = st;
+    return HRM_OK;
+}
+
+// End to end with text out: reads H2D -> K1..K5 -> K7 -> V4 -> SAM text -> D2H (ref: performMappingGpu STEP 1 + STEP 2
+// incl. printtoSAM, main_gpu.cu:1123-1160).  The text buffers are sized by an upper bound per read so that the only
+// host round trip of the output side is the one that returns the byte counts.
+extern "C" hrm_status hrm_mapper_map_reads_sam(hrm_mapper* m, const char* h_reads_ascii, int64_t ascii_pitch,
+                                               const int32_t* h_lengths, int64_t n, uint32_t first_read_id,
+                                               const char* const* h_chrom_names, char* h_sq_out, int64_t sq_cap,
+                                               int64_t* h_sq_written, char* h_rec_out, int64_t rec_cap,
+                                               int64_t* h_rec_written, hrm_read_record* h_records, char* h_cigars,
+                                               int64_t cigar_pitch, hrm_batch_stats* h_stats, hrm_stream stream)
+{
+    HRM_REQUIRE(m != nullptr && h_reads_ascii != nullptr && h_lengths != nullptr && h_rec_written != nullptr, "args");
+    HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && cigar_pitch > 0, "sizes");
+    HRM_REQUIRE(m->comm == nullptr, "hrm_mapper_map_reads_sam runs on the replicated index");
+    cudaStream_t s = as_stream(stream);
+    *h_rec_written = 0;
+    if (h_sq_written) *h_sq_written = 0;
+    if (h_stats) memset(h_stats, 0, sizeof *h_stats);
+    if (n == 0) return HRM_OK;
+    size_t maxname = 12;
+    for (int c = 0; c < m->n_chrom && h_chrom_names; c++)
+        if (h_chrom_names[c] && strlen(h_chrom_names[c]) > maxname) maxname = strlen(h_chrom_names[c]);
+    const int64_t line_bound = 64 + (int64_t)maxname + cigar_pitch + m->cfg.window_size + ascii_pitch;
+    Scratch d_ascii, d_len, d_mapped, d_rec, d_cig, d_fields, d_ll, d_text, d_sq;
+    HRM_TRY(d_ascii.alloc((size_t)(n * ascii_pitch), s));
+    HRM_TRY(d_len.alloc(sizeof(int32_t) * (size_t)n, s));
+    HRM_TRY(d_mapped.alloc(sizeof(hrm_mapped_read) * (size_t)n, s));
+    HRM_TRY(d_rec.alloc(sizeof(hrm_read_record) * (size_t)n, s));
+    HRM_TRY(d_cig.alloc((size_t)(2 * n * cigar_pitch), s));
+    HRM_TRY(d_fields.alloc(sizeof(hrm_sam_fields) * (size_t)n, s));
+    HRM_TRY(d_ll.alloc(sizeof(int32_t) * (size_t)(2 * n), s));
+    HRM_TRY(d_text.alloc((size_t)(n * line_bound), s));
+    if (h_sq_out) HRM_TRY(d_sq.alloc((size_t)(n * 40), s));
+    HRM_CUDA(cudaMemcpyAsync(d_ascii.p, h_reads_ascii, (size_t)(n * ascii_pitch), cudaMemcpyHostToDevice, s));
+    HRM_CUDA(cudaMemcpyAsync(d_len.p, h_lengths, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+    hrm_batch_stats st;
+    memset(&st, 0, sizeof st);
+    HRM_TRY(hrm_map_batch(m, d_ascii.as<char>(), ascii_pitch, d_len.as<int32_t>(), n, d_mapped.as<hrm_mapped_read>(),
+                          h_stats ? &st : nullptr, stream));
+    HRM_TRY(hrm_verify_batch(m, d_ascii.as<char>(), ascii_pitch, d_len.as<int32_t>(), n, d_mapped.as<hrm_mapped_read>(),
+                             d_rec.as<hrm_read_record>(), d_cig.as<char>(), cigar_pitch, h_stats ? &st : nullptr, stream));
+    // the reads of the batch are still packed in the mapper (hrm_verify_batch packed them)
+    const int64_t launches0 = g_launches.load();
+    HRM_TRY(hrm_sam_format_device(m, nullptr, ascii_pitch, d_len.as<int32_t>(), n, d_rec.as<hrm_read_record>(),
+                                  d_cig.as<char>(), cigar_pitch, first_read_id, h_chrom_names, HRM_SAM_RECORDS,
+                                  d_text.as<char>(), n * line_bound, h_rec_written, stream));
+    if (h_rec_out) {
+        HRM_REQUIRE(*h_rec_written <= rec_cap, "record text does not fit rec_cap");
+        HRM_CUDA(cudaMemcpyAsync(h_rec_out, d_text.p, (size_t)*h_rec_written, cudaMemcpyDeviceToHost, s));
+    }
+    if (h_sq_out && h_sq_written) {
+        HRM_TRY(hrm_sam_format_device(m, nullptr, ascii_pitch, d_len.as<int32_t>(), n, d_rec.as<hrm_read_record>(),
+                                      d_cig.as<char>(), cigar_pitch, first_read_id, h_chrom_names, HRM_SAM_SQ_LINES,
+                                      d_sq.as<char>(), n * 40, h_sq_written, stream));
+        HRM_REQUIRE(*h_sq_written <= sq_cap, "@SQ text does not fit sq_cap");
+        HRM_CUDA(cudaMemcpyAsync(h_sq_out, d_sq.p, (size_t)*h_sq_written, cudaMemcpyDeviceToHost, s));
+    }
+    if (h_records)
+        HRM_CUDA(cudaMemcpyAsync(h_records, d_rec.p, sizeof(hrm_read_record) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    if (h_cigars) HRM_CUDA(cudaMemcpyAsync(h_cigars, d_cig.p, (size_t)(2 * n * cigar_pitch), cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    if (h_stats) {
+        st.num_kernel_launches += g_launches.load() - launches0;
+        *h_stats = st;
+    }
     return HRM_OK;
 }
 

@@ -62,8 +62,10 @@ struct hrm_mapper {
     int64_t num_windows = 0;
     int n_chrom = 0;
     std::vector<int64_t> chrom_len;
-    std::string host_genome; // kept for SAM output (RNEXT column prints the window, ref: mappinghandler.cu:257)
     std::vector<int64_t> chrom_off;
+    // chromosome names on the device for the SAM writer (sam.cu), uploaded when they change
+    std::string names_flat;
+    hrm::GrowBuf d_names, d_name_off;
     // per-batch buffers that only grow
     hrm::GrowBuf packed[3];  // reads packed per read conversion
     hrm::GrowBuf sigs, num, off, newoff, passres, misc;
@@ -82,3 +84,16 @@ struct hrm_mapper {
     std::vector<cudaEvent_t> copy_events;
     hrm_comm* comm = nullptr; // key-partitioned index (partition.cu); not owned
 };
+
+namespace hrm {
+// packs the batch once per distinct read conversion used by the passes (mapper.cu)
+hrm_status mapper_pack_batch(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch, const int32_t* d_lengths,
+                             int64_t n, hrm_stream stream);
+// V4 + O1 on the device (sam.cu)
+hrm_status sam_fields(hrm_mapper* m, const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
+                      const char* d_cigars, int64_t cigar_pitch, uint32_t first_read_id, hrm_sam_fields* d_fields,
+                      int32_t* d_line_len, int32_t* d_sq_len, cudaStream_t s);
+hrm_status sam_text(hrm_mapper* m, const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
+                    const char* d_cigars, int64_t cigar_pitch, const hrm_sam_fields* d_fields, const int32_t* d_len,
+                    uint32_t first_read_id, int part, char* d_out, int64_t cap, int64_t* h_written, cudaStream_t s);
+} // namespace hrm

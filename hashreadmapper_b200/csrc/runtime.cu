@@ -141,8 +141,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_offsets_kernel(int64_t
     if (threadIdx.x == 0 && d_total) *d_total = carry;
 }
 
+template <class OutT>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int32_t* __restrict__ in,
-                                                                  int32_t* __restrict__ out, int64_t n,
+                                                                  OutT* __restrict__ out, int64_t n,
                                                                   const int64_t* __restrict__ tile_offsets)
 {
     const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
@@ -159,13 +160,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int32_t*
 #pragma unroll
     for (int t = 0; t < SCAN_ITEMS; t++) {
         const int64_t i = base + t;
-        if (i < n) out[i] = (int32_t)ex;
+        if (i < n) out[i] = (OutT)ex;
         ex += v[t];
-        if (i == n - 1) out[n] = (int32_t)ex;
+        if (i == n - 1) out[n] = (OutT)ex;
     }
 }
 
-__global__ void scan_empty_kernel(int32_t* out, int64_t* d_total)
+template <class OutT>
+__global__ void scan_empty_kernel(OutT* out, int64_t* d_total)
 {
     out[0] = 0;
     if (d_total) *d_total = 0;
@@ -173,10 +175,11 @@ __global__ void scan_empty_kernel(int32_t* out, int64_t* d_total)
 
 size_t exclusive_scan_scratch_bytes(int64_t n) { return sizeof(int64_t) * (size_t)(HRM_SDIV(n, (int64_t)SCAN_TILE) + 1); }
 
-hrm_status exclusive_scan_i32(const int32_t* d_in, int32_t* d_out, int64_t n, int64_t* d_total64, cudaStream_t s)
+template <class OutT>
+static hrm_status exclusive_scan_impl(const int32_t* d_in, OutT* d_out, int64_t n, int64_t* d_total64, cudaStream_t s)
 {
     if (n <= 0) {
-        HRM_LAUNCH(scan_empty_kernel, 1, 1, 0, s, d_out, d_total64);
+        HRM_LAUNCH(scan_empty_kernel<OutT>, 1, 1, 0, s, d_out, d_total64);
         return HRM_OK;
     }
     const int64_t ntiles = HRM_SDIV(n, (int64_t)SCAN_TILE);
@@ -184,8 +187,18 @@ hrm_status exclusive_scan_i32(const int32_t* d_in, int32_t* d_out, int64_t n, in
     HRM_TRY(tiles.alloc(sizeof(int64_t) * (size_t)ntiles, s));
     HRM_LAUNCH(scan_tile_sums_kernel, (unsigned)ntiles, SCAN_THREADS, 0, s, d_in, n, tiles.as<int64_t>());
     HRM_LAUNCH(scan_tile_offsets_kernel, 1, SCAN_THREADS, 0, s, tiles.as<int64_t>(), ntiles, d_total64);
-    HRM_LAUNCH(scan_apply_kernel, (unsigned)ntiles, SCAN_THREADS, 0, s, d_in, d_out, n, tiles.as<int64_t>());
+    HRM_LAUNCH(scan_apply_kernel<OutT>, (unsigned)ntiles, SCAN_THREADS, 0, s, d_in, d_out, n, tiles.as<int64_t>());
     return HRM_OK;
+}
+
+hrm_status exclusive_scan_i32(const int32_t* d_in, int32_t* d_out, int64_t n, int64_t* d_total64, cudaStream_t s)
+{
+    return exclusive_scan_impl<int32_t>(d_in, d_out, n, d_total64, s);
+}
+// same input, 64-bit offsets (byte offsets of text lines: a batch of SAM text exceeds 2 GiB)
+hrm_status exclusive_scan_i32_to_i64(const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* d_total64, cudaStream_t s)
+{
+    return exclusive_scan_impl<int64_t>(d_in, d_out, n, d_total64, s);
 }
 
 } // namespace hrm

@@ -109,6 +109,8 @@ struct GrowBuf {
 // out[i] = sum_{t<i} in[t] for i in [0, n]; out has n+1 entries; *d_total64 (optional) = int64 sum.
 hrm_status exclusive_scan_i32(const int32_t* d_in, int32_t* d_out, int64_t n, int64_t* d_total64,
                               cudaStream_t s);
+hrm_status exclusive_scan_i32_to_i64(const int32_t* d_in, int64_t* d_out, int64_t n, int64_t* d_total64,
+                                     cudaStream_t s);
 size_t exclusive_scan_scratch_bytes(int64_t n);
 
 } // namespace hrm

@@ -1,120 +1,534 @@
-// sam.cu -- O1: SAM-like text output (host side, no device work).
-// ref: Mappinghandler::printtoSAM src/gpu/mappinghandler.cu:196-293 (SW mode), mapqfkt :184-193.
-// Reproduced literally: "@HD", one "@SQ SN:<readId> LN:<windowlength>" per read, "@PG...@CO..." on
-// one line, then per read 12 tab-separated columns + trailing tab; the window bases go to the RNEXT
-// column; unmapped records (flag & 0x4) print the numeric flag in the TAG column.
-// NOT reproduced: the score "recalculation" of mappinghandler.cu:601-766, which reads freed memory
-// and out-of-bounds genome.  Scores are the raw SSW scores, Yf:i:<n> prints 0.
+// sam.cu -- V4 + O1 on the device: score recalculation / conversion count, choice of the alignment, MAPQ, POS and
+// the SAM text itself.
+// ref: Mappinghandler::CSSW recalculateAlignmentScorefk / comparefk src/gpu/mappinghandler.cu:601-766,
+//      mapqfkt :184-193, printtoSAM :196-293 (single host thread, std::ofstream).
+// Semantics = the UB-patched reference of SURVEY's parity contract (Tier 2), i.e. what oracle/ref_shim_sam.cpp
+// runs and oracle/hrm_oracle.c: orc_sam_record restates -- the two query strings owned, rc_ref reading NUL beyond
+// the chromosome; every other quirk kept (alignment 0 walked with the reverse-complement query, the 82-base
+// limit, uint16 score wrap, MAPQ 4 for out-of-range double -> uint32 conversions).  A pass sees its own converted
+// reads and genome (one pass = the reference on pre-converted input); a pass that verifies with G->A is
+// the reference's stage on the complemented sequences, which only changes the query letter tested.
+//
+// Two kernels per batch: sam_fields_kernel (thread per read: V4 + the byte length of the read's record line and
+// of its @SQ line), an exclusive scan, sam_write_kernel (warp per read: the line, bytes striped over the lanes,
+// window and read decoded from the packed genome / packed read).  HBM bound: ~0.35 KB written per read.
+#include "pipeline.cuh"
+#include "hrm_common.cuh"
 #include "mapper.hpp"
 #include <math.h>
 #include <string.h>
+#include <mutex>
 #include <string>
+#include <vector>
 
-namespace {
+namespace hrm {
 
-// ref: mapqfkt mappinghandler.cu:184-193; guarded for s1 == 0 (reference: NaN -> UB)
-uint32_t mapq_of(int s1, int s2)
+// ---- MAPQ --------------------------------------------------------------------------------------------------
+// ref: mapqfkt: uint32 m = -4.343 * log(1 - |s1 - s2| / s1); m = uint32(m + 4.99); min(m, 254), scores uint16.
+// For 0 < |s1 - s2| < s1 the first conversion is floor(v), v = -4.343 * log(x), x = 1 - d / s1 in (0, 1); otherwise the
+// double is -0, inf or NaN and the conversion yields 0 on x86-64.  floor(v) >= t  <=>  x <= X_t, X_t = the largest
+// double with -4.343 * log(X_t) >= t.  The thresholds are found ONCE on the host with the host's own libm (the one the
+// reference's binary would call), so the device needs no log and cannot differ from it by an ulp.
+constexpr int MAPQ_T = 64;
+__constant__ double c_mapq_x[MAPQ_T];
+
+static hrm_status mapq_thresholds_upload()
 {
-    if (s1 <= 0) return 0;
-    const double v = -4.343 * log(1.0 - (double)abs(s1 - s2) / (double)s1);
-    uint32_t m = (uint32_t)v;
-    m = (uint32_t)(m + 4.99);
+    static std::once_flag once[64];
+    static cudaError_t err[64];
+    int dev = 0;
+    HRM_CUDA(cudaGetDevice(&dev));
+    std::call_once(once[dev & 63], [&] {
+        double X[MAPQ_T];
+        for (int t = 1; t <= MAPQ_T; t++) {
+            // positive doubles order like their bit patterns
+            uint64_t lo = 1, hi = 0x3FF0000000000000ULL; // (0, 1.0]: v(lo) is huge, v(1.0) = -0 < t
+            while (hi - lo > 1) {
+                const uint64_t mid = lo + (hi - lo) / 2;
+                double x;
+                memcpy(&x, &mid, 8);
+                if (-4.343 * log(x) >= (double)t) lo = mid;
+                else hi = mid;
+            }
+            memcpy(&X[t - 1], &lo, 8);
+        }
+        err[dev & 63] = cudaMemcpyToSymbol(c_mapq_x, X, sizeof X);
+    });
+    HRM_CUDA(err[dev & 63]);
+    return HRM_OK;
+}
+
+__device__ __forceinline__ int mapq_u16(int s1, int s2)
+{
+    const int d = abs(s1 - s2);
+    if (s1 <= 0 || d == 0 || d >= s1) return 4;
+    const double x = 1 - (double)d / (double)s1;
+    int m = 0;
+#pragma unroll 1
+    for (int t = 0; t < MAPQ_T && x <= c_mapq_x[t]; t++) m++;
+    m += 4;
     return m < 254 ? m : 254;
 }
 
-char comp(char c)
+// ---- small text helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ int dec_digits(uint32_t v)
 {
-    switch (c) {
-    case 'A': return 'T';
-    case 'C': return 'G';
-    case 'G': return 'C';
-    case 'T': return 'A';
-    default: return 'T'; // non-ACGT packs as A (ref: sequencehelpers.hpp:195-211), whose complement is T
+    int n = 1;
+    while (v >= 10) {
+        v /= 10;
+        n++;
+    }
+    return n;
+}
+__device__ __forceinline__ int put_dec(char* o, uint32_t v) // returns the number of characters
+{
+    const int n = dec_digits(v);
+    for (int i = n - 1; i >= 0; i--) {
+        o[i] = (char)('0' + v % 10);
+        v /= 10;
+    }
+    return n;
+}
+__device__ __forceinline__ int put_sdec(char* o, int64_t v)
+{
+    int n = 0;
+    if (v < 0) {
+        o[n++] = '-';
+        v = -v;
+    }
+    return n + put_dec(o + n, (uint32_t)v);
+}
+
+struct SamSrc {
+    VerifyParams VP;
+    const int32_t* read_len;
+    const hrm_read_record* records;
+    const char* cigars;
+    int64_t cigar_pitch;
+    const char* names;        // chromosome names back to back
+    const int32_t* name_off;  // n_chrom + 1
+    uint32_t first_read_id;
+};
+
+// what a record line is made of (shared by the length and the write kernel)
+struct SamRead {
+    bool mapped;
+    int pass, chrom, L, wl, a;
+    int64_t wpos;
+    const uint32_t* rw; // packed read of its pass
+    const uint32_t* cw; // packed chromosome of its pass
+    bool seq_rc;        // SEQ = RC(stored read)
+};
+__device__ __forceinline__ SamRead sam_open(const SamSrc& S, int64_t r, const hrm_mapped_read& m)
+{
+    SamRead R;
+    R.mapped = m.orientation != HRM_ORIENT_NONE && m.pass >= 0 && m.pass < S.VP.num_passes;
+    R.pass = R.mapped ? m.pass : 0;      // unmapped reads print from pass 0 ...
+    R.chrom = R.mapped ? m.chromosome_id : 0; // ... against MappedRead's defaults (mappedread.cuh:6-12)
+    R.wpos = R.mapped ? m.position : 0;
+    const VerifyPass& P = S.VP.pass[R.pass];
+    const int64_t clen = P.G.chrom_len[R.chrom];
+    R.wl = (int)((R.wpos + S.VP.w < clen) ? S.VP.w : clen - R.wpos); // ref: mappinghandler.cu:434-440
+    R.L = S.read_len[r];
+    R.rw = P.reads + r * P.read_pitch;
+    R.cw = P.G.chrom_words[R.chrom];
+    R.seq_rc = R.mapped && m.orientation == HRM_ORIENT_REVCOMP; // ref: :420-425
+    R.a = 0;
+    return R;
+}
+
+// ref: recalculateAlignmentScorefk (:601-745) for alignment h; returns the number of conversions
+__device__ int recalc_conversions(const SamRead& R, int h, const char* cigar, int cigar_len, bool mirror)
+{
+    // h == 0 walks the reverse-complement query (`if(!h) _query = aa.rc_query`, :608), h == 1 the forward one
+    const bool qrc = R.seq_rc != (h == 0);
+    const int qtest = mirror ? 0 : 3; // 'T'; in the complemented (G->A) world that is our 'A'
+    int refPos = 0, altPos = 0, conv = 0, bases = 0;
+    for (int c = 0; c < cigar_len; c++) {
+        const char ch = cigar[c];
+        if (ch >= '0' && ch <= '9') {
+            bases = bases * 10 + (ch - '0');
+            continue;
+        }
+        const int len = bases;
+        bases = 0;
+        const int mx = refPos > altPos ? refPos : altPos;
+        const int bl = 82 - mx < len ? 82 - mx : len; // SEQ_READ_SIZE (:618)
+        if (ch == '=') {
+            for (int i = 0; i < bl; i++) {
+                const int qi = altPos + i, ri = refPos + i;
+                const int q = qrc ? 3 - (int)get_nuc(R.rw, R.L - 1 - qi) : (int)get_nuc(R.rw, qi);
+                if (q != qtest) continue;
+                const int rr = (int)get_nuc(R.cw, R.wpos + ri);
+                if (rr != 1 && rr != 2) continue;
+                if (R.wpos - ri < 0) continue; // rc_ref beyond the chromosome: NUL
+                const int rcw = 3 - (int)get_nuc(R.cw, R.wpos - ri); // rc_ref[i] = complement(chrom[pos - i]) (:447-449)
+                if (rcw == 3 - rr) conv++;
+            }
+            refPos += bl;
+            altPos += bl;
+        } else if (ch == 'X' || ch == 'M') { // 'M' is never produced by the aligner (ssw_cpp.cpp:126-210)
+            refPos += bl;
+            altPos += bl;
+        } else if (ch == 'I' || ch == 'S') {
+            altPos += bl;
+        } else if (ch == 'D' || ch == 'N') {
+            refPos += bl;
+        }
+    }
+    return conv;
+}
+
+__device__ __forceinline__ int sam_tag_len(const SamRead& R, const hrm_sam_fields& f)
+{
+    return R.mapped ? 6 + dec_digits((uint32_t)f.num_conversions[f.chosen]) + 1 + 8 : 1;
+}
+
+__global__ void __launch_bounds__(128) sam_fields_kernel(SamSrc S, int64_t n, hrm_sam_fields* __restrict__ fields,
+                                                         int32_t* __restrict__ line_len, int32_t* __restrict__ sq_len)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        const hrm_read_record& rec = S.records[r];
+        const hrm_mapped_read m = rec.mapped;
+        const SamRead R = sam_open(S, r, m);
+        hrm_sam_fields f;
+        int clen[2] = {0, 0};
+        for (int h = 0; h < 2; h++) {
+            const hrm_alignment& A = rec.alignments[h];
+            int s1 = A.sw_score & 0xffff, s2 = A.sw_score_next_best & 0xffff;
+            int conv = 0;
+            if (R.mapped) {
+                clen[h] = (int)(A.cigar_len < S.cigar_pitch ? A.cigar_len : S.cigar_pitch);
+                conv = recalc_conversions(R, h, S.cigars + (2 * r + h) * S.cigar_pitch, clen[h],
+                                          S.VP.pass[R.pass].verify_conv == HRM_CONV_GA);
+                s1 = (s1 - 4 * conv) & 0xffff; // -2 (the match) + getScore(T, C|G) = -2, on a uint16_t (ssw_cpp.h:15-16)
+                s2 = (s2 - 4 * conv) & 0xffff;
+            } else {
+                s1 = s2 = 0;
+            }
+            f.sw_score[h] = s1;
+            f.sw_score_next_best[h] = s2;
+            f.num_conversions[h] = conv;
+        }
+        const int a = f.sw_score[0] >= f.sw_score[1] ? 0 : 1; // ref: :222
+        f.chosen = a;
+        f.flag = R.mapped ? (rec.alignments[a].flag & 0xffff) : (a == 0 ? 4 : 0);
+        f.mapq = mapq_u16(f.sw_score[a], f.sw_score_next_best[a]);
+        f.window_length = R.wl;
+        f.pos = (int32_t)(R.wpos + (R.mapped ? rec.alignments[a].query_begin : 0)); // ref: :236 (int)
+        fields[r] = f;
+        if (line_len) {
+            const uint32_t id = S.first_read_id + (uint32_t)r;
+            const int namelen = S.name_off[R.chrom + 1] - S.name_off[R.chrom];
+            const int poslen = (f.pos < 0 ? 1 : 0) + dec_digits((uint32_t)(f.pos < 0 ? -f.pos : f.pos));
+            line_len[r] = dec_digits(id) + 1 + dec_digits((uint32_t)f.flag) + 1 + namelen + 1 + poslen + 1 +
+                          dec_digits((uint32_t)f.mapq) + 1 + (R.mapped ? clen[a] : 0) + 1 + R.wl + 4 + R.L + 3 +
+                          sam_tag_len(R, f) + 2;
+            sq_len[r] = 7 + dec_digits(id) + 4 + dec_digits((uint32_t)R.wl) + 1;
+        }
     }
 }
-char canon(char c) { return (c == 'A' || c == 'C' || c == 'G' || c == 'T') ? c : 'A'; }
 
-} // namespace
+// "@SQ\tSN:<readId>\tLN:<windowlength>\n" per read (ref: :207-212)
+__global__ void __launch_bounds__(128) sam_write_sq_kernel(SamSrc S, int64_t n, const hrm_sam_fields* __restrict__ fields,
+                                                           const int64_t* __restrict__ off, char* __restrict__ out,
+                                                           int64_t cap)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        if (off[r + 1] > cap) continue;
+        char b[40];
+        int p = 0;
+        const char h1[] = "@SQ\tSN:", h2[] = "\tLN:";
+        for (int i = 0; i < 7; i++) b[p++] = h1[i];
+        p += put_dec(b + p, S.first_read_id + (uint32_t)r);
+        for (int i = 0; i < 4; i++) b[p++] = h2[i];
+        p += put_dec(b + p, (uint32_t)fields[r].window_length);
+        b[p++] = '\n';
+        char* o = out + off[r];
+        for (int i = 0; i < p; i++) o[i] = b[i];
+    }
+}
 
-extern "C" hrm_status hrm_sam_format(const hrm_mapper* m, const hrm_read_record* h_records, const char* h_cigars,
+// one record line per warp (ref: :251-268 mapped, :272-288 unmapped)
+__global__ void __launch_bounds__(256) sam_write_kernel(SamSrc S, int64_t n, const hrm_sam_fields* __restrict__ fields,
+                                                        const int64_t* __restrict__ off, char* __restrict__ out,
+                                                        int64_t cap)
+{
+    __shared__ char sbuf[8][96];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    char* pre = sbuf[wib];
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; r < n; r += nwarps) {
+        const int64_t o0 = off[r], o1 = off[r + 1];
+        if (o1 > cap) continue; // whole lines only
+        const hrm_read_record& rec = S.records[r];
+        const hrm_mapped_read m = rec.mapped;
+        const SamRead R = sam_open(S, r, m);
+        const hrm_sam_fields f = fields[r];
+        const int a = f.chosen;
+        const int namelen = S.name_off[R.chrom + 1] - S.name_off[R.chrom];
+        const int cl = R.mapped ? (int)(rec.alignments[a].cigar_len < S.cigar_pitch ? rec.alignments[a].cigar_len
+                                                                                     : S.cigar_pitch)
+                                : 0;
+        // lane 0: the numeric pieces.  pre = "<id>\t<flag>\t" | name | "\t<pos>\t<mapq>\t";  tag at pre + 64
+        int p1 = 0, p2 = 0, tl = 0;
+        __syncwarp();
+        if (lane == 0) {
+            p1 = put_dec(pre, S.first_read_id + (uint32_t)r);
+            pre[p1++] = '\t';
+            p1 += put_dec(pre + p1, (uint32_t)f.flag);
+            pre[p1++] = '\t';
+            char* q = pre + 24;
+            q[p2++] = '\t';
+            p2 += put_sdec(q + p2, f.pos);
+            q[p2++] = '\t';
+            p2 += put_dec(q + p2, (uint32_t)f.mapq);
+            q[p2++] = '\t';
+            char* t = pre + 56;
+            if (R.mapped) {
+                const char y[] = "Yf:i:<";
+                for (int i = 0; i < 6; i++) t[tl++] = y[i];
+                tl += put_dec(t + tl, (uint32_t)f.num_conversions[a]);
+                const char z[] = ">YZ:A:<";
+                for (int i = 0; i < 7; i++) t[tl++] = z[i];
+                t[tl++] = a == 0 ? '+' : '-';
+                t[tl++] = '>';
+            } else {
+                t[tl++] = '4'; // the TAG column prints AlignerArguments::flag (:287)
+            }
+        }
+        p1 = __shfl_sync(0xffffffffu, p1, 0);
+        p2 = __shfl_sync(0xffffffffu, p2, 0);
+        tl = __shfl_sync(0xffffffffu, tl, 0);
+        __syncwarp();
+        // segment boundaries
+        const int b1 = p1, b2 = b1 + namelen, b3 = b2 + p2, b4 = b3 + cl, b5 = b4 + 1, b6 = b5 + R.wl, b7 = b6 + 4,
+                  b8 = b7 + R.L, b9 = b8 + 3, b10 = b9 + tl, total = b10 + 2;
+        if (total != (int)(o1 - o0)) continue; // cannot happen (same arithmetic as sam_fields_kernel)
+        const char* nm = S.names + S.name_off[R.chrom];
+        const char* cg = S.cigars + (2 * r + a) * S.cigar_pitch;
+        char* o = out + o0;
+        for (int j = lane; j < total; j += 32) {
+            char c;
+            if (j < b1) c = pre[j];
+            else if (j < b2) c = nm[j - b1];
+            else if (j < b3) c = pre[24 + j - b2];
+            else if (j < b4) c = cg[j - b3];
+            else if (j < b5) c = '\t';
+            else if (j < b6) c = "ACGT"[get_nuc(R.cw, R.wpos + (j - b5))];      // RNEXT column: the window (:257)
+            else if (j < b7) c = "\t\t0\t"[j - b6];
+            else if (j < b8) {
+                const int t = j - b7;                                            // SEQ: readsequence (:262)
+                c = "ACGT"[R.seq_rc ? 3 - get_nuc(R.rw, R.L - 1 - t) : get_nuc(R.rw, t)];
+            } else if (j < b9) c = "\t*\t"[j - b8];
+            else if (j < b10) c = pre[56 + j - b9];
+            else c = j == b10 ? '\t' : '\n';
+            o[j] = c;
+        }
+    }
+}
+
+static unsigned sgrid(int64_t items, int per_block, int per_sm)
+{
+    int64_t g = HRM_SDIV(items, (int64_t)per_block);
+    const int64_t cap = (int64_t)num_sms() * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+} // namespace hrm
+
+using namespace hrm;
+
+// chromosome names on the device (uploaded when they change)
+static hrm_status upload_names(hrm_mapper* m, const char* const* h_chrom_names, cudaStream_t s)
+{
+    std::string flat;
+    std::vector<int32_t> off(1, 0);
+    for (int c = 0; c < m->n_chrom; c++) {
+        if (h_chrom_names && h_chrom_names[c]) flat += h_chrom_names[c];
+        else flat += std::to_string(c);
+        off.push_back((int32_t)flat.size());
+    }
+    if (m->names_flat == flat && m->d_names.p) return HRM_OK;
+    HRM_TRY(m->d_names.reserve(flat.size() + 16));
+    HRM_TRY(m->d_name_off.reserve(sizeof(int32_t) * off.size()));
+    HRM_CUDA(cudaMemcpyAsync(m->d_names.p, flat.data(), flat.size(), cudaMemcpyHostToDevice, s));
+    HRM_CUDA(cudaMemcpyAsync(m->d_name_off.p, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice, s));
+    HRM_CUDA(cudaStreamSynchronize(s)); // the host vectors die here
+    m->names_flat = flat;
+    return HRM_OK;
+}
+
+static hrm_status make_src(hrm_mapper* m, const int32_t* d_lengths, const hrm_read_record* d_records, const char* d_cigars,
+                           int64_t cigar_pitch, uint32_t first_read_id, SamSrc& S)
+{
+    const hrm_mapper_config& cfg = m->cfg;
+    memset(&S, 0, sizeof S);
+    S.VP.num_passes = cfg.num_passes;
+    S.VP.w = cfg.window_size;
+    S.VP.mapper_type = cfg.mapper_type;
+    for (int p = 0; p < cfg.num_passes; p++) {
+        HRM_REQUIRE(m->packed[cfg.read_conversion[p]].p != nullptr, "reads of the batch are not packed");
+        S.VP.pass[p].reads = m->packed[cfg.read_conversion[p]].as<uint32_t>();
+        S.VP.pass[p].read_pitch = m->packed_pitch;
+        S.VP.pass[p].G = m->genome[cfg.genome_conversion[p]]->dev();
+        S.VP.pass[p].verify_conv = cfg.verify_conversion[p];
+    }
+    S.read_len = d_lengths;
+    S.records = d_records;
+    S.cigars = d_cigars;
+    S.cigar_pitch = cigar_pitch;
+    S.names = m->d_names.as<char>();
+    S.name_off = m->d_name_off.as<int32_t>();
+    S.first_read_id = first_read_id;
+    return HRM_OK;
+}
+
+namespace hrm {
+// V4 of a batch whose reads are packed in the mapper (pack_batch ran on this batch): fields (+ line lengths)
+hrm_status sam_fields(hrm_mapper* m, const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
+                      const char* d_cigars, int64_t cigar_pitch, uint32_t first_read_id, hrm_sam_fields* d_fields,
+                      int32_t* d_line_len, int32_t* d_sq_len, cudaStream_t s)
+{
+    if (n == 0) return HRM_OK;
+    HRM_TRY(mapq_thresholds_upload());
+    SamSrc S;
+    HRM_TRY(make_src(m, d_lengths, d_records, d_cigars, cigar_pitch, first_read_id, S));
+    HRM_LAUNCH(sam_fields_kernel, sgrid(n, 128, 16), 128, 0, s, S, n, d_fields, d_line_len, d_sq_len);
+    return HRM_OK;
+}
+
+// the text of one part (0: @SQ lines, 1: record lines) of a batch into d_out; *h_written = bytes of the part.
+// Lines that would cross `cap` are not written.  Synchronises the stream (the size comes back to the host).
+hrm_status sam_text(hrm_mapper* m, const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
+                    const char* d_cigars, int64_t cigar_pitch, const hrm_sam_fields* d_fields, const int32_t* d_len,
+                    uint32_t first_read_id, int part, char* d_out, int64_t cap, int64_t* h_written, cudaStream_t s)
+{
+    *h_written = 0;
+    if (n == 0) return HRM_OK;
+    SamSrc S;
+    HRM_TRY(make_src(m, d_lengths, d_records, d_cigars, cigar_pitch, first_read_id, S));
+    Scratch off;
+    HRM_TRY(off.alloc(sizeof(int64_t) * (size_t)(n + 2), s));
+    int64_t* d_total = off.as<int64_t>() + n + 1;
+    HRM_TRY(exclusive_scan_i32_to_i64(d_len, off.as<int64_t>(), n, d_total, s));
+    if (d_out && cap > 0) {
+        if (part == HRM_SAM_SQ_LINES)
+            HRM_LAUNCH(sam_write_sq_kernel, sgrid(n, 128, 16), 128, 0, s, S, n, d_fields, off.as<int64_t>(), d_out, cap);
+        else
+            HRM_LAUNCH(sam_write_kernel, sgrid(n, 8, 8), 256, 0, s, S, n, d_fields, off.as<int64_t>(), d_out, cap);
+    }
+    HRM_CUDA(cudaMemcpyAsync(h_written, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    return HRM_OK;
+}
+} // namespace hrm
+
+extern "C" hrm_status hrm_sam_fields_batch(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch,
+                                           const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
+                                           const char* d_cigars, int64_t cigar_pitch, hrm_sam_fields* d_fields,
+                                           hrm_stream stream)
+{
+    HRM_REQUIRE(m != nullptr && d_fields != nullptr, "args");
+    HRM_REQUIRE(m->d_win_prefix != nullptr, "hrm_mapper_set_genome has not been called");
+    HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && cigar_pitch > 0, "sizes");
+    if (n == 0) return HRM_OK;
+    HRM_TRY(upload_names(m, nullptr, as_stream(stream)));
+    HRM_TRY(mapper_pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
+    return sam_fields(m, d_lengths, n, d_records, d_cigars, cigar_pitch, 0, d_fields, nullptr, nullptr, as_stream(stream));
+}
+
+extern "C" hrm_status hrm_sam_format_device(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch,
+                                            const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
+                                            const char* d_cigars, int64_t cigar_pitch, uint32_t first_read_id,
+                                            const char* const* h_chrom_names, int part, char* d_out, int64_t cap,
+                                            int64_t* h_written, hrm_stream stream)
+{
+    HRM_REQUIRE(m != nullptr && h_written != nullptr, "args");
+    HRM_REQUIRE(m->d_win_prefix != nullptr, "hrm_mapper_set_genome has not been called");
+    HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && cigar_pitch > 0, "sizes");
+    HRM_REQUIRE(part == HRM_SAM_SQ_LINES || part == HRM_SAM_RECORDS, "part");
+    cudaStream_t s = as_stream(stream);
+    *h_written = 0;
+    if (n == 0) return HRM_OK;
+    HRM_TRY(upload_names(m, h_chrom_names, s));
+    // d_reads_ascii == NULL: the batch is still packed in the mapper (hrm_verify_batch just ran on it)
+    if (d_reads_ascii) HRM_TRY(mapper_pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
+    Scratch fields, len;
+    HRM_TRY(fields.alloc(sizeof(hrm_sam_fields) * (size_t)n, s));
+    HRM_TRY(len.alloc(sizeof(int32_t) * (size_t)(2 * n), s));
+    HRM_TRY(sam_fields(m, d_lengths, n, d_records, d_cigars, cigar_pitch, first_read_id, fields.as<hrm_sam_fields>(),
+                       len.as<int32_t>(), len.as<int32_t>() + n, s));
+    return sam_text(m, d_lengths, n, d_records, d_cigars, cigar_pitch, fields.as<hrm_sam_fields>(),
+                    len.as<int32_t>() + (part == HRM_SAM_SQ_LINES ? n : 0), first_read_id, part, d_out, cap, h_written, s);
+}
+
+// Host buffers in, host text out: copies to the device, formats there, copies the text back (no CPU formatter).
+extern "C" hrm_status hrm_sam_format(hrm_mapper* m, const hrm_read_record* h_records, const char* h_cigars,
                                      int64_t cigar_pitch, const char* h_reads_ascii, int64_t ascii_pitch,
                                      const int32_t* h_lengths, int64_t n, uint32_t first_read_id,
                                      const char* const* h_chrom_names, int with_header, char* h_out, int64_t cap,
                                      int64_t* h_written)
 {
-    using hrm::set_error;
     HRM_REQUIRE(m != nullptr && h_records != nullptr && h_cigars != nullptr && h_reads_ascii != nullptr &&
                     h_lengths != nullptr && h_written != nullptr,
                 "args");
-    HRM_REQUIRE(n >= 0 && cigar_pitch > 0 && ascii_pitch > 0, "sizes");
-    std::string out;
-    out.reserve((size_t)n * 640 + 256);
-    if (with_header) {
-        out += "@HD\tVN:1.4\n";
-        for (int64_t i = 0; i < n; i++) {
-            out += "@SQ\tSN:";
-            out += std::to_string(first_read_id + (uint32_t)i);
-            out += "\tLN:";
-            out += std::to_string(h_records[i].window_length);
-            out += "\n";
+    HRM_REQUIRE(m->d_win_prefix != nullptr, "hrm_mapper_set_genome has not been called");
+    HRM_REQUIRE(n >= 0 && cigar_pitch > 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0, "sizes");
+    cudaStream_t s = cudaStreamPerThread;
+    static const char HD[] = HRM_SAM_HD, PG[] = HRM_SAM_PG_CO;
+    const int64_t hd = (int64_t)sizeof(HD) - 1, pg = (int64_t)sizeof(PG) - 1;
+    int64_t at = 0;
+    auto emit_host = [&](const char* b, int64_t l) {
+        if (h_out && at < cap) memcpy(h_out + at, b, (size_t)(at + l <= cap ? l : cap - at));
+        at += l;
+    };
+    if (n == 0) {
+        if (with_header) {
+            emit_host(HD, hd);
+            emit_host(PG, pg);
         }
-        out += "@PG\tHashreadmapper\tID:1.0";
-        out += "@CO: QNAME\tFLAG\tRNAME\tPOS\tMAPQ\tCIGAR\tRNEXT\tPNEXT\tTLEN\tSEQ\tQUAL\tTAG\n";
+        *h_written = at;
+        return HRM_OK;
     }
-    const std::string& G = m->host_genome;
-    const int w = m->cfg.window_size;
-    for (int64_t i = 0; i < n; i++) {
-        const hrm_read_record& R = h_records[i];
-        const bool mapped = R.mapped.orientation != HRM_ORIENT_NONE;
-        const int a = R.alignments[0].sw_score >= R.alignments[1].sw_score ? 0 : 1;
-        const hrm_alignment& A = R.alignments[a];
-        const int chrom = mapped ? R.mapped.chromosome_id : 0;
-        const int64_t wpos = mapped ? R.mapped.position : 0;
-        const int64_t clen = m->chrom_off[chrom + 1] - m->chrom_off[chrom];
-        const int64_t wl = (wpos + w < clen) ? w : clen - wpos; // ref: mappinghandler.cu:434-440
-        const char* win = G.data() + (m->chrom_off[chrom] - m->chrom_off[0]) + wpos;
-        const int L = h_lengths[i];
-        const char* rd = h_reads_ascii + i * ascii_pitch;
-        std::string seq((size_t)L, 'A');
-        if (mapped && R.mapped.orientation == HRM_ORIENT_REVCOMP)
-            for (int t = 0; t < L; t++) seq[t] = comp(rd[L - 1 - t]);
-        else
-            for (int t = 0; t < L; t++) seq[t] = canon(rd[t]);
-        const uint32_t flag = mapped ? (uint32_t)A.flag : 0x4u;
-        const uint32_t mapq = mapped ? mapq_of(A.sw_score, A.sw_score_next_best) : 0u;
-        const int64_t pos = wpos + (mapped ? A.query_begin : 0); // ref: POS = windowPos + query_begin (:236,:250)
-        out += std::to_string(first_read_id + (uint32_t)i);
-        out += '\t';
-        out += std::to_string(flag);
-        out += '\t';
-        out += h_chrom_names ? h_chrom_names[chrom] : std::to_string(chrom).c_str();
-        out += '\t';
-        out += std::to_string(pos);
-        out += '\t';
-        out += std::to_string(mapq);
-        out += '\t';
-        if (mapped) {
-            const char* c = h_cigars + (2 * i + a) * cigar_pitch;
-            const int64_t cl = A.cigar_len < cigar_pitch ? A.cigar_len : cigar_pitch;
-            out.append(c, (size_t)cl);
+    Scratch d_rec, d_cig, d_ascii, d_len, fields, len, text;
+    HRM_TRY(d_rec.alloc(sizeof(hrm_read_record) * (size_t)n, s));
+    HRM_TRY(d_cig.alloc((size_t)(2 * n * cigar_pitch), s));
+    HRM_TRY(d_ascii.alloc((size_t)(n * ascii_pitch), s));
+    HRM_TRY(d_len.alloc(sizeof(int32_t) * (size_t)n, s));
+    HRM_TRY(fields.alloc(sizeof(hrm_sam_fields) * (size_t)n, s));
+    HRM_TRY(len.alloc(sizeof(int32_t) * (size_t)(2 * n), s));
+    HRM_CUDA(cudaMemcpyAsync(d_rec.p, h_records, sizeof(hrm_read_record) * (size_t)n, cudaMemcpyHostToDevice, s));
+    HRM_CUDA(cudaMemcpyAsync(d_cig.p, h_cigars, (size_t)(2 * n * cigar_pitch), cudaMemcpyHostToDevice, s));
+    HRM_CUDA(cudaMemcpyAsync(d_ascii.p, h_reads_ascii, (size_t)(n * ascii_pitch), cudaMemcpyHostToDevice, s));
+    HRM_CUDA(cudaMemcpyAsync(d_len.p, h_lengths, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+    HRM_TRY(upload_names(m, h_chrom_names, s));
+    HRM_TRY(mapper_pack_batch(m, d_ascii.as<char>(), ascii_pitch, d_len.as<int32_t>(), n, (hrm_stream)s));
+    HRM_TRY(sam_fields(m, d_len.as<int32_t>(), n, d_rec.as<hrm_read_record>(), d_cig.as<char>(), cigar_pitch, first_read_id,
+                       fields.as<hrm_sam_fields>(), len.as<int32_t>(), len.as<int32_t>() + n, s));
+    // sizes first, then the text of each part straight behind the previous one
+    for (int part = with_header ? 0 : 1; part < 2; part++) {
+        if (part == 0) emit_host(HD, hd);
+        const int32_t* d_l = len.as<int32_t>() + (part == HRM_SAM_SQ_LINES ? n : 0);
+        int64_t bytes = 0;
+        HRM_TRY(sam_text(m, d_len.as<int32_t>(), n, d_rec.as<hrm_read_record>(), d_cig.as<char>(), cigar_pitch,
+                         fields.as<hrm_sam_fields>(), d_l, first_read_id, part, nullptr, 0, &bytes, s));
+        if (h_out && at < cap && bytes > 0) {
+            const int64_t room = cap - at;
+            HRM_TRY(text.alloc((size_t)bytes, s));
+            int64_t again = 0;
+            HRM_TRY(sam_text(m, d_len.as<int32_t>(), n, d_rec.as<hrm_read_record>(), d_cig.as<char>(), cigar_pitch,
+                             fields.as<hrm_sam_fields>(), d_l, first_read_id, part, text.as<char>(), bytes, &again, s));
+            HRM_CUDA(cudaMemcpyAsync(h_out + at, text.p, (size_t)(bytes <= room ? bytes : room), cudaMemcpyDeviceToHost, s));
+            HRM_CUDA(cudaStreamSynchronize(s));
         }
-        out += '\t';
-        out.append(win, (size_t)wl);
-        out += "\t\t0\t";
-        out += seq;
-        out += "\t*\t";
-        if (mapped) {
-            out += "Yf:i:<0>";
-            out += a == 0 ? "YZ:A:<+>" : "YZ:A:<->";
-        } else {
-            out += std::to_string(flag);
-        }
-        out += "\t\n";
+        at += bytes;
+        if (part == 0) emit_host(PG, pg);
     }
-    *h_written = (int64_t)out.size();
-    if (h_out && cap > 0) {
-        const size_t c = out.size() < (size_t)cap ? out.size() : (size_t)cap;
-        memcpy(h_out, out.data(), c);
-    }
+    *h_written = at;
     return HRM_OK;
 }

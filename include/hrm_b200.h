@@ -47,7 +47,7 @@ typedef void* hrm_stream;
 
 const char* hrm_last_error(void);   /* thread-local text of the last failure */
 int hrm_abi_version(void);          /* HRM_ABI_VERSION this library was built with */
-#define HRM_ABI_VERSION 1
+#define HRM_ABI_VERSION 2
 int hrm_device_count(void);         /* number of visible CUDA devices (0 => nothing can run) */
 
 /* ------------------------------------------------------------------------------------------
@@ -513,16 +513,72 @@ int hrm_key_owner(uint64_t key, int world);
 hrm_status hrm_minhasher_set_partition(hrm_minhasher* mh, int rank, int world);
 hrm_status hrm_mapper_set_partition(hrm_mapper* m, hrm_comm* comm);
 
-/* ref: Mappinghandler::printtoSAM src/gpu/mappinghandler.cu:196-293 (SW mode).  Host-side text
- * formatting of n records into h_out (capacity cap); *h_written = bytes needed.  `with_header`
- * emits the @HD/@SQ/@PG/@CO block.  first_read_id = id of record 0.  h_chrom_names: n_chrom
- * NUL-terminated names.  The score "recalculation" of mappinghandler.cu:601-766 depends on
- * undefined behaviour and is NOT applied: scores are the raw SSW scores. */
-hrm_status hrm_sam_format(const hrm_mapper* m, const hrm_read_record* h_records,
+/* ------------------------------------------------------------------------------------------
+ * V4 + O1 -- score recalculation, conversion count, choice of the alignment, MAPQ, POS and the SAM text,
+ * all on the device.
+ * ref: recalculateAlignmentScorefk / comparefk src/gpu/mappinghandler.cu:601-766, mapqfkt :184-193,
+ *      printtoSAM :196-293 (SW mode).
+ * Semantics: the reference with the two patches of SURVEY's parity contract (the two query strings owned;
+ * rc_ref reads NUL beyond the chromosome) and every other quirk kept -- alignment 0 is walked with the
+ * reverse-complement query, only the first 82 bases are examined, scores are uint16_t and wrap, MAPQ is 4
+ * whenever the reference's double -> uint32_t conversion is out of range (x86-64).  A pass sees its own
+ * converted reads and genome (= the reference run on pre-converted input); unmapped reads print from pass 0.
+ * The checker is the reference's own Mappinghandler compiled unmodified (oracle/ref_shim_sam.cpp).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t sw_score[2];            /* after the recalculation, as the reference's uint16_t holds them */
+    int32_t sw_score_next_best[2];
+    int32_t num_conversions[2];     /* Yf:i:<n> of alignment 0 / 1 */
+    int32_t chosen;                 /* 0: alignment 0 printed (YZ:A:<+>), 1: alignment 1 (YZ:A:<->); ref :222 */
+    int32_t flag;                   /* FLAG column */
+    int32_t mapq;                   /* MAPQ column */
+    int32_t window_length;          /* LN of the read's @SQ line */
+    int64_t pos;                    /* POS column = window start + query_begin (ref :236) */
+} hrm_sam_fields;
+
+/* V4 alone: d_fields[n] from the records and cigars of hrm_verify_batch (same reads, same order). */
+hrm_status hrm_sam_fields_batch(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch,
+                                const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
+                                const char* d_cigars, int64_t cigar_pitch, hrm_sam_fields* d_fields,
+                                hrm_stream stream);
+
+/* The SAM file of printtoSAM is  HRM_SAM_HD | the @SQ line of every read | HRM_SAM_PG_CO | the record line of
+ * every read.  The two per-read parts are produced separately so that a run of many batches can be assembled. */
+#define HRM_SAM_HD "@HD\tVN:1.4\n"
+#define HRM_SAM_PG_CO "@PG\tHashreadmapper\tID:1.0@CO: QNAME\tFLAG\tRNAME\tPOS\tMAPQ\tCIGAR\tRNEXT\tPNEXT\tTLEN\tSEQ\tQUAL\tTAG\n"
+#define HRM_SAM_SQ_LINES 0
+#define HRM_SAM_RECORDS 1
+
+/* Text of one part for n reads into DEVICE memory.  *h_written = bytes of the part (pass d_out = NULL to size
+ * it); lines that would cross `cap` are not written.  cigar_pitch must cover the longest cigar (longer strings
+ * print truncated, hrm_alignment.cigar_len tells).  h_chrom_names: n_chrom NUL-terminated names (NULL: the
+ * chromosome index).  first_read_id = id of read 0 (QNAME = read id, ref :252).  d_reads_ascii = NULL: the
+ * batch is still packed inside the mapper (hrm_verify_batch just ran on these reads).  Synchronises the stream. */
+hrm_status hrm_sam_format_device(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch,
+                                 const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
+                                 const char* d_cigars, int64_t cigar_pitch, uint32_t first_read_id,
+                                 const char* const* h_chrom_names, int part, char* d_out, int64_t cap,
+                                 int64_t* h_written, hrm_stream stream);
+
+/* Host buffers in, host text out (records / cigars as hrm_mapper_map_reads returned them): copies them to the
+ * device, formats there and copies the text back.  `with_header` emits HRM_SAM_HD, the @SQ lines and
+ * HRM_SAM_PG_CO in front of the records.  *h_written = bytes needed (h_out = NULL to size). */
+hrm_status hrm_sam_format(hrm_mapper* m, const hrm_read_record* h_records,
                           const char* h_cigars, int64_t cigar_pitch, const char* h_reads_ascii,
                           int64_t ascii_pitch, const int32_t* h_lengths, int64_t n,
                           uint32_t first_read_id, const char* const* h_chrom_names, int with_header,
                           char* h_out, int64_t cap, int64_t* h_written);
+
+/* End to end, text out: reads H2D, seeding + filter + SHD + verification + V4, SAM text D2H.
+ * ref: STEP 1 + STEP 2 of performMappingGpu (main_gpu.cu:1123-1160) incl. the SAM writer.
+ * h_sq_out / h_rec_out receive the @SQ lines / the record lines of these reads (pinned for full PCIe speed);
+ * h_records / h_cigars (may be NULL) additionally receive the binary records.  Synchronous. */
+hrm_status hrm_mapper_map_reads_sam(hrm_mapper* m, const char* h_reads_ascii, int64_t ascii_pitch,
+                                    const int32_t* h_lengths, int64_t n, uint32_t first_read_id,
+                                    const char* const* h_chrom_names, char* h_sq_out, int64_t sq_cap,
+                                    int64_t* h_sq_written, char* h_rec_out, int64_t rec_cap,
+                                    int64_t* h_rec_written, hrm_read_record* h_records, char* h_cigars,
+                                    int64_t cigar_pitch, hrm_batch_stats* h_stats, hrm_stream stream);
 
 #ifdef __cplusplus
 }

@@ -57,7 +57,9 @@ def make(port, name, w=128, k=16):
     mapped["hammingDistance"][unm] = 0
     mapped["shift"][unm] = 0
     return {"genome": g, "off": off, "names": NAMES[:len(lengths)], "reads": r, "lens": lens, "mapped": mapped,
-            "conv": conv if conv else 1, "w": w}
+            "conv": conv if conv else 1, "w": w, "k": k,
+            # what the device path is given: unconverted text + the conversions of its single pass
+            "raw_genome": genome, "raw_reads": reads, "rconv": rconv, "gconv": gconv}
 
 
 def reference_sam(po, case):

@@ -266,7 +266,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "library does not export " + name
         assert name in hb.SIGNATURES, "python binding lacks " + name
-    assert lib.hrm_abi_version() == 1
+    assert lib.hrm_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():
