@@ -2,9 +2,9 @@
 // the SAM text itself.
 // ref: Mappinghandler::CSSW recalculateAlignmentScorefk / comparefk src/gpu/mappinghandler.cu:601-766,
 //      mapqfkt :184-193, printtoSAM :196-293 (single host thread, std::ofstream).
-// Semantics = the UB-patched reference of SURVEY's parity contract (Tier 2), i.e. what oracle/ref_shim_sam.cpp
-// runs and oracle/hrm_oracle.c: orc_sam_record restates -- the two query strings owned, rc_ref reading NUL beyond
-// the chromosome; every other quirk kept (alignment 0 walked with the reverse-complement query, the 82-base
+// Semantics = the UB-patched reference of SURVEY's parity contract (Tier 2; the test suite compiles the reference's
+// own Mappinghandler with exactly these patches as the checker) -- the two query strings owned, rc_ref reading NUL
+// beyond the chromosome; every other quirk kept (alignment 0 walked with the reverse-complement query, the 82-base
 // limit, uint16 score wrap, MAPQ 4 for out-of-range double -> uint32 conversions).  A pass sees its own converted
 // reads and genome (one pass = the reference on pre-converted input); a pass that verifies with G->A is
 // the reference's stage on the complemented sequences, which only changes the query letter tested.

@@ -523,7 +523,7 @@ hrm_status hrm_mapper_set_partition(hrm_mapper* m, hrm_comm* comm);
  * reverse-complement query, only the first 82 bases are examined, scores are uint16_t and wrap, MAPQ is 4
  * whenever the reference's double -> uint32_t conversion is out of range (x86-64).  A pass sees its own
  * converted reads and genome (= the reference run on pre-converted input); unmapped reads print from pass 0.
- * The checker is the reference's own Mappinghandler compiled unmodified (oracle/ref_shim_sam.cpp).
+ * The parity tests check this against the reference's own Mappinghandler compiled unmodified.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t sw_score[2];            /* after the recalculation, as the reference's uint16_t holds them */
