@@ -136,12 +136,21 @@ def workload_name(reads, genome_bp, nchrom, shape="150bp directional BS reads"):
     return "%s x %s per step vs %.4g Mbp synthetic reference, %d chromosome(s)" % (rd, shape, genome_bp / 1e6, nchrom)
 
 
-def cpu_sample(args, n_reads):
-    """bounded sample of the workload for the CPU arm: S reads drawn from a `cpu_genome_bp` reference"""
+def host_cores():
+    """CPU cores this process may run on (torchrun exports OMP_NUM_THREADS=1: the thread count is set explicitly)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_sample(args, n_reads, sample_reads=None, sample_bp=None):
+    """bounded sample of the workload for the CPU arm: S reads drawn from a reference of sample_bp bases (one chromosome,
+    same generator and seeds as the workload)"""
     from hashreadmapper_b200 import synth
-    sub_bp = min(args.genome_bp, args.cpu_genome_bp)
+    sub_bp = int(min(args.genome_bp, sample_bp or args.cpu_genome_bp))
     genome, off = synth.make_genome([sub_bp], seed=20240601)
-    S = min(args.cpu_sample, n_reads)
+    S = int(min(sample_reads or args.cpu_sample, n_reads))
     reads, lens, _ = synth.make_reads(genome, off, S, args.read_len, error_rate=args.error_rate,
                                       indel_frac=args.indel_frac, seed=20240602)
     return genome, off, reads, lens, S, args.genome_bp / float(sub_bp)
@@ -160,31 +169,68 @@ def reference_step(ref, port, genome_ct, genome_ga, off, reads, lens):
     return tot, int(mapped.sum())
 
 
+def read_shape(args):
+    shape = "%dbp %s BS reads" % (args.read_len, "non-directional" if args.nondirectional else "directional")
+    if args.error_rate != ERR or args.indel_frac:
+        shape += " (%.3g %% errors, %.3g %% of them indels)" % (100 * args.error_rate, 100 * args.indel_frac)
+    return shape
+
+
+def base_config(args, world, partitioned=False):
+    """the keys both arms share (the reference arm runs a bounded sample of exactly this workload)"""
+    nchrom = 24 if (args.genome_bp >= (1 << 31) or args.chromosomes > 1) else 1
+    return {"workload": workload_name(args.reads, args.genome_bp, nchrom, read_shape(args)), "reads_per_gpu": args.reads,
+            "genome_bp": args.genome_bp, "k": K_, "hashmaps": H_, "window": W_, "min_table_hits": T_,
+            "passes": "C->T index + G->A index" if not args.nondirectional else
+                      "C->T and G->A reads x C->T and G->A index (4 passes)", "verification": "SW+CIGAR",
+            "parallelism": ("reads sharded x%d, index replicated" % world) if not partitioned else
+                           ("reads sharded x%d, index key-partitioned x%d, NCCL all-to-all" % (world, world))}
+
+
 def run_reference(args, rank, world):
-    """--impl reference: rank 0 alone times the reference's CPU implementation of the path"""
+    """--impl reference: rank 0 alone times the reference's CPU implementation of the path (all host cores).
+    A step = the reference's whole CPU pipeline, both 3N passes, on a bounded sample (S reads against G_s bases) of the
+    workload; the sample is sized from a calibration step so that K + W steps take about --ref-budget-s seconds, up to
+    1 M reads against 500 Mbp.  value = reads / (window streaming scaled to the full genome + per-read
+    stages scaled to the full batch): the reference streams every window once per batch whatever the batch holds."""
     if rank != 0:
         return
     from oracle.pyoracle import Oracle, have_ref
-    from hashreadmapper_b200 import synth
-    nchrom = 24 if (args.genome_bp >= (1 << 31) or args.chromosomes > 1) else 1
-    cfg = {"workload": workload_name(args.reads, args.genome_bp, nchrom),
-           "reads_per_gpu": args.reads, "genome_bp": args.genome_bp, "k": K_, "hashmaps": H_, "window": W_,
-           "min_table_hits": T_, "passes": "C->T index + G->A index", "verification": "SW+CIGAR"}
+    cfg = base_config(args, world, args.index == "partitioned")
     if not have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhrm_ref.so was not built "
                           "(needs /root/reference at build time)"}))
         return
     ref, port = Oracle("ref"), Oracle("port")
-    genome, off, reads, lens, S, wscale = cpu_sample(args, args.reads)
-    reads_ct = np.frombuffer(port.convert_ascii(reads.tobytes(), 1), dtype=np.uint8).reshape(reads.shape)
-    g_ct, g_ga = port.convert_ascii(genome, 1), port.convert_ascii(genome, 2)
-    cores = ref.lib.ref_num_threads()
+    ref.lib.ref_set_num_threads(host_cores())
+    cores = int(ref.lib.ref_num_threads())
+
+    def prepare(S_want, bp_want):
+        genome, off, reads, lens, S, wscale = cpu_sample(args, args.reads, S_want, bp_want)
+        reads_ct = np.frombuffer(port.convert_ascii(reads.tobytes(), 1), dtype=np.uint8).reshape(reads.shape)
+        return port.convert_ascii(genome, 1), port.convert_ascii(genome, 2), off, reads_ct, lens, S, wscale
+
+    # calibration (untimed): cost per read and per streamed base on this box
+    g_ct, g_ga, off, r_ct, lens, S0, _ = prepare(20_000, 23_000_000)
+    reference_step(ref, port, g_ct, g_ga, off, r_ct[:2000], lens[:2000])
+    t, _ = reference_step(ref, port, g_ct, g_ga, off, r_ct, lens)
+    per_read = (t[0] + t[2] + t[3]) / S0
+    per_bp = t[1] / float(off[-1])
+    nsteps = args.steps + 0.25 * args.warmup
+    step_budget = max(args.ref_budget_s / max(nsteps, 1.0), 1.0)
+    # split the step evenly between the two terms, within [50 k, 1 M] reads and [46, 500] Mbp
+    S = int(min(max(0.5 * step_budget / per_read, 50_000), 1_000_000, args.reads))
+    bp = int(min(max(0.5 * step_budget / per_bp, 46_000_000), 500_000_000, args.genome_bp))
+    if args.cpu_sample_fixed:
+        S, bp = min(args.cpu_sample, args.reads), min(args.cpu_genome_bp, args.genome_bp)
+    g_ct, g_ga, off, r_ct, lens, S, wscale = prepare(S, bp)
+    wS = max(S // 4, 1000)
     for _ in range(args.warmup):
-        reference_step(ref, port, g_ct, g_ga, off, reads_ct[:max(S // 10, 1000)], lens[:max(S // 10, 1000)])
+        reference_step(ref, port, g_ct, g_ga, off, r_ct[:wS], lens[:wS])
     t0 = time.perf_counter()
     acc = np.zeros(4)
     for _ in range(args.steps):
-        t, nm = reference_step(ref, port, g_ct, g_ga, off, reads_ct, lens)
+        t, nm = reference_step(ref, port, g_ct, g_ga, off, r_ct, lens)
         acc += t
     wall = time.perf_counter() - t0
     ms = wall / args.steps * 1e3
@@ -196,18 +242,76 @@ def run_reference(args, rank, world):
     line = {"metric": "reads mapped/sec", "value": value, "unit": "reads/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 integer", "data": "synthetic",
-            "config": dict(cfg, reference_sample_reads=S, reference_sample_genome_bp=min(args.genome_bp, args.cpu_genome_bp)),
+            "config": cfg,
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "reference",
-                             "sample": ("%d of %d reads per step against %.0f Mbp of reference; window streaming "
-                                        "(%.2f s) scaled x%.1f to %.0f Mbp and counted once per step, per-read stages "
-                                        "(%.2f s) scaled x%.1f to the full batch; measured on the sample alone: %.0f reads/s"
-                                        % (S, args.reads, min(args.genome_bp, args.cpu_genome_bp) / 1e6, per[1], wscale,
-                                           args.genome_bp / 1e6, per[0] + per[2] + per[3], scale, S / (ms / 1e3))),
+                             "sample_reads": S, "sample_genome_bp": int(off[-1]),
+                             "sample": ("each step = the reference's whole CPU pipeline (both 3N passes) on %d of %d reads "
+                                        "against %.0f of %.0f Mbp, %d OpenMP threads; window streaming (%.2f s per step, "
+                                        "measured) scaled x%.1f to the full genome and counted once per batch, per-read "
+                                        "stages (%.2f s, measured) scaled x%.1f to the full batch; measured on the sample "
+                                        "alone: %.0f reads/s"
+                                        % (S, args.reads, off[-1] / 1e6, args.genome_bp / 1e6, cores, per[1], wscale,
+                                           per[0] + per[2] + per[3], scale, S / (ms / 1e3))),
                              "stage_seconds_per_step": {"reads_build": per[0], "windows_query_filter": per[1],
                                                         "shd": per[2], "verify_ssw": per[3]}},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def parity_check(args, mp, cfg, genome, off, names, reads, lens, K):
+    """After the timed region: K reads of the timed batch through the end-to-end SAM entry point, compared BYTE FOR BYTE
+    with the oracle on the full-size index -- seeding by the reference's own CPU functions (oracle/_ref, OpenMP over the
+    whole genome, both passes; the scalar port when the genome is small), stage V + SAM by the C restatement that is
+    pinned to the reference's Mappinghandler.  Test infrastructure used as the checker, outside every timed region."""
+    import hashreadmapper_b200._lib as L
+    from oracle import pyoracle as po
+    t0 = time.perf_counter()
+    port = po.Oracle("port")
+    ref = None
+    if po.have_ref():
+        ref = po.Oracle("ref")
+        ref.lib.ref_set_num_threads(host_cores())
+    elif off[-1] > 200_000_000:
+        return {"parity_checked": 0, "parity_ok": None, "parity_note": "oracle/_ref not built and the genome is too large "
+                "for the scalar port"}
+    idx = np.linspace(0, len(lens) - 1, K).astype(np.int64)
+    r, l = np.ascontiguousarray(reads[idx]), np.ascontiguousarray(lens[idx])
+    genomes, rows, passes = [], [], []
+    for p in range(cfg.num_passes):
+        g = port.convert_ascii(genome, cfg.genome_conversion[p])
+        rr = np.frombuffer(port.convert_ascii(r.tobytes(), cfg.read_conversion[p]), dtype=np.uint8).reshape(r.shape)
+        genomes.append(g)
+        rows.append(rr)
+        if ref is not None:
+            passes.append(po.ref_cpu_pipeline(ref, g, off, rr, l, k=K_, w=W_, H=H_, min_hits=T_, mapper_type=0,
+                                              want_alignments=False)[0])
+        else:
+            passes.append(port.map_pass_refdir(g, off, rr, l, k=K_, w=W_, H=H_, min_hits=T_)[0])
+    best = passes[0].copy()
+    which = np.where(best["orientation"] != 3, 0, -1).astype(np.int32)
+    for p, cur in enumerate(passes[1:], start=1):
+        better = (cur["orientation"] != 3) & ((best["orientation"] == 3) | (cur["hammingDistance"] < best["hammingDistance"]))
+        best[better] = cur[better]
+        which[better] = p
+    exp, _ = po.port_sam_format(port, genomes, off, names, rows, l, best, np.maximum(which, 0),
+                                [cfg.verify_conversion[p] for p in range(cfg.num_passes)], w=W_)
+    sq, rc, _, rec, cig = mp.mapReadsSam(r, l, cigar_pitch=256, want_records=True)
+    got = L.SAM_HD + sq.tobytes() + L.SAM_PG_CO + rc.tobytes()
+    m = best["orientation"] != 3
+    same_mapped = bool((rec["mapped"]["orientation"] == best["orientation"]).all() and
+                       (rec["mapped"]["position"][m] == best["position"][m]).all())
+    nbad = 0
+    if got != exp:
+        a, b = got.split(b"\n"), exp.split(b"\n")
+        nbad = sum(1 for x, y in zip(a, b) if x != y) + abs(len(a) - len(b))
+    return {"parity_checked": int(K), "parity_ok": bool(got == exp), "parity_mapped_reads_identical": same_mapped,
+            "parity_sam_bytes": len(exp), "parity_sam_lines_differing": int(nbad),
+            "parity_mapped_in_sample": int(m.sum()),
+            "parity_oracle": ("seeding: the reference's own CPU functions (oracle/_ref, %d threads) over the full %.0f Mbp, "
+                              "every pass; stage V + SAM: the C restatement pinned to the reference's Mappinghandler"
+                              % (host_cores(), off[-1] / 1e6)) if ref is not None else "scalar C restatement",
+            "parity_seconds": time.perf_counter() - t0}
 
 
 def main():
@@ -218,9 +322,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=4_000_000, help="reads per GPU per step (one batch)")
     ap.add_argument("--genome-bp", type=int, default=3_100_000_000)
-    ap.add_argument("--cpu-genome-bp", type=int, default=46_000_000,
-                    help="reference bases the CPU baseline streams (window streaming is scaled to --genome-bp)")
-    ap.add_argument("--cpu-sample", type=int, default=50_000, help="reads in the CPU-baseline sample")
+    ap.add_argument("--cpu-genome-bp", type=int, default=100_000_000,
+                    help="reference bases the in-line CPU baseline streams (window streaming is scaled to --genome-bp)")
+    ap.add_argument("--cpu-sample", type=int, default=100_000, help="reads in the in-line CPU-baseline sample")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0,
+                    help="--impl reference: seconds the K timed steps should take in total (sizes the sample)")
+    ap.add_argument("--cpu-sample-fixed", action="store_true",
+                    help="--impl reference: use --cpu-sample / --cpu-genome-bp instead of the calibrated sample")
+    ap.add_argument("--check", type=int, default=2000,
+                    help="reads of the timed batch compared with the oracle after the timed region (0: off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--load-factor", type=float, default=None, help="hash-table load factor (default: the library's)")
     ap.add_argument("--read-len", type=int, default=READ_LEN)
@@ -262,7 +372,8 @@ def main():
         comm = api.Comm()
         mp.setPartition(comm)
     t0 = time.perf_counter()
-    mp.setGenome(genome, off, ["chr%d" % (i + 1) for i in range(len(off) - 1)])
+    names = ["chr%d" % (i + 1) for i in range(len(off) - 1)]
+    mp.setGenome(genome, off, names)
     torch.cuda.synchronize()
     index_s = time.perf_counter() - t0
     info = mp.info()
