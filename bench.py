@@ -396,7 +396,12 @@ def main():
         step()
     # one accounted step (untimed) for the roofline bookkeeping
     torch.cuda.synchronize()
+    i0 = mp.info()
     _, st = mp.mapBatch(d_reads, d_lens, want_stats=True)
+    i1 = mp.info()
+    st_collect = {"enumerated": i1.collect_ids_counted - i0.collect_ids_counted,
+                  "skipped": i1.collect_ids_skipped - i0.collect_ids_skipped,
+                  "block_reads": i1.collect_reads_block_kernel - i0.collect_reads_block_kernel}
     launches_map = st.num_kernel_launches
     mapped, _ = mp.mapBatch(d_reads, d_lens, want_stats=False)
     from hashreadmapper_b200 import _lib as L
@@ -487,34 +492,66 @@ def main():
             traffic = None
     stage_ms = {k: v[0] / args.steps for k, v in stages.items()}
     stage_sum = sum(stage_ms.values())
-    roofline = {"kernel": "hrm::probe_tm_kernel (K3b hash probe, table-major)" if comm is None else
-                          "hrm::probe_keys_kernel (K3b hash probe of routed keys, owner side)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": probe_launch_ms,
-                "launches_per_step": launches_per_step_probe,
-                "slot_touches_per_launch": P, "lookups_per_launch": Q * H_,
-                "share_of_step": probe_ms / args.steps / ms_per_step if ms_per_step > 0 else None,
-                "note": "algorithmic bytes = 16 B x slots examined + (8H+4) B x reads (SURVEY 8d); a bucket = four 16-B "
-                        "slots = one 64-B HBM access, all four examined per visit"}
+    dram_frac = (traffic / (probe_launch_ms / 1e3) / 1e9 / peak) if (traffic and probe_launch_ms > 0) else None
+    min_bytes = 16.0 * Q * H_ + (8.0 * H_ + 4.0) * Q   # one 16-B slot per lookup: the least a probe must read
+    probe_roofline = {"kernel": "hrm::probe_tm_kernel (K3b hash probe, table-major)" if comm is None else
+                                "hrm::probe_keys_kernel (K3b hash probe of routed keys, owner side)", "bound": "hbm",
+                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": probe_launch_ms,
+                      "launches_per_step": launches_per_step_probe, "slot_touches_per_launch": P,
+                      "lookups_per_launch": Q * H_,
+                      "share_of_step": probe_ms / args.steps / ms_per_step if ms_per_step > 0 else None,
+                      "frac_dram_side": dram_frac,
+                      "frac_one_slot_per_lookup": (min_bytes / (probe_launch_ms / 1e3) / 1e9 / peak) if probe_launch_ms > 0 else None,
+                      "note": "three accountings of the same launch: `frac` counts all four 16-B slots of every 64-B bucket "
+                              "visited (16 B x slots examined + (8H+4) B x reads, SURVEY 8d); `frac_dram_side` = ncu DRAM "
+                              "bytes (profiles/probe_traffic.json) / time, below `frac` because one 78 MB table at a time "
+                              "stays in the 126 MB L2; `frac_one_slot_per_lookup` counts one 16-B slot per lookup"}
+    # the kernel with the largest share of the step: the fused collection (K3b value retrieval + K4)
+    dom_stage = max(stage_ms, key=lambda k_: stage_ms[k_])
+    ids_step = float(st_collect["enumerated"])          # ids the collection kernels read and test, per step
+    ids_skipped_step = float(st_collect["skipped"])
+    coll_launches = max(stages["filter"][1] / args.steps, 1.0)
+    coll_ms = stage_ms["filter"]
+    coll_bytes = 4.0 * ids_step + 8.0 * H_ * n * cfg.num_passes + 8.0 * n * cfg.num_passes
+    coll_ach = coll_bytes / (coll_ms / 1e3) / 1e9 if coll_ms > 0 else 0.0
+    ctraffic = None
+    tp2 = os.path.join(ROOT, "profiles", "collect_traffic.json")
+    if os.path.exists(tp2):
+        try:
+            ctraffic = json.load(open(tp2)).get("dram_bytes_per_launch")
+        except Exception:
+            ctraffic = None
+    collect_roofline = {"kernel": "hrm::collect_bloom_kernel (+ the block kernel for skewed reads): K3b value retrieval + K4 "
+                                  "candidate collection, fused", "bound": "hbm", "achieved": coll_ach,
+                        "peak": peak, "unit": "GB/s", "frac": coll_ach / peak, "traffic": ctraffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": coll_bytes / coll_launches, "launch_ms": coll_ms / coll_launches,
+                        "launches_per_step": coll_launches, "share_of_step": coll_ms / ms_per_step if ms_per_step > 0 else None,
+                        "ids_enumerated_per_step": ids_step, "ids_skipped_per_step": ids_skipped_step,
+                        "frac_if_no_bucket_were_skipped": (4.0 * (ids_step + ids_skipped_step) / (coll_ms / 1e3) / 1e9 / peak)
+                        if coll_ms > 0 else None,
+                        "reads_to_block_kernel_per_step": float(st_collect["block_reads"]),
+                        "note": "algorithmic bytes = 4 B x ids enumerated + the 8-B (offset, count) bucket ranges of every "
+                                "(read, table) + the 8-B list header per read (DESIGN 3); launch_ms spans the kernels of one "
+                                "pass' collection (CUDA events on the launching stream)"}
+    roofline = collect_roofline if (dom_stage == "filter" and comm is None) else probe_roofline
+    other = probe_roofline if roofline is collect_roofline else collect_roofline
 
     line = {"metric": "reads mapped/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/u64 integer", "data": "synthetic",
-            "config": {"workload": wl_name, "reads_per_gpu": n, "genome_bp": args.genome_bp, "k": K_, "hashmaps": H_, "window": W_,
-                       "min_table_hits": T_, "passes": "C->T index + G->A index" if not args.nondirectional else
-                       "C->T and G->A reads x C->T and G->A index (4 passes)", "verification": "SW+CIGAR",
-                       "load_factor": float(cfg.load_factor),
-                       "parallelism": ("reads sharded x%d, index replicated" % world) if comm is None else
-                                      ("reads sharded x%d, index key-partitioned x%d, NCCL all-to-all" % (world, world)),
-                       "l2": "inputs larger than L2 (reads %.0f MB + index %.0f MB per GPU)"
-                             % (reads.nbytes / 1e6, info.index_device_bytes / 1e6),
-                       "index_build_s": index_s, "windows": int(info.num_windows),
-                       "index_device_bytes": int(info.index_device_bytes), "table_slots": int(info.table_slots_total),
-                       "table_keys": int(info.num_keys_total)},
+            "config": dict(base_config(args, world, comm is not None),
+                           load_factor=float(cfg.load_factor),
+                           l2="inputs larger than L2 (reads %.0f MB + index %.0f MB per GPU)"
+                              % (reads.nbytes / 1e6, info.index_device_bytes / 1e6),
+                           index_build_s=index_s, windows=int(info.num_windows),
+                           index_device_bytes=int(info.index_device_bytes), table_slots=int(info.table_slots_total),
+                           table_keys=int(info.num_keys_total)),
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "hrm_mapper_map_reads (pinned host buffers)"},
             "gpu_launches": int(launches_step * args.steps),
             "roofline": roofline,
+            "roofline_probe" if roofline is collect_roofline else "roofline_collect": other,
             "stages_ms_per_step": stage_ms, "stages_unaccounted_ms": ms_per_step - stage_sum,
             "mapped_fraction": n_mapped / n, "mapped_at_true_locus_fraction": float(ok.sum()) / max(n_mapped, 1),
             "candidates_per_read": st.num_candidates / n, "values_per_read": st.num_values / n,
@@ -526,6 +563,13 @@ def main():
         line["exchange"] = {"backend": "NCCL ncclSend/ncclRecv groups", "bytes_sent_rank0": int(ci.bytes_sent),
                             "exchanges_rank0": int(ci.exchanges)}
 
+    # ---- parity at the quoted size: K reads of the timed batch against the oracle (outside every timed region) -----
+    if world == 1 and args.check > 0:
+        try:
+            line.update(parity_check(args, mp, cfg, genome, off, names, reads, lens, min(args.check, n)))
+        except Exception as e:
+            line.update({"parity_checked": 0, "parity_ok": None, "parity_note": "failed: %r" % (e,)})
+
     # ---- CPU baseline: the reference's own functions on this box's host cores (rank 0, N = 1) -------
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -536,6 +580,7 @@ def main():
             g_ct, g_ga = port.convert_ascii(g_s, 1), port.convert_ascii(g_s, 2)
             if have_ref():
                 ref = Oracle("ref")
+                ref.lib.ref_set_num_threads(host_cores())
                 t0 = time.perf_counter()
                 per, nm = reference_step(ref, port, g_ct, g_ga, off_s, r_ct, l_s)
                 wall = time.perf_counter() - t0

@@ -61,7 +61,8 @@ class MapperConfig(C.Structure):
 class MapperInfo(C.Structure):
     _fields_ = [("num_windows", C.c_int64), ("index_device_bytes", C.c_int64), ("genome_device_bytes", C.c_int64),
                 ("num_keys_total", C.c_int64), ("table_slots_total", C.c_int64), ("num_passes", C.c_int32),
-                ("reserved", C.c_int32), ("collect_ids_counted", C.c_int64), ("collect_ids_skipped", C.c_int64)]
+                ("reserved", C.c_int32), ("collect_ids_counted", C.c_int64), ("collect_ids_skipped", C.c_int64),
+                ("collect_reads_block_kernel", C.c_int64)]
 
 
 class CommInfo(C.Structure):
@@ -132,6 +133,9 @@ SIGNATURES = {
     "hrm_readstore_gather": (I32, [P, C.c_int, P, I64, P, I64, VP]),
     "hrm_readstore_gather_contiguous": (I32, [P, C.c_int, P, I64, U32, I64, VP]),
     "hrm_readstore_gather_lengths": (I32, [P, C.c_int, P, P, I64, VP]),
+    "hrm_readstore_are_ambiguous": (I32, [P, C.c_int, P, P, I64, VP]),
+    "hrm_readstore_ambiguous_ids": (I32, [P, P]),
+    "hrm_readstore_set_ambiguous": (I32, [P, P, VP]),
     "hrm_readstore_info": (I32, [P, C.POINTER(ReadstoreInfo)]),
     "hrm_genome_create_from_ascii": (I32, [C.POINTER(P), P, P, C.c_int, C.c_int, VP]),
     "hrm_genome_destroy": (None, [P]),
@@ -167,6 +171,9 @@ SIGNATURES = {
     "hrm_sam_format": (I32, [P, P, P, I64, P, I64, P, I64, U32, P, C.c_int, P, I64, C.POINTER(I64)]),
     "hrm_sam_fields_batch": (I32, [P, P, I64, P, I64, P, P, I64, P, VP]),
     "hrm_sam_format_device": (I32, [P, P, I64, P, I64, P, P, I64, U32, P, C.c_int, P, I64, C.POINTER(I64), VP]),
+    "hrm_mapper_stage_reads": (I32, [P, C.c_int, P, I64, P, I64]),
+    "hrm_mapper_map_staged": (I32, [P, C.c_int, P, P, I64, U32, P, P, I64, P, I64, C.POINTER(BatchStats), VP]),
+    "hrm_mapper_finish": (I32, [P, C.c_int, C.POINTER(I64), C.POINTER(I64)]),
     "hrm_mapper_map_reads_sam": (I32, [P, P, I64, P, I64, U32, P, P, I64, C.POINTER(I64), P, I64, C.POINTER(I64), P, P,
                                        I64, C.POINTER(BatchStats), VP]),
 }

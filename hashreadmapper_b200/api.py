@@ -245,6 +245,19 @@ def segment_ids(offsets, total):
 class ReadStorage:
     """Mirror of GpuReadStorage (include/gpu/gpureadstorage.cuh:22-119)."""
 
+    @classmethod
+    def from2Bit(cls, seq2bit: torch.Tensor, lengths: torch.Tensor, ambiguous: torch.Tensor = None):
+        """adopts packed device rows (+ the ambiguity flags hrm_ingest_reads produced)"""
+        self = cls.__new__(cls)
+        self.lib = L.load()
+        _dev()
+        self.h = C.c_void_p()
+        n, pw = seq2bit.shape
+        check(self.lib.hrm_readstore_create_from_2bit(C.byref(self.h), _ptr(seq2bit), pw, _ptr(lengths), n, _stream()))
+        if ambiguous is not None:
+            check(self.lib.hrm_readstore_set_ambiguous(self.h, _ptr(ambiguous), _stream()))
+        return self
+
     def __init__(self, ascii_rows: np.ndarray, lengths: np.ndarray, conversion=L.CONV_NONE):
         self.lib = L.load()
         _dev()
@@ -297,6 +310,20 @@ class ReadStorage:
         out = torch.empty((n,), dtype=torch.int32, device=ids.device)
         check(self.lib.hrm_readstore_gather_lengths(self.h, handle, _ptr(out), _ptr(ids), n, _stream()))
         return out
+
+    def areSequencesAmbiguous(self, handle, ids: torch.Tensor):
+        n = ids.numel()
+        out = torch.empty((n,), dtype=torch.uint8, device=ids.device)
+        check(self.lib.hrm_readstore_are_ambiguous(self.h, handle, _ptr(out), _ptr(ids), n, _stream()))
+        return out
+
+    def getNumberOfReadsWithN(self):
+        return self.getInfo().num_reads_with_n
+
+    def getIdsOfAmbiguousReads(self):
+        out = np.zeros(max(int(self.getNumberOfReadsWithN()), 1), dtype=np.uint32)
+        check(self.lib.hrm_readstore_ambiguous_ids(self.h, _ptr(out)))
+        return out[:int(self.getNumberOfReadsWithN())]
 
 
 # ---- S2 ----------------------------------------------------------------------------------------
@@ -571,6 +598,26 @@ class Mapper:
         if want_records:
             return sq_out[:sqw.value], rec_out[:recw.value], st, records, cigars
         return sq_out[:sqw.value], rec_out[:recw.value], st
+
+    # ---- double-buffered pipeline (host buffers should be pinned) ----
+    def stageReads(self, slot, reads_ascii: np.ndarray, lengths: np.ndarray):
+        n, pitch = reads_ascii.shape
+        check(self.lib.hrm_mapper_stage_reads(self.h, slot, _ptr(reads_ascii), pitch, _ptr(lengths), n))
+
+    def mapStaged(self, slot, records=None, cigars=None, cigar_pitch=64, first_read_id=0, sq_out=None, rec_out=None,
+                  want_stats=False):
+        st = L.BatchStats()
+        check(self.lib.hrm_mapper_map_staged(self.h, slot, _ptr(records), _ptr(cigars), cigar_pitch, first_read_id,
+                                             self._names(), _ptr(sq_out), sq_out.size if sq_out is not None else 0,
+                                             _ptr(rec_out), rec_out.size if rec_out is not None else 0,
+                                             C.byref(st) if want_stats else None, _stream()))
+        return st
+
+    def finish(self, slot):
+        """-> (@SQ text bytes, record text bytes) now in the host buffers given to mapStaged"""
+        sqw, recw = C.c_int64(0), C.c_int64(0)
+        check(self.lib.hrm_mapper_finish(self.h, slot, C.byref(sqw), C.byref(recw)))
+        return sqw.value, recw.value
 
     def samFormat(self, records, cigars, reads_ascii, lengths, first_read_id=0, with_header=True):
         n = len(records)

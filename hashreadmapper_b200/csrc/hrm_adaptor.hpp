@@ -1,6 +1,6 @@
-// hrm_adaptor.hpp -- the reference-side binding: a C++ class that derives from the reference's abstract
-// care::gpu::GpuMinhasher (include/gpu/gpuminhasher.cuh:20-110) and forwards every virtual to the C ABI
-// of libhrm_b200.so.  Drop this header next to the reference's sources, compile it with the reference
+// hrm_adaptor.hpp -- the reference-side binding: two C++ classes that derive from the reference's abstract
+// care::gpu::GpuMinhasher (include/gpu/gpuminhasher.cuh:20-110) and care::gpu::GpuReadStorage
+// (include/gpu/gpureadstorage.cuh:22-119) and forward every virtual to the C ABI of libhrm_b200.so.  Drop this header next to the reference's sources, compile it with the reference
 // (nvcc, -I<reference>/include, rmm on the include path as in the reference's Makefile:23-31), link
 // -lhrm_b200, and construct B200Minhasher where constructGpuMinhasherFromGpuReadStorage
 // (src/gpu/gpuminhasherconstruction.cu:256-330) constructs FakeGpuMinhasher / SingleGpuMinhasher.
@@ -13,7 +13,8 @@
 // tests/test_host_logic.py::test_adaptor_compiles_against_reference compiles this header against the
 // reference's own headers when /root/reference is present.
 #pragma once
-#include <gpu/gpuminhasher.cuh>   // the reference's interface
+#include <gpu/gpuminhasher.cuh>   // the reference's interfaces
+#include <gpu/gpureadstorage.cuh>
 
 #include <fstream>
 #include <stdexcept>
@@ -142,6 +143,106 @@ private:
         return i;
     }
     hrm_minhasher* mh_ = nullptr;
+};
+
+// ref: class GpuReadStorage include/gpu/gpureadstorage.cuh:22-119 (the reference's implementation:
+// MultiGpuReadStorage include/gpu/multigpureadstorage.cuh:655-905,1515-1560).  Construct it where performMappingGpu
+// builds its MultiGpuReadStorage from the ChunkedReadStorage (src/gpu/main_gpu.cu:1010-1040); WindowBatchProcessor
+// keeps calling gatherSequences / gatherSequenceLengths through `const GpuReadStorage*` (main_gpu.cu:591-607).
+// Reads live 2-bit packed in HBM; quality scores are not stored (the mapping path never reads them).
+class B200ReadStorage : public care::gpu::GpuReadStorage {
+public:
+    // host ASCII rows (what the reference's encoder threads are given, chunkedreadstorageconstruction.hpp:273-314)
+    B200ReadStorage(const char* h_ascii, std::int64_t ascii_pitch, const int* h_lengths, std::int64_t n,
+                    cudaStream_t stream = nullptr)
+    {
+        hrm_check(hrm_readstore_create_from_ascii(&rs_, h_ascii, ascii_pitch, h_lengths, n, HRM_CONV_NONE, stream));
+    }
+    // already packed device rows (what ChunkedReadStorage holds, chunkedreadstorage.hpp:44-80) + optional
+    // per-read ambiguity flags on the device
+    B200ReadStorage(const unsigned int* d_seq2bit, std::size_t pitchInInts, const int* d_lengths, std::int64_t n,
+                    const std::uint8_t* d_ambiguous, cudaStream_t stream = nullptr)
+    {
+        hrm_check(hrm_readstore_create_from_2bit(&rs_, d_seq2bit, (std::int64_t)pitchInInts, d_lengths, n, stream));
+        if (d_ambiguous) hrm_check(hrm_readstore_set_ambiguous(rs_, d_ambiguous, stream));
+    }
+    ~B200ReadStorage() override { hrm_readstore_destroy(rs_); }
+    B200ReadStorage(const B200ReadStorage&) = delete;
+    B200ReadStorage& operator=(const B200ReadStorage&) = delete;
+
+    care::ReadStorageHandle makeHandle() const override
+    {
+        const int id = hrm_readstore_handle_create(rs_);
+        if (id < 0) hrm_check(id);
+        return constructHandle(id);
+    }
+    void destroyHandle(care::ReadStorageHandle& handle) const override
+    {
+        hrm_check(hrm_readstore_handle_destroy(rs_, handle.getId()));
+        handle = constructHandle(std::numeric_limits<int>::max());
+    }
+    void areSequencesAmbiguous(care::ReadStorageHandle& handle, bool* d_result, const read_number* d_readIds,
+                               int numSequences, cudaStream_t stream) const override
+    {
+        static_assert(sizeof(bool) == 1, "bool flags are bytes");
+        hrm_check(hrm_readstore_are_ambiguous(rs_, handle.getId(), reinterpret_cast<std::uint8_t*>(d_result), d_readIds,
+                                              numSequences, stream));
+    }
+    void gatherSequences(care::ReadStorageHandle& handle, unsigned int* d_sequence_data, size_t outSequencePitchInInts,
+                         const AsyncConstBufferWrapper<read_number> /*h_readIds*/, const read_number* d_readIds,
+                         int numSequences, cudaStream_t stream, rmm::mr::device_memory_resource* /*mr*/) const override
+    {
+        hrm_check(hrm_readstore_gather(rs_, handle.getId(), d_sequence_data, (std::int64_t)outSequencePitchInInts,
+                                       d_readIds, numSequences, stream));
+    }
+    void gatherContiguousSequences(care::ReadStorageHandle& handle, unsigned int* d_sequence_data,
+                                   size_t outSequencePitchInInts, read_number firstIndex, int numSequences,
+                                   cudaStream_t stream, rmm::mr::device_memory_resource* /*mr*/) const override
+    {
+        hrm_check(hrm_readstore_gather_contiguous(rs_, handle.getId(), d_sequence_data,
+                                                  (std::int64_t)outSequencePitchInInts, firstIndex, numSequences, stream));
+    }
+    // quality scores are not part of the mapping path (canUseQualityScores() == false): contract violation
+    void gatherQualities(care::ReadStorageHandle&, char*, size_t, const AsyncConstBufferWrapper<read_number>,
+                         const read_number*, int, cudaStream_t, rmm::mr::device_memory_resource*) const override
+    {
+        throw std::runtime_error("libhrm_b200: B200ReadStorage stores no quality scores");
+    }
+    void gatherContiguousQualities(care::ReadStorageHandle&, char*, size_t, read_number, int, cudaStream_t,
+                                   rmm::mr::device_memory_resource*) const override
+    {
+        throw std::runtime_error("libhrm_b200: B200ReadStorage stores no quality scores");
+    }
+    void gatherSequenceLengths(care::ReadStorageHandle& handle, int* d_lengths, const read_number* d_readIds,
+                               int numSequences, cudaStream_t stream) const override
+    {
+        hrm_check(hrm_readstore_gather_lengths(rs_, handle.getId(), d_lengths, d_readIds, numSequences, stream));
+    }
+    void getIdsOfAmbiguousReads(read_number* ids) const override { hrm_check(hrm_readstore_ambiguous_ids(rs_, ids)); }
+    std::int64_t getNumberOfReadsWithN() const override { return info().num_reads_with_n; }
+    ::MemoryUsage getMemoryInfo() const override
+    {
+        ::MemoryUsage mu{};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        mu.device[dev] = (std::size_t)info().device_bytes;
+        return mu;
+    }
+    ::MemoryUsage getMemoryInfo(const care::ReadStorageHandle&) const override { return ::MemoryUsage{}; }
+    read_number getNumberOfReads() const override { return (read_number)info().num_reads; }
+    bool canUseQualityScores() const override { return false; }
+    int getSequenceLengthLowerBound() const override { return info().length_lower_bound; }
+    int getSequenceLengthUpperBound() const override { return info().length_upper_bound; }
+    bool isPairedEnd() const override { return info().is_paired_end != 0; }
+
+private:
+    hrm_readstore_info_t info() const
+    {
+        hrm_readstore_info_t i{};
+        hrm_readstore_info(rs_, &i);
+        return i;
+    }
+    hrm_readstore* rs_ = nullptr;
 };
 
 } // namespace hrm_b200

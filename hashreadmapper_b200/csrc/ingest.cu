@@ -7,7 +7,7 @@
 //      the ids of reads that contained such characters (:293-297).
 // Here: the text of a chunk is in device memory; line starts come from two passes over the text (newlines per
 // 1 KiB tile by byte-SIMD compare, scan of the tile counts, positions written tile by tile), a record
-// is 4 lines (FASTQ, first byte '@') or 2 lines (FASTA, first byte '>'; sequences on one line), the cyclic
+// is 4 lines (FASTQ, first byte '@') or a header line ('>') and every line up to the next header (FASTA), the cyclic
 // replacement index of a read is an exclusive scan of the per-read counts of replaced characters, rebased at
 // every 65536th read of the file.  One warp per read copies and normalises its sequence.
 // Traffic: the text three times (count, positions, copy), rows once.
@@ -155,6 +155,107 @@ __global__ void __launch_bounds__(256) copy_reads_kernel(const char* __restrict_
     }
 }
 
+// ---- FASTA with sequences over several lines (ref: kseqpp reads every line up to the next '>' into one sequence,
+// include/kseqpp/kseqpp.hpp; readlibraryio.hpp:288-326 hands the joined sequence on) ---------------------------
+// is_header[l] = 1 if line l starts with '>'
+__global__ void __launch_bounds__(256) fasta_headers_kernel(const char* __restrict__ text, int64_t nbytes,
+                                                            const int64_t* __restrict__ line_start, int64_t total_lines,
+                                                            int32_t* __restrict__ is_header)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < total_lines; l += stride) {
+        const int64_t b = line_start[l];
+        is_header[l] = (b < nbytes && text[b] == '>') ? 1 : 0;
+    }
+}
+
+// header_line[r] = line of the r-th header
+__global__ void __launch_bounds__(256) fasta_record_lines_kernel(const int32_t* __restrict__ is_header,
+                                                                 const int32_t* __restrict__ rec_excl, int64_t total_lines,
+                                                                 int64_t* __restrict__ header_line)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < total_lines; l += stride)
+        if (is_header[l]) header_line[rec_excl[l]] = l;
+}
+
+// text extent [b, e) of line l without its newline / carriage return
+__device__ __forceinline__ void line_extent(const char* __restrict__ text, int64_t nbytes,
+                                            const int64_t* __restrict__ line_start, int64_t nlines, int64_t l, int64_t& b,
+                                            int64_t& e)
+{
+    b = line_start[l];
+    e = l + 1 <= nlines ? line_start[l + 1] - 1 : nbytes;
+    if (e > b && text[e - 1] == '\r') e--;
+}
+
+__global__ void __launch_bounds__(256) fasta_extents_kernel(const char* __restrict__ text, int64_t nbytes,
+                                                            const int64_t* __restrict__ line_start, int64_t nlines,
+                                                            int64_t total_lines, const int64_t* __restrict__ header_line,
+                                                            int64_t nreads, int64_t pitch, int32_t* __restrict__ len,
+                                                            int32_t* __restrict__ ninvalid, int* __restrict__ error)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < nreads; r += nwarps) {
+        const int64_t l0 = header_line[r] + 1, l1 = r + 1 < nreads ? header_line[r + 1] : total_lines;
+        int64_t L = 0;
+        int bad = 0;
+        for (int64_t l = l0; l < l1; l++) {
+            int64_t b, e;
+            line_extent(text, nbytes, line_start, nlines, l, b, e);
+            L += e - b;
+            for (int64_t i = b + lane; i < e; i += 32) bad += !ingest_valid_base((unsigned char)text[i]);
+        }
+        bad = __reduce_add_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            if (L > pitch) atomicExch(error, 2);
+            len[r] = (int32_t)(L > pitch ? pitch : L);
+            ninvalid[r] = bad;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) fasta_copy_kernel(const char* __restrict__ text, int64_t nbytes,
+                                                         const int64_t* __restrict__ line_start, int64_t nlines,
+                                                         int64_t total_lines, const int64_t* __restrict__ header_line,
+                                                         const int32_t* __restrict__ ninvalid,
+                                                         const int32_t* __restrict__ invalid_excl, int64_t nreads,
+                                                         int64_t first_read_id, int carry, char* __restrict__ rows,
+                                                         int64_t pitch, uint8_t* __restrict__ ambiguous)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < nreads; r += nwarps) {
+        const int64_t in_batch = (first_read_id + r) % INGEST_BATCH;
+        const int64_t batch_first = r - in_batch;
+        int running = batch_first >= 0 ? invalid_excl[r] - invalid_excl[batch_first] : invalid_excl[r] + carry;
+        const int64_t l0 = header_line[r] + 1, l1 = r + 1 < nreads ? header_line[r + 1] : total_lines;
+        char* row = rows + r * pitch;
+        int64_t at = 0;
+        for (int64_t l = l0; l < l1; l++) {
+            int64_t b, e;
+            line_extent(text, nbytes, line_start, nlines, l, b, e);
+            const int Ln = (int)(e - b);
+            for (int i0 = 0; i0 < Ln; i0 += 32) {
+                const int i = i0 + lane;
+                unsigned char c = i < Ln ? (unsigned char)text[b + i] : (unsigned char)'A';
+                const bool bad = !ingest_valid_base(c);
+                const unsigned m = __ballot_sync(0xffffffffu, bad);
+                if (bad) c = (unsigned char)("ACGT"[(running + __popc(m & ((1u << lane) - 1u))) & 3]);
+                else if (c >= 'a') c = (unsigned char)(c - 32);
+                if (i < Ln && at + i < pitch) row[at + i] = (char)c;
+                running += __popc(m);
+            }
+            at += Ln;
+        }
+        for (int64_t i = at + lane; i < pitch; i += 32) row[i] = 0;
+        if (lane == 0 && ambiguous) ambiguous[r] = ninvalid[r] > 0 ? 1 : 0;
+    }
+}
+
 static unsigned igrid(int64_t items)
 {
     int64_t g = HRM_SDIV(items, (int64_t)256);
@@ -167,6 +268,65 @@ static unsigned igrid(int64_t items)
 } // namespace hrm
 
 using namespace hrm;
+
+// replaced characters of the (unfinished) last batch of 65536 reads, for the next chunk of the same file
+static hrm_status ingest_carry_out(const int32_t* d_invx, int64_t nreads, int64_t first_read_id, int32_t carry_replaced,
+                                   int32_t* h_carry_replaced_out, cudaStream_t s)
+{
+    const int64_t last_in_batch = (first_read_id + nreads) % INGEST_BATCH; // reads of that batch inside this chunk
+    int32_t tail[2] = {0, 0};
+    const int64_t last_first = nreads - last_in_batch;
+    HRM_CUDA(cudaMemcpyAsync(&tail[0], d_invx + nreads, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (last_first > 0) HRM_CUDA(cudaMemcpyAsync(&tail[1], d_invx + last_first, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    if (h_carry_replaced_out)
+        *h_carry_replaced_out = last_in_batch == 0 ? 0 : (last_first >= 0 ? (tail[0] - tail[1]) & 3 : (tail[0] + carry_replaced) & 3);
+    return HRM_OK;
+}
+
+static hrm_status ingest_fasta(const char* d_text, int64_t nbytes, int64_t ntiles, const int32_t* d_tile_excl, int64_t nlines,
+                               int64_t total_lines, int64_t first_read_id, int32_t carry_replaced, char* d_rows,
+                               int64_t pitch, int32_t* d_lengths, uint8_t* d_ambiguous, int64_t max_reads,
+                               int64_t* h_num_reads, int32_t* h_carry_replaced_out, cudaStream_t s)
+{
+    Scratch lstart, ishdr, recx, tot, hline, ninv, invx, err;
+    HRM_TRY(lstart.alloc(sizeof(int64_t) * ((size_t)nlines + 2), s));
+    HRM_TRY(ishdr.alloc(sizeof(int32_t) * ((size_t)total_lines + 1), s));
+    HRM_TRY(recx.alloc(sizeof(int32_t) * ((size_t)total_lines + 2), s));
+    HRM_TRY(tot.alloc(sizeof(int64_t), s));
+    HRM_LAUNCH(line_starts_kernel, igrid(ntiles * 32), 256, 0, s, d_text, nbytes, ntiles, d_tile_excl, lstart.as<int64_t>());
+    HRM_LAUNCH(fasta_headers_kernel, igrid(total_lines), 256, 0, s, d_text, nbytes, lstart.as<int64_t>(), total_lines,
+               ishdr.as<int32_t>());
+    HRM_TRY(exclusive_scan_i32(ishdr.as<int32_t>(), recx.as<int32_t>(), total_lines, tot.as<int64_t>(), s));
+    int64_t nreads = 0;
+    HRM_CUDA(cudaMemcpyAsync(&nreads, tot.p, sizeof nreads, cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    HRM_REQUIRE(nreads <= max_reads, "more reads in the text than max_reads");
+    if (nreads == 0) return HRM_OK;
+    HRM_TRY(hline.alloc(sizeof(int64_t) * (size_t)nreads, s));
+    HRM_TRY(ninv.alloc(sizeof(int32_t) * (size_t)nreads, s));
+    HRM_TRY(invx.alloc(sizeof(int32_t) * ((size_t)nreads + 1), s));
+    HRM_TRY(err.alloc(sizeof(int) * 2, s));
+    HRM_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int) * 2, s));
+    HRM_LAUNCH(fasta_record_lines_kernel, igrid(total_lines), 256, 0, s, ishdr.as<int32_t>(), recx.as<int32_t>(), total_lines,
+               hline.as<int64_t>());
+    HRM_LAUNCH(fasta_extents_kernel, igrid(nreads * 32), 256, 0, s, d_text, nbytes, lstart.as<int64_t>(), nlines, total_lines,
+               hline.as<int64_t>(), nreads, pitch, d_lengths, ninv.as<int32_t>(), err.as<int>());
+    HRM_TRY(exclusive_scan_i32(ninv.as<int32_t>(), invx.as<int32_t>(), nreads, nullptr, s));
+    int h_err = 0;
+    HRM_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof h_err, cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    if (h_err == 2) {
+        set_error("a sequence is longer than the row pitch");
+        return HRM_ERR_INVALID;
+    }
+    HRM_LAUNCH(fasta_copy_kernel, igrid(nreads * 32), 256, 0, s, d_text, nbytes, lstart.as<int64_t>(), nlines, total_lines,
+               hline.as<int64_t>(), ninv.as<int32_t>(), invx.as<int32_t>(), nreads, first_read_id, carry_replaced & 3, d_rows,
+               pitch, d_ambiguous);
+    HRM_TRY(ingest_carry_out(invx.as<int32_t>(), nreads, first_read_id, carry_replaced, h_carry_replaced_out, s));
+    *h_num_reads = nreads;
+    return HRM_OK;
+}
 
 extern "C" hrm_status hrm_ingest_reads(const char* d_text, int64_t nbytes, int64_t first_read_id,
                                        int32_t carry_replaced, char* d_rows, int64_t pitch, int32_t* d_lengths,
@@ -199,7 +359,10 @@ extern "C" hrm_status hrm_ingest_reads(const char* d_text, int64_t nbytes, int64
     HRM_REQUIRE(head[0] == '@' || head[0] == '>', "not FASTQ ('@') or FASTA ('>') text");
     const int lpr = head[0] == '@' ? 4 : 2;
     const int64_t total_lines = nlines + (last != '\n' ? 1 : 0); // a last line without newline still counts
-    HRM_REQUIRE(total_lines % lpr == 0, "incomplete record (or multi-line sequences: not supported on the device)");
+    if (lpr == 2) // FASTA: records are delimited by their header lines, sequences may span any number of lines
+        return ingest_fasta(d_text, nbytes, ntiles, texcl.as<int32_t>(), nlines, total_lines, first_read_id, carry_replaced,
+                            d_rows, pitch, d_lengths, d_ambiguous, max_reads, h_num_reads, h_carry_replaced_out, s);
+    HRM_REQUIRE(total_lines % lpr == 0, "incomplete FASTQ record");
     const int64_t nreads = total_lines / lpr;
     HRM_REQUIRE(nreads <= max_reads, "more reads in the text than max_reads");
     if (nreads == 0) return HRM_OK;
@@ -228,16 +391,7 @@ extern "C" hrm_status hrm_ingest_reads(const char* d_text, int64_t nbytes, int64
     }
     HRM_LAUNCH(copy_reads_kernel, igrid(nreads * 32), 256, 0, s, d_text, sbeg.as<int64_t>(), d_lengths, ninv.as<int32_t>(),
                invx.as<int32_t>(), nreads, first_read_id, carry_replaced & 3, d_rows, pitch, d_ambiguous);
-    // replaced characters of the (unfinished) last batch, for the next chunk
-    const int64_t last_in_batch = (first_read_id + nreads) % INGEST_BATCH; // reads of that batch inside this chunk
-    int32_t tail[2] = {0, 0};
-    const int64_t last_first = nreads - last_in_batch;
-    HRM_CUDA(cudaMemcpyAsync(&tail[0], invx.as<int32_t>() + nreads, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (last_first > 0)
-        HRM_CUDA(cudaMemcpyAsync(&tail[1], invx.as<int32_t>() + last_first, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    HRM_CUDA(cudaStreamSynchronize(s));
-    if (h_carry_replaced_out)
-        *h_carry_replaced_out = last_in_batch == 0 ? 0 : (last_first >= 0 ? (tail[0] - tail[1]) & 3 : (tail[0] + carry_replaced) & 3);
+    HRM_TRY(ingest_carry_out(invx.as<int32_t>(), nreads, first_read_id, carry_replaced, h_carry_replaced_out, s));
     *h_num_reads = nreads;
     return HRM_OK;
 }

@@ -372,12 +372,9 @@ hrm_status filter_segments(uint32_t* d_values, uint32_t* d_scratch, const int32_
     HRM_CUDA(cudaMemsetAsync(big_count, 0, sizeof(int32_t), s));
     HRM_LAUNCH(filter_small_kernel, k4_grid((int64_t)n * 32, 16), K4_THREADS, 0, s, d_values, d_offsets, n, min_hits,
                d_new_counts, big_list, big_count);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(filter_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(sizeof(uint32_t) * K4_BLOCK_CAP));
-        attr_set = true;
-    }
+    // the attribute is per device: set before every launch (a process may drive several GPUs)
+    HRM_CUDA(cudaFuncSetAttribute(filter_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(uint32_t) * K4_BLOCK_CAP)));
     if (min_hits >= 2) { // counting kernel first; what it cannot hold goes on to the sort kernel
         Scratch srt;
         HRM_TRY(srt.alloc(sizeof(int32_t) * ((size_t)n + 1), s));
@@ -385,11 +382,7 @@ hrm_status filter_segments(uint32_t* d_values, uint32_t* d_scratch, const int32_
         int32_t* sort_list = srt.as<int32_t>() + 1;
         HRM_CUDA(cudaMemsetAsync(sort_count, 0, sizeof(int32_t), s));
         const size_t smem_count = sizeof(uint32_t) * (2 * K4_BLOCK_SLOTS + K4_SURV_CAP + 2 * K4_MAX_GROUPS);
-        static bool attr2_set = false;
-        if (!attr2_set) {
-            cudaFuncSetAttribute(filter_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count);
-            attr2_set = true;
-        }
+        HRM_CUDA(cudaFuncSetAttribute(filter_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count));
         HRM_LAUNCH(filter_count_kernel, (unsigned)(num_sms() * 3), K4_THREADS, smem_count, s, d_values, d_scratch, d_offsets,
                    min_hits,
                    d_new_counts, big_list, big_count, sort_list, sort_count);

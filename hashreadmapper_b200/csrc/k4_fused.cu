@@ -47,11 +47,13 @@ struct CollectParams {
     int* overflow;
     int32_t* big_list;
     int32_t* big_count;
+    int32_t* big2_list;         // reads the block-wide filter kernel hands on to the counting-table kernel
+    int32_t* big2_count;
     int warp_cap;               // reads with more ids go straight to the block kernel (test hook)
     int warp_slots;             // table slots of a warp (power of two)
     int slots;                  // table slots of the block kernel (power of two)
     int fill;                   // target ids per range
-    unsigned long long* stats;  // [0] ids enumerated, [1] ids skipped (largest buckets), [2] ranges
+    unsigned long long* stats;  // [0] ids enumerated, [1] ids skipped (largest buckets), [2] ranges, [3] reads -> block kernel
 };
 
 __device__ __forceinline__ uint32_t collect_hash(uint32_t v) { return v * 0x9E3779B1u; }
@@ -442,6 +444,430 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_warp_kernel(CollectPa
     }
 }
 
+// ---- warp per read, duplicate detection by a blocked Bloom filter -----------------------------------------
+// The ids a read enumerates are close to uniform over ~2^25 windows and nearly all distinct: at human-genome scale
+// a read-pass walks ~2000 ids and 1-3 of them occur more than once.  An id with multiplicity >= T has multiplicity
+// >= T - L >= 2 in the enumerated buckets, i.e. it is a DUPLICATE there.  So instead of counting every id exactly
+// (hash table: probe loops, id ranges to keep the table small, range-boundary searches in every bucket) the warp
+// only detects duplicates: one 32-bit word of a shared-memory bitmap per id, three bits of it set by ONE atomicOr;
+// an id whose three bits were all set before is a candidate (every second or later occurrence of an id is, plus
+// ~0.1 false positives per 1000 ids).  Each distinct candidate is then counted EXACTLY: lane t searches bucket t
+// (all H buckets, the skipped ones included), so the multiplicities are the reference's.  The buckets are read
+// once, front to back, with 128-bit loads; nothing is searched before the enumeration.
+//   one atomic per id, exactly-once semantics: two lanes that hold the same id in the same instruction are
+//   serialised by the atomic on their common word, so the later one sees all three bits.
+// Reads that enumerate more ids than the bitmap resolves (E > 3 * words) or that overflow the candidate list go to
+// the block kernel through big_list.
+constexpr int BLOOM_CAND = 96;  // candidate events per read a warp can hold (<= COLLECT_WFIN)
+constexpr int BLOOM_MLP = 2;    // 128-bit id loads a lane keeps in flight
+
+__host__ __device__ inline size_t bloom_slice_words(int words, int H)
+{
+    const size_t w = (size_t)words + 2 * BLOOM_CAND + 4 * (size_t)H + 4;
+    return (w + 3) & ~(size_t)3;
+}
+
+__global__ void __launch_bounds__(COLLECT_THREADS) collect_bloom_kernel(CollectParams P)
+{
+    extern __shared__ __align__(16) uint32_t wdyn[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int H = P.H, T = P.min_hits, WMAX = P.warp_slots;
+    uint32_t* bm = wdyn + (size_t)wid * bloom_slice_words(WMAX, H); // [WMAX]
+    uint32_t* cand = bm + WMAX;                                     // [BLOOM_CAND]
+    uint32_t* ccnt = cand + BLOOM_CAND;                             // [BLOOM_CAND]
+    uint32_t* offv = ccnt + BLOOM_CAND;                             // [H]
+    int* cntv = reinterpret_cast<int*>(offv + H);                   // [H]
+    int* skipf = cntv + H;                                          // [H]
+    int* cpre = skipf + H;                                          // [H + 1] prefix of 16-byte chunks per bucket
+    int* wcount = cpre + H + 1;
+    const int L = T - 2 < 2 ? (T - 2 < 0 ? 0 : T - 2) : 2; // buckets not enumerated
+    const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+    unsigned long long st_enum = 0, st_skip = 0, st_big = 0;
+    const uint4* __restrict__ vals4 = reinterpret_cast<const uint4*>(P.table_values);
+    for (int rd = warp0; rd < P.n; rd += nwarps) {
+        __syncwarp();
+        int total = 0;
+        for (int t0 = 0; t0 < H; t0 += 32) {
+            const int t = t0 + lane;
+            const uint2 r = t < H ? P.ranges[(int64_t)rd * P.rq + (int64_t)t * P.rt] : make_uint2(0u, 0u);
+            if (t < H) {
+                offv[t] = r.x;
+                cntv[t] = (int)r.y;
+                skipf[t] = 0;
+            }
+            total += __reduce_add_sync(0xffffffffu, (int)r.y);
+        }
+        if (lane == 0) *wcount = 0;
+        __syncwarp();
+        if (total < T) {
+            if (lane == 0) {
+                P.lists[rd] = make_int2(0, 0);
+                st_enum += (unsigned long long)total;
+            }
+            continue;
+        }
+        // the L largest buckets are searched for the candidates only
+        int skipped = 0;
+        for (int l = 0; l < L; l++) {
+            unsigned best = 0u;
+            for (int t = lane; t < H; t += 32)
+                if (!skipf[t] && cntv[t] > 0) {
+                    const unsigned key = ((unsigned)cntv[t] << 8) | (unsigned)(255 - t); // ties: lowest table
+                    best = key > best ? key : best;
+                }
+            best = __reduce_max_sync(0xffffffffu, best);
+            if (best == 0u) break;
+            const int t = 255 - (int)(best & 255u);
+            if (lane == 0) skipf[t] = 1;
+            skipped += (int)(best >> 8);
+            __syncwarp();
+        }
+        const int E = total - skipped;
+        if (total > P.warp_cap || E > 3 * WMAX) {
+            if (lane == 0) {
+                P.big_list[atomicAdd(P.big_count, 1)] = rd;
+                st_big++;
+            }
+            continue;
+        }
+        int W = 64, shift = 32 - 6;
+        while (W < WMAX && W < E) {
+            W <<= 1;
+            shift--;
+        }
+        {
+            uint4* b4 = reinterpret_cast<uint4*>(bm);
+            for (int i = lane; i < W / 4; i += 32) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        // 16-byte chunks of the enumerated buckets as one flat sequence
+        int ctotal = 0;
+        for (int t0 = 0; t0 < H; t0 += 32) {
+            const int t = t0 + lane;
+            const int nch = (t < H && !skipf[t] && cntv[t] > 0) ? (int)(((offv[t] & 3u) + (uint32_t)cntv[t] + 3u) >> 2) : 0;
+            int incl = nch;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (t < H) cpre[t] = ctotal + incl - nch;
+            ctotal += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) cpre[H] = ctotal;
+        __syncwarp();
+        int tcur = 0, cnext = 0;
+        int64_t cbase = 0;           // chunk c of the current bucket lies at vals4[cbase + c]
+        uint32_t lo = 0, hi = 0;     // element range of the current bucket
+        for (int c0 = 0; c0 < ctotal; c0 += 32 * BLOOM_MLP) {
+            uint4 v[BLOOM_MLP];
+            uint32_t e0[BLOOM_MLP], vlo[BLOOM_MLP], vhi[BLOOM_MLP];
+#pragma unroll
+            for (int u = 0; u < BLOOM_MLP; u++) {
+                const int c = c0 + u * 32 + lane;
+                vlo[u] = 1u;
+                vhi[u] = 0u; // nothing valid
+                e0[u] = 0u;
+                if (c < ctotal) {
+                    if (c >= cnext) {
+                        while (cpre[tcur + 1] <= c) tcur++;
+                        cnext = cpre[tcur + 1];
+                        lo = offv[tcur];
+                        hi = lo + (uint32_t)cntv[tcur];
+                        cbase = (int64_t)(lo >> 2) - cpre[tcur];
+                    }
+                    v[u] = __ldg(vals4 + cbase + c);
+                    e0[u] = (uint32_t)((cbase + c) << 2);
+                    vlo[u] = lo;
+                    vhi[u] = hi;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BLOOM_MLP; u++) {
+                const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t e = e0[u] + j;
+                    if (e >= vlo[u] && e < vhi[u]) {
+                        const uint32_t h = x[j] * 0x9E3779B1u;
+                        const uint32_t g = (h ^ (h >> 15)) * 0x2C1B3C6Du;
+                        const uint32_t mask = (1u << (g >> 27)) | (1u << ((g >> 22) & 31u)) | (1u << ((g >> 17) & 31u));
+                        const uint32_t old = atomicOr(&bm[h >> shift], mask);
+                        if ((old & mask) == mask) {
+                            const int at = atomicAdd(wcount, 1);
+                            if (at < BLOOM_CAND) cand[at] = x[j];
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        int nc = *wcount;
+        if (lane == 0) {
+            st_enum += (unsigned long long)E;
+            st_skip += (unsigned long long)skipped;
+        }
+        if (nc > BLOOM_CAND) { // too many duplicates for the warp's list: the block kernel redoes the read
+            if (lane == 0) {
+                P.big_list[atomicAdd(P.big_count, 1)] = rd;
+                st_enum -= (unsigned long long)E;
+                st_skip -= (unsigned long long)skipped;
+                st_big++;
+            }
+            continue;
+        }
+        int nfin = 0;
+        if (nc > 0) {
+            // distinct candidates, ascending
+            if (nc > 1) collect_sort_warp(cand, nc, lane);
+            int nu = 0;
+            for (int c0 = 0; c0 < nc; c0 += 32) {
+                const int c = c0 + lane;
+                const uint32_t id = c < nc ? cand[c] : 0u;
+                const bool first = c < nc && (c == 0 || cand[c - 1] != id);
+                __syncwarp();
+                const unsigned m = __ballot_sync(0xffffffffu, first);
+                if (first) cand[nu + __popc(m & ((1u << lane) - 1u))] = id; // nu + rank <= c: never ahead of the readers
+                nu += __popc(m);
+                __syncwarp();
+            }
+            for (int c = lane; c < nu; c += 32) ccnt[c] = 0u;
+            __syncwarp();
+            // exact multiplicity: (candidate, bucket) pairs over the lanes
+            for (int x = lane; x < nu * H; x += 32) {
+                const int c = x / H, t = x - c * H;
+                const int cnt = cntv[t];
+                if (cnt > 0) {
+                    const uint32_t id = cand[c];
+                    const uint32_t* p = P.table_values + offv[t];
+                    const int pos = collect_lower_bound_interp(p, cnt, id, P.id_space);
+                    if (pos < cnt && __ldg(p + pos) == id) atomicAdd(&ccnt[c], 1u);
+                }
+            }
+            __syncwarp();
+            for (int c0 = 0; c0 < nu; c0 += 32) {
+                const int c = c0 + lane;
+                const uint32_t id = c < nu ? cand[c] : 0u;
+                const bool keep = c < nu && ccnt[c] >= (uint32_t)T;
+                __syncwarp();
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) cand[nfin + __popc(m & ((1u << lane) - 1u))] = id;
+                nfin += __popc(m);
+                __syncwarp();
+            }
+        }
+        unsigned long long start = 0;
+        if (lane == 0 && nfin > 0) start = atomicAdd(P.cursor, (unsigned long long)nfin);
+        start = __shfl_sync(0xffffffffu, start, 0);
+        if (start + (unsigned long long)nfin > P.out_cap) {
+            if (lane == 0) *P.overflow = 1;
+            nfin = 0;
+        }
+        for (int i = lane; i < nfin; i += 32) P.out[start + i] = cand[i];
+        if (lane == 0) P.lists[rd] = make_int2((int)start, nfin);
+    }
+    if (lane == 0 && P.stats) {
+        if (st_enum) atomicAdd(P.stats, st_enum);
+        if (st_skip) atomicAdd(P.stats + 1, st_skip);
+        if (st_big) atomicAdd(P.stats + 3, st_big);
+    }
+}
+
+// ---- block per read, same duplicate detection with a block-wide filter ----------------------------------
+// Reads of big_list (more ids than a warp's filter resolves, or too many candidates for a warp's list): 256
+// threads, a filter of up to `slots` words (E <= 3 * words), up to COLLECT_FINAL_CAP candidates.  What still does
+// not fit goes on to big2_list for the counting-table kernel below.
+constexpr int BLOOMB_THREADS = 256;
+
+__global__ void __launch_bounds__(BLOOMB_THREADS) collect_bloom_block_kernel(CollectParams P)
+{
+    extern __shared__ __align__(16) uint32_t bdyn[];
+    const int WMAX = P.slots;
+    uint32_t* bm = bdyn;                              // [WMAX]
+    uint32_t* cand = bm + WMAX;                       // [COLLECT_FINAL_CAP]
+    uint32_t* ccnt = cand + COLLECT_FINAL_CAP;        // [COLLECT_FINAL_CAP]
+    __shared__ uint32_t offv[MAX_TABLES];
+    __shared__ int cntv[MAX_TABLES];
+    __shared__ int skip[MAX_TABLES];
+    __shared__ int cpre[MAX_TABLES + 1];
+    __shared__ int s_ncand, s_nu, s_nfin, s_E, s_skipped;
+    __shared__ unsigned long long s_start;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, H = P.H, T = P.min_hits;
+    const int L = T - 2 < 2 ? (T - 2 < 0 ? 0 : T - 2) : 2;
+    const int nbig = *P.big_count;
+    unsigned long long st_enum = 0, st_skip = 0;
+    const uint4* __restrict__ vals4 = reinterpret_cast<const uint4*>(P.table_values);
+    for (int bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+        const int rd = P.big_list[bi];
+        __syncthreads();
+        if (tid < H) {
+            const uint2 r = P.ranges[(int64_t)rd * P.rq + (int64_t)tid * P.rt];
+            offv[tid] = r.x;
+            cntv[tid] = (int)r.y;
+            skip[tid] = 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int l = 0; l < L; l++) { // the L largest buckets (ties: lowest table)
+                int best = -1;
+                for (int t = 0; t < H; t++)
+                    if (!skip[t] && cntv[t] > 0 && (best < 0 || cntv[t] > cntv[best])) best = t;
+                if (best >= 0) skip[best] = 1;
+            }
+            int64_t E = 0, SK = 0;
+            int ct = 0;
+            for (int t = 0; t < H; t++) {
+                cpre[t] = ct;
+                if (skip[t]) SK += cntv[t];
+                else {
+                    E += cntv[t];
+                    if (cntv[t] > 0) ct += (int)(((offv[t] & 3u) + (uint32_t)cntv[t] + 3u) >> 2);
+                }
+            }
+            cpre[H] = ct;
+            s_E = E > 0x7fffffff ? 0x7fffffff : (int)E;
+            s_skipped = (int)SK;
+            s_ncand = 0;
+            s_nu = 0;
+            s_nfin = 0;
+        }
+        __syncthreads();
+        const int E = s_E;
+        if (E > 3 * WMAX) { // the counting-table kernel takes it
+            if (tid == 0) P.big2_list[atomicAdd(P.big2_count, 1)] = rd;
+            continue;
+        }
+        int W = 64, shift = 32 - 6;
+        while (W < WMAX && W < E) {
+            W <<= 1;
+            shift--;
+        }
+        {
+            uint4* b4 = reinterpret_cast<uint4*>(bm);
+            for (int i = tid; i < W / 4; i += BLOOMB_THREADS) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        const int ctotal = cpre[H];
+        int tcur = 0, cnext = 0;
+        int64_t cbase = 0;
+        uint32_t lo = 0, hi = 0;
+        for (int c0 = 0; c0 < ctotal; c0 += BLOOMB_THREADS * BLOOM_MLP) {
+            uint4 v[BLOOM_MLP];
+            uint32_t e0[BLOOM_MLP], vlo[BLOOM_MLP], vhi[BLOOM_MLP];
+#pragma unroll
+            for (int u = 0; u < BLOOM_MLP; u++) {
+                const int c = c0 + u * BLOOMB_THREADS + tid;
+                vlo[u] = 1u;
+                vhi[u] = 0u;
+                e0[u] = 0u;
+                if (c < ctotal) {
+                    if (c >= cnext) {
+                        while (cpre[tcur + 1] <= c) tcur++;
+                        cnext = cpre[tcur + 1];
+                        lo = offv[tcur];
+                        hi = lo + (uint32_t)cntv[tcur];
+                        cbase = (int64_t)(lo >> 2) - cpre[tcur];
+                    }
+                    v[u] = __ldg(vals4 + cbase + c);
+                    e0[u] = (uint32_t)((cbase + c) << 2);
+                    vlo[u] = lo;
+                    vhi[u] = hi;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BLOOM_MLP; u++) {
+                const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t e = e0[u] + j;
+                    if (e >= vlo[u] && e < vhi[u]) {
+                        const uint32_t h = x[j] * 0x9E3779B1u;
+                        const uint32_t g = (h ^ (h >> 15)) * 0x2C1B3C6Du;
+                        const uint32_t mask = (1u << (g >> 27)) | (1u << ((g >> 22) & 31u)) | (1u << ((g >> 17) & 31u));
+                        const uint32_t old = atomicOr(&bm[h >> shift], mask);
+                        if ((old & mask) == mask) {
+                            const int at = atomicAdd(&s_ncand, 1);
+                            if (at < COLLECT_FINAL_CAP) cand[at] = x[j];
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int nc = s_ncand;
+        if (nc > COLLECT_FINAL_CAP) {
+            if (tid == 0) P.big2_list[atomicAdd(P.big2_count, 1)] = rd;
+            continue;
+        }
+        if (tid == 0) {
+            st_enum += (unsigned long long)E;
+            st_skip += (unsigned long long)s_skipped;
+        }
+        if (nc > 1) bitonic_sort<true>(cand, nc, tid, BLOOMB_THREADS);
+        __syncthreads();
+        if (wid == 0) { // distinct candidates, in place (writes never pass the readers)
+            int nu = 0;
+            for (int c0 = 0; c0 < nc; c0 += 32) {
+                const int c = c0 + lane;
+                const uint32_t id = c < nc ? cand[c] : 0u;
+                const bool first = c < nc && (c == 0 || cand[c - 1] != id);
+                __syncwarp();
+                const unsigned m = __ballot_sync(0xffffffffu, first);
+                if (first) cand[nu + __popc(m & ((1u << lane) - 1u))] = id;
+                nu += __popc(m);
+                __syncwarp();
+            }
+            if (lane == 0) s_nu = nu;
+        }
+        __syncthreads();
+        const int nu = s_nu;
+        for (int c = tid; c < nu; c += BLOOMB_THREADS) ccnt[c] = 0u;
+        __syncthreads();
+        for (int x = tid; x < nu * H; x += BLOOMB_THREADS) { // exact multiplicity over all H buckets
+            const int c = x / H, t = x - c * H;
+            const int cnt = cntv[t];
+            if (cnt > 0) {
+                const uint32_t id = cand[c];
+                const uint32_t* p = P.table_values + offv[t];
+                const int pos = collect_lower_bound_interp(p, cnt, id, P.id_space);
+                if (pos < cnt && __ldg(p + pos) == id) atomicAdd(&ccnt[c], 1u);
+            }
+        }
+        __syncthreads();
+        if (wid == 0) {
+            int nfin = 0;
+            for (int c0 = 0; c0 < nu; c0 += 32) {
+                const int c = c0 + lane;
+                const uint32_t id = c < nu ? cand[c] : 0u;
+                const bool keep = c < nu && ccnt[c] >= (uint32_t)T;
+                __syncwarp();
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) cand[nfin + __popc(m & ((1u << lane) - 1u))] = id;
+                nfin += __popc(m);
+                __syncwarp();
+            }
+            if (lane == 0) {
+                unsigned long long start = 0;
+                if (nfin > 0) start = atomicAdd(P.cursor, (unsigned long long)nfin);
+                if (start + (unsigned long long)nfin > P.out_cap) {
+                    *P.overflow = 1;
+                    nfin = 0;
+                }
+                s_start = start;
+                s_nfin = nfin;
+                P.lists[rd] = make_int2((int)start, nfin);
+            }
+        }
+        __syncthreads();
+        const int nfin = s_nfin;
+        const unsigned long long start = s_start;
+        for (int i = tid; i < nfin; i += BLOOMB_THREADS) P.out[start + i] = cand[i];
+    }
+    if (tid == 0 && P.stats) {
+        if (st_enum) atomicAdd(P.stats, st_enum);
+        if (st_skip) atomicAdd(P.stats + 1, st_skip);
+    }
+}
+
 // ---- block per read ----------------------------------------------------------------------------------
 template <bool PACKED>
 __global__ void __launch_bounds__(COLLECT_BIG_THREADS) collect_big_kernel(CollectParams P)
@@ -663,20 +1089,22 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     *h_total = 0;
     if (n == 0) return HRM_OK;
     HRM_REQUIRE(min_hits >= 2 && id_space < 0xFFFFFFFFu, "collect_candidates needs minTableHits >= 2");
-    static const int warp_cap = env_int("HRM_COLLECT_WARP_CAP", 0x7fffffff);
-    static const int wslots_env = env_int("HRM_COLLECT_WARP_SLOTS", 1024);
+    const int warp_cap = env_int("HRM_COLLECT_WARP_CAP", 0x7fffffff);
+    const int wslots_env = env_int("HRM_COLLECT_WARP_SLOTS", 1024);
     int wslots = 128;
     while (wslots < wslots_env && wslots < 8192) wslots <<= 1;
-    static const int slots_env = env_int("HRM_COLLECT_SLOTS", 2048);
+    const int slots_env = env_int("HRM_COLLECT_SLOTS", 2048);
     int slots = 64;
     while (slots < slots_env && slots < 16384) slots <<= 1;
-    static const int fill_env = env_int("HRM_COLLECT_FILL", 0);
+    const int fill_env = env_int("HRM_COLLECT_FILL", 0);
     const int fill = fill_env > 0 ? fill_env : (slots * 3) / 8; // expected ids per range: 3/8 of the table, 7/8 tolerated
-    Scratch ctl, big;
+    Scratch ctl, big, big2;
     HRM_TRY(ctl.alloc(sizeof(unsigned long long) * 8, s));
     HRM_TRY(big.alloc(sizeof(int32_t) * ((size_t)n + 1), s));
+    HRM_TRY(big2.alloc(sizeof(int32_t) * ((size_t)n + 1), s));
     HRM_CUDA(cudaMemsetAsync(ctl.p, 0, sizeof(unsigned long long) * 8, s));
     HRM_CUDA(cudaMemsetAsync(big.p, 0, sizeof(int32_t), s));
+    HRM_CUDA(cudaMemsetAsync(big2.p, 0, sizeof(int32_t), s));
     CollectParams P;
     P.ranges = qh->ranges.as<uint2>();
     P.rq = qh->rq;
@@ -694,11 +1122,20 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     P.lists = d_lists;
     P.big_count = big.as<int32_t>();
     P.big_list = big.as<int32_t>() + 1;
+    P.big2_count = big2.as<int32_t>();
+    P.big2_list = big2.as<int32_t>() + 1;
     P.warp_cap = warp_cap;
     P.warp_slots = wslots;
     P.slots = slots;
     P.fill = fill;
-    static const bool allow_packed = env_int("HRM_COLLECT_UNPACKED", 0) == 0;
+    const int impl_ranges = env_int("HRM_COLLECT_RANGES", 0); // 1: the counting-table warp kernel (id ranges)
+    const int bloom_words_env = env_int("HRM_COLLECT_BLOOM_WORDS", 2048);
+    int bwords = 64;
+    while (bwords < bloom_words_env && bwords < 8192) bwords <<= 1;
+    const int bblock_env = env_int("HRM_COLLECT_BLOOM_BLOCK_WORDS", 32768);
+    int bblock_words = 64;
+    while (bblock_words < bblock_env && bblock_words < 32768) bblock_words <<= 1;
+    const bool allow_packed = env_int("HRM_COLLECT_UNPACKED", 0) == 0;
     const bool packed = allow_packed && id_space < (1u << (32 - COLLECT_PACK_BITS)) - 1u && mh->H < (1 << COLLECT_PACK_BITS);
     const size_t smem = sizeof(uint32_t) * ((size_t)((packed ? 1 : 2) + 1) * slots + COLLECT_FINAL_CAP);
     // warp kernel: 2 warps per block so that the slices of many blocks fill the SM's shared memory
@@ -707,7 +1144,35 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     int wres = 1;
     // one wave of resident blocks, each loops over the list of big reads
     int resident = 1;
-    if (packed) {
+    if (!impl_ranges) {
+        P.warp_slots = bwords;
+        const size_t bsmem = sizeof(uint32_t) * bloom_slice_words(bwords, mh->H) * (wthreads / 32);
+        cudaFuncSetAttribute(collect_bloom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wres, collect_bloom_kernel, wthreads, bsmem));
+        HRM_LAUNCH(collect_bloom_kernel, (unsigned)(num_sms() * (wres > 0 ? wres : 1)), wthreads, bsmem, s, P);
+        // skewed reads: block-wide filter, then (what is left) the counting-table kernel on big2_list
+        CollectParams PB = P;
+        PB.slots = bblock_words;
+        const size_t bbsmem = sizeof(uint32_t) * ((size_t)bblock_words + 2 * COLLECT_FINAL_CAP);
+        int bres = 1;
+        cudaFuncSetAttribute(collect_bloom_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bbsmem);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bres, collect_bloom_block_kernel, BLOOMB_THREADS, bbsmem));
+        HRM_LAUNCH(collect_bloom_block_kernel, (unsigned)(num_sms() * (bres > 0 ? bres : 1)), BLOOMB_THREADS, bbsmem, s, PB);
+        CollectParams PC = P;
+        PC.big_count = P.big2_count;
+        PC.big_list = P.big2_list;
+        if (packed) {
+            cudaFuncSetAttribute(collect_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, collect_big_kernel<true>, COLLECT_BIG_THREADS, smem));
+            HRM_LAUNCH(collect_big_kernel<true>, (unsigned)(num_sms() * (resident > 0 ? resident : 1)), COLLECT_BIG_THREADS,
+                       smem, s, PC);
+        } else {
+            cudaFuncSetAttribute(collect_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, collect_big_kernel<false>, COLLECT_BIG_THREADS, smem));
+            HRM_LAUNCH(collect_big_kernel<false>, (unsigned)(num_sms() * (resident > 0 ? resident : 1)), COLLECT_BIG_THREADS,
+                       smem, s, PC);
+        }
+    } else if (packed) {
         cudaFuncSetAttribute(collect_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
         HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wres, collect_warp_kernel<true>, wthreads, wsmem));
         HRM_LAUNCH(collect_warp_kernel<true>, (unsigned)(num_sms() * (wres > 0 ? wres : 1)), wthreads, wsmem, s, P);
@@ -732,7 +1197,7 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     if (h_stats3) {
         h_stats3[0] = (int64_t)h[2];
         h_stats3[1] = (int64_t)h[3];
-        h_stats3[2] = (int64_t)h[4];
+        h_stats3[2] = (int64_t)h[5]; // reads handed to the block kernel
     }
     return HRM_OK;
 }

@@ -133,6 +133,15 @@ extern "C" void hrm_mapper_destroy(hrm_mapper* m)
     }
     if (m->d_win_prefix) cudaFree(m->d_win_prefix);
     for (auto e : m->copy_events) cudaEventDestroy(e);
+    if (m->pipe_ready) {
+        for (int i = 0; i < HRM_PIPE_SLOTS; i++) {
+            cudaEventDestroy(m->slot[i].staged);
+            cudaEventDestroy(m->slot[i].computed);
+            cudaEventDestroy(m->slot[i].drained);
+        }
+        cudaStreamDestroy(m->pipe_in);
+        cudaStreamDestroy(m->pipe_out);
+    }
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     delete m;
 }
@@ -203,6 +212,7 @@ extern "C" hrm_status hrm_mapper_info(const hrm_mapper* m, hrm_mapper_info_t* ou
     out->num_passes = m->cfg.num_passes;
     out->collect_ids_counted = m->collect_enumerated;
     out->collect_ids_skipped = m->collect_skipped;
+    out->collect_reads_block_kernel = m->collect_block_reads;
     for (int c = 0; c < 3; c++) {
         if (m->genome[c]) out->genome_device_bytes += m->genome[c]->device_bytes();
         if (m->index[c]) {
@@ -386,6 +396,7 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
                     st.num_candidates += ctotal;
                     m->collect_enumerated += cst[0];
                     m->collect_skipped += cst[1];
+                    m->collect_block_reads += cst[2];
                     collected = true;
                 }
             }
@@ -635,6 +646,127 @@ extern "C" hrm_status hrm_mapper_map_reads_sam(hrm_mapper* m, const char* h_read
     return HRM_OK;
 }
 
+
+// ---- double-buffered end-to-end pipeline ---------------------------------------------------------------------
+// ref: the reference's driver overlaps nothing: every window batch is H2D -> kernels -> D2H with >= 6 stream syncs
+// (main_gpu.cu:471-854) and STEP 2 starts when STEP 1 has ended (main_gpu.cu:1123-1160).  Here a batch lives in one of
+// HRM_PIPE_SLOTS slots: its reads are staged (H2D on a copy-in stream) while the previous batch computes, its results
+// leave (D2H on a copy-out stream) while the next batch computes; the kernels of all batches run in order on the
+// caller's stream.  Host syncs inside the compute (candidate totals, text size) only ever wait for the batch at hand.
+static hrm_status pipe_init(hrm_mapper* m)
+{
+    if (m->pipe_ready) return HRM_OK;
+    HRM_CUDA(cudaStreamCreateWithFlags(&m->pipe_in, cudaStreamNonBlocking));
+    HRM_CUDA(cudaStreamCreateWithFlags(&m->pipe_out, cudaStreamNonBlocking));
+    for (int i = 0; i < HRM_PIPE_SLOTS; i++) {
+        HRM_CUDA(cudaEventCreateWithFlags(&m->slot[i].staged, cudaEventDisableTiming));
+        HRM_CUDA(cudaEventCreateWithFlags(&m->slot[i].computed, cudaEventDisableTiming));
+        HRM_CUDA(cudaEventCreateWithFlags(&m->slot[i].drained, cudaEventDisableTiming));
+    }
+    m->pipe_ready = true;
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_mapper_stage_reads(hrm_mapper* m, int slot, const char* h_reads_ascii, int64_t ascii_pitch,
+                                             const int32_t* h_lengths, int64_t n)
+{
+    HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
+    HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0, "sizes");
+    HRM_REQUIRE(n == 0 || (h_reads_ascii != nullptr && h_lengths != nullptr), "buffers");
+    HRM_REQUIRE(m->comm == nullptr, "the staged pipeline runs on the replicated index");
+    HRM_TRY(pipe_init(m));
+    PipeSlot& S = m->slot[slot];
+    // the slot's previous batch must have left the device before its buffers are overwritten
+    if (S.busy) HRM_CUDA(cudaEventSynchronize(S.drained));
+    S.busy = false;
+    S.n = n;
+    S.pitch = ascii_pitch;
+    HRM_TRY(S.ascii.reserve((size_t)(n * ascii_pitch)));
+    HRM_TRY(S.len.reserve(sizeof(int32_t) * (size_t)n));
+    if (n > 0) {
+        HRM_CUDA(cudaMemcpyAsync(S.ascii.p, h_reads_ascii, (size_t)(n * ascii_pitch), cudaMemcpyHostToDevice, m->pipe_in));
+        HRM_CUDA(cudaMemcpyAsync(S.len.p, h_lengths, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, m->pipe_in));
+    }
+    HRM_CUDA(cudaEventRecord(S.staged, m->pipe_in));
+    S.is_staged = true;
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_mapper_map_staged(hrm_mapper* m, int slot, hrm_read_record* h_records, char* h_cigars,
+                                            int64_t cigar_pitch, uint32_t first_read_id,
+                                            const char* const* h_chrom_names, char* h_sq_out, int64_t sq_cap,
+                                            char* h_rec_out, int64_t rec_cap, hrm_batch_stats* h_stats, hrm_stream stream)
+{
+    HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
+    HRM_REQUIRE(cigar_pitch > 0, "cigar_pitch");
+    PipeSlot& S = m->slot[slot];
+    HRM_REQUIRE(m->pipe_ready && S.is_staged, "hrm_mapper_stage_reads has not been called for this slot");
+    cudaStream_t s = as_stream(stream);
+    const int64_t n = S.n;
+    S.is_staged = false;
+    S.sq_written = S.rec_written = 0;
+    if (h_stats) memset(h_stats, 0, sizeof *h_stats);
+    if (n == 0) return HRM_OK;
+    const bool want_text = h_rec_out != nullptr;
+    size_t maxname = 12;
+    for (int c = 0; c < m->n_chrom && h_chrom_names; c++)
+        if (h_chrom_names[c] && strlen(h_chrom_names[c]) > maxname) maxname = strlen(h_chrom_names[c]);
+    const int64_t line_bound = 64 + (int64_t)maxname + cigar_pitch + m->cfg.window_size + S.pitch;
+    HRM_TRY(S.mapped.reserve(sizeof(hrm_mapped_read) * (size_t)n));
+    HRM_TRY(S.rec.reserve(sizeof(hrm_read_record) * (size_t)n));
+    HRM_TRY(S.cig.reserve((size_t)(2 * n * cigar_pitch)));
+    if (want_text) {
+        HRM_TRY(S.text.reserve((size_t)(n * line_bound)));
+        if (h_sq_out) HRM_TRY(S.sq.reserve((size_t)(n * 40)));
+    }
+    HRM_CUDA(cudaStreamWaitEvent(s, S.staged, 0));
+    hrm_batch_stats st;
+    memset(&st, 0, sizeof st);
+    const char* d_ascii = S.ascii.as<char>();
+    const int32_t* d_len = S.len.as<int32_t>();
+    HRM_TRY(hrm_map_batch(m, d_ascii, S.pitch, d_len, n, S.mapped.as<hrm_mapped_read>(), h_stats ? &st : nullptr, stream));
+    HRM_TRY(hrm_verify_batch(m, d_ascii, S.pitch, d_len, n, S.mapped.as<hrm_mapped_read>(), S.rec.as<hrm_read_record>(),
+                             S.cig.as<char>(), cigar_pitch, h_stats ? &st : nullptr, stream));
+    if (want_text) {
+        const int64_t launches0 = g_launches.load();
+        HRM_TRY(hrm_sam_format_device(m, nullptr, S.pitch, d_len, n, S.rec.as<hrm_read_record>(), S.cig.as<char>(),
+                                      cigar_pitch, first_read_id, h_chrom_names, HRM_SAM_RECORDS, S.text.as<char>(),
+                                      n * line_bound, &S.rec_written, stream));
+        HRM_REQUIRE(S.rec_written <= rec_cap, "record text does not fit rec_cap");
+        if (h_sq_out) {
+            HRM_TRY(hrm_sam_format_device(m, nullptr, S.pitch, d_len, n, S.rec.as<hrm_read_record>(), S.cig.as<char>(),
+                                          cigar_pitch, first_read_id, h_chrom_names, HRM_SAM_SQ_LINES, S.sq.as<char>(),
+                                          n * 40, &S.sq_written, stream));
+            HRM_REQUIRE(S.sq_written <= sq_cap, "@SQ text does not fit sq_cap");
+        }
+        st.num_kernel_launches += g_launches.load() - launches0;
+    }
+    HRM_CUDA(cudaEventRecord(S.computed, s));
+    HRM_CUDA(cudaStreamWaitEvent(m->pipe_out, S.computed, 0));
+    cudaStream_t co = m->pipe_out;
+    if (want_text) {
+        HRM_CUDA(cudaMemcpyAsync(h_rec_out, S.text.p, (size_t)S.rec_written, cudaMemcpyDeviceToHost, co));
+        if (h_sq_out) HRM_CUDA(cudaMemcpyAsync(h_sq_out, S.sq.p, (size_t)S.sq_written, cudaMemcpyDeviceToHost, co));
+    }
+    if (h_records)
+        HRM_CUDA(cudaMemcpyAsync(h_records, S.rec.p, sizeof(hrm_read_record) * (size_t)n, cudaMemcpyDeviceToHost, co));
+    if (h_cigars) HRM_CUDA(cudaMemcpyAsync(h_cigars, S.cig.p, (size_t)(2 * n * cigar_pitch), cudaMemcpyDeviceToHost, co));
+    HRM_CUDA(cudaEventRecord(S.drained, co));
+    S.busy = true;
+    if (h_stats) *h_stats = st;
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_mapper_finish(hrm_mapper* m, int slot, int64_t* h_sq_written, int64_t* h_rec_written)
+{
+    HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
+    PipeSlot& S = m->slot[slot];
+    if (S.busy) HRM_CUDA(cudaEventSynchronize(S.drained));
+    S.busy = false;
+    if (h_sq_written) *h_sq_written = S.sq_written;
+    if (h_rec_written) *h_rec_written = S.rec_written;
+    return HRM_OK;
+}
 
 extern "C" hrm_status hrm_mapper_set_partition(hrm_mapper* m, hrm_comm* comm)
 {

@@ -52,6 +52,16 @@ struct StageTimer {
 };
 } // namespace hrm
 
+namespace hrm {
+// one batch of the double-buffered end-to-end pipeline (mapper.cu: hrm_mapper_stage_reads / map_staged / finish)
+struct PipeSlot {
+    GrowBuf ascii, len, mapped, rec, cig, text, sq;
+    cudaEvent_t staged = nullptr, computed = nullptr, drained = nullptr;
+    int64_t n = 0, pitch = 0, sq_written = 0, rec_written = 0;
+    bool is_staged = false, busy = false;
+};
+} // namespace hrm
+
 struct hrm_mapper {
     hrm_mapper_config cfg;
     // one genome + index per distinct genome conversion
@@ -75,6 +85,7 @@ struct hrm_mapper {
     int64_t value_budget = 1LL << 30; // candidate values retrieved per range of reads (int offsets, 8 B scratch each)
     bool use_fused = true;            // K3b retrieval + K4 fused (k4_fused.cu) on the replicated index
     int64_t collect_enumerated = 0, collect_skipped = 0; // ids counted / skipped (largest buckets) by the fused path
+    int64_t collect_block_reads = 0;                     // reads the warp kernel handed to the block kernel
     int64_t part_chunk = 1 << 17;     // reads per routed query of the key-partitioned index
     // reads per pipelined chunk of hrm_mapper_map_reads (copies of neighbouring chunks under compute).  Default: one
     // chunk -- measured on B200 at 1 M reads: 8.05 M reads/s as one chunk, 6.44 M in chunks of 262 144, 5.08 M in
@@ -83,6 +94,10 @@ struct hrm_mapper {
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> copy_events;
     hrm_comm* comm = nullptr; // key-partitioned index (partition.cu); not owned
+    // double-buffered end-to-end pipeline
+    hrm::PipeSlot slot[HRM_PIPE_SLOTS];
+    cudaStream_t pipe_in = nullptr, pipe_out = nullptr;
+    bool pipe_ready = false;
 };
 
 namespace hrm {

@@ -38,6 +38,47 @@ __global__ void __launch_bounds__(256) gather_lengths_kernel(const int32_t* __re
     }
 }
 
+// per read: 1 if any of its first len characters is not A/C/G/T (ref: the reads ChunkedReadStorage records as
+// ambiguous, chunkedreadstorageconstruction.hpp:70-95); thread per read over 16-byte pieces
+__global__ void __launch_bounds__(256) flag_ambiguous_kernel(const char* __restrict__ ascii, int64_t pitch,
+                                                             const int32_t* __restrict__ lengths, int64_t n,
+                                                             uint8_t* __restrict__ flags,
+                                                             unsigned long long* __restrict__ count)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long local = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        const int len = lengths[r];
+        const uint4* row = reinterpret_cast<const uint4*>(ascii + r * pitch);
+        bool bad = false;
+        for (int c = 0; c * 16 < len && !bad; c++) {
+            const uint4 v = row[c];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int t = c * 16 + j;
+                const unsigned ch = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                if (t < len && ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') bad = true;
+            }
+        }
+        flags[r] = bad ? 1 : 0;
+        local += bad ? 1 : 0;
+    }
+    for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+__global__ void __launch_bounds__(256) gather_flags_kernel(const uint8_t* __restrict__ flags,
+                                                           const uint32_t* __restrict__ ids, int64_t n, int64_t nrows,
+                                                           uint8_t* __restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const int64_t id = ids[e];
+        out[e] = (flags && id < nrows) ? flags[id] : 0;
+    }
+}
+
 static unsigned sgrid(int64_t items)
 {
     int64_t g = HRM_SDIV(items, (int64_t)256);
@@ -197,22 +238,18 @@ extern "C" hrm_status hrm_readstore_create_from_ascii(hrm_readstore** out, const
     auto rs = std::unique_ptr<hrm_readstore>(new hrm_readstore);
     rs->n = n;
     int32_t maxlen = 0;
-    int64_t with_n = 0;
     for (int64_t i = 0; i < n; i++) {
         HRM_REQUIRE(h_lengths[i] >= 0 && h_lengths[i] <= ascii_pitch, "read length exceeds pitch");
         maxlen = h_lengths[i] > maxlen ? h_lengths[i] : maxlen;
-        const char* r = h_ascii + i * ascii_pitch;
-        for (int t = 0; t < h_lengths[i]; t++)
-            if (r[t] != 'A' && r[t] != 'C' && r[t] != 'G' && r[t] != 'T') {
-                with_n++;
-                break;
-            }
     }
-    rs->with_n = with_n;
     rs->pitch_words = (maxlen + 15) / 16 > 0 ? (maxlen + 15) / 16 : 1;
     const size_t nn = (size_t)(n > 0 ? n : 1);
     HRM_CUDA(cudaMalloc(&rs->rows, sizeof(uint32_t) * nn * (size_t)rs->pitch_words));
     HRM_CUDA(cudaMalloc(&rs->lengths, sizeof(int32_t) * nn));
+    HRM_CUDA(cudaMalloc(&rs->ambig, nn + 8));
+    unsigned long long* d_count = nullptr;
+    HRM_CUDA(cudaMalloc(&d_count, sizeof(unsigned long long)));
+    HRM_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), s));
     if (n > 0) {
         HRM_CUDA(cudaMemcpyAsync(rs->lengths, h_lengths, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
         const int64_t CH = 1 << 20; // reads per staging chunk
@@ -228,6 +265,8 @@ extern "C" hrm_status hrm_readstore_create_from_ascii(hrm_readstore** out, const
                 st = HRM_ERR_CUDA;
                 break;
             }
+            flag_ambiguous_kernel<<<sgrid(m), 256, 0, s>>>(d_stage, ascii_pitch, rs->lengths + at, m, rs->ambig + at, d_count);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
             st = hrm_encode_2bit(d_stage, ascii_pitch, rs->lengths + at, m, conversion,
                                  rs->rows + at * rs->pitch_words, rs->pitch_words, stream);
             if (st == HRM_OK && cudaStreamSynchronize(s) != cudaSuccess) {
@@ -239,9 +278,16 @@ extern "C" hrm_status hrm_readstore_create_from_ascii(hrm_readstore** out, const
         if (st != HRM_OK) {
             cudaFree(rs->rows);
             cudaFree(rs->lengths);
+            cudaFree(rs->ambig);
+            cudaFree(d_count);
             return st;
         }
     }
+    unsigned long long with_n = 0;
+    HRM_CUDA(cudaMemcpyAsync(&with_n, d_count, sizeof with_n, cudaMemcpyDeviceToHost, s));
+    HRM_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_count);
+    rs->with_n = (int64_t)with_n;
     readstore_finish(rs.get(), h_lengths);
     *out = rs.release();
     return HRM_OK;
@@ -280,6 +326,7 @@ extern "C" void hrm_readstore_destroy(hrm_readstore* rs)
     if (!rs) return;
     if (rs->rows) cudaFree(rs->rows);
     if (rs->lengths) cudaFree(rs->lengths);
+    if (rs->ambig) cudaFree(rs->ambig);
     delete rs;
 }
 
@@ -338,6 +385,50 @@ extern "C" hrm_status hrm_readstore_gather_lengths(const hrm_readstore* rs, int 
     HRM_REQUIRE(n >= 0 && d_ids != nullptr, "args");
     if (n == 0) return HRM_OK;
     HRM_LAUNCH(gather_lengths_kernel, sgrid(n), 256, 0, as_stream(stream), rs->lengths, d_ids, n, rs->n, d_lengths);
+    return HRM_OK;
+}
+
+// ref: GpuReadStorage::areSequencesAmbiguous gpureadstorage.cuh:31-37 (impl multigpureadstorage.cuh:623-653)
+extern "C" hrm_status hrm_readstore_are_ambiguous(const hrm_readstore* rs, int handle, uint8_t* d_result,
+                                                  const uint32_t* d_ids, int64_t n, hrm_stream stream)
+{
+    HRM_REQUIRE(rs != nullptr && rs_handle_ok(rs, handle), "readstore/handle");
+    HRM_REQUIRE(n >= 0 && d_ids != nullptr && d_result != nullptr, "args");
+    if (n == 0) return HRM_OK;
+    HRM_LAUNCH(gather_flags_kernel, sgrid(n), 256, 0, as_stream(stream), rs->ambig, d_ids, n, rs->n, d_result);
+    return HRM_OK;
+}
+
+// carries per-read ambiguity flags (hrm_ingest_reads' d_ambiguous) into a store made from packed rows
+extern "C" hrm_status hrm_readstore_set_ambiguous(hrm_readstore* rs, const uint8_t* d_flags, hrm_stream stream)
+{
+    HRM_REQUIRE(rs != nullptr && d_flags != nullptr, "args");
+    cudaStream_t s = as_stream(stream);
+    const size_t nn = (size_t)(rs->n > 0 ? rs->n : 1);
+    if (!rs->ambig) HRM_CUDA(cudaMalloc(&rs->ambig, nn + 8));
+    std::vector<uint8_t> h((size_t)rs->n);
+    if (rs->n > 0) {
+        HRM_CUDA(cudaMemcpyAsync(rs->ambig, d_flags, (size_t)rs->n, cudaMemcpyDeviceToDevice, s));
+        HRM_CUDA(cudaMemcpyAsync(h.data(), d_flags, (size_t)rs->n, cudaMemcpyDeviceToHost, s));
+        HRM_CUDA(cudaStreamSynchronize(s));
+    }
+    int64_t c = 0;
+    for (uint8_t f : h) c += f != 0;
+    rs->with_n = c;
+    return HRM_OK;
+}
+
+// ref: GpuReadStorage::getIdsOfAmbiguousReads gpureadstorage.cuh:89-91: the ids, ascending, into h_ids
+// (getNumberOfReadsWithN() entries = hrm_readstore_info().num_reads_with_n)
+extern "C" hrm_status hrm_readstore_ambiguous_ids(const hrm_readstore* rs, uint32_t* h_ids)
+{
+    HRM_REQUIRE(rs != nullptr && h_ids != nullptr, "args");
+    if (rs->n == 0 || !rs->ambig || rs->with_n == 0) return HRM_OK;
+    std::vector<uint8_t> h((size_t)rs->n);
+    HRM_CUDA(cudaMemcpy(h.data(), rs->ambig, (size_t)rs->n, cudaMemcpyDeviceToHost));
+    int64_t at = 0;
+    for (int64_t i = 0; i < rs->n; i++)
+        if (h[(size_t)i]) h_ids[at++] = (uint32_t)i;
     return HRM_OK;
 }
 

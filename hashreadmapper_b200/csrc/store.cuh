@@ -33,6 +33,7 @@ struct hrm_readstore {
     int64_t pitch_words = 0;
     uint32_t* rows = nullptr;
     int32_t* lengths = nullptr;
+    uint8_t* ambig = nullptr;  // per read: a non-ACGT character was replaced (NULL: none known)
     int32_t len_min = 0, len_max = 0;
     int64_t with_n = 0;
     std::mutex mtx;

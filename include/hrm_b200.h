@@ -247,6 +247,13 @@ hrm_status hrm_readstore_gather_contiguous(const hrm_readstore* rs, int handle, 
                                            hrm_stream stream);
 hrm_status hrm_readstore_gather_lengths(const hrm_readstore* rs, int handle, int32_t* d_lengths,
                                         const uint32_t* d_ids, int64_t n, hrm_stream stream);
+/* ref: areSequencesAmbiguous (gpureadstorage.cuh:31-37): d_result[e] = 1 if read d_ids[e] held a non-ACGT character */
+hrm_status hrm_readstore_are_ambiguous(const hrm_readstore* rs, int handle, uint8_t* d_result,
+                                       const uint32_t* d_ids, int64_t n, hrm_stream stream);
+/* ref: getIdsOfAmbiguousReads (gpureadstorage.cuh:89-91): ascending ids into h_ids (num_reads_with_n entries) */
+hrm_status hrm_readstore_ambiguous_ids(const hrm_readstore* rs, uint32_t* h_ids);
+/* carries hrm_ingest_reads' d_ambiguous flags (one byte per read, device) into a store created from 2-bit rows */
+hrm_status hrm_readstore_set_ambiguous(hrm_readstore* rs, const uint8_t* d_flags, hrm_stream stream);
 hrm_status hrm_readstore_info(const hrm_readstore* rs, hrm_readstore_info_t* out);
 
 /* ------------------------------------------------------------------------------------------
@@ -402,6 +409,7 @@ typedef struct {
     int32_t reserved;
     int64_t collect_ids_counted;  /* fused collection, since creation: ids counted in shared memory */
     int64_t collect_ids_skipped;  /* ... ids of the largest buckets that were only looked up */
+    int64_t collect_reads_block_kernel; /* ... (read, pass) pairs the warp kernel handed to the block kernel */
 } hrm_mapper_info_t;
 hrm_status hrm_mapper_info(const hrm_mapper* m, hrm_mapper_info_t* out);
 
@@ -579,6 +587,27 @@ hrm_status hrm_mapper_map_reads_sam(hrm_mapper* m, const char* h_reads_ascii, in
                                     int64_t* h_sq_written, char* h_rec_out, int64_t rec_cap,
                                     int64_t* h_rec_written, hrm_read_record* h_records, char* h_cigars,
                                     int64_t cigar_pitch, hrm_batch_stats* h_stats, hrm_stream stream);
+
+/* ---- double-buffered end-to-end pipeline ----------------------------------------------------------------
+ * ref: the batch loop of performMappingGpu (src/gpu/main_gpu.cu:1123-1160), which overlaps nothing.  A batch lives in
+ * one of HRM_PIPE_SLOTS slots:
+ *   hrm_mapper_stage_reads  enqueues the H2D copy of a batch into a slot (returns at once; waits first if the slot's
+ *                           previous results have not left the device yet);
+ *   hrm_mapper_map_staged   runs seeding + filter + SHD + verification (+ V4 and the SAM text when h_rec_out != NULL)
+ *                           of the staged batch on `stream` and enqueues the D2H copies of its results on a copy-out
+ *                           stream (returns when the kernels are enqueued / the text size is known, not when the
+ *                           copies have finished);
+ *   hrm_mapper_finish       waits until the slot's results are in the host buffers; returns the text sizes.
+ * Steady state:  stage(i+1) ; map_staged(i) ; finish(i-1)  -- copies of batches i+1 and i-1 run under the kernels of
+ * batch i.  Host buffers should be pinned.  h_records / h_cigars / h_sq_out / h_rec_out may each be NULL. */
+#define HRM_PIPE_SLOTS 2
+hrm_status hrm_mapper_stage_reads(hrm_mapper* m, int slot, const char* h_reads_ascii, int64_t ascii_pitch,
+                                  const int32_t* h_lengths, int64_t n);
+hrm_status hrm_mapper_map_staged(hrm_mapper* m, int slot, hrm_read_record* h_records, char* h_cigars,
+                                 int64_t cigar_pitch, uint32_t first_read_id, const char* const* h_chrom_names,
+                                 char* h_sq_out, int64_t sq_cap, char* h_rec_out, int64_t rec_cap,
+                                 hrm_batch_stats* h_stats, hrm_stream stream);
+hrm_status hrm_mapper_finish(hrm_mapper* m, int slot, int64_t* h_sq_written, int64_t* h_rec_written);
 
 #ifdef __cplusplus
 }

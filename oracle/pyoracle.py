@@ -317,15 +317,23 @@ def preprocess_reads_model(seqs, first_read_id=0, carry=0):
 
 
 def parse_records_model(text):
-    """4-line FASTQ / 2-line FASTA records -> list of sequence lines (what kseqpp yields for such files)"""
+    """4-line FASTQ records / FASTA records whose sequence spans any number of lines up to the next header ->
+    list of sequences (what kseqpp yields for such files)"""
     lines = text.split(b"\n")
     if lines and lines[-1] == b"":
         lines.pop()
     if not lines:
         return []
-    lpr = 4 if lines[0][:1] == b"@" else 2
-    assert len(lines) % lpr == 0
-    return [lines[i + 1].rstrip(b"\r") for i in range(0, len(lines), lpr)]
+    if lines[0][:1] == b"@":
+        assert len(lines) % 4 == 0
+        return [lines[i + 1].rstrip(b"\r") for i in range(0, len(lines), 4)]
+    out = []
+    for ln in lines:
+        if ln[:1] == b">":
+            out.append(b"")
+        else:
+            out[-1] += ln.rstrip(b"\r")
+    return out
 
 
 # ---- V4 + O1: recalculation, alignment choice, MAPQ, SAM text (TEST INFRASTRUCTURE) --------------------------

@@ -316,6 +316,8 @@ int ref_cigar_parse(const char* s, char* ops, int32_t* lens, int cap)
 }
 
 int ref_num_threads() { return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1; the caller sets the thread count to its CPU affinity explicitly
+void ref_set_num_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
 
 } // extern "C"
 

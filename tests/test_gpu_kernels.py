@@ -378,7 +378,14 @@ def test_ingest_reads(cuda, tmp_path):
         recs = []
         for i in range(n):
             sq = "".join(rng.choice("ACGTACGTACGTNacgtnR") for _ in range(rng.randint(1, maxlen)))
-            recs.append("@r%d x\n%s\n+\n%s\n" % (i, sq, "I" * len(sq)) if fmt == "fastq" else ">r%d\n%s\n" % (i, sq))
+            if fmt == "fastq":
+                recs.append("@r%d x\n%s\n+\n%s\n" % (i, sq, "I" * len(sq)))
+            elif fmt == "fasta":
+                recs.append(">r%d\n%s\n" % (i, sq))
+            else:  # sequences over several lines (60-column files), CRLF line ends in some records
+                w = rng.choice([60, 7, 200])
+                eol = "\r\n" if i % 5 == 0 else "\n"
+                recs.append(">r%d%s%s%s" % (i, eol, eol.join(sq[j:j + w] for j in range(0, len(sq), w)), eol))
         text = "".join(recs).encode()
         return text if trailing_newline else text[:-1]
 
@@ -387,7 +394,7 @@ def test_ingest_reads(cuda, tmp_path):
         return cuda.ingest_reads(t, pitch, cap or text.count(b"\n") + 1, first, carry)
 
     for fmt, n, maxlen, nl in (("fastq", 3000, 150, True), ("fasta", 2000, 100, False), ("fastq", 70000, 24, True),
-                               ("fastq", 1, 5, False)):
+                               ("fastq", 1, 5, False), ("fasta_ml", 3000, 150, True), ("fasta_ml", 66000, 30, False)):
         text = make(fmt, n, maxlen, nl)
         seqs = parse_records_model(text)
         exp, amb, carry_exp = preprocess_reads_model(seqs)
@@ -413,7 +420,8 @@ def test_ingest_reads(cuda, tmp_path):
     # rows feed K1 directly
     enc = cuda.encode_2bit(r1, l1)
     assert enc.shape[0] == 1234
-    # error paths: multi-line FASTA, row too short, garbage
-    for bad in (b">a\nACGT\nACGT\n>b\nAC\n", b"@a\n" + b"A" * 100 + b"\n+\n" + b"I" * 100 + b"\n", b"hello\n"):
+    # error paths: incomplete FASTQ record, row too short (both formats), garbage
+    for bad in (b"@a\nACGT\n+\n", b"@a\n" + b"A" * 100 + b"\n+\n" + b"I" * 100 + b"\n",
+                b">a\n" + b"A" * 40 + b"\n" + b"C" * 40 + b"\n", b"hello\n"):
         with pytest.raises(hb.HrmError):
             run(bad, 64)

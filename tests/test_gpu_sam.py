@@ -129,3 +129,50 @@ def test_sam_end_to_end(cuda, port, conf):
     _, rc1, _ = mp.mapReadsSam(reads[:h], lens[:h], cigar_pitch=256)
     _, rc2, _ = mp.mapReadsSam(reads[h:], lens[h:], first_read_id=h, cigar_pitch=256)
     assert rc1.tobytes() + rc2.tobytes() == rc.tobytes()
+
+
+def test_staged_pipeline(cuda, port):
+    """hrm_mapper_stage_reads / map_staged / finish: batches in flight in two slots give the bytes the one-shot calls give"""
+    import torch
+    import hashreadmapper_b200._lib as L
+    genome, off = synth.make_genome([90_000, 40_001], seed=51)
+    cfg = cuda.directional_config()
+    mp = cuda.Mapper(cfg)
+    mp.setGenome(genome, off, ["chrA", "chrB"])
+    sizes = [3000, 1, 2500, 0, 700]
+    batches, first = [], 0
+    for i, n in enumerate(sizes):
+        reads, lens, _ = synth.make_reads(genome, off, max(n, 1), 150, error_rate=0.02, seed=60 + i)
+        reads, lens = reads[:n], lens[:n]
+        batches.append((torch.from_numpy(reads).pin_memory().numpy() if n else reads, lens, first))
+        first += n
+    exp = []
+    for reads, lens, fid in batches:
+        if len(lens) == 0:
+            exp.append((b"", b"", None, None))
+            continue
+        sq, rc, _, rec, cig = mp.mapReadsSam(reads, lens, first_read_id=fid, cigar_pitch=128, want_records=True)
+        exp.append((sq.tobytes(), rc.tobytes(), rec.copy(), cig.copy()))
+    outs = []
+    for reads, lens, fid in batches:
+        n = len(lens)
+        outs.append({"rec": np.zeros(max(n, 1), dtype=L.RECORD_DTYPE), "cig": np.zeros((2 * max(n, 1), 128), np.uint8),
+                     "sq": np.zeros(max(n, 1) * 40, np.uint8), "txt": np.zeros(max(n, 1) * 600, np.uint8)})
+    mp.stageReads(0, batches[0][0], batches[0][1])
+    sizes_out = [None] * len(batches)
+    for i, (reads, lens, fid) in enumerate(batches):
+        if i + 1 < len(batches):
+            mp.stageReads((i + 1) % 2, batches[i + 1][0], batches[i + 1][1])
+        o = outs[i]
+        mp.mapStaged(i % 2, o["rec"], o["cig"], 128, fid, o["sq"], o["txt"])
+        if i >= 1:
+            sizes_out[i - 1] = mp.finish((i - 1) % 2)
+    sizes_out[-1] = mp.finish((len(batches) - 1) % 2)
+    for i, (reads, lens, fid) in enumerate(batches):
+        n = len(lens)
+        sqw, recw = sizes_out[i]
+        assert outs[i]["sq"][:sqw].tobytes() == exp[i][0] and outs[i]["txt"][:recw].tobytes() == exp[i][1], i
+        if n:
+            for f in ("orientation", "hamming_distance", "shift", "chromosome_id", "position", "pass"):
+                assert (outs[i]["rec"]["mapped"][f][:n] == exp[i][2]["mapped"][f]).all(), f
+            assert (outs[i]["rec"]["alignments"][:n] == exp[i][2]["alignments"]).all()

@@ -392,14 +392,16 @@ def test_routed_query_world_size_2_gloo(tmp_path):
 
 
 def test_adaptor_compiles_against_reference(tmp_path):
-    """drop-in proof: B200Minhasher derives from the reference's abstract care::gpu::GpuMinhasher and is
-    instantiable (every pure virtual overridden) -- compiled against the reference's own headers"""
+    """drop-in proof: B200Minhasher / B200ReadStorage derive from the reference's abstract care::gpu::GpuMinhasher /
+    care::gpu::GpuReadStorage and are instantiable (every pure virtual overridden) -- compiled against the
+    reference's own headers.  tests/test_gpu_store.py runs them through the virtual interface on the GPU."""
     R = "/root/reference"
     if not os.path.isdir(R):
         pytest.skip("needs /root/reference (build container only)")
     src = tmp_path / "adapt.cu"
     src.write_text('#include "hrm_adaptor.hpp"\n'
-                   'care::gpu::GpuMinhasher* make(){ return new hrm_b200::B200Minhasher(1000, 65535, 16, 0.8f); }\n')
+                   'care::gpu::GpuMinhasher* make(){ return new hrm_b200::B200Minhasher(1000, 65535, 16, 0.8f); }\n'
+                   'care::gpu::GpuReadStorage* make2(const char* a, const int* l){ return new hrm_b200::B200ReadStorage(a, 160, l, 10); }\n')
     cmd = ["nvcc", "-std=c++17", "-x", "cu", "-w", "--expt-extended-lambda", "--expt-relaxed-constexpr",
            "-gencode", "arch=compute_100a,code=sm_100a", "-I" + R + "/dependencies/rmm/include",
            "-I" + R + "/dependencies/spdlog/include", "-I" + R + "/include", "-I" + os.path.join(ROOT, "include"),

@@ -199,14 +199,17 @@ def test_read_ingestion_model_against_reference_parser(ref, tmp_path):
     import random
     from oracle.pyoracle import parse_records_model, preprocess_reads_model
     rng = random.Random(12)
-    for fmt in ("fastq", "fasta"):
+    for fmt in ("fastq", "fasta", "fasta_multiline"):
         seqs = ["".join(rng.choice("ACGTNacgtnRY-") for _ in range(rng.randint(1, 120))) for _ in range(700)]
         recs = []
         for i, sq in enumerate(seqs):
             if fmt == "fastq":
                 recs.append("@r%d extra words\n%s\n+\n%s\n" % (i, sq, "I" * len(sq)))
-            else:
+            elif fmt == "fasta":
                 recs.append(">r%d\n%s\n" % (i, sq))
+            else:  # 60-column FASTA: the sequence continues until the next header
+                w = rng.choice([60, 7, 200])
+                recs.append(">r%d\n%s\n" % (i, "\n".join(sq[j:j + w] for j in range(0, len(sq), w))))
         text = "".join(recs).encode()
         path = tmp_path / ("reads." + fmt)
         path.write_bytes(text)
