@@ -404,7 +404,8 @@ def test_adaptor_compiles_against_reference(tmp_path):
                    'care::gpu::GpuReadStorage* make2(const char* a, const int* l){ return new hrm_b200::B200ReadStorage(a, 160, l, 10); }\n')
     cmd = ["nvcc", "-std=c++17", "-x", "cu", "-w", "--expt-extended-lambda", "--expt-relaxed-constexpr",
            "-gencode", "arch=compute_100a,code=sm_100a", "-I" + R + "/dependencies/rmm/include",
-           "-I" + R + "/dependencies/spdlog/include", "-I" + R + "/include", "-I" + os.path.join(ROOT, "include"),
+           "-I" + R + "/dependencies/spdlog/include", "-I" + R + "/include", "-I/usr/local/cuda/include/nvtx3",
+           "-I" + os.path.join(ROOT, "include"),
            "-I" + os.path.join(ROOT, "hashreadmapper_b200", "csrc"), "-c", str(src), "-o", str(tmp_path / "adapt.o")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
