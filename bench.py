@@ -332,6 +332,7 @@ def main():
     ap.add_argument("--check", type=int, default=2000,
                     help="reads of the timed batch compared with the oracle after the timed region (0: off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-text", action="store_true", help="skip the SAM-text end-to-end figure")
     ap.add_argument("--load-factor", type=float, default=None, help="hash-table load factor (default: the library's)")
     ap.add_argument("--read-len", type=int, default=READ_LEN)
     ap.add_argument("--error-rate", type=float, default=ERR)
@@ -442,27 +443,71 @@ def main():
     ms_per_step = total_ms / args.steps
     value = world * n * args.steps / (total_ms / 1e3)
 
-    # ---- end to end: pinned host buffers through hrm_mapper_map_reads --------------------------------
+    # ---- end to end: pinned host buffers through the double-buffered pipeline --------------------------------
+    # every step: H2D of that step's reads (pinned), the whole hot path, D2H of its records + CIGARs; the copies of steps
+    # i+1 and i-1 run under the kernels of step i (hrm_mapper_stage_reads / map_staged / finish)
     h_reads = torch.from_numpy(reads).pin_memory()
     h_lens = torch.from_numpy(lens).pin_memory()
-    h_rec = torch.empty((n * hb.RECORD_DTYPE.itemsize,), dtype=torch.uint8).pin_memory()
-    h_cig = torch.empty((2 * n, CIG), dtype=torch.uint8).pin_memory()
-    rec_np = h_rec.numpy().view(hb.RECORD_DTYPE)
-    for _ in range(2):
-        mp.mapReads(h_reads.numpy(), h_lens.numpy(), CIG, rec_np, h_cig.numpy())
+    h_rec = [torch.empty((n * hb.RECORD_DTYPE.itemsize,), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    h_cig = [torch.empty((2 * n, CIG), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    rec_np = [h.numpy().view(hb.RECORD_DTYPE) for h in h_rec]
+
+    def e2e_run(steps, text=None):
+        """steps batches through the pipeline; text = None: records + CIGARs out; else (sq buffers, record text buffers)"""
+        mp.stageReads(0, h_reads.numpy(), h_lens.numpy())
+        sizes = (0, 0)
+        for i in range(steps):
+            if i + 1 < steps:
+                mp.stageReads((i + 1) % 2, h_reads.numpy(), h_lens.numpy())
+            if text is None:
+                mp.mapStaged(i % 2, rec_np[i % 2], h_cig[i % 2].numpy(), CIG)
+            else:
+                mp.mapStaged(i % 2, None, None, 128, i * n, text[0][i % 2], text[1][i % 2])
+            if i >= 1:
+                sizes = mp.finish((i - 1) % 2)
+        sizes = mp.finish((steps - 1) % 2)
+        return sizes
+
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        mp.mapReads(h_reads.numpy(), h_lens.numpy(), CIG, rec_np, h_cig.numpy())
+    e2e_run(args.steps)
     torch.cuda.synchronize()
     e2e_s = parallel.max_over_ranks(time.perf_counter() - t0)
-    clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * n * args.steps / e2e_s
-    n_mapped = int((rec_np["mapped"]["orientation"] != 3).sum())
-    ok = ((rec_np["mapped"]["orientation"] != 3) & (rec_np["mapped"]["chromosome_id"] == truth["chrom"]) &
-          (rec_np["mapped"]["position"] + rec_np["mapped"]["shift"] == truth["pos"]))
+    last = rec_np[(args.steps - 1) % 2]
+    n_mapped = int((last["mapped"]["orientation"] != 3).sum())
+    ok = ((last["mapped"]["orientation"] != 3) & (last["mapped"]["chromosome_id"] == truth["chrom"]) &
+          (last["mapped"]["position"] + last["mapped"]["shift"] == truth["pos"]))
     h2d = n * reads.shape[1] + n * 4
     d2h = n * hb.RECORD_DTYPE.itemsize + 2 * n * CIG
+    # the one-shot call (serial copy -> compute -> copy), for comparison
+    mp.mapReads(h_reads.numpy(), h_lens.numpy(), CIG, rec_np[0], h_cig[0].numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 2)):
+        mp.mapReads(h_reads.numpy(), h_lens.numpy(), CIG, rec_np[0], h_cig[0].numpy())
+    torch.cuda.synchronize()
+    oneshot_value = world * n * max(1, args.steps // 2) / parallel.max_over_ranks(time.perf_counter() - t0)
+    # ---- end to end with TEXT out: reads in -> SAM text (V4 + O1 on the device) out, same pipeline ----------------
+    e2e_text = None
+    if comm is None and not args.no_text:
+        del h_rec, h_cig, rec_np
+        line_bound = 96 + 128 + W_ + reads.shape[1]
+        tx_rec = [torch.empty((n * line_bound,), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+        tx_sq = [torch.empty((n * 40,), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+        e2e_run(2, (tx_sq, tx_rec))
+        barrier()
+        t0 = time.perf_counter()
+        sqw, recw = e2e_run(args.steps, (tx_sq, tx_rec))
+        torch.cuda.synchronize()
+        text_s = parallel.max_over_ranks(time.perf_counter() - t0)
+        e2e_text = {"value": world * n * args.steps / text_s, "unit": "reads/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(sqw + recw),
+                    "sam_bytes_per_read": float(sqw + recw) / n,
+                    "api": "hrm_mapper_stage_reads / hrm_mapper_map_staged (V4 + SAM text on the device) / hrm_mapper_finish"}
+        del tx_rec, tx_sq
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -548,7 +593,10 @@ def main():
                            index_device_bytes=int(info.index_device_bytes), table_slots=int(info.table_slots_total),
                            table_keys=int(info.num_keys_total)),
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "hrm_mapper_map_reads (pinned host buffers)"},
+                    "api": "hrm_mapper_stage_reads / hrm_mapper_map_staged / hrm_mapper_finish (pinned host buffers, two "
+                           "batches in flight)",
+                    "one_shot_value": oneshot_value, "one_shot_api": "hrm_mapper_map_reads (serial copy, compute, copy)"},
+            "e2e_text": e2e_text,
             "gpu_launches": int(launches_step * args.steps),
             "roofline": roofline,
             "roofline_probe" if roofline is collect_roofline else "roofline_collect": other,

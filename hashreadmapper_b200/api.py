@@ -604,6 +604,13 @@ class Mapper:
         n, pitch = reads_ascii.shape
         check(self.lib.hrm_mapper_stage_reads(self.h, slot, _ptr(reads_ascii), pitch, _ptr(lengths), n))
 
+    def stageFastq(self, slot, text: np.ndarray, pitch, max_reads, first_read_id=0, carry=0):
+        """FASTQ / FASTA text (uint8, pinned) -> staged batch; returns (number of reads, carry for the next chunk)"""
+        nr, co = C.c_int64(0), C.c_int32(0)
+        check(self.lib.hrm_mapper_stage_fastq(self.h, slot, _ptr(text), text.size, first_read_id, carry, pitch, max_reads,
+                                              C.byref(nr), C.byref(co)))
+        return nr.value, co.value
+
     def mapStaged(self, slot, records=None, cigars=None, cigar_pitch=64, first_read_id=0, sq_out=None, rec_out=None,
                   want_stats=False):
         st = L.BatchStats()

@@ -49,6 +49,7 @@ struct CollectParams {
     int32_t* big_count;
     int32_t* big2_list;         // reads the block-wide filter kernel hands on to the counting-table kernel
     int32_t* big2_count;
+    int xslots_warp, xslots_block; // exact-table slots of the duplicate-detection kernels (powers of two)
     int warp_cap;               // reads with more ids go straight to the block kernel (test hook)
     int warp_slots;             // table slots of a warp (power of two)
     int slots;                  // table slots of the block kernel (power of two)
@@ -444,427 +445,372 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_warp_kernel(CollectPa
     }
 }
 
-// ---- warp per read, duplicate detection by a blocked Bloom filter -----------------------------------------
-// The ids a read enumerates are close to uniform over ~2^25 windows and nearly all distinct: at human-genome scale
-// a read-pass walks ~2000 ids and 1-3 of them occur more than once.  An id with multiplicity >= T has multiplicity
-// >= T - L >= 2 in the enumerated buckets, i.e. it is a DUPLICATE there.  So instead of counting every id exactly
-// (hash table: probe loops, id ranges to keep the table small, range-boundary searches in every bucket) the warp
-// only detects duplicates: one 32-bit word of a shared-memory bitmap per id, three bits of it set by ONE atomicOr;
-// an id whose three bits were all set before is a candidate (every second or later occurrence of an id is, plus
-// ~0.1 false positives per 1000 ids).  Each distinct candidate is then counted EXACTLY: lane t searches bucket t
-// (all H buckets, the skipped ones included), so the multiplicities are the reference's.  The buckets are read
-// once, front to back, with 128-bit loads; nothing is searched before the enumeration.
-//   one atomic per id, exactly-once semantics: two lanes that hold the same id in the same instruction are
-//   serialised by the atomic on their common word, so the later one sees all three bits.
-// Reads that enumerate more ids than the bitmap resolves (E > 3 * words) or that overflow the candidate list go to
-// the block kernel through big_list.
-constexpr int BLOOM_CAND = 96;  // candidate events per read a warp can hold (<= COLLECT_WFIN)
-constexpr int BLOOM_MLP = 2;    // 128-bit id loads a lane keeps in flight
+// ---- duplicate detection: blocked Bloom filter in front of a small exact table ---------------------------------
+// An id with multiplicity >= T over the H buckets of a read has multiplicity >= T - L >= 2 in the H - L smallest
+// ("enumerated") buckets, i.e. it is a DUPLICATE there.  At human-genome scale a read-pass walks ~2000 enumerated ids
+// of which ~100 are second or later occurrences (low-complexity windows that share many sketches) and 1-3 survive.
+//   phase 1  the enumerated buckets are streamed once, front to back, with 128-bit loads.  Every id sets three bits
+//            of ONE 32-bit word of a shared-memory bitmap with one atomicOr; an id whose three bits were all set
+//            before is an EVENT: a second or later occurrence (always), or a false positive (~0.1 %).  Events -- 5 % of
+//            the ids -- are counted in a small exact table (id << 6 | count, one atomic each).  Two lanes holding the same
+//            id in the same instruction are serialised by the atomic on their common word: the later one sees the bits.
+//   phase 2  the L largest buckets are streamed the same way but only TESTED: an id whose bits are set is looked up in
+//            the exact table and, if present, counted.  No bucket is ever binary-searched for a candidate.
+//   phase 3  table entry (id, c): c = events + hits in the largest buckets, and the id's multiplicity is c + 1 unless its
+//            very first occurrence was itself a false positive (then c).  c >= T: survivor.  c == T - 1: the one ambiguous
+//            case, settled exactly by searching all H buckets (lane per bucket).  c < T - 1: dropped.
+// Everything a read touches is read once and coalesced: 4 B per id.  The same code runs warp-per-read (table in a
+// slice of shared memory, most reads) and block-per-read (BLOCK = true: the reads of big_list, whose enumerated ids or
+// events exceed the warp's tables).  What exceeds the block's tables goes on to big2_list (counting-table kernel).
+constexpr int DUP_MLP = 2;         // 128-bit id loads a lane keeps in flight
+constexpr int DUP_WFIN = 128;      // survivors / ambiguous ids per read (warp)
+constexpr int DUP_BTHREADS = 256;  // threads of the block variant
+// events are queued and handled by all lanes together (a queue holds two iterations' worth of events)
+constexpr int DUP_WQ = 2 * 32 * 4 * DUP_MLP;           // warp: 512 entries
+constexpr int DUP_BQ = 2 * DUP_BTHREADS * 4 * DUP_MLP; // block: 4096 entries
 
-__host__ __device__ inline size_t bloom_slice_words(int words, int H)
+__host__ __device__ inline size_t dup_slice_words(int words, int xslots, int qcap, int H)
 {
-    const size_t w = (size_t)words + 2 * BLOOM_CAND + 4 * (size_t)H + 4;
+    const size_t w = (size_t)words + xslots + (size_t)qcap + 5 * (size_t)H + 16;
     return (w + 3) & ~(size_t)3;
 }
 
-__global__ void __launch_bounds__(COLLECT_THREADS) collect_bloom_kernel(CollectParams P)
+// word of the bitmap (top bits of a multiplicative hash) and three bits inside it (its low 15 bits: a permutation of
+// the id's low 15 bits, so two ids share a mask only if they are a multiple of 32768 apart)
+__device__ __forceinline__ void dup_hash(uint32_t id, int shift, uint32_t& word, uint32_t& mask)
 {
-    extern __shared__ __align__(16) uint32_t wdyn[];
+    const uint32_t h = id * 0x9E3779B1u;
+    word = h >> shift;
+    mask = (1u << (h & 31u)) | (1u << ((h >> 5) & 31u)) | (1u << ((h >> 10) & 31u));
+}
+
+template <bool BLOCK>
+__global__ void __launch_bounds__(BLOCK ? DUP_BTHREADS : COLLECT_THREADS) collect_dup_kernel(CollectParams P)
+{
+    extern __shared__ __align__(16) uint32_t ddyn[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int H = P.H, T = P.min_hits, WMAX = P.warp_slots;
-    uint32_t* bm = wdyn + (size_t)wid * bloom_slice_words(WMAX, H); // [WMAX]
-    uint32_t* cand = bm + WMAX;                                     // [BLOOM_CAND]
-    uint32_t* ccnt = cand + BLOOM_CAND;                             // [BLOOM_CAND]
-    uint32_t* offv = ccnt + BLOOM_CAND;                             // [H]
-    int* cntv = reinterpret_cast<int*>(offv + H);                   // [H]
-    int* skipf = cntv + H;                                          // [H]
-    int* cpre = skipf + H;                                          // [H + 1] prefix of 16-byte chunks per bucket
-    int* wcount = cpre + H + 1;
-    const int L = T - 2 < 2 ? (T - 2 < 0 ? 0 : T - 2) : 2; // buckets not enumerated
-    const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+    const int tid = BLOCK ? (int)threadIdx.x : lane;
+    const int nthr = BLOCK ? DUP_BTHREADS : 32;
+    const int H = P.H, T = P.min_hits;
+    const int WMAX = BLOCK ? P.slots : P.warp_slots;      // bitmap words (power of two)
+    const int XS = BLOCK ? P.xslots_block : P.xslots_warp; // exact-table slots (power of two)
+    const int QCAP = BLOCK ? DUP_BQ : DUP_WQ;
+    const int FINCAP = BLOCK ? COLLECT_FINAL_CAP : DUP_WFIN;
+    uint32_t* base = ddyn + (BLOCK ? (size_t)0 : (size_t)wid * dup_slice_words(WMAX, XS, QCAP, H));
+    uint32_t* bm = base;                          // [WMAX]
+    uint32_t* xt = bm + WMAX;                     // [XS] id << 6 | count
+    uint32_t* q = xt + XS;                        // [QCAP] queued events of phases 1 / 2; afterwards:
+    uint32_t* fin = q;                            //   [FINCAP] survivors
+    uint32_t* amb = q + FINCAP;                   //   [FINCAP] ambiguous ids (their exact counts reuse the bitmap)
+    uint32_t* offv = q + QCAP;                    // [H]
+    int* cntv = reinterpret_cast<int*>(offv + H); // [H]
+    int* skipf = cntv + H;                        // [H]
+    int* cpre = skipf + H;                        // [H + 1] 16-byte chunks of the enumerated buckets (flat prefix)
+    int* cpre2 = cpre + H + 1;                    // [H + 1] ... of the largest buckets
+    int* sc = cpre2 + H + 1;                      // 0 distinct ids in xt, 1 bad, 2 nfin, 3 namb, 4 E, 5 SK, 6 total, 7 start, 8 queue tail
+    const uint32_t xmask = (uint32_t)XS - 1u;
+    int xshift = 32;
+    for (int x = XS; x > 1; x >>= 1) xshift--;
+    const int xcap = (XS / 4) * 3;
+    const int L = T - 2 < 2 ? (T - 2 < 0 ? 0 : T - 2) : 2; // buckets tested, not inserted
+    auto gsync = [&]() {
+        if (BLOCK) __syncthreads();
+        else __syncwarp();
+    };
     unsigned long long st_enum = 0, st_skip = 0, st_big = 0;
     const uint4* __restrict__ vals4 = reinterpret_cast<const uint4*>(P.table_values);
-    for (int rd = warp0; rd < P.n; rd += nwarps) {
-        __syncwarp();
-        int total = 0;
-        for (int t0 = 0; t0 < H; t0 += 32) {
-            const int t = t0 + lane;
-            const uint2 r = t < H ? P.ranges[(int64_t)rd * P.rq + (int64_t)t * P.rt] : make_uint2(0u, 0u);
-            if (t < H) {
-                offv[t] = r.x;
-                cntv[t] = (int)r.y;
-                skipf[t] = 0;
+    const int first = BLOCK ? (int)blockIdx.x : (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int step = BLOCK ? (int)gridDim.x : (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+    const int nitems = BLOCK ? *P.big_count : P.n;
+    for (int it = first; it < nitems; it += step) {
+        const int rd = BLOCK ? P.big_list[it] : it;
+        gsync();
+        if (!BLOCK || wid == 0) { // one warp sets the read up: lane t owns buckets t and t + 32
+            const int ta = lane, tb = lane + 32;
+            const uint2 ra = ta < H ? P.ranges[(int64_t)rd * P.rq + (int64_t)ta * P.rt] : make_uint2(0u, 0u);
+            const uint2 rb = tb < H ? P.ranges[(int64_t)rd * P.rq + (int64_t)tb * P.rt] : make_uint2(0u, 0u);
+            int sa = 0, sb = 0;
+            for (int l = 0; l < L; l++) { // the L largest buckets (ties: lowest table)
+                const unsigned ka = (!sa && ra.y > 0u) ? ((ra.y << 8) | (unsigned)(255 - ta)) : 0u;
+                const unsigned kb = (!sb && rb.y > 0u) ? ((rb.y << 8) | (unsigned)(255 - tb)) : 0u;
+                const unsigned best = __reduce_max_sync(0xffffffffu, ka > kb ? ka : kb);
+                if (best == 0u) break;
+                const int t = 255 - (int)(best & 255u);
+                sa |= t == ta;
+                sb |= t == tb;
             }
-            total += __reduce_add_sync(0xffffffffu, (int)r.y);
-        }
-        if (lane == 0) *wcount = 0;
-        __syncwarp();
-        if (total < T) {
+            const int cha = ra.y > 0u ? (int)(((ra.x & 3u) + ra.y + 3u) >> 2) : 0;
+            const int chb = rb.y > 0u ? (int)(((rb.x & 3u) + rb.y + 3u) >> 2) : 0;
+            // flat chunk prefixes in table order: tables 0..31 then 32..63
+            int v1a = sa ? 0 : cha, v2a = sa ? cha : 0, v1b = sb ? 0 : chb, v2b = sb ? chb : 0;
+            int i1a = v1a, i2a = v2a, i1b = v1b, i2b = v2b;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o1 = __shfl_up_sync(0xffffffffu, i1a, d), o2 = __shfl_up_sync(0xffffffffu, i2a, d);
+                const int o3 = __shfl_up_sync(0xffffffffu, i1b, d), o4 = __shfl_up_sync(0xffffffffu, i2b, d);
+                if (lane >= d) {
+                    i1a += o1;
+                    i2a += o2;
+                    i1b += o3;
+                    i2b += o4;
+                }
+            }
+            const int t1a = __shfl_sync(0xffffffffu, i1a, 31), t2a = __shfl_sync(0xffffffffu, i2a, 31);
+            const int t1b = __shfl_sync(0xffffffffu, i1b, 31), t2b = __shfl_sync(0xffffffffu, i2b, 31);
+            if (ta < H) {
+                offv[ta] = ra.x;
+                cntv[ta] = (int)ra.y;
+                skipf[ta] = sa;
+                cpre[ta] = i1a - v1a;
+                cpre2[ta] = i2a - v2a;
+            }
+            if (tb < H) {
+                offv[tb] = rb.x;
+                cntv[tb] = (int)rb.y;
+                skipf[tb] = sb;
+                cpre[tb] = t1a + i1b - v1b;
+                cpre2[tb] = t2a + i2b - v2b;
+            }
+            const unsigned ea = sa ? 0u : ra.y, eb = sb ? 0u : rb.y, ka2 = sa ? ra.y : 0u, kb2 = sb ? rb.y : 0u;
+            const unsigned E = __reduce_add_sync(0xffffffffu, ea + eb), SK = __reduce_add_sync(0xffffffffu, ka2 + kb2);
             if (lane == 0) {
+                cpre[H] = t1a + t1b;
+                cpre2[H] = t2a + t2b;
+                sc[0] = 0;
+                sc[1] = 0;
+                sc[2] = 0;
+                sc[3] = 0;
+                sc[4] = (int)E;   // <= 64 * 65535
+                sc[5] = (int)SK;
+                sc[6] = (int)(E + SK);
+                sc[8] = 0;
+            }
+        }
+        gsync();
+        const int E = sc[4], SK = sc[5], total = sc[6];
+        if (total < T) {
+            if (tid == 0) {
                 P.lists[rd] = make_int2(0, 0);
                 st_enum += (unsigned long long)total;
             }
             continue;
         }
-        // the L largest buckets are searched for the candidates only
-        int skipped = 0;
-        for (int l = 0; l < L; l++) {
-            unsigned best = 0u;
-            for (int t = lane; t < H; t += 32)
-                if (!skipf[t] && cntv[t] > 0) {
-                    const unsigned key = ((unsigned)cntv[t] << 8) | (unsigned)(255 - t); // ties: lowest table
-                    best = key > best ? key : best;
-                }
-            best = __reduce_max_sync(0xffffffffu, best);
-            if (best == 0u) break;
-            const int t = 255 - (int)(best & 255u);
-            if (lane == 0) skipf[t] = 1;
-            skipped += (int)(best >> 8);
-            __syncwarp();
-        }
-        const int E = total - skipped;
-        if (total > P.warp_cap || E > 3 * WMAX) {
-            if (lane == 0) {
-                P.big_list[atomicAdd(P.big_count, 1)] = rd;
+        if ((!BLOCK && total > P.warp_cap) || E > 6 * WMAX) { // more ids than the bitmap resolves
+            if (tid == 0) {
+                if (BLOCK) P.big2_list[atomicAdd(P.big2_count, 1)] = rd;
+                else P.big_list[atomicAdd(P.big_count, 1)] = rd;
                 st_big++;
             }
             continue;
         }
         int W = 64, shift = 32 - 6;
-        while (W < WMAX && W < E) {
+        while (W < WMAX && 2 * W < E) { // >= half a word per id: ~6 bits of 32 set in a word at the end
             W <<= 1;
             shift--;
         }
         {
             uint4* b4 = reinterpret_cast<uint4*>(bm);
-            for (int i = lane; i < W / 4; i += 32) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = tid; i < W / 4; i += nthr) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+            uint4* x4 = reinterpret_cast<uint4*>(xt);
+            for (int i = tid; i < XS / 4; i += nthr) x4[i] = make_uint4(COLLECT_EMPTY, COLLECT_EMPTY, COLLECT_EMPTY, COLLECT_EMPTY);
         }
-        // 16-byte chunks of the enumerated buckets as one flat sequence
-        int ctotal = 0;
-        for (int t0 = 0; t0 < H; t0 += 32) {
-            const int t = t0 + lane;
-            const int nch = (t < H && !skipf[t] && cntv[t] > 0) ? (int)(((offv[t] & 3u) + (uint32_t)cntv[t] + 3u) >> 2) : 0;
-            int incl = nch;
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += o;
-            }
-            if (t < H) cpre[t] = ctotal + incl - nch;
-            ctotal += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (lane == 0) cpre[H] = ctotal;
-        __syncwarp();
-        int tcur = 0, cnext = 0;
-        int64_t cbase = 0;           // chunk c of the current bucket lies at vals4[cbase + c]
-        uint32_t lo = 0, hi = 0;     // element range of the current bucket
-        for (int c0 = 0; c0 < ctotal; c0 += 32 * BLOOM_MLP) {
-            uint4 v[BLOOM_MLP];
-            uint32_t e0[BLOOM_MLP], vlo[BLOOM_MLP], vhi[BLOOM_MLP];
-#pragma unroll
-            for (int u = 0; u < BLOOM_MLP; u++) {
-                const int c = c0 + u * 32 + lane;
-                vlo[u] = 1u;
-                vhi[u] = 0u; // nothing valid
-                e0[u] = 0u;
-                if (c < ctotal) {
-                    if (c >= cnext) {
-                        while (cpre[tcur + 1] <= c) tcur++;
-                        cnext = cpre[tcur + 1];
-                        lo = offv[tcur];
-                        hi = lo + (uint32_t)cntv[tcur];
-                        cbase = (int64_t)(lo >> 2) - cpre[tcur];
+        gsync();
+        // queued events -> exact table, all lanes busy.  phase 0: insert / count; phase 1: count where present
+        auto drain = [&](int phase) {
+            gsync();
+            const int nq = sc[8];
+            for (int i = tid; i < nq; i += nthr) {
+                const uint32_t id = q[i];
+                uint32_t hh = collect_hash(id) >> xshift;
+                if (phase == 0) {
+                    if (sc[0] >= xcap) { // the exact table is full: a bigger one takes the read
+                        sc[1] = 1;
+                        continue;
                     }
-                    v[u] = __ldg(vals4 + cbase + c);
-                    e0[u] = (uint32_t)((cbase + c) << 2);
-                    vlo[u] = lo;
-                    vhi[u] = hi;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < BLOOM_MLP; u++) {
-                const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t e = e0[u] + j;
-                    if (e >= vlo[u] && e < vhi[u]) {
-                        const uint32_t h = x[j] * 0x9E3779B1u;
-                        const uint32_t g = (h ^ (h >> 15)) * 0x2C1B3C6Du;
-                        const uint32_t mask = (1u << (g >> 27)) | (1u << ((g >> 22) & 31u)) | (1u << ((g >> 17) & 31u));
-                        const uint32_t old = atomicOr(&bm[h >> shift], mask);
-                        if ((old & mask) == mask) {
-                            const int at = atomicAdd(wcount, 1);
-                            if (at < BLOOM_CAND) cand[at] = x[j];
+                    while (true) {
+                        uint32_t cur = xt[hh];
+                        if (cur == COLLECT_EMPTY) {
+                            cur = atomicCAS(&xt[hh], COLLECT_EMPTY, (id << COLLECT_PACK_BITS) | 1u);
+                            if (cur == COLLECT_EMPTY) {
+                                atomicAdd(&sc[0], 1);
+                                break;
+                            }
                         }
+                        if ((cur >> COLLECT_PACK_BITS) == id) {
+                            atomicAdd(&xt[hh], 1u);
+                            break;
+                        }
+                        hh = (hh + 1) & xmask;
+                    }
+                } else {
+                    while (true) {
+                        const uint32_t cur = xt[hh];
+                        if (cur == COLLECT_EMPTY) break;
+                        if ((cur >> COLLECT_PACK_BITS) == id) {
+                            atomicAdd(&xt[hh], 1u);
+                            break;
+                        }
+                        hh = (hh + 1) & xmask;
                     }
                 }
             }
+            gsync();
+            if (tid == 0) sc[8] = 0;
+            gsync();
+        };
+        // phases 1 and 2: the same streaming loop over a flat sequence of 16-byte chunks
+#pragma unroll 1
+        for (int phase = 0; phase < 2; phase++) {
+            const int* cp = phase == 0 ? cpre : cpre2;
+            const int ctotal = cp[H];
+            int tcur = 0, cnext = 0;
+            int64_t cbase = 0;       // chunk c of the current bucket lies at vals4[cbase + c]
+            uint32_t lo = 0, hi = 0; // element range of the current bucket
+            for (int c0 = 0; c0 < ctotal; c0 += nthr * DUP_MLP) {
+                uint4 v[DUP_MLP];
+                uint32_t e0[DUP_MLP], vlo[DUP_MLP], vhi[DUP_MLP];
+#pragma unroll
+                for (int u = 0; u < DUP_MLP; u++) {
+                    const int c = c0 + u * nthr + tid;
+                    vlo[u] = 1u;
+                    vhi[u] = 0u; // nothing valid
+                    e0[u] = 0u;
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (c < ctotal) {
+                        if (c >= cnext) {
+                            while (cp[tcur + 1] <= c) tcur++;
+                            cnext = cp[tcur + 1];
+                            lo = offv[tcur];
+                            hi = lo + (uint32_t)cntv[tcur];
+                            cbase = (int64_t)(lo >> 2) - cp[tcur];
+                        }
+                        v[u] = __ldg(vals4 + cbase + c);
+                        e0[u] = (uint32_t)((cbase + c) << 2);
+                        vlo[u] = lo;
+                        vhi[u] = hi;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < DUP_MLP; u++) {
+                    const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t e = e0[u] + j;
+                        const bool valid = e >= vlo[u] && e < vhi[u];
+                        uint32_t word, mask;
+                        dup_hash(x[j], shift, word, mask);
+                        bool ev;
+                        if (phase == 0) {
+                            // invalid lanes OR nothing into the word: no branch around the atomic
+                            const uint32_t old = atomicOr(&bm[valid ? word : (uint32_t)lane], valid ? mask : 0u);
+                            ev = valid && (old & mask) == mask;
+                        } else {
+                            ev = valid && (bm[word] & mask) == mask;
+                        }
+                        if (ev) q[atomicAdd(&sc[8], 1)] = x[j];
+                    }
+                }
+                // a queue holds two iterations' worth of events: drain when the next one might not fit
+                if (c0 + nthr * DUP_MLP < ctotal) {
+                    gsync();
+                    if (sc[8] > QCAP / 2) drain(phase);
+                }
+            }
+            drain(phase);
+            if (sc[1]) break;
         }
-        __syncwarp();
-        int nc = *wcount;
-        if (lane == 0) {
-            st_enum += (unsigned long long)E;
-            st_skip += (unsigned long long)skipped;
-        }
-        if (nc > BLOOM_CAND) { // too many duplicates for the warp's list: the block kernel redoes the read
-            if (lane == 0) {
-                P.big_list[atomicAdd(P.big_count, 1)] = rd;
-                st_enum -= (unsigned long long)E;
-                st_skip -= (unsigned long long)skipped;
+        if (sc[1]) {
+            if (tid == 0) {
+                if (BLOCK) P.big2_list[atomicAdd(P.big2_count, 1)] = rd;
+                else P.big_list[atomicAdd(P.big_count, 1)] = rd;
                 st_big++;
             }
             continue;
         }
-        int nfin = 0;
-        if (nc > 0) {
-            // distinct candidates, ascending
-            if (nc > 1) collect_sort_warp(cand, nc, lane);
-            int nu = 0;
-            for (int c0 = 0; c0 < nc; c0 += 32) {
-                const int c = c0 + lane;
-                const uint32_t id = c < nc ? cand[c] : 0u;
-                const bool first = c < nc && (c == 0 || cand[c - 1] != id);
-                __syncwarp();
-                const unsigned m = __ballot_sync(0xffffffffu, first);
-                if (first) cand[nu + __popc(m & ((1u << lane) - 1u))] = id; // nu + rank <= c: never ahead of the readers
-                nu += __popc(m);
-                __syncwarp();
-            }
-            for (int c = lane; c < nu; c += 32) ccnt[c] = 0u;
-            __syncwarp();
-            // exact multiplicity: (candidate, bucket) pairs over the lanes
-            for (int x = lane; x < nu * H; x += 32) {
-                const int c = x / H, t = x - c * H;
-                const int cnt = cntv[t];
-                if (cnt > 0) {
-                    const uint32_t id = cand[c];
-                    const uint32_t* p = P.table_values + offv[t];
-                    const int pos = collect_lower_bound_interp(p, cnt, id, P.id_space);
-                    if (pos < cnt && __ldg(p + pos) == id) atomicAdd(&ccnt[c], 1u);
-                }
-            }
-            __syncwarp();
-            for (int c0 = 0; c0 < nu; c0 += 32) {
-                const int c = c0 + lane;
-                const uint32_t id = c < nu ? cand[c] : 0u;
-                const bool keep = c < nu && ccnt[c] >= (uint32_t)T;
-                __syncwarp();
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (keep) cand[nfin + __popc(m & ((1u << lane) - 1u))] = id;
-                nfin += __popc(m);
-                __syncwarp();
-            }
-        }
-        unsigned long long start = 0;
-        if (lane == 0 && nfin > 0) start = atomicAdd(P.cursor, (unsigned long long)nfin);
-        start = __shfl_sync(0xffffffffu, start, 0);
-        if (start + (unsigned long long)nfin > P.out_cap) {
-            if (lane == 0) *P.overflow = 1;
-            nfin = 0;
-        }
-        for (int i = lane; i < nfin; i += 32) P.out[start + i] = cand[i];
-        if (lane == 0) P.lists[rd] = make_int2((int)start, nfin);
-    }
-    if (lane == 0 && P.stats) {
-        if (st_enum) atomicAdd(P.stats, st_enum);
-        if (st_skip) atomicAdd(P.stats + 1, st_skip);
-        if (st_big) atomicAdd(P.stats + 3, st_big);
-    }
-}
-
-// ---- block per read, same duplicate detection with a block-wide filter ----------------------------------
-// Reads of big_list (more ids than a warp's filter resolves, or too many candidates for a warp's list): 256
-// threads, a filter of up to `slots` words (E <= 3 * words), up to COLLECT_FINAL_CAP candidates.  What still does
-// not fit goes on to big2_list for the counting-table kernel below.
-constexpr int BLOOMB_THREADS = 256;
-
-__global__ void __launch_bounds__(BLOOMB_THREADS) collect_bloom_block_kernel(CollectParams P)
-{
-    extern __shared__ __align__(16) uint32_t bdyn[];
-    const int WMAX = P.slots;
-    uint32_t* bm = bdyn;                              // [WMAX]
-    uint32_t* cand = bm + WMAX;                       // [COLLECT_FINAL_CAP]
-    uint32_t* ccnt = cand + COLLECT_FINAL_CAP;        // [COLLECT_FINAL_CAP]
-    __shared__ uint32_t offv[MAX_TABLES];
-    __shared__ int cntv[MAX_TABLES];
-    __shared__ int skip[MAX_TABLES];
-    __shared__ int cpre[MAX_TABLES + 1];
-    __shared__ int s_ncand, s_nu, s_nfin, s_E, s_skipped;
-    __shared__ unsigned long long s_start;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, H = P.H, T = P.min_hits;
-    const int L = T - 2 < 2 ? (T - 2 < 0 ? 0 : T - 2) : 2;
-    const int nbig = *P.big_count;
-    unsigned long long st_enum = 0, st_skip = 0;
-    const uint4* __restrict__ vals4 = reinterpret_cast<const uint4*>(P.table_values);
-    for (int bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
-        const int rd = P.big_list[bi];
-        __syncthreads();
-        if (tid < H) {
-            const uint2 r = P.ranges[(int64_t)rd * P.rq + (int64_t)tid * P.rt];
-            offv[tid] = r.x;
-            cntv[tid] = (int)r.y;
-            skip[tid] = 0;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            for (int l = 0; l < L; l++) { // the L largest buckets (ties: lowest table)
-                int best = -1;
-                for (int t = 0; t < H; t++)
-                    if (!skip[t] && cntv[t] > 0 && (best < 0 || cntv[t] > cntv[best])) best = t;
-                if (best >= 0) skip[best] = 1;
-            }
-            int64_t E = 0, SK = 0;
-            int ct = 0;
-            for (int t = 0; t < H; t++) {
-                cpre[t] = ct;
-                if (skip[t]) SK += cntv[t];
-                else {
-                    E += cntv[t];
-                    if (cntv[t] > 0) ct += (int)(((offv[t] & 3u) + (uint32_t)cntv[t] + 3u) >> 2);
-                }
-            }
-            cpre[H] = ct;
-            s_E = E > 0x7fffffff ? 0x7fffffff : (int)E;
-            s_skipped = (int)SK;
-            s_ncand = 0;
-            s_nu = 0;
-            s_nfin = 0;
-        }
-        __syncthreads();
-        const int E = s_E;
-        if (E > 3 * WMAX) { // the counting-table kernel takes it
-            if (tid == 0) P.big2_list[atomicAdd(P.big2_count, 1)] = rd;
-            continue;
-        }
-        int W = 64, shift = 32 - 6;
-        while (W < WMAX && W < E) {
-            W <<= 1;
-            shift--;
-        }
-        {
-            uint4* b4 = reinterpret_cast<uint4*>(bm);
-            for (int i = tid; i < W / 4; i += BLOOMB_THREADS) b4[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncthreads();
-        const int ctotal = cpre[H];
-        int tcur = 0, cnext = 0;
-        int64_t cbase = 0;
-        uint32_t lo = 0, hi = 0;
-        for (int c0 = 0; c0 < ctotal; c0 += BLOOMB_THREADS * BLOOM_MLP) {
-            uint4 v[BLOOM_MLP];
-            uint32_t e0[BLOOM_MLP], vlo[BLOOM_MLP], vhi[BLOOM_MLP];
-#pragma unroll
-            for (int u = 0; u < BLOOM_MLP; u++) {
-                const int c = c0 + u * BLOOMB_THREADS + tid;
-                vlo[u] = 1u;
-                vhi[u] = 0u;
-                e0[u] = 0u;
-                if (c < ctotal) {
-                    if (c >= cnext) {
-                        while (cpre[tcur + 1] <= c) tcur++;
-                        cnext = cpre[tcur + 1];
-                        lo = offv[tcur];
-                        hi = lo + (uint32_t)cntv[tcur];
-                        cbase = (int64_t)(lo >> 2) - cpre[tcur];
-                    }
-                    v[u] = __ldg(vals4 + cbase + c);
-                    e0[u] = (uint32_t)((cbase + c) << 2);
-                    vlo[u] = lo;
-                    vhi[u] = hi;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < BLOOM_MLP; u++) {
-                const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t e = e0[u] + j;
-                    if (e >= vlo[u] && e < vhi[u]) {
-                        const uint32_t h = x[j] * 0x9E3779B1u;
-                        const uint32_t g = (h ^ (h >> 15)) * 0x2C1B3C6Du;
-                        const uint32_t mask = (1u << (g >> 27)) | (1u << ((g >> 22) & 31u)) | (1u << ((g >> 17) & 31u));
-                        const uint32_t old = atomicOr(&bm[h >> shift], mask);
-                        if ((old & mask) == mask) {
-                            const int at = atomicAdd(&s_ncand, 1);
-                            if (at < COLLECT_FINAL_CAP) cand[at] = x[j];
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        const int nc = s_ncand;
-        if (nc > COLLECT_FINAL_CAP) {
-            if (tid == 0) P.big2_list[atomicAdd(P.big2_count, 1)] = rd;
-            continue;
-        }
         if (tid == 0) {
             st_enum += (unsigned long long)E;
-            st_skip += (unsigned long long)s_skipped;
+            st_skip += (unsigned long long)SK;
         }
-        if (nc > 1) bitonic_sort<true>(cand, nc, tid, BLOOMB_THREADS);
-        __syncthreads();
-        if (wid == 0) { // distinct candidates, in place (writes never pass the readers)
-            int nu = 0;
-            for (int c0 = 0; c0 < nc; c0 += 32) {
-                const int c = c0 + lane;
-                const uint32_t id = c < nc ? cand[c] : 0u;
-                const bool first = c < nc && (c == 0 || cand[c - 1] != id);
-                __syncwarp();
-                const unsigned m = __ballot_sync(0xffffffffu, first);
-                if (first) cand[nu + __popc(m & ((1u << lane) - 1u))] = id;
-                nu += __popc(m);
-                __syncwarp();
-            }
-            if (lane == 0) s_nu = nu;
-        }
-        __syncthreads();
-        const int nu = s_nu;
-        for (int c = tid; c < nu; c += BLOOMB_THREADS) ccnt[c] = 0u;
-        __syncthreads();
-        for (int x = tid; x < nu * H; x += BLOOMB_THREADS) { // exact multiplicity over all H buckets
-            const int c = x / H, t = x - c * H;
-            const int cnt = cntv[t];
-            if (cnt > 0) {
-                const uint32_t id = cand[c];
-                const uint32_t* p = P.table_values + offv[t];
-                const int pos = collect_lower_bound_interp(p, cnt, id, P.id_space);
-                if (pos < cnt && __ldg(p + pos) == id) atomicAdd(&ccnt[c], 1u);
-            }
-        }
-        __syncthreads();
-        if (wid == 0) {
-            int nfin = 0;
-            for (int c0 = 0; c0 < nu; c0 += 32) {
-                const int c = c0 + lane;
-                const uint32_t id = c < nu ? cand[c] : 0u;
-                const bool keep = c < nu && ccnt[c] >= (uint32_t)T;
-                __syncwarp();
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (keep) cand[nfin + __popc(m & ((1u << lane) - 1u))] = id;
-                nfin += __popc(m);
-                __syncwarp();
-            }
-            if (lane == 0) {
-                unsigned long long start = 0;
-                if (nfin > 0) start = atomicAdd(P.cursor, (unsigned long long)nfin);
-                if (start + (unsigned long long)nfin > P.out_cap) {
-                    *P.overflow = 1;
-                    nfin = 0;
+        // phase 3: c >= T survives, c == T - 1 is settled exactly
+        if (sc[0] > 0) {
+            for (int i = tid; i < XS; i += nthr) {
+                const uint32_t x = xt[i];
+                if (x == COLLECT_EMPTY) continue;
+                const uint32_t c = x & ((1u << COLLECT_PACK_BITS) - 1u), id = x >> COLLECT_PACK_BITS;
+                if (c >= (uint32_t)T) {
+                    const int at = atomicAdd(&sc[2], 1);
+                    if (at < FINCAP) fin[at] = id;
+                } else if (c + 1u == (uint32_t)T) {
+                    const int at = atomicAdd(&sc[3], 1);
+                    if (at < FINCAP) amb[at] = id;
                 }
-                s_start = start;
-                s_nfin = nfin;
-                P.lists[rd] = make_int2((int)start, nfin);
+            }
+            gsync();
+            const int namb = sc[3];
+            if (namb > FINCAP || sc[2] > FINCAP) {
+                if (tid == 0) sc[1] = 1;
+            } else if (namb > 0) {
+                uint32_t* acnt = bm; // the bitmap is free now
+                for (int c = tid; c < namb; c += nthr) acnt[c] = 0u;
+                gsync();
+                for (int x = tid; x < namb * H; x += nthr) { // exact multiplicity over all H buckets
+                    const int c = x / H, t = x - c * H;
+                    const int cnt = cntv[t];
+                    if (cnt > 0) {
+                        const uint32_t id = amb[c];
+                        const uint32_t* p = P.table_values + offv[t];
+                        const int pos = collect_lower_bound_interp(p, cnt, id, P.id_space);
+                        if (pos < cnt && __ldg(p + pos) == id) atomicAdd(&acnt[c], 1u);
+                    }
+                }
+                gsync();
+                for (int c = tid; c < namb; c += nthr)
+                    if (acnt[c] >= (uint32_t)T) {
+                        const int at = atomicAdd(&sc[2], 1);
+                        if (at < FINCAP) fin[at] = amb[c];
+                    }
+            }
+            gsync();
+            if (sc[1] || sc[2] > FINCAP) {
+                if (tid == 0) {
+                    if (BLOCK) P.big2_list[atomicAdd(P.big2_count, 1)] = rd;
+                    else P.big_list[atomicAdd(P.big_count, 1)] = rd;
+                    st_big++;
+                    st_enum -= (unsigned long long)E;
+                    st_skip -= (unsigned long long)SK;
+                }
+                continue;
             }
         }
-        __syncthreads();
-        const int nfin = s_nfin;
-        const unsigned long long start = s_start;
-        for (int i = tid; i < nfin; i += BLOOMB_THREADS) P.out[start + i] = cand[i];
+        const int nfin = sc[2];
+        if (nfin > 1) {
+            if (BLOCK) bitonic_sort<true>(fin, nfin, tid, nthr);
+            else collect_sort_warp(fin, nfin, lane);
+        }
+        gsync();
+        if (tid == 0) {
+            unsigned long long start = 0;
+            int nf = nfin;
+            if (nf > 0) start = atomicAdd(P.cursor, (unsigned long long)nf);
+            if (start + (unsigned long long)nf > P.out_cap) {
+                *P.overflow = 1;
+                nf = 0;
+            }
+            P.lists[rd] = make_int2((int)start, nf);
+            sc[2] = nf;
+            sc[7] = (int)(start & 0x7fffffffu); // out_cap < 2^31
+        }
+        gsync();
+        {
+            const int nf = sc[2];
+            const unsigned long long start = (unsigned long long)(unsigned)sc[7];
+            for (int i = tid; i < nf; i += nthr) P.out[start + i] = fin[i];
+        }
     }
     if (tid == 0 && P.stats) {
         if (st_enum) atomicAdd(P.stats, st_enum);
         if (st_skip) atomicAdd(P.stats + 1, st_skip);
+        if (st_big && !BLOCK) atomicAdd(P.stats + 3, st_big);
+        if (st_big && BLOCK) atomicAdd(P.stats + 4, st_big);
     }
 }
 
@@ -1099,10 +1045,10 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     const int fill_env = env_int("HRM_COLLECT_FILL", 0);
     const int fill = fill_env > 0 ? fill_env : (slots * 3) / 8; // expected ids per range: 3/8 of the table, 7/8 tolerated
     Scratch ctl, big, big2;
-    HRM_TRY(ctl.alloc(sizeof(unsigned long long) * 8, s));
+    HRM_TRY(ctl.alloc(sizeof(unsigned long long) * 32, s));
     HRM_TRY(big.alloc(sizeof(int32_t) * ((size_t)n + 1), s));
     HRM_TRY(big2.alloc(sizeof(int32_t) * ((size_t)n + 1), s));
-    HRM_CUDA(cudaMemsetAsync(ctl.p, 0, sizeof(unsigned long long) * 8, s));
+    HRM_CUDA(cudaMemsetAsync(ctl.p, 0, sizeof(unsigned long long) * 32, s));
     HRM_CUDA(cudaMemsetAsync(big.p, 0, sizeof(int32_t), s));
     HRM_CUDA(cudaMemsetAsync(big2.p, 0, sizeof(int32_t), s));
     CollectParams P;
@@ -1129,12 +1075,18 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     P.slots = slots;
     P.fill = fill;
     const int impl_ranges = env_int("HRM_COLLECT_RANGES", 0); // 1: the counting-table warp kernel (id ranges)
-    const int bloom_words_env = env_int("HRM_COLLECT_BLOOM_WORDS", 2048);
+    const int bloom_words_env = env_int("HRM_COLLECT_BLOOM_WORDS", 1024);
     int bwords = 64;
     while (bwords < bloom_words_env && bwords < 8192) bwords <<= 1;
     const int bblock_env = env_int("HRM_COLLECT_BLOOM_BLOCK_WORDS", 32768);
     int bblock_words = 64;
     while (bblock_words < bblock_env && bblock_words < 32768) bblock_words <<= 1;
+    const int xwarp_env = env_int("HRM_COLLECT_XSLOTS", 1024), xblock_env = env_int("HRM_COLLECT_BLOCK_XSLOTS", 8192);
+    int xwarp = 256, xblock = 2048; // the table keeps a quarter of its slots free: more than one slot per thread
+    while (xwarp < xwarp_env && xwarp < 4096) xwarp <<= 1;
+    while (xblock < xblock_env && xblock < 8192) xblock <<= 1;
+    P.xslots_warp = xwarp;
+    P.xslots_block = xblock;
     const bool allow_packed = env_int("HRM_COLLECT_UNPACKED", 0) == 0;
     const bool packed = allow_packed && id_space < (1u << (32 - COLLECT_PACK_BITS)) - 1u && mh->H < (1 << COLLECT_PACK_BITS);
     const size_t smem = sizeof(uint32_t) * ((size_t)((packed ? 1 : 2) + 1) * slots + COLLECT_FINAL_CAP);
@@ -1144,20 +1096,20 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     int wres = 1;
     // one wave of resident blocks, each loops over the list of big reads
     int resident = 1;
-    if (!impl_ranges) {
+    if (!impl_ranges && packed) {
         P.warp_slots = bwords;
-        const size_t bsmem = sizeof(uint32_t) * bloom_slice_words(bwords, mh->H) * (wthreads / 32);
-        cudaFuncSetAttribute(collect_bloom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
-        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wres, collect_bloom_kernel, wthreads, bsmem));
-        HRM_LAUNCH(collect_bloom_kernel, (unsigned)(num_sms() * (wres > 0 ? wres : 1)), wthreads, bsmem, s, P);
-        // skewed reads: block-wide filter, then (what is left) the counting-table kernel on big2_list
-        CollectParams PB = P;
-        PB.slots = bblock_words;
-        const size_t bbsmem = sizeof(uint32_t) * ((size_t)bblock_words + 2 * COLLECT_FINAL_CAP);
+        P.slots = bblock_words;
+        const size_t bsmem = sizeof(uint32_t) * dup_slice_words(bwords, xwarp, DUP_WQ, mh->H) * (wthreads / 32);
+        cudaFuncSetAttribute(collect_dup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wres, collect_dup_kernel<false>, wthreads, bsmem));
+        HRM_LAUNCH(collect_dup_kernel<false>, (unsigned)(num_sms() * (wres > 0 ? wres : 1)), wthreads, bsmem, s, P);
+        // skewed reads: the same scheme block-wide, then (what is left) the counting-table kernel on big2_list
+        const size_t bbsmem = sizeof(uint32_t) * dup_slice_words(bblock_words, xblock, DUP_BQ, mh->H);
         int bres = 1;
-        cudaFuncSetAttribute(collect_bloom_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bbsmem);
-        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bres, collect_bloom_block_kernel, BLOOMB_THREADS, bbsmem));
-        HRM_LAUNCH(collect_bloom_block_kernel, (unsigned)(num_sms() * (bres > 0 ? bres : 1)), BLOOMB_THREADS, bbsmem, s, PB);
+        cudaFuncSetAttribute(collect_dup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bbsmem);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bres, collect_dup_kernel<true>, DUP_BTHREADS, bbsmem));
+        HRM_LAUNCH(collect_dup_kernel<true>, (unsigned)(num_sms() * (bres > 0 ? bres : 1)), DUP_BTHREADS, bbsmem, s, P);
+        P.slots = slots;
         CollectParams PC = P;
         PC.big_count = P.big2_count;
         PC.big_list = P.big2_list;
@@ -1189,11 +1141,13 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
         HRM_LAUNCH(collect_big_kernel<false>, (unsigned)(num_sms() * (resident > 0 ? resident : 1)), COLLECT_BIG_THREADS,
                    smem, s, P);
     }
-    unsigned long long h[8];
+    unsigned long long h[32];
     HRM_CUDA(cudaMemcpyAsync(h, ctl.p, sizeof h, cudaMemcpyDeviceToHost, s));
     HRM_CUDA(cudaStreamSynchronize(s)); // the one sync of the pass: overflow flag + candidate total
     *h_total = (int64_t)h[0];
     *h_overflow = (int)(h[1] & 0xFFFFFFFFull);
+    if (getenv("HRM_COLLECT_DEBUG"))
+        fprintf(stderr, "collect: n=%d inserted=%llu tested=%llu warp->block=%llu block->table=%llu\n", n, h[2], h[3], h[5], h[6]);
     if (h_stats3) {
         h_stats3[0] = (int64_t)h[2];
         h_stats3[1] = (int64_t)h[3];

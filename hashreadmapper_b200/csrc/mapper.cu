@@ -692,6 +692,37 @@ extern "C" hrm_status hrm_mapper_stage_reads(hrm_mapper* m, int slot, const char
     return HRM_OK;
 }
 
+// FASTQ / FASTA text instead of ASCII rows: the text goes H2D on the copy-in stream and is parsed there by
+// hrm_ingest_reads (device-side reader, ingest.cu).  Blocks the calling thread until the batch is parsed (the reader
+// sizes its buffers from the line count); call it from a second host thread to overlap it with hrm_mapper_map_staged
+// of the other slot -- the two calls share no state.
+extern "C" hrm_status hrm_mapper_stage_fastq(hrm_mapper* m, int slot, const char* h_text, int64_t nbytes,
+                                             int64_t first_read_id, int32_t carry_replaced, int64_t ascii_pitch,
+                                             int64_t max_reads, int64_t* h_num_reads, int32_t* h_carry_replaced_out)
+{
+    HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
+    HRM_REQUIRE(nbytes >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && max_reads >= 0 && h_num_reads != nullptr, "sizes");
+    HRM_REQUIRE(nbytes == 0 || h_text != nullptr, "text");
+    HRM_REQUIRE(m->comm == nullptr, "the staged pipeline runs on the replicated index");
+    HRM_TRY(pipe_init(m));
+    PipeSlot& S = m->slot[slot];
+    if (S.busy) HRM_CUDA(cudaEventSynchronize(S.drained));
+    S.busy = false;
+    S.pitch = ascii_pitch;
+    S.n = 0;
+    HRM_TRY(S.fastq.reserve((size_t)nbytes + 16));
+    HRM_TRY(S.ascii.reserve((size_t)(max_reads * ascii_pitch)));
+    HRM_TRY(S.len.reserve(sizeof(int32_t) * (size_t)max_reads));
+    if (nbytes > 0) HRM_CUDA(cudaMemcpyAsync(S.fastq.p, h_text, (size_t)nbytes, cudaMemcpyHostToDevice, m->pipe_in));
+    HRM_TRY(hrm_ingest_reads(S.fastq.as<char>(), nbytes, first_read_id, carry_replaced, S.ascii.as<char>(), ascii_pitch,
+                             S.len.as<int32_t>(), nullptr, max_reads, h_num_reads, h_carry_replaced_out,
+                             (hrm_stream)m->pipe_in));
+    S.n = *h_num_reads;
+    HRM_CUDA(cudaEventRecord(S.staged, m->pipe_in));
+    S.is_staged = true;
+    return HRM_OK;
+}
+
 extern "C" hrm_status hrm_mapper_map_staged(hrm_mapper* m, int slot, hrm_read_record* h_records, char* h_cigars,
                                             int64_t cigar_pitch, uint32_t first_read_id,
                                             const char* const* h_chrom_names, char* h_sq_out, int64_t sq_cap,

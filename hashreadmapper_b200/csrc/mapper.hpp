@@ -55,7 +55,7 @@ struct StageTimer {
 namespace hrm {
 // one batch of the double-buffered end-to-end pipeline (mapper.cu: hrm_mapper_stage_reads / map_staged / finish)
 struct PipeSlot {
-    GrowBuf ascii, len, mapped, rec, cig, text, sq;
+    GrowBuf ascii, len, mapped, rec, cig, text, sq, fastq;
     cudaEvent_t staged = nullptr, computed = nullptr, drained = nullptr;
     int64_t n = 0, pitch = 0, sq_written = 0, rec_written = 0;
     bool is_staged = false, busy = false;

@@ -359,8 +359,9 @@ extern "C" hrm_status hrm_readstore_gather(const hrm_readstore* rs, int handle, 
                                            hrm_stream stream)
 {
     HRM_REQUIRE(rs != nullptr && rs_handle_ok(rs, handle), "readstore/handle");
-    HRM_REQUIRE(n >= 0 && out_pitch_words > 0 && d_ids != nullptr, "args");
+    HRM_REQUIRE(n >= 0 && out_pitch_words > 0, "args");
     if (n == 0) return HRM_OK;
+    HRM_REQUIRE(d_ids != nullptr && d_out != nullptr, "buffers");
     HRM_LAUNCH(gather_rows_kernel, sgrid(n * out_pitch_words), 256, 0, as_stream(stream), rs->rows, rs->pitch_words,
                d_ids, 0u, n, rs->n, d_out, out_pitch_words);
     return HRM_OK;
@@ -382,8 +383,9 @@ extern "C" hrm_status hrm_readstore_gather_lengths(const hrm_readstore* rs, int 
                                                    const uint32_t* d_ids, int64_t n, hrm_stream stream)
 {
     HRM_REQUIRE(rs != nullptr && rs_handle_ok(rs, handle), "readstore/handle");
-    HRM_REQUIRE(n >= 0 && d_ids != nullptr, "args");
+    HRM_REQUIRE(n >= 0, "args");
     if (n == 0) return HRM_OK;
+    HRM_REQUIRE(d_ids != nullptr && d_lengths != nullptr, "buffers");
     HRM_LAUNCH(gather_lengths_kernel, sgrid(n), 256, 0, as_stream(stream), rs->lengths, d_ids, n, rs->n, d_lengths);
     return HRM_OK;
 }
@@ -393,8 +395,9 @@ extern "C" hrm_status hrm_readstore_are_ambiguous(const hrm_readstore* rs, int h
                                                   const uint32_t* d_ids, int64_t n, hrm_stream stream)
 {
     HRM_REQUIRE(rs != nullptr && rs_handle_ok(rs, handle), "readstore/handle");
-    HRM_REQUIRE(n >= 0 && d_ids != nullptr && d_result != nullptr, "args");
+    HRM_REQUIRE(n >= 0, "args");
     if (n == 0) return HRM_OK;
+    HRM_REQUIRE(d_ids != nullptr && d_result != nullptr, "buffers");
     HRM_LAUNCH(gather_flags_kernel, sgrid(n), 256, 0, as_stream(stream), rs->ambig, d_ids, n, rs->n, d_result);
     return HRM_OK;
 }

@@ -603,6 +603,13 @@ hrm_status hrm_mapper_map_reads_sam(hrm_mapper* m, const char* h_reads_ascii, in
 #define HRM_PIPE_SLOTS 2
 hrm_status hrm_mapper_stage_reads(hrm_mapper* m, int slot, const char* h_reads_ascii, int64_t ascii_pitch,
                                   const int32_t* h_lengths, int64_t n);
+/* Same as hrm_mapper_stage_reads from FASTQ / FASTA TEXT in host memory (whole records, < 2 GiB): H2D on the copy-in
+ * stream, parsed on the device by hrm_ingest_reads (same arguments and semantics).  Blocks the calling thread until
+ * the batch is parsed; to overlap it with hrm_mapper_map_staged of the other slot call it from a second host thread
+ * (the two calls share no state). */
+hrm_status hrm_mapper_stage_fastq(hrm_mapper* m, int slot, const char* h_text, int64_t nbytes, int64_t first_read_id,
+                                  int32_t carry_replaced, int64_t ascii_pitch, int64_t max_reads,
+                                  int64_t* h_num_reads, int32_t* h_carry_replaced_out);
 hrm_status hrm_mapper_map_staged(hrm_mapper* m, int slot, hrm_read_record* h_records, char* h_cigars,
                                  int64_t cigar_pitch, uint32_t first_read_id, const char* const* h_chrom_names,
                                  char* h_sq_out, int64_t sq_cap, char* h_rec_out, int64_t rec_cap,

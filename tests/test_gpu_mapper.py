@@ -202,22 +202,26 @@ def test_fused_collection_paths(cuda, tmp_path, min_hits):
     import sys
     worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "collect_worker.py")
     variants = {"general": {"HRM_COLLECT": "0"},
-                "default": {},                                     # duplicate detection (blocked Bloom filter) per warp
-                "bloom_tiny": {"HRM_COLLECT_BLOOM_WORDS": "64"},   # most reads go on to the block-wide filter kernel
-                # ... and from there to the counting-table kernel
-                "bloom_tiny_block_tiny": {"HRM_COLLECT_BLOOM_WORDS": "64", "HRM_COLLECT_BLOOM_BLOCK_WORDS": "64"},
-                "bloom_block_small": {"HRM_COLLECT_BLOOM_WORDS": "64", "HRM_COLLECT_BLOOM_BLOCK_WORDS": "512"},
-                "bloom_all_block": {"HRM_COLLECT_WARP_CAP": "8", "HRM_COLLECT_RANGES": "0"},
-                "bloom_small": {"HRM_COLLECT_BLOOM_WORDS": "256"},
-                "bloom_big": {"HRM_COLLECT_BLOOM_WORDS": "8192"},
+                "default": {},  # duplicate detection: Bloom filter + exact event table, warp per read
+                # small filters / small event tables: reads overflow to the block-wide variant and on to the table kernel
+                "dup_tiny_filter": {"HRM_COLLECT_BLOOM_WORDS": "64"},
+                "dup_tiny_tables": {"HRM_COLLECT_BLOOM_WORDS": "64", "HRM_COLLECT_XSLOTS": "256",
+                                    "HRM_COLLECT_BLOOM_BLOCK_WORDS": "64", "HRM_COLLECT_BLOCK_XSLOTS": "2048"},
+                "dup_small_events": {"HRM_COLLECT_XSLOTS": "256"},
+                "dup_block_small": {"HRM_COLLECT_BLOOM_WORDS": "64", "HRM_COLLECT_BLOOM_BLOCK_WORDS": "512"},
+                "dup_big": {"HRM_COLLECT_BLOOM_WORDS": "8192", "HRM_COLLECT_XSLOTS": "4096"},
+                "dup_all_block": {"HRM_COLLECT_WARP_CAP": "8"},
+                # ... through to the counting-table block kernel with many id ranges / tiny tables
+                "dup_to_table": {"HRM_COLLECT_WARP_CAP": "8", "HRM_COLLECT_BLOOM_BLOCK_WORDS": "64", "HRM_COLLECT_SLOTS": "256",
+                                 "HRM_COLLECT_FILL": "40"},
+                "dup_to_table_tiny": {"HRM_COLLECT_WARP_CAP": "4", "HRM_COLLECT_BLOOM_BLOCK_WORDS": "64",
+                                      "HRM_COLLECT_SLOTS": "64", "HRM_COLLECT_FILL": "12"},
                 # the counting-table warp kernel with id ranges (HRM_COLLECT_RANGES=1)
                 "warp_table": {"HRM_COLLECT_RANGES": "1"},
                 "warp_ranges": {"HRM_COLLECT_RANGES": "1", "HRM_COLLECT_WARP_SLOTS": "64"},
                 "warp_ranges_unpacked": {"HRM_COLLECT_RANGES": "1", "HRM_COLLECT_WARP_SLOTS": "128",
                                          "HRM_COLLECT_UNPACKED": "1"},
-                "block": {"HRM_COLLECT_WARP_CAP": "8"},
-                "ranges": {"HRM_COLLECT_WARP_CAP": "8", "HRM_COLLECT_SLOTS": "256", "HRM_COLLECT_FILL": "40"},
-                "tiny": {"HRM_COLLECT_WARP_CAP": "4", "HRM_COLLECT_SLOTS": "64", "HRM_COLLECT_FILL": "12"},
+                "block": {"HRM_COLLECT_RANGES": "1", "HRM_COLLECT_WARP_CAP": "8"},
                 "probe_qm": {"HRM_PROBE_TM": "0"},  # query-major probe ([n][H] signatures and ranges) + fused collection
                 "probe_qm_general": {"HRM_PROBE_TM": "0", "HRM_COLLECT": "0"},
                 "unpacked": {"HRM_COLLECT_UNPACKED": "1"},

@@ -176,3 +176,57 @@ def test_staged_pipeline(cuda, port):
             for f in ("orientation", "hamming_distance", "shift", "chromosome_id", "position", "pass"):
                 assert (outs[i]["rec"]["mapped"][f][:n] == exp[i][2]["mapped"][f]).all(), f
             assert (outs[i]["rec"]["alignments"][:n] == exp[i][2]["alignments"]).all()
+
+
+def test_fastq_text_to_sam_text(cuda, port):
+    """FASTQ text in host memory -> hrm_mapper_stage_fastq (H2D + device-side reader) -> map -> SAM text, staged from a
+    second host thread while the other slot computes; same bytes as the row-based entry point on the parsed reads"""
+    import threading
+    import torch
+    genome, off = synth.make_genome([120_000], seed=71)
+    mp = cuda.Mapper(cuda.directional_config())
+    mp.setGenome(genome, off, ["chrF"])
+    texts, rows_, first = [], [], 0
+    for b, n in enumerate([2000, 1500, 2500]):
+        reads, lens, _ = synth.make_reads(genome, off, n, 150, error_rate=0.02, seed=80 + b)
+        reads[3, 10] = ord("N")  # replaced by the reader's ACGT cycle
+        recs = []
+        for i in range(n):
+            sq = bytes(reads[i, :lens[i]]).decode()
+            recs.append("@r%d\n%s\n+\n%s\n" % (first + i, sq, "I" * len(sq)))
+        t = np.frombuffer("".join(recs).encode(), dtype=np.uint8).copy()
+        texts.append(torch.from_numpy(t).pin_memory().numpy())
+        first += n
+    # expected: parse each text on the device, then the one-shot row entry point
+    exp, fid, carry = [], 0, 0
+    for t in texts:
+        r, l, a, c2 = cuda.ingest_reads(torch.from_numpy(t).cuda(), 160, 4000, fid, carry)
+        sq, rc, _ = mp.mapReadsSam(r.cpu().numpy(), l.cpu().numpy(), first_read_id=fid, cigar_pitch=128)
+        exp.append((sq.tobytes(), rc.tobytes()))
+        fid += r.shape[0]
+        carry = c2
+    outs = [{"sq": np.zeros(4000 * 40, np.uint8), "txt": np.zeros(4000 * 600, np.uint8)} for _ in texts]
+    state = {"fid": 0, "carry": 0, "n": [0] * len(texts), "first": [0] * len(texts)}
+
+    def stage(i):
+        state["first"][i] = state["fid"]
+        n, c2 = mp.stageFastq(i % 2, texts[i], 160, 4000, state["fid"], state["carry"])
+        state["n"][i] = n
+        state["fid"] += n
+        state["carry"] = c2
+    stage(0)
+    sizes = [None] * len(texts)
+    for i in range(len(texts)):
+        th = None
+        if i + 1 < len(texts):
+            th = threading.Thread(target=stage, args=(i + 1,))
+            th.start()
+        mp.mapStaged(i % 2, None, None, 128, state["first"][i], outs[i]["sq"], outs[i]["txt"])
+        if th is not None:
+            th.join()
+        if i >= 1:
+            sizes[i - 1] = mp.finish((i - 1) % 2)
+    sizes[-1] = mp.finish((len(texts) - 1) % 2)
+    for i in range(len(texts)):
+        assert outs[i]["sq"][:sizes[i][0]].tobytes() == exp[i][0], i
+        assert outs[i]["txt"][:sizes[i][1]].tobytes() == exp[i][1], i

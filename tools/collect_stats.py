@@ -26,7 +26,7 @@ settings = [{}] + [dict(e.split("=") for e in s.split(",")) for s in sys.argv[3:
 ref = None
 for env in settings:
     for k in list(os.environ):
-        if k.startswith("HRM_COLLECT"):
+        if k.startswith("HRM_COLLECT") and k != "HRM_COLLECT_DEBUG":
             del os.environ[k]
     os.environ.update(env)
     mp.mapBatch(d_reads, d_lens, want_stats=False)
