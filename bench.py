@@ -579,8 +579,18 @@ def main():
                         "note": "algorithmic bytes = 4 B x ids enumerated + the 8-B (offset, count) bucket ranges of every "
                                 "(read, table) + the 8-B list header per read (DESIGN 3); launch_ms spans the kernels of one "
                                 "pass' collection (CUDA events on the launching stream)"}
-    roofline = collect_roofline if (dom_stage == "filter" and comm is None) else probe_roofline
+    # `roofline` = the HBM-bound kernel with the largest share of the step (the fused collection on the replicated index);
+    # verification (K7) is integer-ALU bound: its figures are reported beside it, not against the HBM peak
+    roofline = collect_roofline if comm is None else probe_roofline
     other = probe_roofline if roofline is collect_roofline else collect_roofline
+    qp, rp = ((args.read_len + 15) // 16) * 16, W_
+    cells = 2.0 * 2.0 * qp * rp * n   # 2 alignments x (forward + reverse pass) x padded read x window, upper bound
+    verify_info = {"kernel": "hrm::sw_pair_passes_kernel (K7a: both SW passes, s16x2 DPX wavefront) + band ladder (K7b: trace "
+                             "back + CIGAR)", "bound": "integer ALU (ncu: ALU pipe 80 % in K7a, profiles/README.md)",
+                   "stage_ms": stage_ms["verify"], "share_of_step": stage_ms["verify"] / ms_per_step if ms_per_step > 0 else None,
+                   "cell_updates_per_step_upper_bound": cells,
+                   "gcups_over_the_whole_stage": cells / (stage_ms["verify"] / 1e3) / 1e9 if stage_ms["verify"] > 0 else None}
+    dominant_stage = dom_stage
 
     line = {"metric": "reads mapped/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -600,6 +610,7 @@ def main():
             "gpu_launches": int(launches_step * args.steps),
             "roofline": roofline,
             "roofline_probe" if roofline is collect_roofline else "roofline_collect": other,
+            "verify_alu": verify_info, "dominant_stage": dominant_stage,
             "stages_ms_per_step": stage_ms, "stages_unaccounted_ms": ms_per_step - stage_sum,
             "mapped_fraction": n_mapped / n, "mapped_at_true_locus_fraction": float(ok.sum()) / max(n_mapped, 1),
             "candidates_per_read": st.num_candidates / n, "values_per_read": st.num_values / n,

@@ -420,3 +420,28 @@ def sam_complement_text_columns(sam):
             ln = b"\t".join(c)
         out.append(ln)
     return b"\n".join(out)
+
+
+# ---- C1: the reference's own CUDA candidate filter (needs a GPU; TEST INFRASTRUCTURE) ------------------------------
+REF_C1_SO = os.path.join(HERE, "_ref", "libhrm_ref_c1.so")
+
+
+def have_ref_c1():
+    return os.path.exists(REF_C1_SO)
+
+
+def ref_unique_by_count(values, offsets, min_count):
+    """GpuSegmentedUniqueByCount::unique (include/gpu/cuda_unique_by_count.cuh:33-215) on the current CUDA device.
+    values uint32 [total], offsets int32 [nseg + 1] -> (survivors of all segments back to back, lengths [nseg])"""
+    lib = C.CDLL(REF_C1_SO)
+    values = np.ascontiguousarray(values, dtype=np.uint32)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+    nseg = offsets.shape[0] - 1
+    out = np.zeros(max(values.shape[0], 1), dtype=np.uint32)
+    lens = np.zeros(max(nseg, 1), dtype=np.int32)
+    rc = lib.ref_unique_by_count(_p(values, C.c_uint32), int(values.shape[0]), int(nseg), _p(offsets, C.c_int32),
+                                 int(min_count), _p(out, C.c_uint32), _p(lens, C.c_int32))
+    if rc != 0:
+        raise RuntimeError("ref_unique_by_count failed: %d" % rc)
+    lens = lens[:nseg]
+    return out[:int(lens.sum())], lens
