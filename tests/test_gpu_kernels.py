@@ -425,3 +425,30 @@ def test_ingest_reads(cuda, tmp_path):
                 b">a\n" + b"A" * 40 + b"\n" + b"C" * 40 + b"\n", b"hello\n"):
         with pytest.raises(hb.HrmError):
             run(bad, 64)
+
+
+@pytest.mark.parametrize("min_hits", [4, 2, 7])
+def test_k4_against_reference_unique_by_count(cuda, min_hits):
+    """C1 pinned to the REFERENCE'S OWN CUDA implementation: GpuSegmentedUniqueByCount::unique
+    (include/gpu/cuda_unique_by_count.cuh:33-215, compiled from the header where it lies into oracle/_ref/libhrm_ref_c1.so)
+    runs on this GPU on the same segments as hrm_filter_by_frequency"""
+    from oracle import pyoracle as po
+    if not po.have_ref_c1():
+        pytest.skip("oracle/_ref/libhrm_ref_c1.so not built (needs /root/reference at build time)")
+    rng = np.random.RandomState(100 + min_hits)
+    sizes = list(rng.randint(0, 60, size=800)) + [0, 1, 255, 256, 257, 1000, 5000, 9000, 20000, 0, 4200, 4300]
+    rng.shuffle(sizes)
+    offs = np.zeros(len(sizes) + 1, np.int64)
+    offs[1:] = np.cumsum(sizes)
+    vals = np.zeros(int(offs[-1]), np.uint32)
+    for i, n in enumerate(sizes):
+        hi = max(2, n // 4 + 1)
+        vals[offs[i]:offs[i + 1]] = rng.randint(0, hi, size=n).astype(np.uint32) * 65537 + (1 << 31) * (i % 2)
+    ev, el = po.ref_unique_by_count(vals, offs.astype(np.int32), min_hits)
+    dv = tt(cuda, vals.view(np.int32))
+    dnum = tt(cuda, np.array(sizes, np.int32))
+    doff = tt(cuda, offs.astype(np.int32))
+    total = cuda.filter_by_frequency(dv, dnum, doff, min_hits)
+    assert total == len(ev) and total > 0
+    assert (dnum.cpu().numpy() == el).all()
+    assert (as_u32(dv)[:total] == ev).all()

@@ -241,3 +241,75 @@ def test_fused_collection_paths(cuda, tmp_path, min_hits):
     for name in variants:
         assert (res[name] == res["general"]).all(), name
         assert logs[name] == logs["general"], (name, logs[name], logs["general"])
+
+
+@pytest.mark.parametrize("conf", ["configs0_full", "configs1_sample"])
+def test_baseline_configs_against_the_reference_cpu_path(cuda, port, ref, conf):
+    """BASELINE configs at their stated index sizes against the REFERENCE'S OWN CPU functions (oracle/_ref:
+    cpuhashtable.hpp tables over the reads, windows streamed in batches of 2048, hammingdistance templates, ssw.c):
+    configs[0] in full (10 k reads x 5 Mbp); configs[1]'s 46 Mbp index with a 20 k-read sample of its 1 M reads
+    (the table-major probe, the duplicate-detection collection on real bucket skew).  MappedRead + both raw SSW
+    alignments per read, both 3N passes merged."""
+    import torch
+    from oracle.pyoracle import ref_cpu_pipeline
+    if conf == "configs0_full":
+        genome, off = synth.make_genome([5_000_000], seed=20240601)
+        reads, lens, _ = synth.make_reads(genome, off, 10_000, 150, error_rate=0.0, seed=20240602)
+    else:
+        genome, off = synth.make_genome([46_000_000], seed=20240601)
+        reads, lens, _ = synth.make_reads(genome, off, 20_000, 150, error_rate=0.01, seed=20240602)
+    cfg = cuda.directional_config()
+    mp = cuda.Mapper(cfg)
+    mp.setGenome(genome, off, ["chrS"])
+    rec, cig, st = mp.mapReads(reads, lens, cigar_pitch=128)
+    passes, sws = [], []
+    for p in range(2):
+        g = port.convert_ascii(genome, cfg.genome_conversion[p])
+        r = np.frombuffer(port.convert_ascii(reads.tobytes(), cfg.read_conversion[p]), dtype=np.uint8).reshape(reads.shape)
+        # stage V of pass 1 verifies with G->A: the reference's C->T stage on the complemented text (see DESIGN.md)
+        if cfg.verify_conversion[p] == 2:
+            from oracle.pyoracle import complement_ascii
+            out, _, _, _ = ref_cpu_pipeline(ref, g, off, r, lens, want_alignments=False)
+            gc_ = complement_ascii(g)
+            rc_ = np.frombuffer(complement_ascii(r.tobytes()), dtype=np.uint8).reshape(r.shape)
+            sw = verify_with_reference(ref, gc_, off, rc_, lens, out)
+        else:
+            out, sw, _, _ = ref_cpu_pipeline(ref, g, off, r, lens, want_alignments=True)
+        passes.append(out)
+        sws.append(sw)
+    exp, which = merge(passes)
+    check_mapped(rec["mapped"], exp, which)
+    m = exp["orientation"] != 3
+    assert m.mean() > 0.9
+    names = [n for n in rec["alignments"].dtype.names if n != "cigar_len"]
+    for p in range(2):
+        sel = m & (which == p)
+        for a in range(2):
+            for n in names:
+                assert (rec["alignments"][n][sel, a] == sws[p][n][sel, a]).all(), (p, a, n)
+
+
+def verify_with_reference(ref, genome, off, reads, lens, mapped):
+    """2 x Aligner::Align per mapped read by the reference's own ssw (ref_ssw_align_batch), C->T inputs built as
+    mappinghandler.cu:397-553 builds them"""
+    import ctypes as C
+    from oracle.pyoracle import ALIGN_DTYPE, _p
+    n = len(lens)
+    sw = np.zeros((n, 2), dtype=ALIGN_DTYPE)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    for i in np.nonzero(mapped["orientation"] != 3)[0]:
+        L = int(lens[i])
+        rd = bytes(reads[i, :L])
+        if mapped["orientation"][i] == 2:
+            rd = rd.translate(comp)[::-1]
+        rc = rd.translate(comp)[::-1]
+        pos = int(mapped["position"][i])
+        c = int(mapped["chromosomeId"][i])
+        chrom = genome[off[c]:off[c + 1]]
+        win = chrom[pos:pos + 128]
+        q0, q1, w3 = rd.replace(b"C", b"T"), rc.replace(b"C", b"T"), win.replace(b"C", b"T")
+        for a, q in enumerate((q0, q1)):
+            al, _ = ref.ssw_align(q, w3, max(15, L // 2))
+            for k, nme in enumerate(ALIGN_DTYPE.names[:9]):
+                sw[nme][i, a] = al[k]
+    return sw
