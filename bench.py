@@ -314,6 +314,22 @@ def parity_check(args, mp, cfg, genome, off, names, reads, lens, K):
             "parity_seconds": time.perf_counter() - t0}
 
 
+class StdoutToStderr:
+    """routes file descriptor 1 to stderr while C libraries initialise (NCCL prints its version line on stdout): the
+    bench prints exactly one line on stdout, the JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,6 +349,9 @@ def main():
                     help="reads of the timed batch compared with the oracle after the timed region (0: off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text", action="store_true", help="skip the SAM-text end-to-end figure")
+    ap.add_argument("--no-partitioned-segment", action="store_true",
+                    help="N > 1: skip the short key-partitioned-index segment appended to the replicated run")
+    ap.add_argument("--partitioned-sample", type=int, default=500_000, help="reads per GPU of that segment")
     ap.add_argument("--load-factor", type=float, default=None, help="hash-table load factor (default: the library's)")
     ap.add_argument("--read-len", type=int, default=READ_LEN)
     ap.add_argument("--error-rate", type=float, default=ERR)
@@ -357,7 +376,9 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with StdoutToStderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
     import hashreadmapper_b200 as hb
     import hashreadmapper_b200.api as api
     from hashreadmapper_b200 import parallel
@@ -370,7 +391,8 @@ def main():
     mp = api.Mapper(cfg)
     comm = None
     if args.index == "partitioned":
-        comm = api.Comm()
+        with StdoutToStderr():
+            comm = api.Comm()
         mp.setPartition(comm)
     t0 = time.perf_counter()
     names = ["chr%d" % (i + 1) for i in range(len(off) - 1)]
@@ -454,6 +476,10 @@ def main():
 
     def e2e_run(steps, text=None):
         """steps batches through the pipeline; text = None: records + CIGARs out; else (sq buffers, record text buffers)"""
+        if comm is not None:  # key-partitioned index: the routed queries are collective, batches run one at a time
+            for i in range(steps):
+                mp.mapReads(h_reads.numpy(), h_lens.numpy(), CIG, rec_np[i % 2], h_cig[i % 2].numpy())
+            return (0, 0)
         mp.stageReads(0, h_reads.numpy(), h_lens.numpy())
         sizes = (0, 0)
         for i in range(steps):
@@ -508,6 +534,49 @@ def main():
                     "api": "hrm_mapper_stage_reads / hrm_mapper_map_staged (V4 + SAM text on the device) / hrm_mapper_finish"}
         del tx_rec, tx_sq
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- N > 1: a short segment on the KEY-PARTITIONED index (BASELINE configs[4]) beside the replicated run ----------
+    part_seg = None
+    if world > 1 and comm is None and not args.no_partitioned_segment:
+        with StdoutToStderr():
+            comm2 = api.Comm()
+        mp2 = api.Mapper(cfg)
+        mp2.setPartition(comm2)
+        t0 = time.perf_counter()
+        mp2.setGenome(genome, off, names)
+        torch.cuda.synchronize()
+        pbuild = time.perf_counter() - t0
+        ns = min(n, args.partitioned_sample)
+        dr, dl = d_reads[:ns].contiguous(), d_lens[:ns].contiguous()
+        m_rep, _ = mp.mapBatch(dr, dl, want_stats=False)
+        m_par, _ = mp2.mapBatch(dr, dl, want_stats=False)
+        same = 1.0 if torch.equal(m_rep, m_par) else 0.0
+        same = -parallel.max_over_ranks(-same)  # min over the ranks
+        ci0 = comm2.info()
+        b0, x0 = ci0.bytes_sent, ci0.exchanges
+        mp2.setProfiling(True)
+        mp2.stageTimes()
+        barrier()
+        p0 = torch.cuda.Event(enable_timing=True)
+        p1 = torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(2):
+            mp2.mapBatch(dr, dl, want_stats=False)
+        p1.record()
+        barrier()
+        pms = parallel.max_over_ranks(p0.elapsed_time(p1)) / 2
+        pst = mp2.stageTimes()
+        ci1 = comm2.info()
+        part_seg = {"reads_per_gpu": int(ns), "seeding_reads_per_s": world * ns / (pms / 1e3), "ms_per_batch": pms,
+                    "route_ms": pst["route"][0] / 2, "probe_ms": pst["probe"][0] / 2, "collect_ms": pst["filter"][0] / 2,
+                    "shd_ms": pst["shd"][0] / 2, "bytes_sent_rank0_per_batch": int((ci1.bytes_sent - b0) // 2),
+                    "alltoall_GBps_rank0": ((ci1.bytes_sent - b0) / 2) / 1e9 / (max(pst["route"][0] / 2, 1e-6) / 1e3),
+                    "exchanges_per_batch": int((ci1.exchanges - x0) // 2), "identical_to_replicated": bool(same == 1.0),
+                    "index_device_bytes_per_gpu": int(mp2.info().index_device_bytes), "index_build_s": pbuild,
+                    "what": "K1..K5 (seeding, routed lookups over NCCL all-to-all, collection, best window) of the first "
+                            "reads of every rank's batch on an index whose tables are split by key over the ranks; the "
+                            "MappedReads are compared with the replicated index on every rank"}
+        del mp2
 
     if rank != 0:
         if world > 1:
@@ -603,10 +672,10 @@ def main():
                            index_device_bytes=int(info.index_device_bytes), table_slots=int(info.table_slots_total),
                            table_keys=int(info.num_keys_total)),
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "hrm_mapper_stage_reads / hrm_mapper_map_staged / hrm_mapper_finish (pinned host buffers, two "
-                           "batches in flight)",
+                    "api": ("hrm_mapper_stage_reads / hrm_mapper_map_staged / hrm_mapper_finish (pinned host buffers, two "
+                            "batches in flight)") if comm is None else "hrm_mapper_map_reads (pinned host buffers)",
                     "one_shot_value": oneshot_value, "one_shot_api": "hrm_mapper_map_reads (serial copy, compute, copy)"},
-            "e2e_text": e2e_text,
+            "e2e_text": e2e_text, "partitioned_segment": part_seg,
             "gpu_launches": int(launches_step * args.steps),
             "roofline": roofline,
             "roofline_probe" if roofline is collect_roofline else "roofline_collect": other,

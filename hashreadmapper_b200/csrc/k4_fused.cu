@@ -1031,6 +1031,16 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
                               uint32_t* d_out, int64_t out_cap, int2* d_lists, int64_t* h_total, int* h_overflow,
                               int64_t* h_stats3, cudaStream_t s)
 {
+    return collect_candidates_from(qh->ranges.as<uint2>(), qh->rq, qh->rt, mh->values, mh->H, n, min_hits, id_space, d_out,
+                                   out_cap, d_lists, h_total, h_overflow, h_stats3, s);
+}
+
+// The same over any array of ascending id lists: (offset, count) of list (q, t) at ranges[q * rq + t * rt], offsets into
+// table_values (the key-partitioned index hands the routed value lists over this way).
+hrm_status collect_candidates_from(const uint2* d_ranges, int64_t rq, int64_t rt, const uint32_t* d_table_values, int H, int n,
+                                   int min_hits, uint32_t id_space, uint32_t* d_out, int64_t out_cap, int2* d_lists,
+                                   int64_t* h_total, int* h_overflow, int64_t* h_stats3, cudaStream_t s)
+{
     *h_overflow = 0;
     *h_total = 0;
     if (n == 0) return HRM_OK;
@@ -1052,12 +1062,12 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     HRM_CUDA(cudaMemsetAsync(big.p, 0, sizeof(int32_t), s));
     HRM_CUDA(cudaMemsetAsync(big2.p, 0, sizeof(int32_t), s));
     CollectParams P;
-    P.ranges = qh->ranges.as<uint2>();
-    P.rq = qh->rq;
-    P.rt = qh->rt;
-    P.table_values = mh->values;
+    P.ranges = d_ranges;
+    P.rq = rq;
+    P.rt = rt;
+    P.table_values = d_table_values;
     P.n = n;
-    P.H = mh->H;
+    P.H = H;
     P.min_hits = min_hits;
     P.id_space = id_space;
     P.out = d_out;
@@ -1088,23 +1098,23 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const QueryHandle* qh, in
     P.xslots_warp = xwarp;
     P.xslots_block = xblock;
     const bool allow_packed = env_int("HRM_COLLECT_UNPACKED", 0) == 0;
-    const bool packed = allow_packed && id_space < (1u << (32 - COLLECT_PACK_BITS)) - 1u && mh->H < (1 << COLLECT_PACK_BITS);
+    const bool packed = allow_packed && id_space < (1u << (32 - COLLECT_PACK_BITS)) - 1u && H < (1 << COLLECT_PACK_BITS);
     const size_t smem = sizeof(uint32_t) * ((size_t)((packed ? 1 : 2) + 1) * slots + COLLECT_FINAL_CAP);
     // warp kernel: 2 warps per block so that the slices of many blocks fill the SM's shared memory
     const int wthreads = 64;
-    const size_t wsmem = sizeof(uint32_t) * collect_warp_slice_words(wslots, mh->H, packed) * (wthreads / 32);
+    const size_t wsmem = sizeof(uint32_t) * collect_warp_slice_words(wslots, H, packed) * (wthreads / 32);
     int wres = 1;
     // one wave of resident blocks, each loops over the list of big reads
     int resident = 1;
     if (!impl_ranges && packed) {
         P.warp_slots = bwords;
         P.slots = bblock_words;
-        const size_t bsmem = sizeof(uint32_t) * dup_slice_words(bwords, xwarp, DUP_WQ, mh->H) * (wthreads / 32);
+        const size_t bsmem = sizeof(uint32_t) * dup_slice_words(bwords, xwarp, DUP_WQ, H) * (wthreads / 32);
         cudaFuncSetAttribute(collect_dup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
         HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wres, collect_dup_kernel<false>, wthreads, bsmem));
         HRM_LAUNCH(collect_dup_kernel<false>, (unsigned)(num_sms() * (wres > 0 ? wres : 1)), wthreads, bsmem, s, P);
         // skewed reads: the same scheme block-wide, then (what is left) the counting-table kernel on big2_list
-        const size_t bbsmem = sizeof(uint32_t) * dup_slice_words(bblock_words, xblock, DUP_BQ, mh->H);
+        const size_t bbsmem = sizeof(uint32_t) * dup_slice_words(bblock_words, xblock, DUP_BQ, H);
         int bres = 1;
         cudaFuncSetAttribute(collect_dup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bbsmem);
         HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bres, collect_dup_kernel<true>, DUP_BTHREADS, bbsmem));

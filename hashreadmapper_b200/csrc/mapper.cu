@@ -261,22 +261,27 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
     st.num_reads = n;
     // key-partitioned index: the routed query is collective and bounded per call, so every rank runs the same number
     // of chunks of at most part_chunk reads (a rank that has run out of reads serves the others' lookups with n = 0)
-    int64_t part_chunks = 1;
-    if (m->comm) {
-        int64_t nmax = n;
-        HRM_TRY(comm_max_i64(m->comm, &nmax, s));
-        part_chunks = nmax > 0 ? HRM_SDIV(nmax, m->part_chunk) : 1;
-    }
+    int64_t nmax_all = n;
+    if (m->comm) HRM_TRY(comm_max_i64(m->comm, &nmax_all, s));
     if (n == 0) {
         if (m->comm) {
             Scratch numoff, values;
             HRM_TRY(numoff.alloc(sizeof(int32_t) * 4, s));
-            for (int p = 0; p < cfg.num_passes; p++)
-                for (int64_t c = 0; c < part_chunks; c++) {
+            for (int p = 0; p < cfg.num_passes; p++) {
+                int64_t chunk = m->part_chunk; // the same sequence of collective queries as the ranks that hold reads
+                for (int64_t base = 0; base < nmax_all || base == 0;) {
                     int64_t total = 0;
-                    HRM_TRY(partitioned_query(m->comm, m->index[cfg.genome_conversion[p]], nullptr, 0,
-                                              numoff.as<int32_t>(), numoff.as<int32_t>() + 1, &total, values, m->timer, s));
+                    const hrm_status qs = partitioned_query(m->comm, m->index[cfg.genome_conversion[p]], nullptr, 0,
+                                                            numoff.as<int32_t>(), numoff.as<int32_t>() + 1, &total, values,
+                                                            m->timer, s);
+                    if (qs == HRM_ERR_OVERFLOW && chunk > 1024) {
+                        chunk /= 2;
+                        continue;
+                    }
+                    HRM_TRY(qs);
+                    base += chunk;
                 }
+            }
             HRM_CUDA(cudaStreamSynchronize(s));
         }
         if (h_stats) *h_stats = st;
@@ -343,15 +348,55 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
             return HRM_OK;
         };
         if (m->comm) {
-            // key-partitioned index: route the lookups to their owners, values come back in table order
-            for (int64_t c = 0; c < part_chunks; c++) {
-                const int64_t lo = c * m->part_chunk < n ? c * m->part_chunk : n;
-                const int64_t cnt = (n - lo) < m->part_chunk ? (n - lo) : m->part_chunk;
-                Scratch values;
+            // key-partitioned index: route the lookups to their owners, values come back in table order.  Every rank
+            // runs the same sequence of collective queries: chunk boundaries depend on (nmax, part_chunk) only, and a
+            // collective overflow (decided identically on all ranks) halves the chunk size for everyone.
+            int64_t chunk = m->part_chunk;
+            for (int64_t base = 0; base < nmax_all || base == 0;) {
+                const int64_t lo = base < n ? base : n;
+                const int64_t cnt = (n - lo) < chunk ? (n - lo) : chunk;
+                Scratch values, rng;
                 int64_t total = 0;
-                HRM_TRY(partitioned_query(m->comm, mh, m->sigs.as<uint64_t>() + lo * H, (int)cnt, m->num.as<int32_t>() + lo,
-                                          m->off.as<int32_t>(), &total, values, T, s));
-                if (cnt > 0) HRM_TRY(filter_and_select(lo, cnt, total, values));
+                const bool fuse = m->use_fused && cfg.min_table_hits >= 2 && m->num_windows < 0xFFFFFFFFLL;
+                if (fuse) HRM_TRY(rng.alloc(sizeof(uint2) * (size_t)(cnt > 0 ? cnt : 1) * H, s));
+                const hrm_status qs = partitioned_query(m->comm, mh, m->sigs.as<uint64_t>() + lo * H, (int)cnt,
+                                                        m->num.as<int32_t>() + lo, m->off.as<int32_t>(), &total, values, T, s,
+                                                        fuse ? rng.as<uint2>() : nullptr);
+                if (qs == HRM_ERR_OVERFLOW && chunk > 1024) {
+                    chunk /= 2; // collective decision: every rank retries this base with half the chunk
+                    continue;
+                }
+                HRM_TRY(qs);
+                base += chunk;
+                if (cnt == 0) continue;
+                bool collected = false;
+                if (fuse) { // the fused collection over the routed value lists (k4_fused.cu)
+                    Scratch cands, lists;
+                    const int64_t cap = cnt * 32 > (1 << 16) ? cnt * 32 : (1 << 16);
+                    HRM_TRY(cands.alloc(sizeof(uint32_t) * (size_t)cap, s));
+                    HRM_TRY(lists.alloc(sizeof(int2) * (size_t)cnt, s));
+                    int64_t ctotal = 0, cst[3] = {0, 0, 0};
+                    int overflow = 0;
+                    T.begin(HRM_STAGE_FILTER, s);
+                    HRM_TRY(collect_candidates_from(rng.as<uint2>(), H, 1, values.as<uint32_t>(), H, (int)cnt, cfg.min_table_hits,
+                                                    (uint32_t)m->num_windows, cands.as<uint32_t>(), cap, lists.as<int2>(),
+                                                    &ctotal, &overflow, cst, s));
+                    T.end(s);
+                    if (!overflow) {
+                        T.begin(HRM_STAGE_SHD, s);
+                        HRM_TRY(best_windows(reads + lo * m->packed_pitch, m->packed_pitch, d_lengths + lo, cnt,
+                                             cands.as<uint32_t>(), nullptr, m->genome[gc], m->d_win_prefix, cfg.k,
+                                             cfg.window_size, cfg.max_hamming_percent, p, passout + lo, s, lists.as<int2>()));
+                        T.end(s);
+                        st.num_values += cst[0] + cst[1];
+                        st.num_candidates += ctotal;
+                        m->collect_enumerated += cst[0];
+                        m->collect_skipped += cst[1];
+                        m->collect_block_reads += cst[2];
+                        collected = true;
+                    }
+                }
+                if (!collected) HRM_TRY(filter_and_select(lo, cnt, total, values));
             }
         } else {
             // K3b probe of the whole batch -> per-read counts and bucket ranges

@@ -9,8 +9,8 @@
 //      its keys only, so the slot arrays -- 8/9 of the index -- shrink by G.
 //
 // One query batch of a rank (its own shard of the reads), all device-side except two count exchanges:
-//   1. route: dest = owner(sig) per (read, table) key, stable partition by dest (CUB radix sort on 8 bits),
-//      keys + table ids gathered into send order;
+//   1. route: dest = owner(sig) per (read, table) key, counting partition by dest (histogram, block-wise reservation
+//      of output ranges, scatter), keys + table ids gathered into send order;
 //   2. counts all-gather (G x G matrix) -> host; all-to-all-v of keys (8 B) and table ids (1 B);
 //   3. owner: probe its shard (one 64-B bucket access per lookup, as K3b), counts back (4 B per key);
 //   4. owner: gather the value lists contiguously per origin; value totals all-gather -> host;
@@ -22,7 +22,6 @@
 #include "k3_table.cuh"
 #include "mapper.hpp"
 #include "partition.cuh"
-#include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <string.h>
 #include <vector>
@@ -110,6 +109,17 @@ hrm_status comm_max_i64(hrm_comm* c, int64_t* v, cudaStream_t s)
     return HRM_OK;
 }
 
+// collective agreement on a status: every rank returns the first non-OK status any rank holds (synchronises the
+// stream).  A rank that failed locally (allocation, argument) never leaves its peers inside a collective.
+hrm_status comm_agree(hrm_comm* c, hrm_status local, cudaStream_t s)
+{
+    int64_t v = -(int64_t)local; // statuses are <= 0
+    hrm_status st = comm_max_i64(c, &v, s);
+    if (st != HRM_OK) return st;
+    if (v != 0 && local == HRM_OK) set_error("another rank failed with status %lld", (long long)-v);
+    return (hrm_status)(-v);
+}
+
 int comm_rank(const hrm_comm* c) { return c ? c->rank : 0; }
 int comm_world(const hrm_comm* c) { return c ? c->world : 1; }
 
@@ -140,7 +150,6 @@ static hrm_status alltoallv(hrm_comm* c, const void* send, const int64_t* scount
 // dest[e] = owner of key e (invalid signatures stay at home: they count 0 anywhere); hist[p] += 1
 __global__ void __launch_bounds__(256) route_dest_kernel(const uint64_t* __restrict__ sigs, int64_t total, int rank,
                                                          int world, uint8_t* __restrict__ dest,
-                                                         uint32_t* __restrict__ order,
                                                          unsigned long long* __restrict__ hist)
 {
     __shared__ unsigned int sh[256];
@@ -151,12 +160,56 @@ __global__ void __launch_bounds__(256) route_dest_kernel(const uint64_t* __restr
         const uint64_t key = sigs[e];
         const int d = key == SLOT_EMPTY ? rank : (int)key_owner(key, (uint32_t)world);
         dest[e] = (uint8_t)d;
-        order[e] = (uint32_t)e;
         atomicAdd(&sh[d], 1u);
     }
     __syncthreads();
     for (int t = threadIdx.x; t < world; t += blockDim.x)
         if (sh[t]) atomicAdd(&hist[t], (unsigned long long)sh[t]);
+}
+
+// counting partition by destination: perm[q] = lookup e, lookups of the same destination contiguous (any order inside
+// a destination: answers come back in the order they were sent).  A block counts its items per destination in shared
+// memory, reserves its ranges with one atomic per destination and scatters.
+__global__ void __launch_bounds__(256) route_partition_kernel(const uint8_t* __restrict__ dest, int64_t total, int world,
+                                                              const unsigned long long* __restrict__ hist,
+                                                              unsigned long long* __restrict__ cursor,
+                                                              uint32_t* __restrict__ perm)
+{
+    __shared__ unsigned int cnt[256], base_lo[256], soff_s[256];
+    __shared__ unsigned long long start[256];
+    constexpr int ITEMS = 16;
+    const int64_t tile = (int64_t)blockDim.x * ITEMS;
+    for (int64_t t0 = (int64_t)blockIdx.x * tile; t0 < total; t0 += (int64_t)gridDim.x * tile) {
+        for (int t = threadIdx.x; t < 256; t += blockDim.x) cnt[t] = 0u;
+        __syncthreads();
+        unsigned int mypos[ITEMS];
+        uint8_t myd[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            const int64_t e = t0 + (int64_t)k * blockDim.x + threadIdx.x;
+            myd[k] = 0;
+            mypos[k] = 0u;
+            if (e < total) {
+                myd[k] = dest[e];
+                mypos[k] = atomicAdd(&cnt[myd[k]], 1u);
+            }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < world) {
+            unsigned long long off = 0; // exclusive prefix of the global histogram = start of the destination's range
+            for (int p = 0; p < (int)threadIdx.x; p++) off += hist[p];
+            start[threadIdx.x] = off + atomicAdd(&cursor[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            const int64_t e = t0 + (int64_t)k * blockDim.x + threadIdx.x;
+            if (e < total) perm[start[myd[k]] + mypos[k]] = (uint32_t)e;
+        }
+        __syncthreads();
+    }
+    (void)base_lo;
+    (void)soff_s;
 }
 
 // send order: keys and table ids of the routed lookups
@@ -196,17 +249,19 @@ __global__ void __launch_bounds__(256) probe_keys_kernel(const uint64_t* __restr
     if ((threadIdx.x & 31) == 0 && visited && touches_out) atomicAdd(touches_out, (unsigned long long)visited);
 }
 
-// owner side: value lists in received order (contiguous per origin)
+// owner side: value lists in received order (contiguous per origin); a warp copies one list, coalesced
 __global__ void __launch_bounds__(256) gather_values_kernel(const uint2* __restrict__ ranges,
                                                             const int32_t* __restrict__ voff, int64_t m,
                                                             const uint32_t* __restrict__ table_values,
                                                             uint32_t* __restrict__ out)
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < m; q += stride) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = warp0; q < m; q += nwarps) {
         const uint2 r = ranges[q];
         const int64_t w = voff[q];
-        for (uint32_t v = 0; v < r.y; v++) out[w + v] = table_values[r.x + v];
+        for (uint32_t v = lane; v < r.y; v += 32) out[w + v] = __ldg(table_values + r.x + v);
     }
 }
 
@@ -281,6 +336,30 @@ __global__ void __launch_bounds__(256) scatter_values_kernel(const int32_t* __re
     }
 }
 
+// (offset into the scattered value array, count) of every (read, table) bucket: what the fused collection takes
+__global__ void __launch_bounds__(256) value_ranges_kernel(const int32_t* __restrict__ cnt_e,
+                                                           const int32_t* __restrict__ offsets, int n, int H,
+                                                           uint2* __restrict__ ranges)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarps) {
+        int w = offsets[i];
+        for (int t0 = 0; t0 < H; t0 += 32) {
+            const int t = t0 + lane;
+            const int cnt = t < H ? cnt_e[i * H + t] : 0;
+            int incl = cnt;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (t < H) ranges[i * H + t] = make_uint2((uint32_t)(w + incl - cnt), (uint32_t)cnt);
+            w += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
+
 static unsigned pgrid(int64_t items)
 {
     int64_t g = HRM_SDIV(items, (int64_t)256);
@@ -292,7 +371,8 @@ static unsigned pgrid(int64_t items)
 
 // ---- the routed query ------------------------------------------------------------------------------
 hrm_status partitioned_query(hrm_comm* c, hrm_minhasher* mh, const uint64_t* d_sigs, int n, int32_t* d_num_per_seq,
-                             int32_t* d_offsets, int64_t* h_total, Scratch& values, StageTimer& T, cudaStream_t s)
+                             int32_t* d_offsets, int64_t* h_total, Scratch& values, StageTimer& T, cudaStream_t s,
+                             uint2* d_ranges)
 {
     const int H = mh->H, G = c->world;
     NcclApi* api = c->api;
@@ -301,36 +381,34 @@ hrm_status partitioned_query(hrm_comm* c, hrm_minhasher* mh, const uint64_t* d_s
     HRM_REQUIRE(G <= 255, "at most 255 ranks");
     // 1. route
     T.begin(HRM_STAGE_ROUTE, s);
-    Scratch dest, dest2, order, perm, cub_tmp, small, skeys, stabs;
+    Scratch dest, perm, small, skeys, stabs;
     const size_t tt = (size_t)(total > 0 ? total : 1);
-    HRM_TRY(dest.alloc(tt, s));
-    HRM_TRY(dest2.alloc(tt, s));
-    HRM_TRY(order.alloc(sizeof(uint32_t) * tt, s));
-    HRM_TRY(perm.alloc(sizeof(uint32_t) * tt, s));
-    HRM_TRY(skeys.alloc(sizeof(uint64_t) * tt, s));
-    HRM_TRY(stabs.alloc(tt, s));
-    // small: [0..G) hist, [G..G+G*G) count matrix, then value-total row + matrix, then pick indices/outputs
-    const size_t small_words = (size_t)(2 * G + 2 * G * G + 4 * (G + 1) + 16);
-    HRM_TRY(small.alloc(sizeof(int64_t) * small_words, s));
+    hrm_status ast = HRM_OK; // allocation status: agreed on collectively before the first exchange
+    auto A = [&](hrm_status st) {
+        if (ast == HRM_OK && st != HRM_OK) ast = st;
+    };
+    A(dest.alloc(tt, s));
+    A(perm.alloc(sizeof(uint32_t) * tt, s));
+    A(skeys.alloc(sizeof(uint64_t) * tt, s));
+    A(stabs.alloc(tt, s));
+    // small: [0..G) hist, [G..G+G*G) count matrix, then value-total row + matrix, then pick indices/outputs, cursors
+    const size_t small_words = (size_t)(3 * G + 2 * G * G + 4 * (G + 1) + 16);
+    A(small.alloc(sizeof(int64_t) * small_words, s));
+    HRM_TRY(comm_agree(c, ast, s)); // every rank returns the same status: nobody is left inside a collective
     int64_t* d_hist = small.as<int64_t>();
     int64_t* d_cmat = d_hist + G;
     int64_t* d_vrow = d_cmat + (size_t)G * G;
     int64_t* d_vmat = d_vrow + G;
     int64_t* d_idx = d_vmat + (size_t)G * G;
     int64_t* d_pick = d_idx + 2 * (G + 1);
+    int64_t* d_cursor = d_pick + 2 * (G + 1);
     HRM_CUDA(cudaMemsetAsync(small.p, 0, sizeof(int64_t) * small_words, s));
     if (total > 0) {
         HRM_LAUNCH(route_dest_kernel, pgrid(total), 256, 0, s, d_sigs, total, c->rank, G, dest.as<uint8_t>(),
-                   order.as<uint32_t>(), reinterpret_cast<unsigned long long*>(d_hist));
-        int bits = 1;
-        while ((1 << bits) < G) bits++;
-        size_t tmp_bytes = 0;
-        HRM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dest.as<uint8_t>(), dest2.as<uint8_t>(),
-                                                 order.as<uint32_t>(), perm.as<uint32_t>(), (int)total, 0, bits, s));
-        HRM_TRY(cub_tmp.alloc(tmp_bytes, s));
-        HRM_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, dest.as<uint8_t>(), dest2.as<uint8_t>(),
-                                                 order.as<uint32_t>(), perm.as<uint32_t>(), (int)total, 0, bits, s));
-        g_launches.fetch_add(1);
+                   reinterpret_cast<unsigned long long*>(d_hist));
+        HRM_LAUNCH(route_partition_kernel, pgrid(HRM_SDIV(total, (int64_t)16)), 256, 0, s, dest.as<uint8_t>(), total, G,
+                   reinterpret_cast<const unsigned long long*>(d_hist), reinterpret_cast<unsigned long long*>(d_cursor),
+                   perm.as<uint32_t>());
         HRM_LAUNCH(route_gather_kernel, pgrid(total), 256, 0, s, d_sigs, perm.as<uint32_t>(), total, H,
                    skeys.as<uint64_t>(), stabs.as<uint8_t>());
     }
@@ -346,17 +424,26 @@ hrm_status partitioned_query(hrm_comm* c, hrm_minhasher* mh, const uint64_t* d_s
         soff[p + 1] = soff[p] + scount[p];
         roff[p + 1] = roff[p] + rcount[p];
     }
-    HRM_REQUIRE(soff[G] == total, "routing histogram does not add up");
     const int64_t m = roff[G];
-    HRM_REQUIRE(m < (1LL << 31), "too many routed lookups for one rank: use smaller batches");
+    // every rank holds the whole matrix, so every rank takes the same decision for every rank's totals
+    for (int p = 0; p < G; p++) {
+        int64_t mp = 0;
+        for (int q = 0; q < G; q++) mp += cmat[(size_t)q * G + p];
+        if (mp >= (1LL << 31)) {
+            set_error("too many routed lookups for rank %d (%lld): use smaller batches", p, (long long)mp);
+            return HRM_ERR_OVERFLOW;
+        }
+    }
     Scratch rkeys, rtabs, ranges, rcnt, voff, cnt_back;
     const size_t mm = (size_t)(m > 0 ? m : 1);
-    HRM_TRY(rkeys.alloc(sizeof(uint64_t) * mm, s));
-    HRM_TRY(rtabs.alloc(mm, s));
-    HRM_TRY(ranges.alloc(sizeof(uint2) * mm, s));
-    HRM_TRY(rcnt.alloc(sizeof(int32_t) * mm, s));
-    HRM_TRY(voff.alloc(sizeof(int32_t) * (mm + 1), s));
-    HRM_TRY(cnt_back.alloc(sizeof(int32_t) * tt, s));
+    A(soff[G] == total ? HRM_OK : HRM_ERR_INVALID);
+    A(rkeys.alloc(sizeof(uint64_t) * mm, s));
+    A(rtabs.alloc(mm, s));
+    A(ranges.alloc(sizeof(uint2) * mm, s));
+    A(rcnt.alloc(sizeof(int32_t) * mm, s));
+    A(voff.alloc(sizeof(int32_t) * (mm + 1), s));
+    A(cnt_back.alloc(sizeof(int32_t) * tt, s));
+    HRM_TRY(comm_agree(c, ast, s));
     HRM_TRY(alltoallv(c, skeys.p, scount.data(), soff.data(), rkeys.p, rcount.data(), roff.data(), sizeof(uint64_t), s));
     HRM_TRY(alltoallv(c, stabs.p, scount.data(), soff.data(), rtabs.p, rcount.data(), roff.data(), 1, s));
     T.end(s);
@@ -381,35 +468,44 @@ hrm_status partitioned_query(hrm_comm* c, hrm_minhasher* mh, const uint64_t* d_s
         vsoff[p + 1] = vsoff[p] + vsend[p];
         vrow[p] = vsend[p];
     }
-    HRM_REQUIRE(vsoff[G] < (1LL << 31), "too many routed values for one rank: use smaller batches");
     HRM_CUDA(cudaMemcpyAsync(d_vrow, vrow.data(), sizeof(int64_t) * (size_t)G, cudaMemcpyHostToDevice, s));
     HRM_NCCL(api, api->AllGather(d_vrow, d_vmat, (size_t)G, ncclInt64, c->comm, s));
     std::vector<int64_t> vmat((size_t)G * G);
     HRM_CUDA(cudaMemcpyAsync(vmat.data(), d_vmat, sizeof(int64_t) * vmat.size(), cudaMemcpyDeviceToHost, s));
-    Scratch svals;
-    HRM_TRY(svals.alloc(sizeof(uint32_t) * (size_t)(vsoff[G] > 0 ? vsoff[G] : 1), s));
-    if (m > 0)
-        HRM_LAUNCH(gather_values_kernel, pgrid(m), 256, 0, s, ranges.as<uint2>(), voff.as<int32_t>(), m, mh->values,
-                   svals.as<uint32_t>());
     HRM_CUDA(cudaStreamSynchronize(s));
+    // collective decision: values any rank sends (row sums) or receives (column sums) must fit int offsets
+    for (int p = 0; p < G; p++) {
+        int64_t sent = 0, recv = 0;
+        for (int q = 0; q < G; q++) {
+            sent += vmat[(size_t)p * G + q];
+            recv += vmat[(size_t)q * G + p];
+        }
+        if (sent > 0x7fffffffLL || recv > 0x7fffffffLL) {
+            set_error("candidate values routed through rank %d exceed int (%lld sent, %lld received): smaller batches",
+                      p, (long long)sent, (long long)recv);
+            return HRM_ERR_OVERFLOW;
+        }
+    }
     for (int p = 0; p < G; p++) {
         vrecv[p] = vmat[(size_t)p * G + c->rank];
         vroff[p + 1] = vroff[p] + vrecv[p];
     }
     const int64_t vtotal = vroff[G];
-    if (vtotal > 0x7fffffffLL) {
-        set_error("candidate values of one batch exceed int: use smaller batches");
-        return HRM_ERR_OVERFLOW;
-    }
-    Scratch rvals, src_off, cnt_e, src_e;
-    HRM_TRY(rvals.alloc(sizeof(uint32_t) * (size_t)(vtotal > 0 ? vtotal : 1), s));
+    Scratch svals, rvals, src_off, cnt_e, src_e;
+    A(svals.alloc(sizeof(uint32_t) * (size_t)(vsoff[G] > 0 ? vsoff[G] : 1), s));
+    A(rvals.alloc(sizeof(uint32_t) * (size_t)(vtotal > 0 ? vtotal : 1), s));
+    A(src_off.alloc(sizeof(int32_t) * (tt + 1), s));
+    A(cnt_e.alloc(sizeof(int32_t) * tt, s));
+    A(src_e.alloc(sizeof(int32_t) * tt, s));
+    A(values.alloc(sizeof(uint32_t) * (size_t)(vtotal > 0 ? vtotal : 1), s));
+    HRM_TRY(comm_agree(c, ast, s));
+    if (m > 0)
+        HRM_LAUNCH(gather_values_kernel, pgrid(m * 32), 256, 0, s, ranges.as<uint2>(), voff.as<int32_t>(), m, mh->values,
+                   svals.as<uint32_t>());
     HRM_TRY(alltoallv(c, svals.p, vsend.data(), vsoff.data(), rvals.p, vrecv.data(), vroff.data(), sizeof(uint32_t), s));
     T.end(s);
     // 5. origin: per-read totals, offsets, values in table order
     T.begin(HRM_STAGE_RETRIEVE, s);
-    HRM_TRY(src_off.alloc(sizeof(int32_t) * (tt + 1), s));
-    HRM_TRY(cnt_e.alloc(sizeof(int32_t) * tt, s));
-    HRM_TRY(src_e.alloc(sizeof(int32_t) * tt, s));
     HRM_TRY(exclusive_scan_i32(cnt_back.as<int32_t>(), src_off.as<int32_t>(), total, nullptr, s));
     if (total > 0) {
         HRM_LAUNCH(unsort_kernel, pgrid(total), 256, 0, s, perm.as<uint32_t>(), cnt_back.as<int32_t>(),
@@ -417,10 +513,11 @@ hrm_status partitioned_query(hrm_comm* c, hrm_minhasher* mh, const uint64_t* d_s
         HRM_LAUNCH(read_totals_kernel, pgrid(n), 256, 0, s, cnt_e.as<int32_t>(), n, H, d_num_per_seq);
     }
     HRM_TRY(exclusive_scan_i32(d_num_per_seq, d_offsets, n, nullptr, s));
-    HRM_TRY(values.alloc(sizeof(uint32_t) * (size_t)(vtotal > 0 ? vtotal : 1), s));
     if (vtotal > 0)
         HRM_LAUNCH(scatter_values_kernel, pgrid((int64_t)n * 32), 256, 0, s, cnt_e.as<int32_t>(), src_e.as<int32_t>(),
                    d_offsets, n, H, rvals.as<uint32_t>(), values.as<uint32_t>());
+    if (d_ranges && total > 0)
+        HRM_LAUNCH(value_ranges_kernel, pgrid((int64_t)n * 32), 256, 0, s, cnt_e.as<int32_t>(), d_offsets, n, H, d_ranges);
     T.end(s);
     *h_total = vtotal;
     return HRM_OK;

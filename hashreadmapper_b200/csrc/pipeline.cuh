@@ -22,6 +22,10 @@ hrm_status collect_candidates(const hrm_minhasher* mh, const struct QueryHandle*
                               uint32_t* d_out, int64_t out_cap, int2* d_lists, int64_t* h_total, int* h_overflow,
                               int64_t* h_stats3, cudaStream_t s);
 
+hrm_status collect_candidates_from(const uint2* d_ranges, int64_t rq, int64_t rt, const uint32_t* d_table_values, int H, int n,
+                                   int min_hits, uint32_t id_space, uint32_t* d_out, int64_t out_cap, int2* d_lists,
+                                   int64_t* h_total, int* h_overflow, int64_t* h_stats3, cudaStream_t s);
+
 // verification inputs of one pass: reads packed with the pass' read conversion, genome packed with
 // its genome conversion, stage-V conversion applied on the fly
 struct VerifyPass {
