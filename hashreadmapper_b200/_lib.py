@@ -137,6 +137,8 @@ SIGNATURES = {
     "hrm_readstore_ambiguous_ids": (I32, [P, P]),
     "hrm_readstore_set_ambiguous": (I32, [P, P, VP]),
     "hrm_readstore_info": (I32, [P, C.POINTER(ReadstoreInfo)]),
+    "hrm_readstore_write_reference_format": (I32, [P, P, C.POINTER(I64)]),
+    "hrm_readstore_read_reference_format": (I32, [C.POINTER(P), P, I64, VP]),
     "hrm_genome_create_from_ascii": (I32, [C.POINTER(P), P, P, C.c_int, C.c_int, VP]),
     "hrm_genome_destroy": (None, [P]),
     "hrm_genome_num_chromosomes": (C.c_int, [P]),
@@ -161,6 +163,7 @@ SIGNATURES = {
     "hrm_mapper_set_profiling": (I32, [P, C.c_int]),
     "hrm_mapper_stage_times": (I32, [P, C.POINTER(C.c_float), C.POINTER(I32)]),
     "hrm_ingest_reads": (I32, [P, I64, I64, I32, P, I64, P, P, I64, C.POINTER(I64), C.POINTER(I32), VP]),
+    "hrm_inflate_gzip": (I32, [P, I64, P, I64, C.POINTER(I64)]),
     "hrm_comm_unique_id": (I32, [P, I64]),
     "hrm_comm_create": (I32, [C.POINTER(P), C.c_int, C.c_int, P]),
     "hrm_comm_destroy": (None, [P]),

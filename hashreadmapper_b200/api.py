@@ -311,6 +311,25 @@ class ReadStorage:
         check(self.lib.hrm_readstore_gather_lengths(self.h, handle, _ptr(out), _ptr(ids), n, _stream()))
         return out
 
+    def saveToBytes(self) -> bytes:
+        """the reference's preprocessed-reads dump (ChunkedReadStorage::saveToFile)"""
+        size = C.c_int64(0)
+        check(self.lib.hrm_readstore_write_reference_format(self.h, None, C.byref(size)))
+        buf = np.empty(size.value, dtype=np.uint8)
+        check(self.lib.hrm_readstore_write_reference_format(self.h, _ptr(buf), C.byref(size)))
+        return buf[:size.value].tobytes()
+
+    @classmethod
+    def loadFromBytes(cls, data: bytes):
+        """from a dump the reference (or saveToBytes) wrote"""
+        self = cls.__new__(cls)
+        self.lib = L.load()
+        _dev()
+        self.h = C.c_void_p()
+        buf = np.frombuffer(data, dtype=np.uint8)
+        check(self.lib.hrm_readstore_read_reference_format(C.byref(self.h), _ptr(buf), buf.size, _stream()))
+        return self
+
     def areSequencesAmbiguous(self, handle, ids: torch.Tensor):
         n = ids.numel()
         out = torch.empty((n,), dtype=torch.uint8, device=ids.device)
@@ -413,6 +432,22 @@ def edit_distance(queries, query_len, targets, target_len):
     check(lib.hrm_edit_distance(_ptr(queries), queries.shape[1], _ptr(query_len), _ptr(targets), targets.shape[1],
                                 _ptr(target_len), n, _ptr(out), _stream()))
     return out
+
+
+def inflate_gzip(data: bytes, cap=None) -> bytes:
+    """gzip'd FASTQ / FASTA bytes -> text (host side, zlib)"""
+    lib = L.load()
+    src = np.frombuffer(data, dtype=np.uint8)
+    cap = cap or max(1 << 16, 8 * src.size)
+    while True:
+        out = np.empty(cap, dtype=np.uint8)
+        written = C.c_int64(0)
+        st = lib.hrm_inflate_gzip(_ptr(src), src.size, _ptr(out), cap, C.byref(written))
+        if st == L.HRM_ERR_OVERFLOW:
+            cap *= 4
+            continue
+        check(st)
+        return out[:written.value].tobytes()
 
 
 # ---- the fused mapper --------------------------------------------------------------------------

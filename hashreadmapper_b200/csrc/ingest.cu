@@ -395,3 +395,60 @@ extern "C" hrm_status hrm_ingest_reads(const char* d_text, int64_t nbytes, int64
     *h_num_reads = nreads;
     return HRM_OK;
 }
+
+// ---- gzip'd read files (ref: kseqpp reads .gz through zlib's gzread, include/kseqpp/kseqpp.hpp; the reference's
+// file reader accepts both, include/readlibraryio.hpp:288-326) -------------------------------------------------------
+// Host-side inflate of a whole gzip stream (all members) into a host buffer whose text then goes to
+// hrm_ingest_reads / hrm_mapper_stage_fastq.  *h_written = bytes produced; HRM_ERR_OVERFLOW when cap is too small
+// (*h_written = bytes produced so far: grow and call again).  Decompression is I/O decoding, not part of the mapping path.
+#include <zlib.h>
+extern "C" hrm_status hrm_inflate_gzip(const void* h_in, int64_t nbytes, void* h_out, int64_t cap, int64_t* h_written)
+{
+    HRM_REQUIRE(h_in != nullptr && h_out != nullptr && h_written != nullptr && nbytes >= 0 && cap >= 0, "args");
+    *h_written = 0;
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, 15 + 32) != Z_OK) { // zlib or gzip header, detected
+        set_error("inflateInit2 failed");
+        return HRM_ERR_INVALID;
+    }
+    const unsigned char* in = (const unsigned char*)h_in;
+    unsigned char* out = (unsigned char*)h_out;
+    int64_t ipos = 0, opos = 0;
+    hrm_status st = HRM_OK;
+    bool ended = nbytes == 0; // the last member reached its end marker
+    while (ipos < nbytes) {
+        const int64_t ichunk = (nbytes - ipos) < (1LL << 30) ? (nbytes - ipos) : (1LL << 30);
+        zs.next_in = const_cast<unsigned char*>(in + ipos);
+        zs.avail_in = (uInt)ichunk;
+        int rc = Z_OK;
+        while (zs.avail_in > 0 && rc != Z_STREAM_END) {
+            const int64_t ochunk = (cap - opos) < (1LL << 30) ? (cap - opos) : (1LL << 30);
+            if (ochunk == 0) {
+                st = HRM_ERR_OVERFLOW;
+                break;
+            }
+            zs.next_out = out + opos;
+            zs.avail_out = (uInt)ochunk;
+            rc = inflate(&zs, Z_NO_FLUSH);
+            opos += ochunk - (int64_t)zs.avail_out;
+            if (rc != Z_OK && rc != Z_STREAM_END && rc != Z_BUF_ERROR) {
+                set_error("inflate failed: %s", zs.msg ? zs.msg : "corrupt gzip data");
+                st = HRM_ERR_INVALID;
+                break;
+            }
+        }
+        ipos += ichunk - (int64_t)zs.avail_in;
+        if (st != HRM_OK) break;
+        ended = rc == Z_STREAM_END;
+        if (ended && ipos < nbytes) inflateReset(&zs); // next member of a multi-member file
+    }
+    inflateEnd(&zs);
+    *h_written = opos;
+    if (st == HRM_OK && !ended) {
+        set_error("truncated gzip stream");
+        return HRM_ERR_INVALID;
+    }
+    if (st == HRM_ERR_OVERFLOW) set_error("output buffer too small for the inflated text");
+    return st;
+}

@@ -448,3 +448,180 @@ extern "C" hrm_status hrm_readstore_info(const hrm_readstore* rs, hrm_readstore_
     out->device_bytes = rs->n * (rs->pitch_words * 4 + 4);
     return HRM_OK;
 }
+
+// ---- ChunkedReadStorage dump format (--save-preprocessedreads-to / --load-preprocessedreads-from) -------
+// ref: ChunkedReadStorage::saveToFile include/chunkedreadstorage.hpp:246-400, loadFromFile :160-243,
+//      LengthStore<uint32_t>::writeToStream / readFromStream include/lengthstorage.hpp:164-204 (lengths minus the
+//      minimum, bitsPerLength bits each, MSB first in 32-bit words, :115-160, :215-290).
+// Layout: u64 numReads | i32 lengthUpperBound | i32 lengthLowerBound | u8 hasQualities | i32 qualityBits |
+//         u64 lengthsBytes, sequencesBytes, qualitiesBytes, ambigBytes | LengthStore | u64 pitchInInts, u64 numInts,
+//         u32 rows[numReads * pitch] | (no qualities: u64 0, u64 0) | u64 numAmbiguous, u32 ids[].
+// The packed rows are the reference's own 2-bit layout, so a dump written here loads in the reference and back.
+namespace {
+struct ByteWriter {
+    char* p;
+    int64_t cap, at = 0;
+    void put(const void* src, size_t n)
+    {
+        if (p && at + (int64_t)n <= cap) memcpy(p + at, src, n);
+        at += (int64_t)n;
+    }
+    template <class T> void val(T v) { put(&v, sizeof v); }
+};
+int length_bits(int diff) // ref: LengthStore(int, int, int64) lengthstorage.hpp:24-55
+{
+    if (diff == 0) return 0;
+    uint32_t n = (uint32_t)diff;
+    n |= n >> 1;
+    n |= n >> 2;
+    n |= n >> 4;
+    n |= n >> 8;
+    n |= n >> 16;
+    n += 1;
+    int b = 0;
+    while ((1u << b) < n) b++;
+    return b;
+}
+} // namespace
+
+extern "C" hrm_status hrm_readstore_write_reference_format(const hrm_readstore* rs, void* h_buf, int64_t* h_size)
+{
+    HRM_REQUIRE(rs != nullptr && h_size != nullptr, "args");
+    const int64_t n = rs->n, pitch = rs->pitch_words;
+    const int bits = length_bits(rs->len_max - rs->len_min);
+    const uint64_t len_words = ((uint64_t)bits * (uint64_t)n + 31) / 32;
+    const uint64_t lengthsBytes = 4 * 4 + 4 + 8 + 8 + 8 + len_words * 4;
+    const uint64_t seqBytes = 8 + 8 + (uint64_t)n * pitch * 4;
+    const uint64_t qualBytes = 16;
+    const uint64_t ambigBytes = 8 + (uint64_t)rs->with_n * 4;
+    const int64_t total = 8 + 4 + 4 + 1 + 4 + 32 + (int64_t)(lengthsBytes + seqBytes + qualBytes + ambigBytes);
+    if (!h_buf) {
+        *h_size = total;
+        return HRM_OK;
+    }
+    HRM_REQUIRE(*h_size >= total, "buffer too small");
+    ByteWriter w{(char*)h_buf, *h_size};
+    w.val<uint64_t>((uint64_t)n);
+    w.val<int32_t>(rs->len_max); // saveToFile writes the upper bound first (:252-259)
+    w.val<int32_t>(rs->len_min);
+    w.val<uint8_t>(0);
+    w.val<int32_t>(8);
+    w.val<uint64_t>(lengthsBytes);
+    w.val<uint64_t>(seqBytes);
+    w.val<uint64_t>(qualBytes);
+    w.val<uint64_t>(ambigBytes);
+    // LengthStore
+    std::vector<int32_t> lens((size_t)n);
+    if (n > 0) HRM_CUDA(cudaMemcpy(lens.data(), rs->lengths, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> packed((size_t)len_words, 0u);
+    for (int64_t i = 0; bits > 0 && i < n; i++) { // MSB first
+        const uint32_t v = (uint32_t)(lens[(size_t)i] - rs->len_min);
+        const uint64_t first = (uint64_t)bits * (uint64_t)i;
+        for (int b = 0; b < bits; b++) {
+            const uint64_t pos = first + (uint64_t)b;
+            if ((v >> (bits - 1 - b)) & 1u) packed[(size_t)(pos >> 5)] |= 1u << (31 - (int)(pos & 31));
+        }
+    }
+    w.val<int32_t>(32);
+    w.val<int32_t>(bits);
+    w.val<int32_t>(rs->len_min);
+    w.val<int32_t>(rs->len_max);
+    w.val<uint32_t>(bits > 0 ? (uint32_t)((1ull << bits) - 1) : 0u);
+    w.val<int64_t>(n);
+    w.val<uint64_t>(len_words);
+    w.val<uint64_t>(len_words * 4);
+    w.put(packed.data(), (size_t)len_words * 4);
+    // sequences: straight from the device into the buffer
+    w.val<uint64_t>((uint64_t)pitch);
+    w.val<uint64_t>((uint64_t)n * pitch);
+    if (n > 0) HRM_CUDA(cudaMemcpy((char*)h_buf + w.at, rs->rows, sizeof(uint32_t) * (size_t)(n * pitch), cudaMemcpyDeviceToHost));
+    w.at += (int64_t)sizeof(uint32_t) * n * pitch;
+    w.val<uint64_t>(0); // no quality scores: pitch 0, 0 elements (:330-373)
+    w.val<uint64_t>(0);
+    std::vector<uint32_t> ids((size_t)rs->with_n);
+    if (rs->with_n > 0) HRM_TRY(hrm_readstore_ambiguous_ids(rs, ids.data()));
+    w.val<uint64_t>((uint64_t)rs->with_n);
+    w.put(ids.data(), ids.size() * 4);
+    *h_size = w.at;
+    return HRM_OK;
+}
+
+extern "C" hrm_status hrm_readstore_read_reference_format(hrm_readstore** out, const void* h_buf, int64_t size,
+                                                          hrm_stream stream)
+{
+    HRM_REQUIRE(out != nullptr && h_buf != nullptr && size >= 53, "args");
+    *out = nullptr;
+    HRM_TRY(ensure_device());
+    const char* p = (const char*)h_buf;
+    const char* end = p + size;
+    auto need = [&](uint64_t n) { return (uint64_t)(end - p) >= n; };
+    auto rd64 = [&]() { uint64_t v; memcpy(&v, p, 8); p += 8; return v; };
+    auto rd32 = [&]() { int32_t v; memcpy(&v, p, 4); p += 4; return v; };
+    const uint64_t n = rd64();
+    rd32(); // the two length bounds (written upper first, read lower first by the reference: unused)
+    rd32();
+    p += 1; // hasQualities
+    rd32(); // quality bits
+    const uint64_t lengthsBytes = rd64(), seqBytes = rd64(), qualBytes = rd64(), ambigBytes = rd64();
+    HRM_REQUIRE(n < (1ull << 32), "read ids are 32 bit");
+    HRM_REQUIRE(need(lengthsBytes) && lengthsBytes >= 48, "truncated length section");
+    const char* after_len = p + lengthsBytes;
+    const int dtb = rd32(), bits = rd32(), minL = rd32(), maxL = rd32();
+    p += 4; // bitsMask
+    const uint64_t ne = rd64(), rawElems = rd64(), rawBytes = rd64();
+    HRM_REQUIRE(dtb == 32 && bits >= 0 && bits <= 31 && minL >= 0 && minL <= maxL && ne == n && rawBytes == rawElems * 4 &&
+                    rawBytes <= lengthsBytes - 48 && rawElems >= ((uint64_t)bits * n + 31) / 32,
+                "length store");
+    std::vector<int32_t> lens((size_t)n, minL);
+    for (uint64_t i = 0; bits > 0 && i < n; i++) {
+        uint32_t v = 0;
+        const uint64_t first = (uint64_t)bits * i;
+        for (int b = 0; b < bits; b++) {
+            const uint64_t pos = first + (uint64_t)b;
+            uint32_t wv;
+            memcpy(&wv, p + (pos >> 5) * 4, 4);
+            v = (v << 1) | ((wv >> (31 - (int)(pos & 31))) & 1u);
+        }
+        lens[(size_t)i] = minL + (int32_t)v;
+        HRM_REQUIRE(lens[(size_t)i] <= maxL, "length beyond the stored maximum");
+    }
+    p = after_len;
+    HRM_REQUIRE(need(seqBytes) && seqBytes >= 16, "truncated sequence section");
+    const uint64_t pitch = rd64(), numInts = rd64();
+    HRM_REQUIRE(pitch >= 1 && pitch <= 4096 && numInts == n * pitch && seqBytes == 16 + numInts * 4, "sequence section");
+    HRM_REQUIRE(pitch * 16 >= (uint64_t)maxL, "pitch too small for the longest read");
+    const char* seq = p;
+    p += numInts * 4;
+    HRM_REQUIRE(need(qualBytes), "truncated quality section");
+    p += qualBytes;
+    HRM_REQUIRE(need(8), "truncated ambiguity section");
+    const uint64_t na = rd64();
+    HRM_REQUIRE(na <= n && need(na * 4) && ambigBytes == 8 + na * 4, "ambiguity section");
+    cudaStream_t s = as_stream(stream);
+    auto rs = std::unique_ptr<hrm_readstore>(new hrm_readstore);
+    rs->n = (int64_t)n;
+    rs->pitch_words = (int64_t)pitch;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    HRM_CUDA(cudaMalloc(&rs->rows, sizeof(uint32_t) * nn * (size_t)pitch));
+    HRM_CUDA(cudaMalloc(&rs->lengths, sizeof(int32_t) * nn));
+    HRM_CUDA(cudaMalloc(&rs->ambig, nn + 8));
+    std::vector<uint8_t> flags((size_t)n, 0);
+    for (uint64_t i = 0; i < na; i++) {
+        uint32_t id;
+        memcpy(&id, p + i * 4, 4);
+        HRM_REQUIRE(id < n, "ambiguous read id out of range");
+        flags[id] = 1;
+    }
+    if (n > 0) {
+        HRM_CUDA(cudaMemcpyAsync(rs->rows, seq, (size_t)numInts * 4, cudaMemcpyHostToDevice, s));
+        HRM_CUDA(cudaMemcpyAsync(rs->lengths, lens.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, s));
+        HRM_CUDA(cudaMemcpyAsync(rs->ambig, flags.data(), (size_t)n, cudaMemcpyHostToDevice, s));
+        HRM_CUDA(cudaStreamSynchronize(s));
+    }
+    int64_t c = 0;
+    for (uint8_t f : flags) c += f;
+    rs->with_n = c;
+    readstore_finish(rs.get(), lens.data());
+    *out = rs.release();
+    return HRM_OK;
+}

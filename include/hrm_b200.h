@@ -255,6 +255,14 @@ hrm_status hrm_readstore_ambiguous_ids(const hrm_readstore* rs, uint32_t* h_ids)
 /* carries hrm_ingest_reads' d_ambiguous flags (one byte per read, device) into a store created from 2-bit rows */
 hrm_status hrm_readstore_set_ambiguous(hrm_readstore* rs, const uint8_t* d_flags, hrm_stream stream);
 hrm_status hrm_readstore_info(const hrm_readstore* rs, hrm_readstore_info_t* out);
+/* The reference's preprocessed-reads dump (`--save-preprocessedreads-to` / `--load-preprocessedreads-from`):
+ * ref: ChunkedReadStorage::saveToFile / loadFromFile include/chunkedreadstorage.hpp:160-400, LengthStore
+ *      include/lengthstorage.hpp:164-204.  write: the bytes the reference would save for a storage with these
+ * reads (no quality scores); h_buf == NULL returns the size in *h_size.  read: builds a device read store from
+ * such a dump.  Dumps are interchangeable with the reference's. */
+hrm_status hrm_readstore_write_reference_format(const hrm_readstore* rs, void* h_buf, int64_t* h_size);
+hrm_status hrm_readstore_read_reference_format(hrm_readstore** out, const void* h_buf, int64_t size,
+                                               hrm_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * S2 -- genome and reference windows.
@@ -490,6 +498,11 @@ hrm_status hrm_ingest_reads(const char* d_text, int64_t nbytes, int64_t first_re
                             char* d_rows, int64_t pitch, int32_t* d_lengths, uint8_t* d_ambiguous,
                             int64_t max_reads, int64_t* h_num_reads, int32_t* h_carry_replaced_out,
                             hrm_stream stream);
+
+/* gzip'd read files (ref: the reference's reader goes through zlib, include/kseqpp/, readlibraryio.hpp:288-326):
+ * host-side inflate of a whole gzip stream (all members) into a host buffer; the text then goes to
+ * hrm_ingest_reads / hrm_mapper_stage_fastq.  *h_written = bytes produced; HRM_ERR_OVERFLOW when cap is too small. */
+hrm_status hrm_inflate_gzip(const void* h_in, int64_t nbytes, void* h_out, int64_t cap, int64_t* h_written);
 
 /* ---- key-partitioned index over the GPUs of one box (BASELINE config 5) -------------
  * ref: the reference's multi-GPU minhasher distributes whole tables (hash function j on GPU j mod G),

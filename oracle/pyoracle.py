@@ -445,3 +445,31 @@ def ref_unique_by_count(values, offsets, min_count):
         raise RuntimeError("ref_unique_by_count failed: %d" % rc)
     lens = lens[:nseg]
     return out[:int(lens.sum())], lens
+
+
+# ---- the reference's preprocessed-reads dump (TEST INFRASTRUCTURE) -------------------------------------------------
+def ref_readstorage_save(path, reads, read_len, ambig_ids):
+    """ChunkedReadStorage::saveToFile (include/chunkedreadstorage.hpp:246-400) for these ASCII rows"""
+    lib = C.CDLL(REF_SAM_SO)
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    read_len = np.ascontiguousarray(read_len, dtype=np.int32)
+    ambig_ids = np.ascontiguousarray(ambig_ids, dtype=np.uint32)
+    rc = lib.ref_readstorage_save(str(path).encode(), _p(reads, C.c_char), reads.shape[1], _p(read_len, C.c_int32),
+                                  C.c_int64(read_len.shape[0]), _p(ambig_ids, C.c_uint32), C.c_int64(ambig_ids.shape[0]))
+    if rc != 0:
+        raise RuntimeError("ref_readstorage_save failed")
+
+
+def ref_readstorage_load(path, pitch_ints, cap):
+    """ChunkedReadStorage::loadFromFile (:160-243) -> (2-bit rows uint32 [n, pitch], lengths, ambiguous ids)"""
+    lib = C.CDLL(REF_SAM_SO)
+    lib.ref_readstorage_load.restype = C.c_int64
+    rows = np.zeros((cap, pitch_ints), dtype=np.uint32)
+    lens = np.zeros(cap, dtype=np.int32)
+    amb = np.zeros(cap, dtype=np.uint32)
+    na = C.c_int64(0)
+    n = lib.ref_readstorage_load(str(path).encode(), _p(rows, C.c_uint32), C.c_int64(pitch_ints), _p(lens, C.c_int32),
+                                 C.c_int64(cap), _p(amb, C.c_uint32), C.byref(na))
+    if n < 0:
+        raise RuntimeError("ref_readstorage_load failed: %d" % n)
+    return rows[:n], lens[:n], np.sort(amb[:na.value])

@@ -156,3 +156,61 @@ int ref_mapping_sam(const char* genome, const int64_t* chrom_off, int nchrom, co
 }
 
 } // extern "C"
+
+// ---- the reference's preprocessed-reads dump (ChunkedReadStorage::saveToFile / loadFromFile) -----------------------
+extern "C" {
+
+// builds a ChunkedReadStorage from ASCII rows the way constructChunkedReadStorageFromFiles appends batches and saves it
+int ref_readstorage_save(const char* path, const char* reads, int read_pitch, const int32_t* read_len, int64_t n_reads,
+                         const uint32_t* ambig_ids, int64_t n_ambig)
+{
+    try {
+        int maxlen = 0;
+        for (int64_t r = 0; r < n_reads; r++) maxlen = std::max(maxlen, (int)read_len[r]);
+        const int pitchInts = SequenceHelpers::getEncodedNumInts2Bit(std::max(maxlen, 1));
+        ChunkedReadStorage st(false, false, 8);
+        const int64_t half = n_reads / 2; // two append batches, like the reference's 65536-read parser batches
+        for (int part = 0; part < 2; part++) {
+            const int64_t b = part == 0 ? 0 : half, e = part == 0 ? half : n_reads;
+            if (e <= b) continue;
+            std::vector<int> lens(read_len + b, read_len + e);
+            std::vector<unsigned int> enc((size_t)(e - b) * pitchInts, 0u);
+            for (int64_t r = b; r < e; r++)
+                SequenceHelpers::encodeSequence2Bit(enc.data() + (r - b) * pitchInts, reads + r * (int64_t)read_pitch, read_len[r]);
+            st.appendConsecutiveReads((read_number)b, (int)(e - b), std::move(lens), std::move(enc), pitchInts, {}, 0);
+        }
+        st.appendAmbiguousReadIds(std::vector<read_number>(ambig_ids, ambig_ids + n_ambig));
+        st.appendingFinished(std::size_t(1) << 40);
+        st.saveToFile(path);
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_readstorage_save: %s\n", e.what());
+        return -1;
+    }
+}
+
+// loads a dump with the reference's loadFromFile and hands every read back (2-bit rows, lengths, ambiguous ids)
+int64_t ref_readstorage_load(const char* path, uint32_t* rows, int64_t pitch_ints, int32_t* lens, int64_t cap,
+                             uint32_t* ambig_ids, int64_t* n_ambig)
+{
+    try {
+        ChunkedReadStorage st(false, false, 8);
+        st.loadFromFile(path);
+        const int64_t n = (int64_t)st.getNumberOfReads();
+        if (n > cap) return -2;
+        std::vector<read_number> ids((size_t)n);
+        for (int64_t i = 0; i < n; i++) ids[(size_t)i] = (read_number)i;
+        if (n > 0) {
+            st.gatherSequences(rows, (std::size_t)pitch_ints, ids.data(), (int)n);
+            st.gatherSequenceLengths(lens, ids.data(), (int)n);
+        }
+        *n_ambig = st.getNumberOfReadsWithN();
+        st.getIdsOfAmbiguousReads(ambig_ids);
+        return n;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "ref_readstorage_load: %s\n", e.what());
+        return -1;
+    }
+}
+
+} // extern "C"

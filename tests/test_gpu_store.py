@@ -167,3 +167,49 @@ def test_adaptors_through_the_virtual_interface(cuda, port, tmp_path):
     cnum, ctotal = mh.determineNumValues(h, d_q, torch.from_numpy(qlens).cuda())
     cvals, coff = mh.retrieveValues(h, nq, ctotal, cnum)
     assert ctotal == total and (cnum.cpu().numpy() == num).all() and (cvals.cpu().numpy().view(np.uint32) == vals).all()
+
+
+@pytest.mark.parametrize("same_length", [False, True])
+def test_preprocessed_reads_dump(cuda, port, tmp_path, same_length):
+    """the reference's preprocessed-reads dump (ChunkedReadStorage::saveToFile / loadFromFile): a dump written here is
+    loaded by the reference's own loadFromFile, a dump the reference wrote is loaded here, and for the same reads the
+    two files are byte-identical"""
+    import torch
+    from oracle import pyoracle as po
+    seqs = make_reads(5, 3000)
+    if same_length:
+        seqs = [s[:36].ljust(36, b"A") for s in seqs]
+    a, lens = rows(seqs)
+    norm = [bytes(c if c in b"ACGT" else ord("A") for c in s) for s in seqs]  # what the packed rows hold
+    exp = pack_rows(port, seqs)
+    amb = np.array([any(c not in b"ACGT" for c in s) for s in seqs])
+    st = cuda.ReadStorage(a, lens)
+    dump = st.saveToBytes()
+    # round trip through our own loader
+    st2 = cuda.ReadStorage.loadFromBytes(dump)
+    h = st2.makeHandle()
+    assert (st2.gatherContiguousSequences(h, 0, len(seqs)).cpu().numpy().view(np.uint32) == exp).all()
+    ids = torch.arange(len(seqs), dtype=torch.int32).cuda()
+    assert (st2.gatherSequenceLengths(h, ids).cpu().numpy() == lens).all()
+    assert (st2.getIdsOfAmbiguousReads() == np.nonzero(amb)[0]).all()
+    i1, i2 = st.getInfo(), st2.getInfo()
+    assert (i1.num_reads, i1.length_lower_bound, i1.length_upper_bound, i1.num_reads_with_n, i1.pitch_words) == \
+           (i2.num_reads, i2.length_lower_bound, i2.length_upper_bound, i2.num_reads_with_n, i2.pitch_words)
+    with pytest.raises(Exception):
+        cuda.ReadStorage.loadFromBytes(dump[:len(dump) // 2])
+    if not po.have_ref_sam():
+        pytest.skip("oracle/_ref/libhrm_ref_sam.so not built: the reference side of the check needs /root/reference")
+    # our file -> the reference's loadFromFile
+    p1 = tmp_path / "ours.bin"
+    p1.write_bytes(dump)
+    r_rows, r_lens, r_amb = po.ref_readstorage_load(p1, exp.shape[1], len(seqs) + 10)
+    assert (r_rows == exp).all() and (r_lens == lens).all() and (r_amb == np.nonzero(amb)[0]).all()
+    # the reference's saveToFile -> our loader; and the two files byte for byte
+    p2 = tmp_path / "ref.bin"
+    po.ref_readstorage_save(p2, np.frombuffer(b"".join(s.ljust(a.shape[1], b"\0") for s in norm), dtype=np.uint8)
+                            .reshape(len(seqs), a.shape[1]), lens, np.nonzero(amb)[0])
+    ref_dump = p2.read_bytes()
+    st3 = cuda.ReadStorage.loadFromBytes(ref_dump)
+    assert (st3.gatherContiguousSequences(st3.makeHandle(), 0, len(seqs)).cpu().numpy().view(np.uint32) == exp).all()
+    assert (st3.getIdsOfAmbiguousReads() == np.nonzero(amb)[0]).all()
+    assert ref_dump == dump

@@ -409,3 +409,20 @@ def test_adaptor_compiles_against_reference(tmp_path):
            "-I" + os.path.join(ROOT, "hashreadmapper_b200", "csrc"), "-c", str(src), "-o", str(tmp_path / "adapt.o")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_inflate_gzip():
+    """gzip'd read files: single member, several members (bgzip-style), tiny output buffer, corrupt data"""
+    import gzip
+    import hashreadmapper_b200 as hb
+    import hashreadmapper_b200.api as api
+    rng = random.Random(3)
+    text = "".join("@r%d\n%s\n+\n%s\n" % (i, "".join(rng.choice("ACGTN") for _ in range(150)), "I" * 150)
+                   for i in range(5000)).encode()
+    assert api.inflate_gzip(gzip.compress(text)) == text
+    parts = [text[i:i + 70000] for i in range(0, len(text), 70000)]
+    assert api.inflate_gzip(b"".join(gzip.compress(p) for p in parts)) == text
+    assert api.inflate_gzip(gzip.compress(text), cap=1000) == text
+    assert api.inflate_gzip(gzip.compress(b"")) == b""
+    with pytest.raises(hb.HrmError):
+        api.inflate_gzip(gzip.compress(text)[:5000] + b"garbage" * 100)
