@@ -50,6 +50,7 @@ struct CollectParams {
     int32_t* big2_list;         // reads the block-wide filter kernel hands on to the counting-table kernel
     int32_t* big2_count;
     int xslots_warp, xslots_block; // exact-table slots of the duplicate-detection kernels (powers of two)
+    int* work;                  // work counter of the block variant
     int warp_cap;               // reads with more ids go straight to the block kernel (test hook)
     int warp_slots;             // table slots of a warp (power of two)
     int slots;                  // table slots of the block kernel (power of two)
@@ -462,12 +463,12 @@ __global__ void __launch_bounds__(COLLECT_THREADS) collect_warp_kernel(CollectPa
 // Everything a read touches is read once and coalesced: 4 B per id.  The same code runs warp-per-read (table in a
 // slice of shared memory, most reads) and block-per-read (BLOCK = true: the reads of big_list, whose enumerated ids or
 // events exceed the warp's tables).  What exceeds the block's tables goes on to big2_list (counting-table kernel).
-constexpr int DUP_MLP = 2;         // 128-bit id loads a lane keeps in flight
+constexpr int DUP_MLP = 4;         // 128-bit id loads a lane keeps in flight
 constexpr int DUP_WFIN = 128;      // survivors / ambiguous ids per read (warp)
 constexpr int DUP_BTHREADS = 256;  // threads of the block variant
-// events are queued and handled by all lanes together (a queue holds two iterations' worth of events)
-constexpr int DUP_WQ = 2 * 32 * 4 * DUP_MLP;           // warp: 512 entries
-constexpr int DUP_BQ = 2 * DUP_BTHREADS * 4 * DUP_MLP; // block: 4096 entries
+// events are queued and handled by all lanes together; a queue holds one iteration's worth of ids (every id an event)
+constexpr int DUP_WQ = 32 * 4 * DUP_MLP;           // warp: 512 entries
+constexpr int DUP_BQ = DUP_BTHREADS * 4 * DUP_MLP; // block: 4096 entries
 
 __host__ __device__ inline size_t dup_slice_words(int words, int xslots, int qcap, int H)
 {
@@ -519,10 +520,17 @@ __global__ void __launch_bounds__(BLOCK ? DUP_BTHREADS : COLLECT_THREADS) collec
     };
     unsigned long long st_enum = 0, st_skip = 0, st_big = 0;
     const uint4* __restrict__ vals4 = reinterpret_cast<const uint4*>(P.table_values);
-    const int first = BLOCK ? (int)blockIdx.x : (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int step = BLOCK ? (int)gridDim.x : (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+    const int first = BLOCK ? 0 : (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int step = BLOCK ? 1 : (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
     const int nitems = BLOCK ? *P.big_count : P.n;
     for (int it = first; it < nitems; it += step) {
+        if (BLOCK) { // reads of very different sizes: blocks take the next one from a counter
+            __syncthreads();
+            if (tid == 0) sc[9] = atomicAdd(P.work, 1);
+            __syncthreads();
+            it = sc[9];
+            if (it >= nitems) break;
+        }
         const int rd = BLOCK ? P.big_list[it] : it;
         gsync();
         if (!BLOCK || wid == 0) { // one warp sets the read up: lane t owns buckets t and t + 32
@@ -709,10 +717,10 @@ __global__ void __launch_bounds__(BLOCK ? DUP_BTHREADS : COLLECT_THREADS) collec
                         if (ev) q[atomicAdd(&sc[8], 1)] = x[j];
                     }
                 }
-                // a queue holds two iterations' worth of events: drain when the next one might not fit
+                // the queue holds one iteration's worth of ids: empty it before the next iteration adds to it
                 if (c0 + nthr * DUP_MLP < ctotal) {
                     gsync();
-                    if (sc[8] > QCAP / 2) drain(phase);
+                    if (sc[8] > 0) drain(phase);
                 }
             }
             drain(phase);
@@ -1088,15 +1096,16 @@ hrm_status collect_candidates_from(const uint2* d_ranges, int64_t rq, int64_t rt
     const int bloom_words_env = env_int("HRM_COLLECT_BLOOM_WORDS", 1024);
     int bwords = 64;
     while (bwords < bloom_words_env && bwords < 8192) bwords <<= 1;
-    const int bblock_env = env_int("HRM_COLLECT_BLOOM_BLOCK_WORDS", 32768);
+    const int bblock_env = env_int("HRM_COLLECT_BLOOM_BLOCK_WORDS", 8192);
     int bblock_words = 64;
     while (bblock_words < bblock_env && bblock_words < 32768) bblock_words <<= 1;
-    const int xwarp_env = env_int("HRM_COLLECT_XSLOTS", 1024), xblock_env = env_int("HRM_COLLECT_BLOCK_XSLOTS", 8192);
+    const int xwarp_env = env_int("HRM_COLLECT_XSLOTS", 1024), xblock_env = env_int("HRM_COLLECT_BLOCK_XSLOTS", 4096);
     int xwarp = 256, xblock = 2048; // the table keeps a quarter of its slots free: more than one slot per thread
     while (xwarp < xwarp_env && xwarp < 4096) xwarp <<= 1;
     while (xblock < xblock_env && xblock < 8192) xblock <<= 1;
     P.xslots_warp = xwarp;
     P.xslots_block = xblock;
+    P.work = reinterpret_cast<int*>(ctl.as<unsigned long long>() + 24);
     const bool allow_packed = env_int("HRM_COLLECT_UNPACKED", 0) == 0;
     const bool packed = allow_packed && id_space < (1u << (32 - COLLECT_PACK_BITS)) - 1u && H < (1 << COLLECT_PACK_BITS);
     const size_t smem = sizeof(uint32_t) * ((size_t)((packed ? 1 : 2) + 1) * slots + COLLECT_FINAL_CAP);

@@ -564,13 +564,13 @@ extern "C" hrm_status hrm_readstore_read_reference_format(hrm_readstore** out, c
     rd32(); // quality bits
     const uint64_t lengthsBytes = rd64(), seqBytes = rd64(), qualBytes = rd64(), ambigBytes = rd64();
     HRM_REQUIRE(n < (1ull << 32), "read ids are 32 bit");
-    HRM_REQUIRE(need(lengthsBytes) && lengthsBytes >= 48, "truncated length section");
+    HRM_REQUIRE(need(lengthsBytes) && lengthsBytes >= 44, "truncated length section");
     const char* after_len = p + lengthsBytes;
     const int dtb = rd32(), bits = rd32(), minL = rd32(), maxL = rd32();
     p += 4; // bitsMask
     const uint64_t ne = rd64(), rawElems = rd64(), rawBytes = rd64();
     HRM_REQUIRE(dtb == 32 && bits >= 0 && bits <= 31 && minL >= 0 && minL <= maxL && ne == n && rawBytes == rawElems * 4 &&
-                    rawBytes <= lengthsBytes - 48 && rawElems >= ((uint64_t)bits * n + 31) / 32,
+                    rawBytes <= lengthsBytes - 44 && rawElems >= ((uint64_t)bits * n + 31) / 32,
                 "length store");
     std::vector<int32_t> lens((size_t)n, minL);
     for (uint64_t i = 0; bits > 0 && i < n; i++) {

@@ -173,7 +173,7 @@ def test_adaptors_through_the_virtual_interface(cuda, port, tmp_path):
 def test_preprocessed_reads_dump(cuda, port, tmp_path, same_length):
     """the reference's preprocessed-reads dump (ChunkedReadStorage::saveToFile / loadFromFile): a dump written here is
     loaded by the reference's own loadFromFile, a dump the reference wrote is loaded here, and for the same reads the
-    two files are byte-identical"""
+    two files are byte-identical (up to the order of the ambiguous ids)"""
     import torch
     from oracle import pyoracle as po
     seqs = make_reads(5, 3000)
@@ -212,4 +212,7 @@ def test_preprocessed_reads_dump(cuda, port, tmp_path, same_length):
     st3 = cuda.ReadStorage.loadFromBytes(ref_dump)
     assert (st3.gatherContiguousSequences(st3.makeHandle(), 0, len(seqs)).cpu().numpy().view(np.uint32) == exp).all()
     assert (st3.getIdsOfAmbiguousReads() == np.nonzero(amb)[0]).all()
-    assert ref_dump == dump
+    # byte for byte up to the ambiguous ids, which the reference writes in the iteration order of a hash set
+    na = int(amb.sum())
+    assert len(ref_dump) == len(dump) and ref_dump[:len(dump) - 4 * na] == dump[:len(dump) - 4 * na]
+    assert sorted(np.frombuffer(ref_dump[len(dump) - 4 * na:], dtype=np.uint32).tolist()) == np.nonzero(amb)[0].tolist()
