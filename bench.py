@@ -446,10 +446,47 @@ def main():
     except Exception:
         pass
     sampler = ClockSampler(uuid)
+    # (1) one batch at a time on one stream: per-stage CUDA-event times and the launch durations of the roofline
     mp.setProfiling(True)
     mp.stageTimes()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    serial_ms = parallel.max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    stages = mp.stageTimes()
+    mp.setProfiling(False)
+
+    # (2) the same K steps through the staged pipeline with device-resident reads (no host copies), for comparison
+    def pipeline_run(steps):
+        if comm is not None:
+            for _ in range(steps):
+                step()
+            return
+        mp.stageDevice(0, d_reads, d_lens, args.read_len)
+        for i in range(steps):
+            mp.mapStaged(i % 2, None, None, CIG)
+            if i >= 1:
+                mp.finish((i - 1) % 2)
+            if i + 1 < steps:
+                mp.stageDevice((i + 1) % 2, d_reads, d_lens, args.read_len)
+        mp.finish((steps - 1) % 2)
+
+    pipeline_run(3)
+    barrier()
+    p0 = torch.cuda.Event(enable_timing=True)
+    p1 = torch.cuda.Event(enable_timing=True)
+    p0.record()
+    pipeline_run(args.steps)
+    p1.record()
+    barrier()
+    pipe_ms = parallel.max_over_ranks(p0.elapsed_time(p1)) / args.steps
+
+    # (3) the headline: K timed steps, one batch at a time, device-resident reads
     barrier()
     if rank == 0:
         sampler.start()
@@ -459,8 +496,6 @@ def main():
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
-    stages = mp.stageTimes()
-    mp.setProfiling(False)
     total_ms = parallel.max_over_ranks(dev_ms)
     ms_per_step = total_ms / args.steps
     value = world * n * args.steps / (total_ms / 1e3)
@@ -483,14 +518,14 @@ def main():
         mp.stageReads(0, h_reads.numpy(), h_lens.numpy())
         sizes = (0, 0)
         for i in range(steps):
-            if i + 1 < steps:
-                mp.stageReads((i + 1) % 2, h_reads.numpy(), h_lens.numpy())
             if text is None:
                 mp.mapStaged(i % 2, rec_np[i % 2], h_cig[i % 2].numpy(), CIG)
             else:
                 mp.mapStaged(i % 2, None, None, 128, i * n, text[0][i % 2], text[1][i % 2])
             if i >= 1:
                 sizes = mp.finish((i - 1) % 2)
+            if i + 1 < steps:
+                mp.stageReads((i + 1) % 2, h_reads.numpy(), h_lens.numpy())
         sizes = mp.finish((steps - 1) % 2)
         return sizes
 
@@ -614,7 +649,7 @@ def main():
                       "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": probe_launch_ms,
                       "launches_per_step": launches_per_step_probe, "slot_touches_per_launch": P,
                       "lookups_per_launch": Q * H_,
-                      "share_of_step": probe_ms / args.steps / ms_per_step if ms_per_step > 0 else None,
+                      "share_of_step": probe_ms / args.steps / serial_ms if serial_ms > 0 else None,
                       "frac_dram_side": dram_frac,
                       "frac_one_slot_per_lookup": (min_bytes / (probe_launch_ms / 1e3) / 1e9 / peak) if probe_launch_ms > 0 else None,
                       "note": "three accountings of the same launch: `frac` counts all four 16-B slots of every 64-B bucket "
@@ -640,7 +675,7 @@ def main():
                                   "candidate collection, fused", "bound": "hbm", "achieved": coll_ach,
                         "peak": peak, "unit": "GB/s", "frac": coll_ach / peak, "traffic": ctraffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": coll_bytes / coll_launches, "launch_ms": coll_ms / coll_launches,
-                        "launches_per_step": coll_launches, "share_of_step": coll_ms / ms_per_step if ms_per_step > 0 else None,
+                        "launches_per_step": coll_launches, "share_of_step": coll_ms / serial_ms if serial_ms > 0 else None,
                         "ids_enumerated_per_step": ids_step, "ids_skipped_per_step": ids_skipped_step,
                         "frac_if_no_bucket_were_skipped": (4.0 * (ids_step + ids_skipped_step) / (coll_ms / 1e3) / 1e9 / peak)
                         if coll_ms > 0 else None,
@@ -656,7 +691,7 @@ def main():
     cells = 2.0 * 2.0 * qp * rp * n   # 2 alignments x (forward + reverse pass) x padded read x window, upper bound
     verify_info = {"kernel": "hrm::sw_pair_passes_kernel (K7a: both SW passes, s16x2 DPX wavefront) + band ladder (K7b: trace "
                              "back + CIGAR)", "bound": "integer ALU (ncu: ALU pipe 80 % in K7a, profiles/README.md)",
-                   "stage_ms": stage_ms["verify"], "share_of_step": stage_ms["verify"] / ms_per_step if ms_per_step > 0 else None,
+                   "stage_ms": stage_ms["verify"], "share_of_step": stage_ms["verify"] / serial_ms if serial_ms > 0 else None,
                    "cell_updates_per_step_upper_bound": cells,
                    "gcups_over_the_whole_stage": cells / (stage_ms["verify"] / 1e3) / 1e9 if stage_ms["verify"] > 0 else None}
     dominant_stage = dom_stage
@@ -680,7 +715,9 @@ def main():
             "roofline": roofline,
             "roofline_probe" if roofline is collect_roofline else "roofline_collect": other,
             "verify_alu": verify_info, "dominant_stage": dominant_stage,
-            "stages_ms_per_step": stage_ms, "stages_unaccounted_ms": ms_per_step - stage_sum,
+            "stages_ms_per_step": stage_ms, "stages_unaccounted_ms": serial_ms - stage_sum,
+            "ms_per_step_with_stage_timers": serial_ms,
+            "value_staged_pipeline_device_resident": world * n / (pipe_ms / 1e3),
             "mapped_fraction": n_mapped / n, "mapped_at_true_locus_fraction": float(ok.sum()) / max(n_mapped, 1),
             "candidates_per_read": st.num_candidates / n, "values_per_read": st.num_values / n,
             "collect_ids_skipped_fraction": (float(mp.info().collect_ids_skipped) /

@@ -175,6 +175,7 @@ SIGNATURES = {
     "hrm_sam_fields_batch": (I32, [P, P, I64, P, I64, P, P, I64, P, VP]),
     "hrm_sam_format_device": (I32, [P, P, I64, P, I64, P, P, I64, U32, P, C.c_int, P, I64, C.POINTER(I64), VP]),
     "hrm_mapper_stage_reads": (I32, [P, C.c_int, P, I64, P, I64]),
+    "hrm_mapper_stage_device": (I32, [P, C.c_int, P, I64, P, I64, C.c_int, VP]),
     "hrm_mapper_stage_fastq": (I32, [P, C.c_int, P, I64, I64, I32, I64, I64, C.POINTER(I64), C.POINTER(I32)]),
     "hrm_mapper_map_staged": (I32, [P, C.c_int, P, P, I64, U32, P, P, I64, P, I64, C.POINTER(BatchStats), VP]),
     "hrm_mapper_finish": (I32, [P, C.c_int, C.POINTER(I64), C.POINTER(I64)]),

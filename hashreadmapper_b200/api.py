@@ -639,6 +639,12 @@ class Mapper:
         n, pitch = reads_ascii.shape
         check(self.lib.hrm_mapper_stage_reads(self.h, slot, _ptr(reads_ascii), pitch, _ptr(lengths), n))
 
+    def stageDevice(self, slot, reads_ascii: torch.Tensor, lengths: torch.Tensor, max_length=None):
+        """reads already on the device (kept alive by the caller until finish(slot))"""
+        n, pitch = reads_ascii.shape
+        check(self.lib.hrm_mapper_stage_device(self.h, slot, _ptr(reads_ascii), pitch, _ptr(lengths), n,
+                                               int(max_length if max_length is not None else pitch), _stream()))
+
     def stageFastq(self, slot, text: np.ndarray, pitch, max_reads, first_read_id=0, carry=0):
         """FASTQ / FASTA text (uint8, pinned) -> staged batch; returns (number of reads, carry for the next chunk)"""
         nr, co = C.c_int64(0), C.c_int32(0)

@@ -1121,6 +1121,8 @@ hrm_status collect_candidates_from(const uint2* d_ranges, int64_t rq, int64_t rt
         const size_t bsmem = sizeof(uint32_t) * dup_slice_words(bwords, xwarp, DUP_WQ, H) * (wthreads / 32);
         cudaFuncSetAttribute(collect_dup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
         HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wres, collect_dup_kernel<false>, wthreads, bsmem));
+        const int wcap = env_int("HRM_COLLECT_BLOCKS_PER_SM", 0);
+        if (wcap > 0 && wres > wcap) wres = wcap;
         HRM_LAUNCH(collect_dup_kernel<false>, (unsigned)(num_sms() * (wres > 0 ? wres : 1)), wthreads, bsmem, s, P);
         // skewed reads: the same scheme block-wide, then (what is left) the counting-table kernel on big2_list
         const size_t bbsmem = sizeof(uint32_t) * dup_slice_words(bblock_words, xblock, DUP_BQ, H);

@@ -1066,7 +1066,8 @@ static bool launch_pair_passes(const PackedSrc& src, int64_t nreads, int QP, int
     const size_t smem = ((size_t)QP + RP + 8 * (size_t)RP) * ppw * 4;
     if (smem > 200 * 1024) return false;
     int64_t blocks = HRM_SDIV(nreads, (int64_t)(ppw * 4));
-    const int64_t cap = (int64_t)num_sms() * 4;
+    static const int per_sm = getenv("HRM_K7A_BLOCKS_PER_SM") ? atoi(getenv("HRM_K7A_BLOCKS_PER_SM")) : 4;
+    const int64_t cap = (int64_t)num_sms() * (per_sm > 0 ? per_sm : 4);
     if (blocks > cap) blocks = cap;
     auto go = [&](auto kern) -> hrm_status {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

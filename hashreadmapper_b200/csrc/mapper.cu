@@ -16,6 +16,7 @@
 #include "partition.cuh"
 #include <string.h>
 #include <stdlib.h>
+#include <mutex>
 #include <vector>
 
 namespace hrm {
@@ -136,11 +137,14 @@ extern "C" void hrm_mapper_destroy(hrm_mapper* m)
     if (m->pipe_ready) {
         for (int i = 0; i < HRM_PIPE_SLOTS; i++) {
             cudaEventDestroy(m->slot[i].staged);
+            cudaEventDestroy(m->slot[i].seeded);
             cudaEventDestroy(m->slot[i].computed);
             cudaEventDestroy(m->slot[i].drained);
         }
         cudaStreamDestroy(m->pipe_in);
         cudaStreamDestroy(m->pipe_out);
+        cudaStreamDestroy(m->pipe_verify);
+        cudaFreeHost(m->pipe_host);
     }
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     delete m;
@@ -231,15 +235,15 @@ hrm_status hrm::mapper_pack_batch(hrm_mapper* m, const char* d_reads_ascii, int6
                                   int64_t n, hrm_stream stream)
 {
     const hrm_mapper_config& cfg = m->cfg;
-    m->packed_pitch = ascii_pitch / 16;
+    m->bc->packed_pitch = ascii_pitch / 16;
     bool done[3] = {false, false, false};
     for (int p = 0; p < cfg.num_passes; p++) {
         const int rc = cfg.read_conversion[p];
         if (done[rc]) continue;
         done[rc] = true;
-        HRM_TRY(m->packed[rc].reserve(sizeof(uint32_t) * (size_t)n * m->packed_pitch));
-        HRM_TRY(hrm_encode_2bit(d_reads_ascii, ascii_pitch, d_lengths, n, rc, m->packed[rc].as<uint32_t>(),
-                                m->packed_pitch, stream));
+        HRM_TRY(m->bc->packed[rc].reserve(sizeof(uint32_t) * (size_t)n * m->bc->packed_pitch));
+        HRM_TRY(hrm_encode_2bit(d_reads_ascii, ascii_pitch, d_lengths, n, rc, m->bc->packed[rc].as<uint32_t>(),
+                                m->bc->packed_pitch, stream));
     }
     return HRM_OK;
 }
@@ -298,44 +302,44 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
     T.begin(HRM_STAGE_PACK, s);
     HRM_TRY(mapper_pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
     T.end(s);
-    HRM_TRY(m->sigs.reserve(sizeof(uint64_t) * (size_t)n * H));
-    HRM_TRY(m->num.reserve(sizeof(int32_t) * ((size_t)n + 1)));
-    HRM_TRY(m->off.reserve(sizeof(int32_t) * ((size_t)n + 1)));
-    HRM_TRY(m->newoff.reserve(sizeof(int32_t) * ((size_t)n + 1)));
-    HRM_TRY(m->passres.reserve(sizeof(hrm_mapped_read) * (size_t)n));
-    HRM_TRY(m->misc.reserve(64));
-    int64_t* d_tot = m->misc.as<int64_t>();           // [0] values total, [1] filtered total
-    unsigned long long* d_cnt = m->misc.as<unsigned long long>() + 2;
+    HRM_TRY(m->bc->sigs.reserve(sizeof(uint64_t) * (size_t)n * H));
+    HRM_TRY(m->bc->num.reserve(sizeof(int32_t) * ((size_t)n + 1)));
+    HRM_TRY(m->bc->off.reserve(sizeof(int32_t) * ((size_t)n + 1)));
+    HRM_TRY(m->bc->newoff.reserve(sizeof(int32_t) * ((size_t)n + 1)));
+    HRM_TRY(m->bc->passres.reserve(sizeof(hrm_mapped_read) * (size_t)n));
+    HRM_TRY(m->bc->misc.reserve(64));
+    int64_t* d_tot = m->bc->misc.as<int64_t>();           // [0] values total, [1] filtered total
+    unsigned long long* d_cnt = m->bc->misc.as<unsigned long long>() + 2;
     int last_rc = -1;
     for (int p = 0; p < cfg.num_passes; p++) {
         const int rc = cfg.read_conversion[p], gc = cfg.genome_conversion[p];
         hrm_minhasher* mh = m->index[gc];
         QueryHandle* qh = minhasher_handle(mh, m->index_handle[gc]);
         HRM_REQUIRE(qh != nullptr, "index handle");
-        const uint32_t* reads = m->packed[rc].as<uint32_t>();
+        const uint32_t* reads = m->bc->packed[rc].as<uint32_t>();
         // K2 (skipped when the previous pass sketched the same converted reads)
         if (rc != last_rc) {
             T.begin(HRM_STAGE_MINHASH, s);
-            HRM_TRY(minhash_rows(reads, m->packed_pitch, d_lengths, n, cfg.k, H, m->sigs.as<uint64_t>(), nullptr, s));
+            HRM_TRY(minhash_rows(reads, m->bc->packed_pitch, d_lengths, n, cfg.k, H, m->bc->sigs.as<uint64_t>(), nullptr, s));
             T.end(s);
         }
         last_rc = rc;
-        hrm_mapped_read* passout = m->passres.as<hrm_mapped_read>();
+        hrm_mapped_read* passout = m->bc->passres.as<hrm_mapped_read>();
         // K4 + K5 of reads [lo, lo + cnt): values in table order at `values`, offsets in m->off[0 .. cnt]
         auto filter_and_select = [&](int64_t lo, int64_t cnt, int64_t total, Scratch& values) -> hrm_status {
             Scratch cands;
             HRM_TRY(cands.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
             T.begin(HRM_STAGE_FILTER, s);
             // K4 count / sort + threshold, then dense candidate lists (cands doubles as K4's partition space first)
-            HRM_TRY(filter_segments(values.as<uint32_t>(), cands.as<uint32_t>(), m->off.as<int32_t>(), (int)cnt,
-                                    cfg.min_table_hits, m->num.as<int32_t>() + lo, m->newoff.as<int32_t>(), d_tot + 1, s));
-            HRM_TRY(compact_segments(values.as<uint32_t>(), m->off.as<int32_t>(), m->newoff.as<int32_t>(), (int)cnt,
+            HRM_TRY(filter_segments(values.as<uint32_t>(), cands.as<uint32_t>(), m->bc->off.as<int32_t>(), (int)cnt,
+                                    cfg.min_table_hits, m->bc->num.as<int32_t>() + lo, m->bc->newoff.as<int32_t>(), d_tot + 1, s));
+            HRM_TRY(compact_segments(values.as<uint32_t>(), m->bc->off.as<int32_t>(), m->bc->newoff.as<int32_t>(), (int)cnt,
                                      cands.as<uint32_t>(), s));
             T.end(s);
             // K5 + per-read arg-min
             T.begin(HRM_STAGE_SHD, s);
-            HRM_TRY(best_windows(reads + lo * m->packed_pitch, m->packed_pitch, d_lengths + lo, cnt, cands.as<uint32_t>(),
-                                 m->newoff.as<int32_t>(), m->genome[gc], m->d_win_prefix, cfg.k, cfg.window_size,
+            HRM_TRY(best_windows(reads + lo * m->bc->packed_pitch, m->bc->packed_pitch, d_lengths + lo, cnt, cands.as<uint32_t>(),
+                                 m->bc->newoff.as<int32_t>(), m->genome[gc], m->d_win_prefix, cfg.k, cfg.window_size,
                                  cfg.max_hamming_percent, p, passout + lo, s));
             T.end(s);
             st.num_values += total;
@@ -359,8 +363,8 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
                 int64_t total = 0;
                 const bool fuse = m->use_fused && cfg.min_table_hits >= 2 && m->num_windows < 0xFFFFFFFFLL;
                 if (fuse) HRM_TRY(rng.alloc(sizeof(uint2) * (size_t)(cnt > 0 ? cnt : 1) * H, s));
-                const hrm_status qs = partitioned_query(m->comm, mh, m->sigs.as<uint64_t>() + lo * H, (int)cnt,
-                                                        m->num.as<int32_t>() + lo, m->off.as<int32_t>(), &total, values, T, s,
+                const hrm_status qs = partitioned_query(m->comm, mh, m->bc->sigs.as<uint64_t>() + lo * H, (int)cnt,
+                                                        m->bc->num.as<int32_t>() + lo, m->bc->off.as<int32_t>(), &total, values, T, s,
                                                         fuse ? rng.as<uint2>() : nullptr);
                 if (qs == HRM_ERR_OVERFLOW && chunk > 1024) {
                     chunk /= 2; // collective decision: every rank retries this base with half the chunk
@@ -384,7 +388,7 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
                     T.end(s);
                     if (!overflow) {
                         T.begin(HRM_STAGE_SHD, s);
-                        HRM_TRY(best_windows(reads + lo * m->packed_pitch, m->packed_pitch, d_lengths + lo, cnt,
+                        HRM_TRY(best_windows(reads + lo * m->bc->packed_pitch, m->bc->packed_pitch, d_lengths + lo, cnt,
                                              cands.as<uint32_t>(), nullptr, m->genome[gc], m->d_win_prefix, cfg.k,
                                              cfg.window_size, cfg.max_hamming_percent, p, passout + lo, s, lists.as<int2>()));
                         T.end(s);
@@ -403,17 +407,17 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
             if (minhasher_wants_table_major(mh)) {
                 // index far larger than L2: probe table by table (transpose + totals are booked under "scan")
                 T.begin(HRM_STAGE_SCAN, s);
-                HRM_TRY(minhasher_tm_prepare(mh, qh, m->sigs.as<uint64_t>(), (int)n, s));
+                HRM_TRY(minhasher_tm_prepare(mh, qh, m->bc->sigs.as<uint64_t>(), (int)n, s));
                 T.end(s);
                 T.begin(HRM_STAGE_PROBE, s);
                 HRM_TRY(minhasher_tm_probe(mh, qh, (int)n, s));
                 T.end(s);
                 T.begin(HRM_STAGE_SCAN, s);
-                HRM_TRY(minhasher_tm_totals(mh, qh, (int)n, m->num.as<int32_t>(), s));
+                HRM_TRY(minhasher_tm_totals(mh, qh, (int)n, m->bc->num.as<int32_t>(), s));
                 T.end(s);
             } else {
                 T.begin(HRM_STAGE_PROBE, s);
-                HRM_TRY(minhasher_count_sigs(mh, qh, m->sigs.as<uint64_t>(), (int)n, m->num.as<int32_t>(), s));
+                HRM_TRY(minhasher_count_sigs(mh, qh, m->bc->sigs.as<uint64_t>(), (int)n, m->bc->num.as<int32_t>(), s));
                 T.end(s);
             }
             // fused retrieval + collection straight from the index (k4_fused.cu); falls through to the general
@@ -433,7 +437,7 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
                 T.end(s);
                 if (!overflow) {
                     T.begin(HRM_STAGE_SHD, s);
-                    HRM_TRY(best_windows(reads, m->packed_pitch, d_lengths, n, cands.as<uint32_t>(), nullptr, m->genome[gc],
+                    HRM_TRY(best_windows(reads, m->bc->packed_pitch, d_lengths, n, cands.as<uint32_t>(), nullptr, m->genome[gc],
                                          m->d_win_prefix, cfg.k, cfg.window_size, cfg.max_hamming_percent, p, passout, s,
                                          lists.as<int2>()));
                     T.end(s);
@@ -458,7 +462,7 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
                 todo.pop_back();
                 int64_t total = 0;
                 T.begin(HRM_STAGE_SCAN, s);
-                HRM_TRY(exclusive_scan_i32(m->num.as<int32_t>() + r.lo, m->off.as<int32_t>(), r.cnt, d_tot, s));
+                HRM_TRY(exclusive_scan_i32(m->bc->num.as<int32_t>() + r.lo, m->bc->off.as<int32_t>(), r.cnt, d_tot, s));
                 HRM_CUDA(cudaMemcpyAsync(&total, d_tot, sizeof total, cudaMemcpyDeviceToHost, s));
                 T.end(s);
                 HRM_CUDA(cudaStreamSynchronize(s));
@@ -476,7 +480,7 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
                 HRM_TRY(values.alloc(sizeof(uint32_t) * (size_t)(total > 0 ? total : 1), s));
                 T.begin(HRM_STAGE_RETRIEVE, s);
                 if (total > 0)
-                    HRM_TRY(minhasher_retrieve(mh, qh, r.lo, (int)r.cnt, values.as<uint32_t>(), m->off.as<int32_t>(), s));
+                    HRM_TRY(minhasher_retrieve(mh, qh, r.lo, (int)r.cnt, values.as<uint32_t>(), m->bc->off.as<int32_t>(), s));
                 T.end(s);
                 HRM_TRY(filter_and_select(r.lo, r.cnt, total, values));
             }
@@ -508,6 +512,44 @@ extern "C" hrm_status hrm_map_batch(hrm_mapper* m, const char* d_reads_ascii, in
     return HRM_OK;
 }
 
+// verification of the batch whose reads are packed in m->bc.  maxlen < 0: taken from the device (one host sync);
+// d_reads_ascii != NULL: pack first.
+static hrm_status verify_batch_impl(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch, const int32_t* d_lengths,
+                                    int64_t n, int maxlen, const hrm_mapped_read* d_mapped, hrm_read_record* d_records,
+                                    char* d_cigars, int64_t cigar_pitch, hrm_batch_stats* h_stats, hrm_stream stream)
+{
+    cudaStream_t s = as_stream(stream);
+    const int64_t launches0 = g_launches.load();
+    if (n == 0) return HRM_OK;
+    const hrm_mapper_config& cfg = m->cfg;
+    m->timer.begin(HRM_STAGE_VERIFY, s);
+    if (d_reads_ascii) HRM_TRY(mapper_pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
+    if (maxlen < 0) {
+        HRM_TRY(m->bc->misc.reserve(64));
+        int* d_maxlen = m->bc->misc.as<int>() + 8;
+        HRM_CUDA(cudaMemsetAsync(d_maxlen, 0, sizeof(int), s));
+        HRM_LAUNCH(max_len_kernel, mgrid(n), 256, 0, s, d_lengths, n, d_maxlen);
+        HRM_CUDA(cudaMemcpyAsync(&maxlen, d_maxlen, sizeof maxlen, cudaMemcpyDeviceToHost, s));
+        HRM_CUDA(cudaStreamSynchronize(s));
+    }
+    HRM_REQUIRE(maxlen <= HRM_SW_MAX_QUERY, "read longer than HRM_SW_MAX_QUERY");
+    VerifyParams VP;
+    memset(&VP, 0, sizeof VP);
+    VP.num_passes = cfg.num_passes;
+    VP.w = cfg.window_size;
+    VP.mapper_type = cfg.mapper_type;
+    for (int p = 0; p < cfg.num_passes; p++) {
+        VP.pass[p].reads = m->bc->packed[cfg.read_conversion[p]].as<uint32_t>();
+        VP.pass[p].read_pitch = m->bc->packed_pitch;
+        VP.pass[p].G = m->genome[cfg.genome_conversion[p]]->dev();
+        VP.pass[p].verify_conv = cfg.verify_conversion[p];
+    }
+    HRM_TRY(verify_reads(VP, d_lengths, n, maxlen, d_mapped, d_records, d_cigars, cigar_pitch, s));
+    m->timer.end(s);
+    if (h_stats) h_stats->num_kernel_launches += g_launches.load() - launches0;
+    return HRM_OK;
+}
+
 extern "C" hrm_status hrm_verify_batch(hrm_mapper* m, const char* d_reads_ascii, int64_t ascii_pitch,
                                        const int32_t* d_lengths, int64_t n, const hrm_mapped_read* d_mapped,
                                        hrm_read_record* d_records, char* d_cigars, int64_t cigar_pitch,
@@ -516,35 +558,8 @@ extern "C" hrm_status hrm_verify_batch(hrm_mapper* m, const char* d_reads_ascii,
     HRM_REQUIRE(m != nullptr, "mapper");
     HRM_REQUIRE(m->d_win_prefix != nullptr, "hrm_mapper_set_genome has not been called");
     HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && cigar_pitch > 0, "sizes");
-    cudaStream_t s = as_stream(stream);
-    const int64_t launches0 = g_launches.load();
-    if (n == 0) return HRM_OK;
-    const hrm_mapper_config& cfg = m->cfg;
-    m->timer.begin(HRM_STAGE_VERIFY, s);
-    HRM_TRY(mapper_pack_batch(m, d_reads_ascii, ascii_pitch, d_lengths, n, stream));
-    HRM_TRY(m->misc.reserve(64));
-    int* d_maxlen = m->misc.as<int>() + 8;
-    HRM_CUDA(cudaMemsetAsync(d_maxlen, 0, sizeof(int), s));
-    HRM_LAUNCH(max_len_kernel, mgrid(n), 256, 0, s, d_lengths, n, d_maxlen);
-    int maxlen = 0;
-    HRM_CUDA(cudaMemcpyAsync(&maxlen, d_maxlen, sizeof maxlen, cudaMemcpyDeviceToHost, s));
-    HRM_CUDA(cudaStreamSynchronize(s));
-    HRM_REQUIRE(maxlen <= HRM_SW_MAX_QUERY, "read longer than HRM_SW_MAX_QUERY");
-    VerifyParams VP;
-    memset(&VP, 0, sizeof VP);
-    VP.num_passes = cfg.num_passes;
-    VP.w = cfg.window_size;
-    VP.mapper_type = cfg.mapper_type;
-    for (int p = 0; p < cfg.num_passes; p++) {
-        VP.pass[p].reads = m->packed[cfg.read_conversion[p]].as<uint32_t>();
-        VP.pass[p].read_pitch = m->packed_pitch;
-        VP.pass[p].G = m->genome[cfg.genome_conversion[p]]->dev();
-        VP.pass[p].verify_conv = cfg.verify_conversion[p];
-    }
-    HRM_TRY(verify_reads(VP, d_lengths, n, maxlen, d_mapped, d_records, d_cigars, cigar_pitch, s));
-    m->timer.end(s);
-    if (h_stats) h_stats->num_kernel_launches += g_launches.load() - launches0;
-    return HRM_OK;
+    return verify_batch_impl(m, d_reads_ascii, ascii_pitch, d_lengths, n, -1, d_mapped, d_records, d_cigars, cigar_pitch,
+                             h_stats, stream);
 }
 
 extern "C" hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_ascii, int64_t ascii_pitch,
@@ -700,15 +715,36 @@ extern "C" hrm_status hrm_mapper_map_reads_sam(hrm_mapper* m, const char* h_read
 // caller's stream.  Host syncs inside the compute (candidate totals, text size) only ever wait for the batch at hand.
 static hrm_status pipe_init(hrm_mapper* m)
 {
+    static std::mutex mtx; // staging may be called from a second host thread
+    std::lock_guard<std::mutex> lk(mtx);
     if (m->pipe_ready) return HRM_OK;
     HRM_CUDA(cudaStreamCreateWithFlags(&m->pipe_in, cudaStreamNonBlocking));
     HRM_CUDA(cudaStreamCreateWithFlags(&m->pipe_out, cudaStreamNonBlocking));
+    HRM_CUDA(cudaStreamCreateWithFlags(&m->pipe_verify, cudaStreamNonBlocking));
+    HRM_CUDA(cudaMallocHost(&m->pipe_host, sizeof(int64_t) * 4 * HRM_PIPE_SLOTS));
     for (int i = 0; i < HRM_PIPE_SLOTS; i++) {
         HRM_CUDA(cudaEventCreateWithFlags(&m->slot[i].staged, cudaEventDisableTiming));
+        HRM_CUDA(cudaEventCreateWithFlags(&m->slot[i].seeded, cudaEventDisableTiming));
         HRM_CUDA(cudaEventCreateWithFlags(&m->slot[i].computed, cudaEventDisableTiming));
         HRM_CUDA(cudaEventCreateWithFlags(&m->slot[i].drained, cudaEventDisableTiming));
     }
     m->pipe_ready = true;
+    return HRM_OK;
+}
+
+// the slot is free again when everything its previous batch queued has finished
+static hrm_status slot_release(hrm_mapper* m, hrm::PipeSlot& S)
+{
+    if (S.busy && S.want_text) {
+        set_error("the slot holds a batch whose SAM text has not been fetched: call hrm_mapper_finish first");
+        return HRM_ERR_STATE;
+    }
+    if (S.busy) {
+        HRM_CUDA(cudaEventSynchronize(S.computed));
+        HRM_CUDA(cudaEventSynchronize(S.drained));
+    }
+    S.busy = false;
+    (void)m;
     return HRM_OK;
 }
 
@@ -721,11 +757,13 @@ extern "C" hrm_status hrm_mapper_stage_reads(hrm_mapper* m, int slot, const char
     HRM_REQUIRE(m->comm == nullptr, "the staged pipeline runs on the replicated index");
     HRM_TRY(pipe_init(m));
     PipeSlot& S = m->slot[slot];
-    // the slot's previous batch must have left the device before its buffers are overwritten
-    if (S.busy) HRM_CUDA(cudaEventSynchronize(S.drained));
-    S.busy = false;
+    HRM_TRY(slot_release(m, S)); // the slot's previous batch must have left the device before its buffers are overwritten
     S.n = n;
     S.pitch = ascii_pitch;
+    S.d_ascii = nullptr;
+    int mx = 0;
+    for (int64_t i = 0; i < n; i++) mx = h_lengths[i] > mx ? h_lengths[i] : mx; // sizes the SW frames without a device sync
+    S.maxlen = mx;
     HRM_TRY(S.ascii.reserve((size_t)(n * ascii_pitch)));
     HRM_TRY(S.len.reserve(sizeof(int32_t) * (size_t)n));
     if (n > 0) {
@@ -733,6 +771,27 @@ extern "C" hrm_status hrm_mapper_stage_reads(hrm_mapper* m, int slot, const char
         HRM_CUDA(cudaMemcpyAsync(S.len.p, h_lengths, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, m->pipe_in));
     }
     HRM_CUDA(cudaEventRecord(S.staged, m->pipe_in));
+    S.is_staged = true;
+    return HRM_OK;
+}
+
+// reads that are already in device memory (they must stay valid until hrm_mapper_finish of the slot)
+extern "C" hrm_status hrm_mapper_stage_device(hrm_mapper* m, int slot, const char* d_reads_ascii, int64_t ascii_pitch,
+                                              const int32_t* d_lengths, int64_t n, int max_length, hrm_stream ready_on)
+{
+    HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
+    HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && max_length >= 0 && max_length <= ascii_pitch, "sizes");
+    HRM_REQUIRE(n == 0 || (d_reads_ascii != nullptr && d_lengths != nullptr), "buffers");
+    HRM_REQUIRE(m->comm == nullptr, "the staged pipeline runs on the replicated index");
+    HRM_TRY(pipe_init(m));
+    PipeSlot& S = m->slot[slot];
+    HRM_TRY(slot_release(m, S));
+    S.n = n;
+    S.pitch = ascii_pitch;
+    S.d_ascii = d_reads_ascii;
+    S.d_len = d_lengths;
+    S.maxlen = max_length;
+    HRM_CUDA(cudaEventRecord(S.staged, as_stream(ready_on)));
     S.is_staged = true;
     return HRM_OK;
 }
@@ -751,10 +810,11 @@ extern "C" hrm_status hrm_mapper_stage_fastq(hrm_mapper* m, int slot, const char
     HRM_REQUIRE(m->comm == nullptr, "the staged pipeline runs on the replicated index");
     HRM_TRY(pipe_init(m));
     PipeSlot& S = m->slot[slot];
-    if (S.busy) HRM_CUDA(cudaEventSynchronize(S.drained));
-    S.busy = false;
+    HRM_TRY(slot_release(m, S));
     S.pitch = ascii_pitch;
     S.n = 0;
+    S.d_ascii = nullptr;
+    S.maxlen = (int)(ascii_pitch < HRM_SW_MAX_QUERY ? ascii_pitch : HRM_SW_MAX_QUERY);
     HRM_TRY(S.fastq.reserve((size_t)nbytes + 16));
     HRM_TRY(S.ascii.reserve((size_t)(max_reads * ascii_pitch)));
     HRM_TRY(S.len.reserve(sizeof(int32_t) * (size_t)max_reads));
@@ -768,6 +828,9 @@ extern "C" hrm_status hrm_mapper_stage_fastq(hrm_mapper* m, int slot, const char
     return HRM_OK;
 }
 
+// Seeding (K1..K5) of the staged batch, then its verification (K7 / K6), V4 and the SAM text, all queued without a host
+// round trip after the seeding; the D2H copies on the copy-out stream.  Returns when the seeding kernels have run (their
+// candidate totals come back to the host) and everything else is queued.
 extern "C" hrm_status hrm_mapper_map_staged(hrm_mapper* m, int slot, hrm_read_record* h_records, char* h_cigars,
                                             int64_t cigar_pitch, uint32_t first_read_id,
                                             const char* const* h_chrom_names, char* h_sq_out, int64_t sq_cap,
@@ -776,11 +839,17 @@ extern "C" hrm_status hrm_mapper_map_staged(hrm_mapper* m, int slot, hrm_read_re
     HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
     HRM_REQUIRE(cigar_pitch > 0, "cigar_pitch");
     PipeSlot& S = m->slot[slot];
-    HRM_REQUIRE(m->pipe_ready && S.is_staged, "hrm_mapper_stage_reads has not been called for this slot");
-    cudaStream_t s = as_stream(stream);
+    HRM_REQUIRE(m->pipe_ready && S.is_staged, "nothing is staged in this slot");
+    // verification on the caller's stream by default.  HRM_PIPE_OVERLAP=1 puts it on a second stream so that it runs under
+    // the seeding of the next batch; measured on B200 (profiles/README.md) the two do not speed each other up -- each kernel
+    // fills the SMs with persistent blocks and the pair is bound by instruction issue -- so it is off by default.
+    static const bool overlap = getenv("HRM_PIPE_OVERLAP") != nullptr && atoi(getenv("HRM_PIPE_OVERLAP")) != 0;
+    cudaStream_t s = as_stream(stream), vs = overlap ? m->pipe_verify : s, co = m->pipe_out;
     const int64_t n = S.n;
     S.is_staged = false;
     S.sq_written = S.rec_written = 0;
+    S.h_sq = S.h_rec = nullptr;
+    S.want_text = false;
     if (h_stats) memset(h_stats, 0, sizeof *h_stats);
     if (n == 0) return HRM_OK;
     const bool want_text = h_rec_out != nullptr;
@@ -788,47 +857,75 @@ extern "C" hrm_status hrm_mapper_map_staged(hrm_mapper* m, int slot, hrm_read_re
     for (int c = 0; c < m->n_chrom && h_chrom_names; c++)
         if (h_chrom_names[c] && strlen(h_chrom_names[c]) > maxname) maxname = strlen(h_chrom_names[c]);
     const int64_t line_bound = 64 + (int64_t)maxname + cigar_pitch + m->cfg.window_size + S.pitch;
+    HRM_REQUIRE(!want_text || (n * line_bound <= rec_cap && (!h_sq_out || n * 40 <= sq_cap)),
+                "text buffers must hold n * (64 + longest chromosome name + cigar_pitch + window + pitch) / n * 40 bytes");
     HRM_TRY(S.mapped.reserve(sizeof(hrm_mapped_read) * (size_t)n));
     HRM_TRY(S.rec.reserve(sizeof(hrm_read_record) * (size_t)n));
     HRM_TRY(S.cig.reserve((size_t)(2 * n * cigar_pitch)));
     if (want_text) {
         HRM_TRY(S.text.reserve((size_t)(n * line_bound)));
+        HRM_TRY(S.fields.reserve(sizeof(hrm_sam_fields) * (size_t)n));
+        HRM_TRY(S.lens2.reserve(sizeof(int32_t) * (size_t)(2 * n)));
+        HRM_TRY(S.offs.reserve(sizeof(int64_t) * (size_t)(2 * n + 4)));
         if (h_sq_out) HRM_TRY(S.sq.reserve((size_t)(n * 40)));
+        HRM_TRY(sam_upload_names(m, h_chrom_names, s));
     }
-    HRM_CUDA(cudaStreamWaitEvent(s, S.staged, 0));
     hrm_batch_stats st;
     memset(&st, 0, sizeof st);
-    const char* d_ascii = S.ascii.as<char>();
-    const int32_t* d_len = S.len.as<int32_t>();
-    HRM_TRY(hrm_map_batch(m, d_ascii, S.pitch, d_len, n, S.mapped.as<hrm_mapped_read>(), h_stats ? &st : nullptr, stream));
-    HRM_TRY(hrm_verify_batch(m, d_ascii, S.pitch, d_len, n, S.mapped.as<hrm_mapped_read>(), S.rec.as<hrm_read_record>(),
-                             S.cig.as<char>(), cigar_pitch, h_stats ? &st : nullptr, stream));
-    if (want_text) {
-        const int64_t launches0 = g_launches.load();
-        HRM_TRY(hrm_sam_format_device(m, nullptr, S.pitch, d_len, n, S.rec.as<hrm_read_record>(), S.cig.as<char>(),
-                                      cigar_pitch, first_read_id, h_chrom_names, HRM_SAM_RECORDS, S.text.as<char>(),
-                                      n * line_bound, &S.rec_written, stream));
-        HRM_REQUIRE(S.rec_written <= rec_cap, "record text does not fit rec_cap");
-        if (h_sq_out) {
-            HRM_TRY(hrm_sam_format_device(m, nullptr, S.pitch, d_len, n, S.rec.as<hrm_read_record>(), S.cig.as<char>(),
-                                          cigar_pitch, first_read_id, h_chrom_names, HRM_SAM_SQ_LINES, S.sq.as<char>(),
-                                          n * 40, &S.sq_written, stream));
-            HRM_REQUIRE(S.sq_written <= sq_cap, "@SQ text does not fit sq_cap");
-        }
-        st.num_kernel_launches += g_launches.load() - launches0;
+    const char* d_ascii = S.d_ascii ? S.d_ascii : S.ascii.as<char>();
+    const int32_t* d_len = S.d_ascii ? S.d_len : S.len.as<int32_t>();
+    // seeding on the caller's stream, in this slot's context (its packed reads stay valid for the verification)
+    m->bc = &m->ctx[slot];
+    HRM_CUDA(cudaStreamWaitEvent(s, S.staged, 0));
+    hrm_status rc = hrm_map_batch(m, d_ascii, S.pitch, d_len, n, S.mapped.as<hrm_mapped_read>(), h_stats ? &st : nullptr, stream);
+    if (rc == HRM_OK) rc = cudaEventRecord(S.seeded, s) == cudaSuccess ? HRM_OK : HRM_ERR_CUDA;
+    // verification + V4 + SAM text on the second stream
+    const int64_t launches0 = g_launches.load();
+    if (rc == HRM_OK) rc = cudaStreamWaitEvent(vs, S.seeded, 0) == cudaSuccess ? HRM_OK : HRM_ERR_CUDA;
+    if (rc == HRM_OK)
+        rc = verify_batch_impl(m, nullptr, S.pitch, d_len, n, S.maxlen, S.mapped.as<hrm_mapped_read>(),
+                               S.rec.as<hrm_read_record>(), S.cig.as<char>(), cigar_pitch, nullptr, (hrm_stream)vs);
+    int64_t* hp = m->pipe_host + 4 * slot; // pinned: [0] record text bytes, [1] @SQ text bytes
+    if (rc == HRM_OK && want_text) {
+        int32_t* ll = S.lens2.as<int32_t>();
+        int64_t* off = S.offs.as<int64_t>();
+        rc = sam_fields(m, d_len, n, S.rec.as<hrm_read_record>(), S.cig.as<char>(), cigar_pitch, first_read_id,
+                        S.fields.as<hrm_sam_fields>(), ll, ll + n, vs);
+        if (rc == HRM_OK)
+            rc = sam_text_async(m, d_len, n, S.rec.as<hrm_read_record>(), S.cig.as<char>(), cigar_pitch,
+                                S.fields.as<hrm_sam_fields>(), ll, first_read_id, HRM_SAM_RECORDS, S.text.as<char>(),
+                                n * line_bound, off, hp, vs);
+        if (rc == HRM_OK && h_sq_out)
+            rc = sam_text_async(m, d_len, n, S.rec.as<hrm_read_record>(), S.cig.as<char>(), cigar_pitch,
+                                S.fields.as<hrm_sam_fields>(), ll + n, first_read_id, HRM_SAM_SQ_LINES, S.sq.as<char>(),
+                                n * 40, off + n + 2, hp + 1, vs);
+        S.want_text = true;
+        S.h_rec = h_rec_out;
+        S.h_sq = h_sq_out;
     }
-    HRM_CUDA(cudaEventRecord(S.computed, s));
-    HRM_CUDA(cudaStreamWaitEvent(m->pipe_out, S.computed, 0));
-    cudaStream_t co = m->pipe_out;
-    if (want_text) {
-        HRM_CUDA(cudaMemcpyAsync(h_rec_out, S.text.p, (size_t)S.rec_written, cudaMemcpyDeviceToHost, co));
-        if (h_sq_out) HRM_CUDA(cudaMemcpyAsync(h_sq_out, S.sq.p, (size_t)S.sq_written, cudaMemcpyDeviceToHost, co));
+    st.num_kernel_launches += g_launches.load() - launches0;
+    m->bc = &m->ctx[HRM_PIPE_SLOTS];
+    if (rc == HRM_OK) rc = cudaEventRecord(S.computed, vs) == cudaSuccess ? HRM_OK : HRM_ERR_CUDA;
+    S.busy = true; // something is queued on the slot's buffers
+    // the next batch's seeding reuses the other context only; this context is reused two batches on, after `computed`
+    if (rc == HRM_OK) rc = cudaStreamWaitEvent(co, S.computed, 0) == cudaSuccess ? HRM_OK : HRM_ERR_CUDA;
+    if (rc == HRM_OK && h_records)
+        rc = cudaMemcpyAsync(h_records, S.rec.p, sizeof(hrm_read_record) * (size_t)n, cudaMemcpyDeviceToHost, co) == cudaSuccess
+                 ? HRM_OK : HRM_ERR_CUDA;
+    if (rc == HRM_OK && h_cigars)
+        rc = cudaMemcpyAsync(h_cigars, S.cig.p, (size_t)(2 * n * cigar_pitch), cudaMemcpyDeviceToHost, co) == cudaSuccess
+                 ? HRM_OK : HRM_ERR_CUDA;
+    cudaEventRecord(S.drained, co);
+    // the other context must not be overwritten by the NEXT seeding before ITS verification has finished: make the
+    // caller's stream wait for the other slot's `computed` (queued two calls ago)
+    PipeSlot& O = m->slot[(slot + 1) % HRM_PIPE_SLOTS];
+    if (O.busy) cudaStreamWaitEvent(s, O.computed, 0);
+    if (rc != HRM_OK) {
+        if (rc == HRM_ERR_CUDA) set_error("CUDA call failed while queueing the staged batch: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaStreamSynchronize(vs); // leave nothing in flight on buffers the caller may now free
+        cudaStreamSynchronize(co);
+        return rc;
     }
-    if (h_records)
-        HRM_CUDA(cudaMemcpyAsync(h_records, S.rec.p, sizeof(hrm_read_record) * (size_t)n, cudaMemcpyDeviceToHost, co));
-    if (h_cigars) HRM_CUDA(cudaMemcpyAsync(h_cigars, S.cig.p, (size_t)(2 * n * cigar_pitch), cudaMemcpyDeviceToHost, co));
-    HRM_CUDA(cudaEventRecord(S.drained, co));
-    S.busy = true;
     if (h_stats) *h_stats = st;
     return HRM_OK;
 }
@@ -837,7 +934,19 @@ extern "C" hrm_status hrm_mapper_finish(hrm_mapper* m, int slot, int64_t* h_sq_w
 {
     HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
     PipeSlot& S = m->slot[slot];
-    if (S.busy) HRM_CUDA(cudaEventSynchronize(S.drained));
+    if (S.busy) {
+        HRM_CUDA(cudaEventSynchronize(S.computed));
+        if (S.want_text) { // the text sizes are known now: copy exactly that much
+            const int64_t* hp = m->pipe_host + 4 * slot;
+            S.rec_written = hp[0];
+            S.sq_written = S.h_sq ? hp[1] : 0;
+            HRM_CUDA(cudaMemcpyAsync(S.h_rec, S.text.p, (size_t)S.rec_written, cudaMemcpyDeviceToHost, m->pipe_out));
+            if (S.h_sq) HRM_CUDA(cudaMemcpyAsync(S.h_sq, S.sq.p, (size_t)S.sq_written, cudaMemcpyDeviceToHost, m->pipe_out));
+            HRM_CUDA(cudaEventRecord(S.drained, m->pipe_out));
+            S.want_text = false;
+        }
+        HRM_CUDA(cudaEventSynchronize(S.drained));
+    }
     S.busy = false;
     if (h_sq_written) *h_sq_written = S.sq_written;
     if (h_rec_written) *h_rec_written = S.rec_written;

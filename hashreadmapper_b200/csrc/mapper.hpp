@@ -53,12 +53,24 @@ struct StageTimer {
 } // namespace hrm
 
 namespace hrm {
+// per-batch device buffers of the fused path (they only grow)
+struct BatchCtx {
+    GrowBuf packed[3];  // reads packed per read conversion
+    GrowBuf sigs, num, off, newoff, passres, misc;
+    int64_t packed_pitch = 0;
+};
+
 // one batch of the double-buffered end-to-end pipeline (mapper.cu: hrm_mapper_stage_reads / map_staged / finish)
 struct PipeSlot {
-    GrowBuf ascii, len, mapped, rec, cig, text, sq, fastq;
-    cudaEvent_t staged = nullptr, computed = nullptr, drained = nullptr;
+    GrowBuf ascii, len, mapped, rec, cig, text, sq, fastq, fields, lens2, offs;
+    const char* d_ascii = nullptr;  // reads staged from device memory (hrm_mapper_stage_device): not owned
+    const int32_t* d_len = nullptr;
+    cudaEvent_t staged = nullptr, seeded = nullptr, computed = nullptr, drained = nullptr;
     int64_t n = 0, pitch = 0, sq_written = 0, rec_written = 0;
-    bool is_staged = false, busy = false;
+    int maxlen = 0;
+    char* h_rec = nullptr;          // host text buffers of the batch in flight (copied out by hrm_mapper_finish)
+    char* h_sq = nullptr;
+    bool is_staged = false, busy = false, want_text = false;
 };
 } // namespace hrm
 
@@ -76,10 +88,10 @@ struct hrm_mapper {
     // chromosome names on the device for the SAM writer (sam.cu), uploaded when they change
     std::string names_flat;
     hrm::GrowBuf d_names, d_name_off;
-    // per-batch buffers that only grow
-    hrm::GrowBuf packed[3];  // reads packed per read conversion
-    hrm::GrowBuf sigs, num, off, newoff, passres, misc;
-    int64_t packed_pitch = 0;
+    // per-batch device state: one context per pipeline slot + one for the plain (one batch at a time) entry points;
+    // `bc` is the context the next hrm_map_batch / hrm_verify_batch / SAM call works on
+    hrm::BatchCtx ctx[HRM_PIPE_SLOTS + 1];
+    hrm::BatchCtx* bc = &ctx[HRM_PIPE_SLOTS];
     unsigned long long touches_seen[3] = {0, 0, 0};
     hrm::StageTimer timer;
     int64_t value_budget = 1LL << 30; // candidate values retrieved per range of reads (int offsets, 8 B scratch each)
@@ -96,7 +108,8 @@ struct hrm_mapper {
     hrm_comm* comm = nullptr; // key-partitioned index (partition.cu); not owned
     // double-buffered end-to-end pipeline
     hrm::PipeSlot slot[HRM_PIPE_SLOTS];
-    cudaStream_t pipe_in = nullptr, pipe_out = nullptr;
+    cudaStream_t pipe_in = nullptr, pipe_out = nullptr, pipe_verify = nullptr;
+    int64_t* pipe_host = nullptr; // pinned: text sizes of the batches in flight
     bool pipe_ready = false;
 };
 
@@ -108,6 +121,13 @@ hrm_status mapper_pack_batch(hrm_mapper* m, const char* d_reads_ascii, int64_t a
 hrm_status sam_fields(hrm_mapper* m, const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
                       const char* d_cigars, int64_t cigar_pitch, uint32_t first_read_id, hrm_sam_fields* d_fields,
                       int32_t* d_line_len, int32_t* d_sq_len, cudaStream_t s);
+hrm_status sam_upload_names(hrm_mapper* m, const char* const* h_chrom_names, cudaStream_t s);
+// same as sam_text without the host round trip: offsets into d_off (n + 2 entries), the byte total into *h_total_pinned
+// when the stream gets there
+hrm_status sam_text_async(hrm_mapper* m, const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
+                          const char* d_cigars, int64_t cigar_pitch, const hrm_sam_fields* d_fields, const int32_t* d_len,
+                          uint32_t first_read_id, int part, char* d_out, int64_t cap, int64_t* d_off,
+                          int64_t* h_total_pinned, cudaStream_t s);
 hrm_status sam_text(hrm_mapper* m, const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
                     const char* d_cigars, int64_t cigar_pitch, const hrm_sam_fields* d_fields, const int32_t* d_len,
                     uint32_t first_read_id, int part, char* d_out, int64_t cap, int64_t* h_written, cudaStream_t s);

@@ -36,6 +36,11 @@ hrm_status ensure_device()
             if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
                 uint64_t thr = UINT64_MAX; // keep freed scratch cached in the pool
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+                // scratch freed on one stream must not be handed to another stream by making that stream WAIT for the
+                // free (the default policy): it would serialise the verification stream and the seeding stream of
+                // the staged pipeline.  Memory whose free has completed is still reused across streams.
+                int off = 0;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
             }
         });
     }

@@ -344,7 +344,14 @@ static unsigned sgrid(int64_t items, int per_block, int per_sm)
 using namespace hrm;
 
 // chromosome names on the device (uploaded when they change)
+namespace hrm {
+hrm_status sam_upload_names(hrm_mapper* m, const char* const* h_chrom_names, cudaStream_t s);
+}
 static hrm_status upload_names(hrm_mapper* m, const char* const* h_chrom_names, cudaStream_t s)
+{
+    return hrm::sam_upload_names(m, h_chrom_names, s);
+}
+hrm_status hrm::sam_upload_names(hrm_mapper* m, const char* const* h_chrom_names, cudaStream_t s)
 {
     std::string flat;
     std::vector<int32_t> off(1, 0);
@@ -372,9 +379,9 @@ static hrm_status make_src(hrm_mapper* m, const int32_t* d_lengths, const hrm_re
     S.VP.w = cfg.window_size;
     S.VP.mapper_type = cfg.mapper_type;
     for (int p = 0; p < cfg.num_passes; p++) {
-        HRM_REQUIRE(m->packed[cfg.read_conversion[p]].p != nullptr, "reads of the batch are not packed");
-        S.VP.pass[p].reads = m->packed[cfg.read_conversion[p]].as<uint32_t>();
-        S.VP.pass[p].read_pitch = m->packed_pitch;
+        HRM_REQUIRE(m->bc->packed[cfg.read_conversion[p]].p != nullptr, "reads of the batch are not packed");
+        S.VP.pass[p].reads = m->bc->packed[cfg.read_conversion[p]].as<uint32_t>();
+        S.VP.pass[p].read_pitch = m->bc->packed_pitch;
         S.VP.pass[p].G = m->genome[cfg.genome_conversion[p]]->dev();
         S.VP.pass[p].verify_conv = cfg.verify_conversion[p];
     }
@@ -399,6 +406,24 @@ hrm_status sam_fields(hrm_mapper* m, const int32_t* d_lengths, int64_t n, const 
     SamSrc S;
     HRM_TRY(make_src(m, d_lengths, d_records, d_cigars, cigar_pitch, first_read_id, S));
     HRM_LAUNCH(sam_fields_kernel, sgrid(n, 128, 16), 128, 0, s, S, n, d_fields, d_line_len, d_sq_len);
+    return HRM_OK;
+}
+
+hrm_status sam_text_async(hrm_mapper* m, const int32_t* d_lengths, int64_t n, const hrm_read_record* d_records,
+                          const char* d_cigars, int64_t cigar_pitch, const hrm_sam_fields* d_fields, const int32_t* d_len,
+                          uint32_t first_read_id, int part, char* d_out, int64_t cap, int64_t* d_off,
+                          int64_t* h_total_pinned, cudaStream_t s)
+{
+    *h_total_pinned = 0;
+    if (n == 0) return HRM_OK;
+    SamSrc S;
+    HRM_TRY(make_src(m, d_lengths, d_records, d_cigars, cigar_pitch, first_read_id, S));
+    HRM_TRY(exclusive_scan_i32_to_i64(d_len, d_off, n, d_off + n + 1, s));
+    if (part == HRM_SAM_SQ_LINES)
+        HRM_LAUNCH(sam_write_sq_kernel, sgrid(n, 128, 16), 128, 0, s, S, n, d_fields, d_off, d_out, cap);
+    else
+        HRM_LAUNCH(sam_write_kernel, sgrid(n, 8, 8), 256, 0, s, S, n, d_fields, d_off, d_out, cap);
+    HRM_CUDA(cudaMemcpyAsync(h_total_pinned, d_off + n + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     return HRM_OK;
 }
 

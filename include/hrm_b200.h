@@ -606,16 +606,24 @@ hrm_status hrm_mapper_map_reads_sam(hrm_mapper* m, const char* h_reads_ascii, in
  * one of HRM_PIPE_SLOTS slots:
  *   hrm_mapper_stage_reads  enqueues the H2D copy of a batch into a slot (returns at once; waits first if the slot's
  *                           previous results have not left the device yet);
- *   hrm_mapper_map_staged   runs seeding + filter + SHD + verification (+ V4 and the SAM text when h_rec_out != NULL)
- *                           of the staged batch on `stream` and enqueues the D2H copies of its results on a copy-out
- *                           stream (returns when the kernels are enqueued / the text size is known, not when the
- *                           copies have finished);
- *   hrm_mapper_finish       waits until the slot's results are in the host buffers; returns the text sizes.
- * Steady state:  stage(i+1) ; map_staged(i) ; finish(i-1)  -- copies of batches i+1 and i-1 run under the kernels of
- * batch i.  Host buffers should be pinned.  h_records / h_cigars / h_sq_out / h_rec_out may each be NULL. */
+ *   hrm_mapper_map_staged   runs seeding + filter + SHD + best window (K1..K5) of the staged batch on `stream` and queues
+ *                           its verification (K6/K7), V4 and -- when h_rec_out != NULL -- the SAM text behind it, and
+ *                           the D2H copies of records / CIGARs on a copy-out stream; returns when the seeding has
+ *                           run, not when the rest has finished (HRM_PIPE_OVERLAP=1: verification on a second stream,
+ *                           under the seeding of the next batch);
+ *   hrm_mapper_finish       waits until the slot's results are in the host buffers (copies the SAM text out, whose
+ *                           size is known only then); returns the text sizes.
+ * Steady state:  map_staged(i) ; finish(i-1) ; stage(i+1)  -- staging into a slot waits for the slot's previous batch,
+ * so the next batch is staged after the previous one was fetched.  Host buffers should be pinned.  h_records / h_cigars /
+ * h_sq_out / h_rec_out may each be NULL; with text, rec_cap >= n * (64 + longest chromosome name + cigar_pitch +
+ * window + ascii_pitch) and sq_cap >= n * 40 (the text is produced into device buffers of that bound). */
 #define HRM_PIPE_SLOTS 2
 hrm_status hrm_mapper_stage_reads(hrm_mapper* m, int slot, const char* h_reads_ascii, int64_t ascii_pitch,
                                   const int32_t* h_lengths, int64_t n);
+/* Same for reads that are ALREADY in device memory (no copy; they must stay valid until hrm_mapper_finish of the slot).
+ * max_length = an upper bound of the read lengths (<= ascii_pitch); ready_on = the stream that produced the buffers. */
+hrm_status hrm_mapper_stage_device(hrm_mapper* m, int slot, const char* d_reads_ascii, int64_t ascii_pitch,
+                                   const int32_t* d_lengths, int64_t n, int max_length, hrm_stream ready_on);
 /* Same as hrm_mapper_stage_reads from FASTQ / FASTA TEXT in host memory (whole records, < 2 GiB): H2D on the copy-in
  * stream, parsed on the device by hrm_ingest_reads (same arguments and semantics).  Blocks the calling thread until
  * the batch is parsed; to overlap it with hrm_mapper_map_staged of the other slot call it from a second host thread

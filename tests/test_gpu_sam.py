@@ -161,13 +161,20 @@ def test_staged_pipeline(cuda, port):
     mp.stageReads(0, batches[0][0], batches[0][1])
     sizes_out = [None] * len(batches)
     for i, (reads, lens, fid) in enumerate(batches):
-        if i + 1 < len(batches):
-            mp.stageReads((i + 1) % 2, batches[i + 1][0], batches[i + 1][1])
         o = outs[i]
         mp.mapStaged(i % 2, o["rec"], o["cig"], 128, fid, o["sq"], o["txt"])
         if i >= 1:
             sizes_out[i - 1] = mp.finish((i - 1) % 2)
+        if i + 1 < len(batches):
+            mp.stageReads((i + 1) % 2, batches[i + 1][0], batches[i + 1][1])
     sizes_out[-1] = mp.finish((len(batches) - 1) % 2)
+    # staging into a slot whose text was never fetched is refused
+    import hashreadmapper_b200 as hb
+    mp.stageReads(0, batches[0][0], batches[0][1])
+    mp.mapStaged(0, None, None, 128, 0, outs[0]["sq"], outs[0]["txt"])
+    with pytest.raises(hb.HrmError):
+        mp.stageReads(0, batches[0][0], batches[0][1])
+    assert mp.finish(0) == sizes_out[0]
     for i, (reads, lens, fid) in enumerate(batches):
         n = len(lens)
         sqw, recw = sizes_out[i]
@@ -217,15 +224,15 @@ def test_fastq_text_to_sam_text(cuda, port):
     stage(0)
     sizes = [None] * len(texts)
     for i in range(len(texts)):
+        if i >= 1:
+            sizes[i - 1] = mp.finish((i - 1) % 2)
         th = None
-        if i + 1 < len(texts):
+        if i + 1 < len(texts):  # parse the next batch (other slot, fetched above) while this one maps
             th = threading.Thread(target=stage, args=(i + 1,))
             th.start()
         mp.mapStaged(i % 2, None, None, 128, state["first"][i], outs[i]["sq"], outs[i]["txt"])
         if th is not None:
             th.join()
-        if i >= 1:
-            sizes[i - 1] = mp.finish((i - 1) % 2)
     sizes[-1] = mp.finish((len(texts) - 1) % 2)
     for i in range(len(texts)):
         assert outs[i]["sq"][:sizes[i][0]].tobytes() == exp[i][0], i
