@@ -658,11 +658,11 @@ def main():
                               "stays in the 126 MB L2; `frac_one_slot_per_lookup` counts one 16-B slot per lookup"}
     # the kernel with the largest share of the step: the fused collection (K3b value retrieval + K4)
     dom_stage = max(stage_ms, key=lambda k_: stage_ms[k_])
-    ids_step = float(st_collect["enumerated"])          # ids the collection kernels read and test, per step
-    ids_skipped_step = float(st_collect["skipped"])
+    ids_step = float(st_collect["enumerated"])          # ids inserted into the duplicate filter, per step
+    ids_skipped_step = float(st_collect["skipped"])     # ids of the two largest buckets: read and tested only
     coll_launches = max(stages["filter"][1] / args.steps, 1.0)
     coll_ms = stage_ms["filter"]
-    coll_bytes = 4.0 * ids_step + 8.0 * H_ * n * cfg.num_passes + 8.0 * n * cfg.num_passes
+    coll_bytes = 4.0 * (ids_step + ids_skipped_step) + 8.0 * H_ * n * cfg.num_passes + 8.0 * n * cfg.num_passes
     coll_ach = coll_bytes / (coll_ms / 1e3) / 1e9 if coll_ms > 0 else 0.0
     ctraffic = None
     tp2 = os.path.join(ROOT, "profiles", "collect_traffic.json")
@@ -671,18 +671,21 @@ def main():
             ctraffic = json.load(open(tp2)).get("dram_bytes_per_launch")
         except Exception:
             ctraffic = None
-    collect_roofline = {"kernel": "hrm::collect_bloom_kernel (+ the block kernel for skewed reads): K3b value retrieval + K4 "
-                                  "candidate collection, fused", "bound": "hbm", "achieved": coll_ach,
+    collect_roofline = {"kernel": "hrm::collect_dup_kernel<false> (warp per read; + <true>, block per read, for the ~2.5 % of "
+                                  "skewed reads): K3b value retrieval + K4 candidate collection, fused", "bound": "hbm",
+                        "achieved": coll_ach,
                         "peak": peak, "unit": "GB/s", "frac": coll_ach / peak, "traffic": ctraffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": coll_bytes / coll_launches, "launch_ms": coll_ms / coll_launches,
                         "launches_per_step": coll_launches, "share_of_step": coll_ms / serial_ms if serial_ms > 0 else None,
-                        "ids_enumerated_per_step": ids_step, "ids_skipped_per_step": ids_skipped_step,
-                        "frac_if_no_bucket_were_skipped": (4.0 * (ids_step + ids_skipped_step) / (coll_ms / 1e3) / 1e9 / peak)
-                        if coll_ms > 0 else None,
+                        "ids_inserted_per_step": ids_step, "ids_tested_per_step": ids_skipped_step,
+                        "frac_dram_side": (ctraffic / (coll_ms / coll_launches / 1e3) / 1e9 / peak)
+                        if (ctraffic and coll_ms > 0) else None,
                         "reads_to_block_kernel_per_step": float(st_collect["block_reads"]),
-                        "note": "algorithmic bytes = 4 B x ids enumerated + the 8-B (offset, count) bucket ranges of every "
-                                "(read, table) + the 8-B list header per read (DESIGN 3); launch_ms spans the kernels of one "
-                                "pass' collection (CUDA events on the launching stream)"}
+                        "note": "algorithmic bytes = 4 B x every id of every bucket a read touches (each is read exactly once: "
+                                "inserted into the duplicate filter or tested against it) + the 8-B (offset, count) range of "
+                                "every (read, table) + the 8-B list header per read (DESIGN 3); launch_ms spans the kernels of "
+                                "one pass' collection (CUDA events on the launching stream); traffic = ncu DRAM bytes of those "
+                                "kernels (profiles/collect_traffic.json)"}
     # `roofline` = the HBM-bound kernel with the largest share of the step (the fused collection on the replicated index);
     # verification (K7) is integer-ALU bound: its figures are reported beside it, not against the HBM peak
     roofline = collect_roofline if comm is None else probe_roofline

@@ -980,6 +980,10 @@ extern "C" hrm_status hrm_minhasher_deserialize(hrm_minhasher** out, const void*
     p += sizeof hd;
     HRM_REQUIRE(memcmp(hd.magic, "HRMB200", 8) == 0 && hd.version == 2, "bad magic/version");
     HRM_REQUIRE(hd.H >= 0 && hd.H <= MAX_TABLES, "bad table count");
+    // counts from the image are bounded by the image before anything is sized from them
+    HRM_REQUIRE(hd.values_count >= 0 && hd.values_count <= (size - (int64_t)sizeof(SerHeader)) / 4 && hd.inserted >= 0 &&
+                    size >= (int64_t)sizeof(SerHeader) + 16LL * hd.H,
+                "bad counts");
     hrm_minhasher* mh = nullptr;
     HRM_TRY(hrm_minhasher_create(&mh, hd.inserted, hd.max_results, hd.k, hd.load));
     mh->H = hd.H;
@@ -994,11 +998,32 @@ extern "C" hrm_status hrm_minhasher_deserialize(hrm_minhasher** out, const void*
         p += 8;
         memcpy(&mh->nkeys[j], p, 8);
         p += 8;
+        if (mh->nbuckets[j] < 0 || mh->nbuckets[j] > (size - need) / BUCKET_BYTES || mh->nkeys[j] < 0) {
+            need = INT64_MAX;
+            break;
+        }
         need += mh->nbuckets[j] * BUCKET_BYTES;
     }
-    if (size < need) {
+    // every slot's value range must lie inside the value array: a corrupt image must not turn into out-of-bounds
+    // device reads at probe time
+    if (need != INT64_MAX && size >= need) {
+        const char* sp = p + hd.values_count * 4;
+        for (int j = 0; j < hd.H && need != INT64_MAX; j++) {
+            const int64_t nslots = mh->nbuckets[j] * BUCKET_SLOTS;
+            for (int64_t i = 0; i < nslots; i++) {
+                Slot sl;
+                memcpy(&sl, sp + i * (int64_t)sizeof(Slot), sizeof sl);
+                if (sl.key != SLOT_EMPTY && (uint64_t)sl.off + sl.cnt > (uint64_t)hd.values_count) {
+                    need = INT64_MAX;
+                    break;
+                }
+            }
+            sp += mh->nbuckets[j] * BUCKET_BYTES;
+        }
+    }
+    if (need == INT64_MAX || size < need) {
         hrm_minhasher_destroy(mh);
-        set_error("truncated minhasher image");
+        set_error("truncated or corrupt minhasher image");
         return HRM_ERR_INVALID;
     }
     cudaError_t e = cudaMalloc(&mh->values, (size_t)(hd.values_count > 0 ? hd.values_count : 1) * 4);
@@ -1187,14 +1212,15 @@ extern "C" hrm_status hrm_minhasher_read_reference_format(hrm_minhasher** out, c
     for (int j = 0; j < H; j++) {
         uint64_t nvals = 0, numKeys = 0, maxProbes = 0, sz = 0, cap = 0, elements = 0;
         float tl = 0.f;
-        HRM_REQUIRE(get(p, end, nvals) && (uint64_t)(end - p) >= nvals * 4, "truncated values");
+        // sizes from the file are bounded by what is left of it BEFORE they are multiplied (no wrap-around)
+        HRM_REQUIRE(get(p, end, nvals) && nvals <= (uint64_t)(end - p) / 4, "truncated values");
         ext[j].vals = (const uint32_t*)p;
         ext[j].nvals = nvals;
         p += nvals * 4;
         HRM_REQUIRE(get(p, end, tl) && get(p, end, numKeys) && get(p, end, maxProbes) && get(p, end, sz) &&
                         get(p, end, cap) && get(p, end, elements),
                     "truncated table header");
-        HRM_REQUIRE((uint64_t)(end - p) >= elements * sizeof(RefSlot), "truncated table storage");
+        HRM_REQUIRE(elements <= (uint64_t)(end - p) / sizeof(RefSlot), "truncated table storage");
         ext[j].storage = (const RefSlot*)p;
         ext[j].elements = elements;
         p += elements * sizeof(RefSlot);
@@ -1229,7 +1255,7 @@ extern "C" hrm_status hrm_minhasher_read_reference_format(hrm_minhasher** out, c
             RefSlot s;
             memcpy(&s, ext[j].storage + i, sizeof s);
             if (s.key == ~0ULL && s.off == 0u && s.cnt == 0) continue; // ref: emptySlot cpuhashtable.hpp:277-278
-            if ((uint64_t)s.off + s.cnt > ext[j].nvals) {
+            if (s.key == SLOT_EMPTY || (uint64_t)s.off + s.cnt > ext[j].nvals) { // ~0 is the device table's empty marker
                 cudaFree(d_err);
                 hrm_minhasher_destroy(mh);
                 set_error("read_reference_format: value range of a key exceeds the value array");

@@ -150,11 +150,38 @@ extern "C" void hrm_mapper_destroy(hrm_mapper* m)
     delete m;
 }
 
+static hrm_status set_genome_impl(hrm_mapper* m, const char* h_ascii, const int64_t* h_chrom_offsets, int n_chrom,
+                                  hrm_stream stream);
+
 extern "C" hrm_status hrm_mapper_set_genome(hrm_mapper* m, const char* h_ascii, const int64_t* h_chrom_offsets,
                                             int n_chrom, hrm_stream stream)
 {
     HRM_REQUIRE(m != nullptr && h_ascii != nullptr && h_chrom_offsets != nullptr && n_chrom >= 1, "args");
-    HRM_REQUIRE(m->genome[0] == nullptr && m->genome[1] == nullptr && m->genome[2] == nullptr, "genome already set");
+    HRM_REQUIRE(m->d_win_prefix == nullptr && m->genome[0] == nullptr && m->genome[1] == nullptr && m->genome[2] == nullptr,
+                "genome already set");
+    const hrm_status st = set_genome_impl(m, h_ascii, h_chrom_offsets, n_chrom, stream);
+    if (st != HRM_OK) { // nothing half-built stays behind: the mapper is as it was before the call and may be retried
+        cudaStreamSynchronize(as_stream(stream));
+        for (int c = 0; c < 3; c++) {
+            if (m->index[c]) hrm_minhasher_destroy(m->index[c]);
+            if (m->genome[c]) hrm_genome_destroy(m->genome[c]);
+            m->index[c] = nullptr;
+            m->genome[c] = nullptr;
+            m->index_handle[c] = -1;
+        }
+        if (m->d_win_prefix) cudaFree(m->d_win_prefix);
+        m->d_win_prefix = nullptr;
+        m->num_windows = 0;
+        m->n_chrom = 0;
+        m->chrom_len.clear();
+        m->chrom_off.clear();
+    }
+    return st;
+}
+
+static hrm_status set_genome_impl(hrm_mapper* m, const char* h_ascii, const int64_t* h_chrom_offsets, int n_chrom,
+                                  hrm_stream stream)
+{
     cudaStream_t s = as_stream(stream);
     const hrm_mapper_config& cfg = m->cfg;
     m->n_chrom = n_chrom;
@@ -608,6 +635,18 @@ extern "C" hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_as
                                  cudaMemcpyHostToDevice, cs));
         HRM_CUDA(cudaEventRecord(m->copy_events[2 * c], cs));
     }
+    // on an error nothing may stay in flight on the copy stream when the scratch buffers die (they are freed on `s`)
+    struct Drain {
+        cudaStream_t a, b;
+        bool armed = true;
+        ~Drain()
+        {
+            if (armed) {
+                cudaStreamSynchronize(a);
+                cudaStreamSynchronize(b);
+            }
+        }
+    } drain{cs, s};
     for (int c = 0; c < nchunks; c++) {
         const int64_t lo = (int64_t)c * chunk, cnt = (n - lo) < chunk ? (n - lo) : chunk;
         HRM_CUDA(cudaStreamWaitEvent(s, m->copy_events[2 * c], 0));
@@ -635,6 +674,7 @@ extern "C" hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_as
     }
     HRM_CUDA(cudaStreamSynchronize(cs));
     HRM_CUDA(cudaStreamSynchronize(s));
+    drain.armed = false;
     if (h_stats) *h_stats = st;
     return HRM_OK;
 }
