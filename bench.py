@@ -349,6 +349,7 @@ def main():
                     help="reads of the timed batch compared with the oracle after the timed region (0: off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text", action="store_true", help="skip the SAM-text end-to-end figure")
+    ap.add_argument("--no-fastq", action="store_true", help="skip the FASTQ-text-in figure")
     ap.add_argument("--no-partitioned-segment", action="store_true",
                     help="N > 1: skip the short key-partitioned-index segment appended to the replicated run")
     ap.add_argument("--partitioned-sample", type=int, default=500_000, help="reads per GPU of that segment")
@@ -567,6 +568,55 @@ def main():
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(sqw + recw),
                     "sam_bytes_per_read": float(sqw + recw) / n,
                     "api": "hrm_mapper_stage_reads / hrm_mapper_map_staged (V4 + SAM text on the device) / hrm_mapper_finish"}
+        # ---- FASTQ text in -> SAM text out: the text goes H2D and is parsed by the device-side reader (hrm_ingest_reads)
+        # from a second host thread while the other slot maps ("FASTQ-in-memory -> SAM-records-in-memory")
+        e2e_fastq = None
+        if not args.no_fastq:
+            import threading
+            L_ = args.read_len
+            hdr = 11  # "@%09d\n"
+            rec_len = hdr + L_ + 3 + L_ + 1
+            fq = torch.empty((n, rec_len), dtype=torch.uint8).pin_memory()
+            fqn = fq.numpy()
+            ids = np.arange(n, dtype=np.int64)
+            fqn[:, 0] = ord("@")
+            for d_ in range(9):
+                fqn[:, 9 - d_] = (ids // (10 ** d_)) % 10 + ord("0")
+            fqn[:, 10] = 10
+            fqn[:, hdr:hdr + L_] = reads[:, :L_]
+            fqn[:, hdr + L_:hdr + L_ + 3] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+            fqn[:, hdr + L_ + 3:hdr + 2 * L_ + 3] = ord("I")
+            fqn[:, rec_len - 1] = 10
+            fq_flat = fqn.reshape(-1)
+            pitch_ = reads.shape[1]
+
+            def fastq_run(steps):
+                mp.stageFastq(0, fq_flat, pitch_, n, 0, 0)
+                sizes = (0, 0)
+                for i in range(steps):
+                    if i >= 1:
+                        sizes = mp.finish((i - 1) % 2)
+                    th = None
+                    if i + 1 < steps:
+                        th = threading.Thread(target=mp.stageFastq, args=((i + 1) % 2, fq_flat, pitch_, n, (i + 1) * n, 0))
+                        th.start()
+                    mp.mapStaged(i % 2, None, None, 128, i * n, tx_sq[i % 2], tx_rec[i % 2])
+                    if th is not None:
+                        th.join()
+                return mp.finish((steps - 1) % 2)
+
+            fastq_run(2)
+            barrier()
+            t0 = time.perf_counter()
+            sqw2, recw2 = fastq_run(args.steps)
+            torch.cuda.synchronize()
+            fq_s = parallel.max_over_ranks(time.perf_counter() - t0)
+            e2e_fastq = {"value": world * n * args.steps / fq_s, "unit": "reads/s", "h2d_bytes_per_step": int(fq_flat.size),
+                         "d2h_bytes_per_step": int(sqw2 + recw2),
+                         "api": "hrm_mapper_stage_fastq (H2D of the FASTQ text + device-side reader, second host thread) / "
+                                "hrm_mapper_map_staged (SAM text on the device) / hrm_mapper_finish"}
+            del fq, fqn, fq_flat
+        e2e_text["from_fastq_text"] = e2e_fastq
         del tx_rec, tx_sq
     clocks = sampler.stop() if rank == 0 else None
 
