@@ -553,11 +553,18 @@ def main():
     oneshot_value = world * n * max(1, args.steps // 2) / parallel.max_over_ranks(time.perf_counter() - t0)
     # ---- end to end with TEXT out: reads in -> SAM text (V4 + O1 on the device) out, same pipeline ----------------
     e2e_text = None
+    text_ok = 0.0
     if comm is None and not args.no_text:
         del h_rec, h_cig, rec_np
         line_bound = 96 + 128 + W_ + reads.shape[1]
-        tx_rec = [torch.empty((n * line_bound,), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
-        tx_sq = [torch.empty((n * 40,), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+        try:  # ~4.4 GB of pinned host memory per rank: every rank must get it, or all skip the figure together
+            tx_rec = [torch.empty((n * line_bound,), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+            tx_sq = [torch.empty((n * 40,), dtype=torch.uint8).pin_memory().numpy() for _ in range(2)]
+            text_ok = 1.0
+        except Exception:
+            text_ok = 0.0
+        text_ok = -parallel.max_over_ranks(-text_ok)
+    if text_ok == 1.0:
         e2e_run(2, (tx_sq, tx_rec))
         barrier()
         t0 = time.perf_counter()

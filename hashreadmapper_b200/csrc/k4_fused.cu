@@ -1099,7 +1099,7 @@ hrm_status collect_candidates_from(const uint2* d_ranges, int64_t rq, int64_t rt
     const int bblock_env = env_int("HRM_COLLECT_BLOOM_BLOCK_WORDS", 8192);
     int bblock_words = 64;
     while (bblock_words < bblock_env && bblock_words < 32768) bblock_words <<= 1;
-    const int xwarp_env = env_int("HRM_COLLECT_XSLOTS", 1024), xblock_env = env_int("HRM_COLLECT_BLOCK_XSLOTS", 4096);
+    const int xwarp_env = env_int("HRM_COLLECT_XSLOTS", 512), xblock_env = env_int("HRM_COLLECT_BLOCK_XSLOTS", 4096);
     int xwarp = 256, xblock = 2048; // the table keeps a quarter of its slots free: more than one slot per thread
     while (xwarp < xwarp_env && xwarp < 4096) xwarp <<= 1;
     while (xblock < xblock_env && xblock < 8192) xblock <<= 1;
