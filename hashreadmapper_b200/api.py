@@ -91,7 +91,7 @@ class Minhasher:
     def __del__(self):
         if getattr(self, "h", None) and self.h.value:
             self.lib.hrm_minhasher_destroy(self.h)
-            self.h = C.c_void_p()
+            self.h = None  # (module globals may be gone at interpreter exit)
 
     def addHashTables(self, n, hash_function_ids=None):
         ids = None
@@ -270,7 +270,7 @@ class ReadStorage:
     def __del__(self):
         if getattr(self, "h", None) and self.h.value:
             self.lib.hrm_readstore_destroy(self.h)
-            self.h = C.c_void_p()
+            self.h = None  # (module globals may be gone at interpreter exit)
 
     def makeHandle(self):
         return self.lib.hrm_readstore_handle_create(self.h)
@@ -361,7 +361,7 @@ class Genome:
     def __del__(self):
         if getattr(self, "h", None) and self.h.value:
             self.lib.hrm_genome_destroy(self.h)
-            self.h = C.c_void_p()
+            self.h = None  # (module globals may be gone at interpreter exit)
 
     def numChromosomes(self):
         return self.lib.hrm_genome_num_chromosomes(self.h)
@@ -509,7 +509,7 @@ class Comm:
     def __del__(self):
         if getattr(self, "h", None) and self.h.value:
             self.lib.hrm_comm_destroy(self.h)
-            self.h = C.c_void_p()
+            self.h = None  # (module globals may be gone at interpreter exit)
 
 
 def key_owner(key, world):
@@ -528,7 +528,7 @@ class Mapper:
     def __del__(self):
         if getattr(self, "h", None) and self.h.value:
             self.lib.hrm_mapper_destroy(self.h)
-            self.h = C.c_void_p()
+            self.h = None  # (module globals may be gone at interpreter exit)
 
     def setGenome(self, ascii: bytes, chrom_offsets, chrom_names=None):
         off = np.ascontiguousarray(chrom_offsets, dtype=np.int64)

@@ -469,6 +469,7 @@ constexpr int DUP_BTHREADS = 256;  // threads of the block variant
 // events are queued and handled by all lanes together; a queue holds one iteration's worth of ids (every id an event)
 constexpr int DUP_WQ = 32 * 4 * DUP_MLP;           // warp: 512 entries
 constexpr int DUP_BQ = DUP_BTHREADS * 4 * DUP_MLP; // block: 4096 entries
+constexpr uint32_t DUP_PAD = 0xFFFFFF00u;          // padding ids (window ids are < 2^26 here: id << 6 | count)
 
 __host__ __device__ inline size_t dup_slice_words(int words, int xslots, int qcap, int H)
 {
@@ -485,6 +486,10 @@ __device__ __forceinline__ void dup_hash(uint32_t id, int shift, uint32_t& word,
     mask = (1u << (h & 31u)) | (1u << ((h >> 5) & 31u)) | (1u << ((h >> 10) & 31u));
 }
 
+// Measured and dropped (4 M reads, human-size index; this form: 96 ms per step): two bits per id instead of three
+// (99 ms: more false events); events compacted with a warp ballot instead of one atomic on the queue tail (103 ms); one
+// queue per thread, applied by the thread itself (136 ms: duplicates come in runs, a few lanes hold most events); one
+// copy of the streaming loop per phase (+5 ms: the kernel is ~45 KB of instructions); two loads in flight (103 ms).
 template <bool BLOCK>
 __global__ void __launch_bounds__(BLOCK ? DUP_BTHREADS : COLLECT_THREADS) collect_dup_kernel(CollectParams P)
 {
@@ -503,12 +508,12 @@ __global__ void __launch_bounds__(BLOCK ? DUP_BTHREADS : COLLECT_THREADS) collec
     uint32_t* q = xt + XS;                        // [QCAP] queued events of phases 1 / 2; afterwards:
     uint32_t* fin = q;                            //   [FINCAP] survivors
     uint32_t* amb = q + FINCAP;                   //   [FINCAP] ambiguous ids (their exact counts reuse the bitmap)
-    uint32_t* offv = q + QCAP;                    // [H]
-    int* cntv = reinterpret_cast<int*>(offv + H); // [H]
-    int* skipf = cntv + H;                        // [H]
-    int* cpre = skipf + H;                        // [H + 1] 16-byte chunks of the enumerated buckets (flat prefix)
-    int* cpre2 = cpre + H + 1;                    // [H + 1] ... of the largest buckets
-    int* sc = cpre2 + H + 1;                      // 0 distinct ids in xt, 1 bad, 2 nfin, 3 namb, 4 E, 5 SK, 6 total, 7 start, 8 queue tail
+    // bucket records, one 16-byte load each: .x / .y = END of the bucket in the flat sequence of 16-byte chunks of
+    // phase 1 (enumerated buckets) / phase 2 (largest buckets) -- a bucket that is not part of a phase ends where its
+    // predecessor ends --, .z = offset of its first id, .w = number of ids
+    uint4* rec = reinterpret_cast<uint4*>(q + QCAP); // [H]
+    int* sc = reinterpret_cast<int*>(rec + H);       // 0 distinct ids in xt, 1 bad, 2 nfin, 3 namb, 4 E, 5 SK, 6 total, 7 start,
+                                                     // 8 queue tail, 9 work item, 10 / 11 chunks of phase 1 / 2
     const uint32_t xmask = (uint32_t)XS - 1u;
     int xshift = 32;
     for (int x = XS; x > 1; x >>= 1) xshift--;
@@ -564,25 +569,13 @@ __global__ void __launch_bounds__(BLOCK ? DUP_BTHREADS : COLLECT_THREADS) collec
             }
             const int t1a = __shfl_sync(0xffffffffu, i1a, 31), t2a = __shfl_sync(0xffffffffu, i2a, 31);
             const int t1b = __shfl_sync(0xffffffffu, i1b, 31), t2b = __shfl_sync(0xffffffffu, i2b, 31);
-            if (ta < H) {
-                offv[ta] = ra.x;
-                cntv[ta] = (int)ra.y;
-                skipf[ta] = sa;
-                cpre[ta] = i1a - v1a;
-                cpre2[ta] = i2a - v2a;
-            }
-            if (tb < H) {
-                offv[tb] = rb.x;
-                cntv[tb] = (int)rb.y;
-                skipf[tb] = sb;
-                cpre[tb] = t1a + i1b - v1b;
-                cpre2[tb] = t2a + i2b - v2b;
-            }
+            if (ta < H) rec[ta] = make_uint4((uint32_t)i1a, (uint32_t)i2a, ra.x, ra.y);
+            if (tb < H) rec[tb] = make_uint4((uint32_t)(t1a + i1b), (uint32_t)(t2a + i2b), rb.x, rb.y);
             const unsigned ea = sa ? 0u : ra.y, eb = sb ? 0u : rb.y, ka2 = sa ? ra.y : 0u, kb2 = sb ? rb.y : 0u;
             const unsigned E = __reduce_add_sync(0xffffffffu, ea + eb), SK = __reduce_add_sync(0xffffffffu, ka2 + kb2);
             if (lane == 0) {
-                cpre[H] = t1a + t1b;
-                cpre2[H] = t2a + t2b;
+                sc[10] = t1a + t1b;
+                sc[11] = t2a + t2b;
                 sc[0] = 0;
                 sc[1] = 0;
                 sc[2] = 0;
@@ -623,16 +616,14 @@ __global__ void __launch_bounds__(BLOCK ? DUP_BTHREADS : COLLECT_THREADS) collec
         }
         gsync();
         // queued events -> exact table, all lanes busy.  phase 0: insert / count; phase 1: count where present
-        auto drain = [&](int phase) {
-            gsync();
-            const int nq = sc[8];
-            for (int i = tid; i < nq; i += nthr) {
-                const uint32_t id = q[i];
+        auto apply = [&](uint32_t id, int phase) {
+            {
+                if (id >= DUP_PAD) return; // padding of a bucket's first / last 16-byte chunk
                 uint32_t hh = collect_hash(id) >> xshift;
                 if (phase == 0) {
                     if (sc[0] >= xcap) { // the exact table is full: a bigger one takes the read
                         sc[1] = 1;
-                        continue;
+                        return;
                     }
                     while (true) {
                         uint32_t cur = xt[hh];
@@ -661,59 +652,75 @@ __global__ void __launch_bounds__(BLOCK ? DUP_BTHREADS : COLLECT_THREADS) collec
                     }
                 }
             }
+        };
+        auto drain = [&](int phase) {
+            gsync();
+            const int nq = sc[8];
+            for (int i = tid; i < nq; i += nthr) apply(q[i], phase);
             gsync();
             if (tid == 0) sc[8] = 0;
             gsync();
         };
-        // phases 1 and 2: the same streaming loop over a flat sequence of 16-byte chunks
+        // phases 1 and 2: the same streaming loop over a flat sequence of 16-byte chunks (one copy of the code: the
+        // compiler switches on the phase around the ids of an iteration)
 #pragma unroll 1
         for (int phase = 0; phase < 2; phase++) {
-            const int* cp = phase == 0 ? cpre : cpre2;
-            const int ctotal = cp[H];
-            int tcur = 0, cnext = 0;
-            int64_t cbase = 0;       // chunk c of the current bucket lies at vals4[cbase + c]
-            uint32_t lo = 0, hi = 0; // element range of the current bucket
+            const int ctotal = sc[10 + phase];
+            int tnext = 0, cfirst = 0, cnext = 0; // the lane's current bucket holds the chunks [cfirst, cnext)
+            uint32_t lo = 0u, hi = 0u;            // its element range
+            uint32_t cbase = 0u;                  // chunk c of it lies at vals4[cbase + c] (offsets are 32 bit)
             for (int c0 = 0; c0 < ctotal; c0 += nthr * DUP_MLP) {
                 uint4 v[DUP_MLP];
-                uint32_t e0[DUP_MLP], vlo[DUP_MLP], vhi[DUP_MLP];
+                uint32_t inv = 0u; // nibble u: the elements of v[u] that are not ids of this read
 #pragma unroll
                 for (int u = 0; u < DUP_MLP; u++) {
                     const int c = c0 + u * nthr + tid;
-                    vlo[u] = 1u;
-                    vhi[u] = 0u; // nothing valid
-                    e0[u] = 0u;
-                    v[u] = make_uint4(0u, 0u, 0u, 0u);
                     if (c < ctotal) {
                         if (c >= cnext) {
-                            while (cp[tcur + 1] <= c) tcur++;
-                            cnext = cp[tcur + 1];
-                            lo = offv[tcur];
-                            hi = lo + (uint32_t)cntv[tcur];
-                            cbase = (int64_t)(lo >> 2) - cp[tcur];
+                            uint4 r;
+                            int end = cnext;
+                            do {
+                                cfirst = end;
+                                r = rec[tnext++];
+                                end = (int)(phase == 0 ? r.x : r.y);
+                            } while (end <= c);
+                            cnext = end;
+                            lo = r.z;
+                            hi = r.z + r.w;
+                            cbase = (lo >> 2) - (uint32_t)cfirst;
                         }
-                        v[u] = __ldg(vals4 + cbase + c);
-                        e0[u] = (uint32_t)((cbase + c) << 2);
-                        vlo[u] = lo;
-                        vhi[u] = hi;
+                        v[u] = __ldg(vals4 + (cbase + (uint32_t)c));
+                        if (c == cfirst || c + 1 == cnext) { // a bucket begins / ends inside its first / last chunk
+                            uint32_t nb = c == cfirst ? (1u << (lo & 3u)) - 1u : 0u;
+                            if (c + 1 == cnext && (hi & 3u) != 0u) nb |= (0xFu << (hi & 3u)) & 0xFu;
+                            inv |= nb << (4 * u);
+                        }
+                    } else {
+                        v[u] = make_uint4(0u, 0u, 0u, 0u);
+                        inv |= 0xFu << (4 * u);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < DUP_MLP; u++) {
-                    const uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                    uint32_t x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                    const uint32_t nb = (inv >> (4 * u)) & 0xFu;
+                    if (nb != 0u) {
+                        if (nb == 0xFu) continue; // past the end of the sequence
+                        // foreign elements become padding ids (distinct per lane and element: distinct bitmap words);
+                        // they go through the filter like ids and are dropped when the queue is drained
+                        const uint32_t pad = DUP_PAD | ((uint32_t)lane << 2);
+                        if (nb & 1u) x[0] = pad;
+                        if (nb & 2u) x[1] = pad | 1u;
+                        if (nb & 4u) x[2] = pad | 2u;
+                        if (nb & 8u) x[3] = pad | 3u;
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint32_t e = e0[u] + j;
-                        const bool valid = e >= vlo[u] && e < vhi[u];
                         uint32_t word, mask;
                         dup_hash(x[j], shift, word, mask);
                         bool ev;
-                        if (phase == 0) {
-                            // invalid lanes OR nothing into the word: no branch around the atomic
-                            const uint32_t old = atomicOr(&bm[valid ? word : (uint32_t)lane], valid ? mask : 0u);
-                            ev = valid && (old & mask) == mask;
-                        } else {
-                            ev = valid && (bm[word] & mask) == mask;
-                        }
+                        if (phase == 0) ev = (atomicOr(&bm[word], mask) & mask) == mask;
+                        else ev = (bm[word] & mask) == mask;
                         if (ev) q[atomicAdd(&sc[8], 1)] = x[j];
                     }
                 }
@@ -762,10 +769,10 @@ __global__ void __launch_bounds__(BLOCK ? DUP_BTHREADS : COLLECT_THREADS) collec
                 gsync();
                 for (int x = tid; x < namb * H; x += nthr) { // exact multiplicity over all H buckets
                     const int c = x / H, t = x - c * H;
-                    const int cnt = cntv[t];
+                    const int cnt = (int)rec[t].w;
                     if (cnt > 0) {
                         const uint32_t id = amb[c];
-                        const uint32_t* p = P.table_values + offv[t];
+                        const uint32_t* p = P.table_values + rec[t].z;
                         const int pos = collect_lower_bound_interp(p, cnt, id, P.id_space);
                         if (pos < cnt && __ldg(p + pos) == id) atomicAdd(&acnt[c], 1u);
                     }
@@ -1118,18 +1125,20 @@ hrm_status collect_candidates_from(const uint2* d_ranges, int64_t rq, int64_t rt
     if (!impl_ranges && packed) {
         P.warp_slots = bwords;
         P.slots = bblock_words;
+        auto wkern = collect_dup_kernel<false>;
+        auto bkern = collect_dup_kernel<true>;
         const size_t bsmem = sizeof(uint32_t) * dup_slice_words(bwords, xwarp, DUP_WQ, H) * (wthreads / 32);
-        cudaFuncSetAttribute(collect_dup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
-        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wres, collect_dup_kernel<false>, wthreads, bsmem));
+        cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wres, wkern, wthreads, bsmem));
         const int wcap = env_int("HRM_COLLECT_BLOCKS_PER_SM", 0);
         if (wcap > 0 && wres > wcap) wres = wcap;
-        HRM_LAUNCH(collect_dup_kernel<false>, (unsigned)(num_sms() * (wres > 0 ? wres : 1)), wthreads, bsmem, s, P);
+        HRM_LAUNCH(wkern, (unsigned)(num_sms() * (wres > 0 ? wres : 1)), wthreads, bsmem, s, P);
         // skewed reads: the same scheme block-wide, then (what is left) the counting-table kernel on big2_list
         const size_t bbsmem = sizeof(uint32_t) * dup_slice_words(bblock_words, xblock, DUP_BQ, H);
         int bres = 1;
-        cudaFuncSetAttribute(collect_dup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bbsmem);
-        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bres, collect_dup_kernel<true>, DUP_BTHREADS, bbsmem));
-        HRM_LAUNCH(collect_dup_kernel<true>, (unsigned)(num_sms() * (bres > 0 ? bres : 1)), DUP_BTHREADS, bbsmem, s, P);
+        cudaFuncSetAttribute(bkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bbsmem);
+        HRM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bres, bkern, DUP_BTHREADS, bbsmem));
+        HRM_LAUNCH(bkern, (unsigned)(num_sms() * (bres > 0 ? bres : 1)), DUP_BTHREADS, bbsmem, s, P);
         P.slots = slots;
         CollectParams PC = P;
         PC.big_count = P.big2_count;
