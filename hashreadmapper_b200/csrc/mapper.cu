@@ -70,6 +70,16 @@ static unsigned mgrid(int64_t items)
 
 using namespace hrm;
 
+// A mapper belongs to one device.  Staging threads (hrm_mapper_stage_* are meant to be called from a second host thread)
+// start with device 0 current, so every entry point binds the calling thread to the mapper's device first.
+static hrm_status bind_device(const hrm_mapper* m)
+{
+    int cur = -1;
+    HRM_CUDA(cudaGetDevice(&cur));
+    if (cur != m->device) HRM_CUDA(cudaSetDevice(m->device));
+    return HRM_OK;
+}
+
 extern "C" void hrm_mapper_default_config(hrm_mapper_config* cfg)
 {
     if (!cfg) return;
@@ -106,8 +116,11 @@ extern "C" hrm_status hrm_mapper_create(hrm_mapper** out, const hrm_mapper_confi
         HRM_REQUIRE(cfg->genome_conversion[p] >= 0 && cfg->genome_conversion[p] <= 2, "genome_conversion");
         HRM_REQUIRE(cfg->verify_conversion[p] >= 0 && cfg->verify_conversion[p] <= 2, "verify_conversion");
     }
+    int dev = 0;
+    HRM_CUDA(cudaGetDevice(&dev));
     auto* m = new hrm_mapper;
     m->cfg = *cfg;
+    m->device = dev;
     if (const char* pc = getenv("HRM_PART_CHUNK")) { // test hook: chunked collective query at small sizes
         const long long v = atoll(pc);
         if (v > 0) m->part_chunk = v;
@@ -128,6 +141,7 @@ extern "C" hrm_status hrm_mapper_create(hrm_mapper** out, const hrm_mapper_confi
 extern "C" void hrm_mapper_destroy(hrm_mapper* m)
 {
     if (!m) return;
+    bind_device(m);
     for (int c = 0; c < 3; c++) {
         if (m->index[c]) hrm_minhasher_destroy(m->index[c]);
         if (m->genome[c]) hrm_genome_destroy(m->genome[c]);
@@ -157,6 +171,7 @@ extern "C" hrm_status hrm_mapper_set_genome(hrm_mapper* m, const char* h_ascii, 
                                             int n_chrom, hrm_stream stream)
 {
     HRM_REQUIRE(m != nullptr && h_ascii != nullptr && h_chrom_offsets != nullptr && n_chrom >= 1, "args");
+    HRM_TRY(bind_device(m));
     HRM_REQUIRE(m->d_win_prefix == nullptr && m->genome[0] == nullptr && m->genome[1] == nullptr && m->genome[2] == nullptr,
                 "genome already set");
     const hrm_status st = set_genome_impl(m, h_ascii, h_chrom_offsets, n_chrom, stream);
@@ -595,6 +610,7 @@ extern "C" hrm_status hrm_mapper_map_reads(hrm_mapper* m, const char* h_reads_as
                                            hrm_stream stream)
 {
     HRM_REQUIRE(m != nullptr && h_reads_ascii != nullptr && h_lengths != nullptr && h_records != nullptr, "args");
+    HRM_TRY(bind_device(m));
     HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && cigar_pitch > 0, "sizes");
     cudaStream_t s = as_stream(stream);
     if (n == 0) {
@@ -690,6 +706,7 @@ extern "C" hrm_status hrm_mapper_map_reads_sam(hrm_mapper* m, const char* h_read
                                                int64_t cigar_pitch, hrm_batch_stats* h_stats, hrm_stream stream)
 {
     HRM_REQUIRE(m != nullptr && h_reads_ascii != nullptr && h_lengths != nullptr && h_rec_written != nullptr, "args");
+    HRM_TRY(bind_device(m));
     HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && cigar_pitch > 0, "sizes");
     HRM_REQUIRE(m->comm == nullptr, "hrm_mapper_map_reads_sam runs on the replicated index");
     cudaStream_t s = as_stream(stream);
@@ -792,6 +809,7 @@ extern "C" hrm_status hrm_mapper_stage_reads(hrm_mapper* m, int slot, const char
                                              const int32_t* h_lengths, int64_t n)
 {
     HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
+    HRM_TRY(bind_device(m));
     HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0, "sizes");
     HRM_REQUIRE(n == 0 || (h_reads_ascii != nullptr && h_lengths != nullptr), "buffers");
     HRM_REQUIRE(m->comm == nullptr, "the staged pipeline runs on the replicated index");
@@ -820,6 +838,7 @@ extern "C" hrm_status hrm_mapper_stage_device(hrm_mapper* m, int slot, const cha
                                               const int32_t* d_lengths, int64_t n, int max_length, hrm_stream ready_on)
 {
     HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
+    HRM_TRY(bind_device(m));
     HRM_REQUIRE(n >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && max_length >= 0 && max_length <= ascii_pitch, "sizes");
     HRM_REQUIRE(n == 0 || (d_reads_ascii != nullptr && d_lengths != nullptr), "buffers");
     HRM_REQUIRE(m->comm == nullptr, "the staged pipeline runs on the replicated index");
@@ -845,6 +864,7 @@ extern "C" hrm_status hrm_mapper_stage_fastq(hrm_mapper* m, int slot, const char
                                              int64_t max_reads, int64_t* h_num_reads, int32_t* h_carry_replaced_out)
 {
     HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
+    HRM_TRY(bind_device(m));
     HRM_REQUIRE(nbytes >= 0 && ascii_pitch > 0 && ascii_pitch % 16 == 0 && max_reads >= 0 && h_num_reads != nullptr, "sizes");
     HRM_REQUIRE(nbytes == 0 || h_text != nullptr, "text");
     HRM_REQUIRE(m->comm == nullptr, "the staged pipeline runs on the replicated index");
@@ -877,6 +897,7 @@ extern "C" hrm_status hrm_mapper_map_staged(hrm_mapper* m, int slot, hrm_read_re
                                             char* h_rec_out, int64_t rec_cap, hrm_batch_stats* h_stats, hrm_stream stream)
 {
     HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
+    HRM_TRY(bind_device(m));
     HRM_REQUIRE(cigar_pitch > 0, "cigar_pitch");
     PipeSlot& S = m->slot[slot];
     HRM_REQUIRE(m->pipe_ready && S.is_staged, "nothing is staged in this slot");
@@ -973,6 +994,7 @@ extern "C" hrm_status hrm_mapper_map_staged(hrm_mapper* m, int slot, hrm_read_re
 extern "C" hrm_status hrm_mapper_finish(hrm_mapper* m, int slot, int64_t* h_sq_written, int64_t* h_rec_written)
 {
     HRM_REQUIRE(m != nullptr && slot >= 0 && slot < HRM_PIPE_SLOTS, "mapper / slot");
+    HRM_TRY(bind_device(m));
     PipeSlot& S = m->slot[slot];
     if (S.busy) {
         HRM_CUDA(cudaEventSynchronize(S.computed));
@@ -996,6 +1018,7 @@ extern "C" hrm_status hrm_mapper_finish(hrm_mapper* m, int slot, int64_t* h_sq_w
 extern "C" hrm_status hrm_mapper_set_partition(hrm_mapper* m, hrm_comm* comm)
 {
     HRM_REQUIRE(m != nullptr, "mapper");
+    HRM_TRY(bind_device(m));
     if (m->d_win_prefix != nullptr) {
         set_error("hrm_mapper_set_partition must precede hrm_mapper_set_genome");
         return HRM_ERR_STATE;
@@ -1014,6 +1037,7 @@ extern "C" hrm_status hrm_mapper_set_profiling(hrm_mapper* m, int enable)
 extern "C" hrm_status hrm_mapper_stage_times(hrm_mapper* m, float* h_ms, int32_t* h_spans)
 {
     HRM_REQUIRE(m != nullptr && h_ms != nullptr, "args");
+    HRM_TRY(bind_device(m));
     for (int i = 0; i < HRM_NUM_STAGES; i++) {
         h_ms[i] = 0.f;
         if (h_spans) h_spans[i] = 0;

@@ -76,6 +76,7 @@ struct PipeSlot {
 
 struct hrm_mapper {
     hrm_mapper_config cfg;
+    int device = 0; // the device that was current at hrm_mapper_create: every entry point makes it current again
     // one genome + index per distinct genome conversion
     hrm_genome* genome[3] = {nullptr, nullptr, nullptr};
     hrm_minhasher* index[3] = {nullptr, nullptr, nullptr};

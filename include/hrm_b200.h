@@ -399,6 +399,9 @@ typedef struct {
 
 void hrm_mapper_default_config(hrm_mapper_config* cfg); /* reference defaults, one NONE pass */
 
+/* A mapper belongs to the CUDA device that is current at hrm_mapper_create; every hrm_mapper_* entry point makes that
+ * device current on the calling thread (the staging calls below are meant for a second host thread, which starts with
+ * device 0 current).  The other handles follow the CUDA convention: the caller selects the device. */
 hrm_status hrm_mapper_create(hrm_mapper** out, const hrm_mapper_config* cfg);
 void hrm_mapper_destroy(hrm_mapper* m);
 

@@ -31,3 +31,43 @@ def test_partitioned_multi_gpu(cuda):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     for k in range(n):
         assert "rank %d/%d OK" % (k, n) in r.stdout
+
+
+STAGING_THREAD_SCRIPT = r"""
+import sys, threading
+import numpy as np, torch
+sys.path.insert(0, %r)
+import hashreadmapper_b200.api as api
+from hashreadmapper_b200 import synth
+torch.cuda.set_device(1)
+genome, off = synth.make_genome([90000], seed=5)
+reads, lens, _ = synth.make_reads(genome, off, 2000, 150, error_rate=0.02, seed=6)
+reads = torch.from_numpy(reads).pin_memory().numpy()
+mp = api.Mapper(api.directional_config())
+mp.setGenome(genome, off, ["chrA"])
+sq, rc, _, rec, cig = mp.mapReadsSam(reads, lens, first_read_id=0, cigar_pitch=128, want_records=True)
+err = []
+def stage():  # a fresh host thread: CUDA's current device is 0 here, the mapper lives on device 1
+    try:
+        mp.stageReads(0, reads, lens)
+    except Exception as e:
+        err.append(e)
+t = threading.Thread(target=stage); t.start(); t.join()
+assert not err, err
+o_sq, o_tx = np.zeros(2000 * 40 + 16, np.uint8), np.zeros(2000 * 600, np.uint8)
+mp.mapStaged(0, None, None, 128, 0, o_sq, o_tx)
+sqw, recw = mp.finish(0)
+assert o_sq[:sqw].tobytes() == sq.tobytes() and o_tx[:recw].tobytes() == rc.tobytes()
+print("staging thread OK")
+"""
+
+
+def test_staging_thread_on_second_device(cuda):
+    """a mapper created on device 1 is staged from a fresh host thread (whose current device is 0): every
+    hrm_mapper_* entry point binds the calling thread to the mapper's device"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-c", STAGING_THREAD_SCRIPT % ROOT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "staging thread OK" in r.stdout
