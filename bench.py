@@ -516,18 +516,31 @@ def main():
             for i in range(steps):
                 mp.mapReads(h_reads.numpy(), h_lens.numpy(), CIG, rec_np[i % 2], h_cig[i % 2].numpy())
             return (0, 0)
+        trace = os.environ.get("BENCH_TRACE") is not None  # host time spent inside each call, per step, to stderr
+        tt = []
+        tp = time.perf_counter()
         mp.stageReads(0, h_reads.numpy(), h_lens.numpy())
         sizes = (0, 0)
         for i in range(steps):
+            t_a = time.perf_counter()
             if text is None:
                 mp.mapStaged(i % 2, rec_np[i % 2], h_cig[i % 2].numpy(), CIG)
             else:
                 mp.mapStaged(i % 2, None, None, 128, i * n, text[0][i % 2], text[1][i % 2])
+            t_b = time.perf_counter()
             if i >= 1:
                 sizes = mp.finish((i - 1) % 2)
+            t_c = time.perf_counter()
             if i + 1 < steps:
                 mp.stageReads((i + 1) % 2, h_reads.numpy(), h_lens.numpy())
+            tt.append((t_a - tp, t_b - t_a, t_c - t_b, time.perf_counter() - t_c))
+        t_a = time.perf_counter()
         sizes = mp.finish((steps - 1) % 2)
+        if trace and rank == 0:
+            sys.stderr.write("trace %s: ms from start / in mapStaged / in finish / in stageReads per step: %s; last finish %.1f ms\n"
+                             % ("text" if text is not None else "records",
+                                " ".join("%.0f/%.0f/%.0f/%.0f" % tuple(1e3 * x for x in t) for t in tt),
+                                1e3 * (time.perf_counter() - t_a)))
         return sizes
 
     e2e_run(2)

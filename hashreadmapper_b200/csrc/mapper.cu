@@ -156,7 +156,7 @@ extern "C" void hrm_mapper_destroy(hrm_mapper* m)
             cudaEventDestroy(m->slot[i].drained);
         }
         cudaStreamDestroy(m->pipe_in);
-        cudaStreamDestroy(m->pipe_out);
+        for (int i = 0; i < HRM_PIPE_SLOTS; i++) cudaStreamDestroy(m->pipe_out[i]);
         cudaStreamDestroy(m->pipe_verify);
         cudaFreeHost(m->pipe_host);
     }
@@ -776,7 +776,7 @@ static hrm_status pipe_init(hrm_mapper* m)
     std::lock_guard<std::mutex> lk(mtx);
     if (m->pipe_ready) return HRM_OK;
     HRM_CUDA(cudaStreamCreateWithFlags(&m->pipe_in, cudaStreamNonBlocking));
-    HRM_CUDA(cudaStreamCreateWithFlags(&m->pipe_out, cudaStreamNonBlocking));
+    for (int i = 0; i < HRM_PIPE_SLOTS; i++) HRM_CUDA(cudaStreamCreateWithFlags(&m->pipe_out[i], cudaStreamNonBlocking));
     HRM_CUDA(cudaStreamCreateWithFlags(&m->pipe_verify, cudaStreamNonBlocking));
     HRM_CUDA(cudaMallocHost(&m->pipe_host, sizeof(int64_t) * 4 * HRM_PIPE_SLOTS));
     for (int i = 0; i < HRM_PIPE_SLOTS; i++) {
@@ -905,7 +905,7 @@ extern "C" hrm_status hrm_mapper_map_staged(hrm_mapper* m, int slot, hrm_read_re
     // the seeding of the next batch; measured on B200 (profiles/README.md) the two do not speed each other up -- each kernel
     // fills the SMs with persistent blocks and the pair is bound by instruction issue -- so it is off by default.
     static const bool overlap = getenv("HRM_PIPE_OVERLAP") != nullptr && atoi(getenv("HRM_PIPE_OVERLAP")) != 0;
-    cudaStream_t s = as_stream(stream), vs = overlap ? m->pipe_verify : s, co = m->pipe_out;
+    cudaStream_t s = as_stream(stream), vs = overlap ? m->pipe_verify : s, co = m->pipe_out[slot];
     const int64_t n = S.n;
     S.is_staged = false;
     S.sq_written = S.rec_written = 0;
@@ -1002,9 +1002,9 @@ extern "C" hrm_status hrm_mapper_finish(hrm_mapper* m, int slot, int64_t* h_sq_w
             const int64_t* hp = m->pipe_host + 4 * slot;
             S.rec_written = hp[0];
             S.sq_written = S.h_sq ? hp[1] : 0;
-            HRM_CUDA(cudaMemcpyAsync(S.h_rec, S.text.p, (size_t)S.rec_written, cudaMemcpyDeviceToHost, m->pipe_out));
-            if (S.h_sq) HRM_CUDA(cudaMemcpyAsync(S.h_sq, S.sq.p, (size_t)S.sq_written, cudaMemcpyDeviceToHost, m->pipe_out));
-            HRM_CUDA(cudaEventRecord(S.drained, m->pipe_out));
+            HRM_CUDA(cudaMemcpyAsync(S.h_rec, S.text.p, (size_t)S.rec_written, cudaMemcpyDeviceToHost, m->pipe_out[slot]));
+            if (S.h_sq) HRM_CUDA(cudaMemcpyAsync(S.h_sq, S.sq.p, (size_t)S.sq_written, cudaMemcpyDeviceToHost, m->pipe_out[slot]));
+            HRM_CUDA(cudaEventRecord(S.drained, m->pipe_out[slot]));
             S.want_text = false;
         }
         HRM_CUDA(cudaEventSynchronize(S.drained));

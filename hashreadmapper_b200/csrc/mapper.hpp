@@ -109,7 +109,9 @@ struct hrm_mapper {
     hrm_comm* comm = nullptr; // key-partitioned index (partition.cu); not owned
     // double-buffered end-to-end pipeline
     hrm::PipeSlot slot[HRM_PIPE_SLOTS];
-    cudaStream_t pipe_in = nullptr, pipe_out = nullptr, pipe_verify = nullptr;
+    // one copy-out stream per slot: the text copy of batch i - 1 is queued (in hrm_mapper_finish, once its size is known)
+    // AFTER batch i has made its own stream wait for its verification -- on a shared stream it would wait for that too
+    cudaStream_t pipe_in = nullptr, pipe_out[HRM_PIPE_SLOTS] = {}, pipe_verify = nullptr;
     int64_t* pipe_host = nullptr; // pinned: text sizes of the batches in flight
     bool pipe_ready = false;
 };

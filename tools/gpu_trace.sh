@@ -1,0 +1,9 @@
+set -x
+timeout 600 python -m pytest tests/test_gpu_sam.py -m gpu -x -q -k "staged or fastq" 2>&1 | tail -3
+BENCH_TRACE=1 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --check 0 > gpurun_out/bench_trace.json 2> gpurun_out/bench_trace.err; echo rc=$?
+grep "^trace" gpurun_out/bench_trace.err | tail -3 | cut -c1-400
+python - <<PY
+import json
+d=json.loads([l for l in open("gpurun_out/bench_trace.json") if l.startswith("{")][0])
+print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "text", d["e2e_text"]["value"], "fastq", d["e2e_text"]["from_fastq_text"]["value"])
+PY
