@@ -589,10 +589,9 @@ def main():
                     "sam_bytes_per_read": float(sqw + recw) / n,
                     "api": "hrm_mapper_stage_reads / hrm_mapper_map_staged (V4 + SAM text on the device) / hrm_mapper_finish"}
         # ---- FASTQ text in -> SAM text out: the text goes H2D and is parsed by the device-side reader (hrm_ingest_reads)
-        # from a second host thread while the other slot maps ("FASTQ-in-memory -> SAM-records-in-memory")
+        # while the other slot is verified ("FASTQ-in-memory -> SAM-records-in-memory")
         e2e_fastq = None
         if not args.no_fastq:
-            import threading
             L_ = args.read_len
             hdr = 11  # "@%09d\n"
             rec_len = hdr + L_ + 3 + L_ + 1
@@ -611,18 +610,15 @@ def main():
             pitch_ = reads.shape[1]
 
             def fastq_run(steps):
+                # same order as the row pipeline: queue batch i, fetch the text of batch i - 1 (its slot is free then),
+                # stage batch i + 1 into that slot -- the H2D copy and the reader's kernels run under batch i's verification
                 mp.stageFastq(0, fq_flat, pitch_, n, 0, 0)
-                sizes = (0, 0)
                 for i in range(steps):
-                    if i >= 1:
-                        sizes = mp.finish((i - 1) % 2)
-                    th = None
-                    if i + 1 < steps:
-                        th = threading.Thread(target=mp.stageFastq, args=((i + 1) % 2, fq_flat, pitch_, n, (i + 1) * n, 0))
-                        th.start()
                     mp.mapStaged(i % 2, None, None, 128, i * n, tx_sq[i % 2], tx_rec[i % 2])
-                    if th is not None:
-                        th.join()
+                    if i >= 1:
+                        mp.finish((i - 1) % 2)
+                    if i + 1 < steps:
+                        mp.stageFastq((i + 1) % 2, fq_flat, pitch_, n, (i + 1) * n, 0)
                 return mp.finish((steps - 1) % 2)
 
             fastq_run(2)
@@ -633,7 +629,7 @@ def main():
             fq_s = parallel.max_over_ranks(time.perf_counter() - t0)
             e2e_fastq = {"value": world * n * args.steps / fq_s, "unit": "reads/s", "h2d_bytes_per_step": int(fq_flat.size),
                          "d2h_bytes_per_step": int(sqw2 + recw2),
-                         "api": "hrm_mapper_stage_fastq (H2D of the FASTQ text + device-side reader, second host thread) / "
+                         "api": "hrm_mapper_stage_fastq (H2D of the FASTQ text + device-side reader) / "
                                 "hrm_mapper_map_staged (SAM text on the device) / hrm_mapper_finish"}
             del fq, fqn, fq_flat
         e2e_text["from_fastq_text"] = e2e_fastq

@@ -1,7 +1,5 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_sam.py -m gpu -x -q -k "staged or fastq" 2>&1 | tail -3
-BENCH_TRACE=1 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --check 0 > gpurun_out/bench_trace.json 2> gpurun_out/bench_trace.err; echo rc=$?
-grep "^trace" gpurun_out/bench_trace.err | tail -3 | cut -c1-400
+python bench.py --steps 6 --warmup 3 --no-cpu-baseline --check 0 > gpurun_out/bench_trace.json 2> gpurun_out/bench_trace.err; echo rc=$?
 python - <<PY
 import json
 d=json.loads([l for l in open("gpurun_out/bench_trace.json") if l.startswith("{")][0])
