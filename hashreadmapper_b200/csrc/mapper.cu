@@ -768,7 +768,7 @@ extern "C" hrm_status hrm_mapper_map_reads_sam(hrm_mapper* m, const char* h_read
 // ref: the reference's driver overlaps nothing: every window batch is H2D -> kernels -> D2H with >= 6 stream syncs
 // (main_gpu.cu:471-854) and STEP 2 starts when STEP 1 has ended (main_gpu.cu:1123-1160).  Here a batch lives in one of
 // HRM_PIPE_SLOTS slots: its reads are staged (H2D on a copy-in stream) while the previous batch computes, its results
-// leave (D2H on a copy-out stream) while the next batch computes; the kernels of all batches run in order on the
+// leave (D2H on the copy-out stream of its slot) while the next batch computes; the kernels of all batches run in order on the
 // caller's stream.  Host syncs inside the compute (candidate totals, text size) only ever wait for the batch at hand.
 static hrm_status pipe_init(hrm_mapper* m)
 {
@@ -889,7 +889,7 @@ extern "C" hrm_status hrm_mapper_stage_fastq(hrm_mapper* m, int slot, const char
 }
 
 // Seeding (K1..K5) of the staged batch, then its verification (K7 / K6), V4 and the SAM text, all queued without a host
-// round trip after the seeding; the D2H copies on the copy-out stream.  Returns when the seeding kernels have run (their
+// round trip after the seeding; the D2H copies on the slot's copy-out stream.  Returns when the seeding kernels have run (their
 // candidate totals come back to the host) and everything else is queued.
 extern "C" hrm_status hrm_mapper_map_staged(hrm_mapper* m, int slot, hrm_read_record* h_records, char* h_cigars,
                                             int64_t cigar_pitch, uint32_t first_read_id,

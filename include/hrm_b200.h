@@ -611,7 +611,7 @@ hrm_status hrm_mapper_map_reads_sam(hrm_mapper* m, const char* h_reads_ascii, in
  *                           previous results have not left the device yet);
  *   hrm_mapper_map_staged   runs seeding + filter + SHD + best window (K1..K5) of the staged batch on `stream` and queues
  *                           its verification (K6/K7), V4 and -- when h_rec_out != NULL -- the SAM text behind it, and
- *                           the D2H copies of records / CIGARs on a copy-out stream; returns when the seeding has
+ *                           the D2H copies of records / CIGARs on the slot's copy-out stream; returns when the seeding has
  *                           run, not when the rest has finished (HRM_PIPE_OVERLAP=1: verification on a second stream,
  *                           under the seeding of the next batch);
  *   hrm_mapper_finish       waits until the slot's results are in the host buffers (copies the SAM text out, whose
